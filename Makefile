@@ -1,0 +1,45 @@
+# Top-level build.  `python -c "import __graft_entry__ as g; g.build()"` runs `make all`.
+#
+#   lib      msufsort_b200/lib/libb200sa.so          hand-written CUDA kernels + C ABI (sm_100a only)
+#   textgen  msufsort_b200/lib/libb200sa_textgen.so  synthetic input generators (host C)
+#   facade   msufsort_b200/lib/libmsufsort.so        the reference-shaped C++ facade (src/library)
+#   oracle   oracle/liboracle.so (+ oracle/_ref/ when /root/reference exists)   TEST INFRASTRUCTURE
+#   emu      tests/emu/libb200sa_emu.so              kernel logic under a CPU SIMT emulator (tests only)
+NVCC      ?= nvcc
+CC        ?= gcc
+CXX       ?= g++
+ARCH      := -gencode arch=compute_100a,code=sm_100a
+NVCCFLAGS := $(ARCH) -lineinfo -O3 -std=c++17 -Xcompiler -fPIC,-fvisibility=hidden -Xptxas -v --expt-relaxed-constexpr
+CSRC      := msufsort_b200/csrc
+LIBDIR    := msufsort_b200/lib
+KSRC      := $(CSRC)/b200sa.cu $(CSRC)/engine.cuh $(CSRC)/common.cuh $(CSRC)/radix_sort.cuh $(CSRC)/sa_kernels.cuh $(CSRC)/bwt_kernels.cuh include/b200sa.h
+
+all: lib textgen facade oracle emu
+
+lib: $(LIBDIR)/libb200sa.so
+$(LIBDIR)/libb200sa.so: $(KSRC)
+	@mkdir -p $(LIBDIR)
+	$(NVCC) $(NVCCFLAGS) -shared -o $@ $(CSRC)/b200sa.cu 2> $(LIBDIR)/ptxas.log || (cat $(LIBDIR)/ptxas.log; exit 1)
+	@grep -E "error|warning" $(LIBDIR)/ptxas.log | grep -v "ptxas info" || true
+
+textgen: $(LIBDIR)/libb200sa_textgen.so
+$(LIBDIR)/libb200sa_textgen.so: $(CSRC)/textgen.c
+	@mkdir -p $(LIBDIR)
+	$(CC) -O2 -std=c11 -fPIC -fvisibility=hidden -shared -o $@ $<
+
+facade: $(LIBDIR)/libmsufsort.so
+$(LIBDIR)/libmsufsort.so: src/library/msufsort/msufsort.cpp src/library/msufsort/msufsort.h src/library/msufsort.h include/b200sa.h $(LIBDIR)/libb200sa.so
+	$(CXX) -O2 -std=c++17 -fPIC -shared -Isrc -Iinclude -o $@ src/library/msufsort/msufsort.cpp -L$(LIBDIR) -lb200sa -Wl,-rpath,'$$ORIGIN'
+
+oracle:
+	$(MAKE) -C oracle
+
+emu: tests/emu/libb200sa_emu.so
+tests/emu/libb200sa_emu.so: $(KSRC) tests/emu/cuda_emu.h
+	$(CXX) -O2 -g -std=c++17 -fPIC -shared -DB200SA_EMU -x c++ -Itests/emu -I$(CSRC) -Wno-unused-function -o $@ $(CSRC)/b200sa.cu
+
+clean:
+	rm -f $(LIBDIR)/*.so $(LIBDIR)/ptxas.log tests/emu/*.so
+	$(MAKE) -C oracle clean
+
+.PHONY: all lib textgen facade oracle emu clean

@@ -1,0 +1,174 @@
+/*
+ * b200sa.h — C ABI of the B200-native suffix-array / Burrows-Wheeler engine.
+ *
+ * This is the drop-in boundary for the hot path of michaelmaniscalco/msufsort.
+ * Every entry point names the reference interface it replaces (paths relative
+ * to the reference tree, src/library/msufsort/...).  The C++ facade in
+ * src/library/msufsort/msufsort.h (same public signatures as the reference's
+ * header) is a thin marshalling layer over these functions; so is the ctypes
+ * mirror in msufsort_b200/api.py.
+ *
+ * Conventions (identical to the reference, see msufsort.cpp:1720,1755-1766,
+ * 1811-1816,1891):
+ *   - the suffix array of an n-byte text has n+1 int32 entries, SA[0] = n (the
+ *     empty suffix / virtual sentinel, smaller than every byte including 0x00),
+ *     SA[1..n] = suffixes in lexicographic order, a proper prefix sorts first;
+ *   - BWT[i] = T[SA[i]-1] over the n+1 rows with the single row whose SA[i]==0
+ *     removed; that row number is the returned sentinel index (1..n); n bytes;
+ *   - the inverse transform takes (n bytes, sentinel index) and returns T.
+ *
+ * All functions return 0 on success and a non-zero B200SA_E* code on failure;
+ * b200sa_last_error() gives the message for the calling thread.  There is no
+ * CPU fallback: without a CUDA device every compute entry point fails with
+ * B200SA_ENODEVICE.
+ *
+ * Pointers named d_* are device pointers.  `stream` is a cudaStream_t passed
+ * as void* (NULL = the context's own stream).  Plain pointers and sizes only:
+ * no C++/torch types cross this boundary.
+ */
+#ifndef B200SA_H
+#define B200SA_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define B200SA_API
+#else
+#define B200SA_API __attribute__((visibility("default")))
+#endif
+
+enum {
+    B200SA_OK = 0,
+    B200SA_EINVAL = 1,     /* bad argument (null pointer, n < 0, n too large for the index type, bad sentinel) */
+    B200SA_ENODEVICE = 2,  /* no usable CUDA device / driver */
+    B200SA_ECUDA = 3,      /* a CUDA runtime call or kernel failed */
+    B200SA_ENOMEM = 4,     /* device or pinned-host allocation failed */
+    B200SA_EINTERNAL = 5,  /* invariant violated (bug) */
+    B200SA_ECOMM = 6       /* NCCL / multi-GPU communication failure */
+};
+
+/* Largest n the int32 entry points accept (SA values must fit int32: n <= 2^31-2).
+ * The reference itself is only correct up to 2^30-2 (flag bits, msufsort.h:84-93). */
+#define B200SA_MAX_N_INT32 ((int64_t)2147483646)
+
+typedef struct b200sa_ctx b200sa_ctx;
+
+/* ---- lifetime -------------------------------------------------------------------------- */
+
+/* Replaces: msufsort::msufsort(int32 numThreads) (msufsort.cpp:39-60) — the reference spawns
+ * a host worker pool; here a context binds one CUDA device, owns one stream, the device
+ * workspace (grown on demand, reused across calls) and pinned staging buffers.  One context
+ * = one job at a time (same as one msufsort object, msufsort.h:281-309). */
+B200SA_API int b200sa_create(b200sa_ctx** out, int device);
+/* Replaces: msufsort::~msufsort() (msufsort.cpp:64-68). */
+B200SA_API void b200sa_destroy(b200sa_ctx* ctx);
+/* Frees the device workspace but keeps the context usable. */
+B200SA_API int b200sa_release_workspace(b200sa_ctx* ctx);
+
+B200SA_API const char* b200sa_last_error(void);
+B200SA_API int b200sa_version(void);
+/* Number of CUDA devices visible (0 when there is none / no driver). */
+B200SA_API int b200sa_device_count(void);
+
+/* ---- host-buffer entry points (what the reference-facing facade binds) ----------------- */
+
+/* Replaces: msufsort::make_suffix_array(uint8_t const*, uint8_t const*) (msufsort.cpp:1730-1767;
+ * template msufsort.h:432-445).  text: n bytes of host memory (pageable or pinned), not modified.
+ * sa_out: n+1 int32.  n == 0 yields sa_out[0] = 0. */
+B200SA_API int b200sa_suffix_array(b200sa_ctx* ctx, const uint8_t* text, int64_t n, int32_t* sa_out);
+
+/* Replaces: msufsort::forward_burrows_wheeler_transform(uint8_t*, uint8_t*) (msufsort.cpp:1771-1817;
+ * template msufsort.h:449-462).  In place over n host bytes; *sentinel_index_out in [1,n]
+ * (0 when n == 0). */
+B200SA_API int b200sa_bwt(b200sa_ctx* ctx, uint8_t* text_inout, int64_t n, int32_t* sentinel_index_out);
+
+/* Replaces: msufsort::reverse_burrows_wheeler_transform(uint8_t*, uint8_t*, int32 sentinelIndex,
+ * int32 numThreads) (msufsort.cpp:1821-2096; template msufsort.h:466-476).  In place. */
+B200SA_API int b200sa_unbwt(b200sa_ctx* ctx, uint8_t* bwt_inout, int64_t n, int32_t sentinel_index);
+
+/* Superset of the reference API: one suffix sort, both results (the reference needs its two
+ * public calls, i.e. two sorts, for this).  sa_out and/or bwt_out may be NULL. */
+B200SA_API int b200sa_suffix_array_bwt(b200sa_ctx* ctx, const uint8_t* text, int64_t n,
+                                       int32_t* sa_out, uint8_t* bwt_out, int32_t* sentinel_index_out);
+
+/* ---- device-resident entry points (kernel-only timing, pipelines, multi-GPU callers) ---- */
+
+/* d_text: n bytes; d_sa_out: n+1 int32.  Work is enqueued on `stream`; the call returns after
+ * the last doubling round has been observed complete (the round loop reads two counters per
+ * round), so results are ready on return. */
+B200SA_API int b200sa_suffix_array_dev(b200sa_ctx* ctx, const uint8_t* d_text, int64_t n,
+                                       int32_t* d_sa_out, void* stream);
+
+/* SA + BWT from one sort.  d_bwt_out: n bytes (must not alias d_text).  d_sa_out may be NULL
+ * (the engine then keeps the SA in its workspace).  *sentinel_index_out is host memory. */
+B200SA_API int b200sa_bwt_dev(b200sa_ctx* ctx, const uint8_t* d_text, int64_t n,
+                              uint8_t* d_bwt_out, int32_t* d_sa_out,
+                              int32_t* sentinel_index_out, void* stream);
+
+/* Inverse BWT.  d_text_out: n bytes (must not alias d_bwt). */
+B200SA_API int b200sa_unbwt_dev(b200sa_ctx* ctx, const uint8_t* d_bwt, int64_t n,
+                                int32_t sentinel_index, uint8_t* d_text_out, void* stream);
+
+/* O(n) validator (the role of validate_suffix_array, main.cpp:236-270, without its O(n*LCP)
+ * byte compare): checks SA[0]==n, that SA is a permutation of [0,n], and for every pair of
+ * neighbouring rows that T[SA[i]] <= T[SA[i+1]] with ties decided by ISA[SA[i]+1] < ISA[SA[i+1]+1].
+ * *bad_rows_out receives the number of offending rows (0 = the SA is correct, hence — the SA
+ * being unique — bit-identical to the reference's). */
+B200SA_API int b200sa_check_suffix_array_dev(b200sa_ctx* ctx, const uint8_t* d_text, int64_t n,
+                                             const int32_t* d_sa, int64_t* bad_rows_out, void* stream);
+
+/* ---- instrumentation --------------------------------------------------------------------- */
+
+enum {
+    B200SA_PH_ALPHABET = 0,   /* byte histogram of the text                                   */
+    B200SA_PH_PACK = 1,       /* initial k-symbol key packing                                 */
+    B200SA_PH_SORT_HIST = 2,  /* radix digit histograms                                       */
+    B200SA_PH_SORT_PASS = 3,  /* radix scatter passes (decoupled look-back)  — dominant       */
+    B200SA_PH_BUILD = 4,      /* (group, rank[i+h]) key build                                 */
+    B200SA_PH_RERANK = 5,     /* head flags, segmented scan, ISA scatter, compaction          */
+    B200SA_PH_BWT = 6,        /* BWT gather                                                   */
+    B200SA_PH_UNBWT_BUILD = 7,/* unBWT: histogram + psi table                                 */
+    B200SA_PH_UNBWT_WALK = 8, /* unBWT: walkers, list ranking, emit                           */
+    B200SA_PH_CHECK = 9,      /* validator                                                    */
+    B200SA_PH_SEGSORT = 10,   /* in-shared-memory sort of small groups (doubling rounds)      */
+    B200SA_PH_COUNT = 16
+};
+
+typedef struct b200sa_profile {
+    /* accumulated since b200sa_profile_reset(); times are CUDA-event device milliseconds on the
+     * launching stream and are only collected while profiling is enabled */
+    double   ms[B200SA_PH_COUNT];
+    uint64_t launches[B200SA_PH_COUNT];      /* kernel launches per phase (always counted)     */
+    uint64_t alg_bytes[B200SA_PH_COUNT];     /* algorithmic bytes moved per phase  */
+    uint64_t rounds;                         /* doubling rounds executed (round 0 included)    */
+    uint64_t sort_passes;                    /* radix scatter passes executed                  */
+    uint64_t sorted_tuples;                  /* sum over passes of tuples scattered            */
+    uint64_t active_tuples;                  /* sum over rounds of active tuples               */
+    uint64_t memsets;                        /* cudaMemsetAsync calls (not kernels of ours)    */
+} b200sa_profile;
+
+B200SA_API int b200sa_set_profiling(b200sa_ctx* ctx, int enabled);
+B200SA_API int b200sa_profile_reset(b200sa_ctx* ctx);
+B200SA_API int b200sa_profile_get(b200sa_ctx* ctx, b200sa_profile* out);
+/* Total kernels of this library launched by this context since creation. */
+B200SA_API uint64_t b200sa_launch_count(b200sa_ctx* ctx);
+
+/* ---- building blocks exported for tests and benches -------------------------------------- */
+
+/* Stable LSD radix sort of (u64 key, u32 value) pairs on bits [begin_bit, end_bit).
+ * d_keys/d_vals hold the input and are clobbered; on return *result_in_alt is 0 when the sorted
+ * data is in d_keys/d_vals and 1 when it is in d_keys_alt/d_vals_alt.  d_vals == NULL means
+ * "values are the element indices 0..m-1". */
+B200SA_API int b200sa_radix_sort_pairs_dev(b200sa_ctx* ctx, uint64_t* d_keys, uint64_t* d_keys_alt,
+                                           uint32_t* d_vals, uint32_t* d_vals_alt, int64_t m,
+                                           int begin_bit, int end_bit, int* result_in_alt, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200SA_H */

@@ -1,0 +1,271 @@
+"""ctypes binding of include/b200sa.h and the reference-shaped Python entry points.
+
+Reference interface mirrored (names, argument meaning, in-place behaviour, return values):
+  maniscalco::make_suffix_array(begin, end, numThreads)                  msufsort.h:432-445
+  maniscalco::forward_burrows_wheeler_transform(begin, end, numThreads)  msufsort.h:449-462
+  maniscalco::reverse_burrows_wheeler_transform(begin, end, sentinelIndex, numThreads)  :466-476
+``numThreads`` is accepted and ignored (the work runs on the GPU); results do not depend on it in
+the reference either.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+from typing import Optional
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+PRODUCT_LIB = os.path.join(_HERE, "lib", "libb200sa.so")
+
+PHASES = {
+    "alphabet": 0, "pack": 1, "sort_hist": 2, "sort_pass": 3, "build": 4, "rerank": 5,
+    "bwt": 6, "unbwt_build": 7, "unbwt_walk": 8, "check": 9, "segsort": 10,
+}
+_PH_COUNT = 16
+
+
+class B200SAError(RuntimeError):
+    """Raised for every non-zero status of the C ABI (the C++ facade throws std::runtime_error)."""
+
+    def __init__(self, code: int, message: str):
+        super().__init__(f"b200sa error {code}: {message}")
+        self.code = code
+
+
+class _Profile(C.Structure):
+    _fields_ = [
+        ("ms", C.c_double * _PH_COUNT),
+        ("launches", C.c_uint64 * _PH_COUNT),
+        ("alg_bytes", C.c_uint64 * _PH_COUNT),
+        ("rounds", C.c_uint64),
+        ("sort_passes", C.c_uint64),
+        ("sorted_tuples", C.c_uint64),
+        ("active_tuples", C.c_uint64),
+        ("memsets", C.c_uint64),
+    ]
+
+
+# every symbol include/b200sa.h declares: (name, restype, argtypes)
+_P = C.c_void_p
+ABI = [
+    ("b200sa_create", C.c_int, [C.POINTER(_P), C.c_int]),
+    ("b200sa_destroy", None, [_P]),
+    ("b200sa_release_workspace", C.c_int, [_P]),
+    ("b200sa_last_error", C.c_char_p, []),
+    ("b200sa_version", C.c_int, []),
+    ("b200sa_device_count", C.c_int, []),
+    ("b200sa_suffix_array", C.c_int, [_P, _P, C.c_int64, _P]),
+    ("b200sa_bwt", C.c_int, [_P, _P, C.c_int64, C.POINTER(C.c_int32)]),
+    ("b200sa_unbwt", C.c_int, [_P, _P, C.c_int64, C.c_int32]),
+    ("b200sa_suffix_array_bwt", C.c_int, [_P, _P, C.c_int64, _P, _P, C.POINTER(C.c_int32)]),
+    ("b200sa_suffix_array_dev", C.c_int, [_P, _P, C.c_int64, _P, _P]),
+    ("b200sa_bwt_dev", C.c_int, [_P, _P, C.c_int64, _P, _P, C.POINTER(C.c_int32), _P]),
+    ("b200sa_unbwt_dev", C.c_int, [_P, _P, C.c_int64, C.c_int32, _P, _P]),
+    ("b200sa_check_suffix_array_dev", C.c_int, [_P, _P, C.c_int64, _P, C.POINTER(C.c_int64), _P]),
+    ("b200sa_set_profiling", C.c_int, [_P, C.c_int]),
+    ("b200sa_profile_reset", C.c_int, [_P]),
+    ("b200sa_profile_get", C.c_int, [_P, C.POINTER(_Profile)]),
+    ("b200sa_launch_count", C.c_uint64, [_P]),
+    ("b200sa_radix_sort_pairs_dev", C.c_int, [_P, _P, _P, _P, _P, C.c_int64, C.c_int, C.c_int, C.POINTER(C.c_int), _P]),
+]
+
+
+class Library:
+    """A loaded copy of the C ABI.  The product always uses :func:`load_library` (the nvcc-built
+    ``msufsort_b200/lib/libb200sa.so``); tests may wrap another CDLL that exports the same ABI."""
+
+    def __init__(self, path_or_cdll):
+        self.cdll = C.CDLL(path_or_cdll) if isinstance(path_or_cdll, str) else path_or_cdll
+        self.path = path_or_cdll if isinstance(path_or_cdll, str) else getattr(path_or_cdll, "_name", "?")
+        for name, restype, argtypes in ABI:
+            fn = getattr(self.cdll, name)  # AttributeError if the symbol is missing
+            fn.restype = restype
+            fn.argtypes = argtypes
+
+    def last_error(self) -> str:
+        msg = self.cdll.b200sa_last_error()
+        return msg.decode("utf-8", "replace") if msg else ""
+
+    def check(self, rc: int) -> None:
+        if rc != 0:
+            raise B200SAError(rc, self.last_error())
+
+
+_lib_lock = threading.Lock()
+_lib: Optional[Library] = None
+
+
+def load_library() -> Library:
+    """Loads the CUDA library.  Fails loudly when it has not been built: there is no fallback."""
+    global _lib
+    with _lib_lock:
+        if _lib is None:
+            if not os.path.exists(PRODUCT_LIB):
+                raise B200SAError(2, f"{PRODUCT_LIB} is missing — run `make lib` (nvcc, sm_100a); "
+                                     "msufsort_b200 has no CPU fallback")
+            _lib = Library(PRODUCT_LIB)
+        return _lib
+
+
+def _ptr(x) -> Optional[int]:
+    """Address of a numpy array / bytearray / torch tensor / raw int."""
+    if x is None:
+        return None
+    if isinstance(x, int):
+        return x
+    if isinstance(x, np.ndarray):
+        return x.ctypes.data
+    if hasattr(x, "data_ptr"):
+        return int(x.data_ptr())
+    if isinstance(x, (bytearray, memoryview)):
+        return C.addressof((C.c_char * len(x)).from_buffer(x))
+    raise TypeError(f"cannot take the address of {type(x)!r}")
+
+
+class Engine:
+    """One context of the C ABI = one GPU, one stream, one reusable device workspace — the
+    analogue of one ``maniscalco::msufsort`` object (msufsort.h:50-75)."""
+
+    def __init__(self, device: int = 0, library: Optional[Library] = None):
+        self.lib = library if library is not None else load_library()
+        self._ctx = _P()
+        self.lib.check(self.lib.cdll.b200sa_create(C.byref(self._ctx), device))
+        self.device = device
+
+    def close(self) -> None:
+        if getattr(self, "_ctx", None) is not None and self._ctx:
+            self.lib.cdll.b200sa_destroy(self._ctx)
+            self._ctx = _P()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # ---- host-buffer entry points (what a user of the reference calls) ----------------------
+    def make_suffix_array(self, data) -> np.ndarray:
+        """SA of ``data`` (bytes-like / uint8 array): int32 array of len(data)+1, SA[0]=len(data)."""
+        buf = np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else data
+        if buf.dtype.itemsize != 1:
+            raise TypeError("input must be a 1-byte element buffer")
+        buf = np.ascontiguousarray(buf)
+        n = buf.size
+        sa = np.empty(n + 1, dtype=np.int32)
+        self.lib.check(self.lib.cdll.b200sa_suffix_array(self._ctx, _ptr(buf) if n else None, n, _ptr(sa)))
+        return sa
+
+    def forward_burrows_wheeler_transform(self, data) -> int:
+        """In-place BWT of a writable buffer; returns the sentinel index."""
+        buf = data if isinstance(data, np.ndarray) else np.frombuffer(data, dtype=np.uint8)
+        if not buf.flags.writeable or not buf.flags.c_contiguous or buf.dtype.itemsize != 1:
+            raise TypeError("forward_burrows_wheeler_transform needs a writable contiguous byte buffer")
+        s = C.c_int32(0)
+        self.lib.check(self.lib.cdll.b200sa_bwt(self._ctx, _ptr(buf) if buf.size else None, buf.size, C.byref(s)))
+        return int(s.value)
+
+    def reverse_burrows_wheeler_transform(self, data, sentinel_index: int) -> None:
+        """In-place inverse BWT."""
+        buf = data if isinstance(data, np.ndarray) else np.frombuffer(data, dtype=np.uint8)
+        if not buf.flags.writeable or not buf.flags.c_contiguous or buf.dtype.itemsize != 1:
+            raise TypeError("reverse_burrows_wheeler_transform needs a writable contiguous byte buffer")
+        self.lib.check(self.lib.cdll.b200sa_unbwt(self._ctx, _ptr(buf) if buf.size else None, buf.size, int(sentinel_index)))
+
+    def suffix_array_and_bwt(self, data):
+        """Superset call: one sort, returns (sa, bwt, sentinel_index)."""
+        buf = np.ascontiguousarray(np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else data)
+        n = buf.size
+        sa = np.empty(n + 1, dtype=np.int32)
+        bwt = np.empty(n, dtype=np.uint8)
+        s = C.c_int32(0)
+        self.lib.check(self.lib.cdll.b200sa_suffix_array_bwt(self._ctx, _ptr(buf) if n else None, n, _ptr(sa),
+                                                             _ptr(bwt) if n else None, C.byref(s)))
+        return sa, bwt, int(s.value)
+
+    # ---- raw-pointer variants of the host entry points (pinned buffers in bench.py) ----------
+    def suffix_array_ptr(self, text_ptr: int, n: int, sa_ptr: int) -> None:
+        self.lib.check(self.lib.cdll.b200sa_suffix_array(self._ctx, text_ptr, n, sa_ptr))
+
+    def bwt_ptr(self, text_ptr: int, n: int) -> int:
+        s = C.c_int32(0)
+        self.lib.check(self.lib.cdll.b200sa_bwt(self._ctx, text_ptr, n, C.byref(s)))
+        return int(s.value)
+
+    def unbwt_ptr(self, bwt_ptr: int, n: int, sentinel_index: int) -> None:
+        self.lib.check(self.lib.cdll.b200sa_unbwt(self._ctx, bwt_ptr, n, int(sentinel_index)))
+
+    # ---- device-resident entry points ---------------------------------------------------------
+    def suffix_array_dev(self, d_text, n: int, d_sa, stream: int = 0) -> None:
+        self.lib.check(self.lib.cdll.b200sa_suffix_array_dev(self._ctx, _ptr(d_text), n, _ptr(d_sa), stream or None))
+
+    def bwt_dev(self, d_text, n: int, d_bwt, d_sa=None, stream: int = 0) -> int:
+        s = C.c_int32(0)
+        self.lib.check(self.lib.cdll.b200sa_bwt_dev(self._ctx, _ptr(d_text), n, _ptr(d_bwt), _ptr(d_sa), C.byref(s), stream or None))
+        return int(s.value)
+
+    def unbwt_dev(self, d_bwt, n: int, sentinel_index: int, d_out, stream: int = 0) -> None:
+        self.lib.check(self.lib.cdll.b200sa_unbwt_dev(self._ctx, _ptr(d_bwt), n, int(sentinel_index), _ptr(d_out), stream or None))
+
+    def check_suffix_array_dev(self, d_text, n: int, d_sa, stream: int = 0) -> int:
+        bad = C.c_int64(-1)
+        self.lib.check(self.lib.cdll.b200sa_check_suffix_array_dev(self._ctx, _ptr(d_text), n, _ptr(d_sa), C.byref(bad), stream or None))
+        return int(bad.value)
+
+    def radix_sort_pairs_dev(self, d_keys, d_keys_alt, d_vals, d_vals_alt, m: int, begin_bit: int, end_bit: int, stream: int = 0) -> int:
+        side = C.c_int(0)
+        self.lib.check(self.lib.cdll.b200sa_radix_sort_pairs_dev(self._ctx, _ptr(d_keys), _ptr(d_keys_alt), _ptr(d_vals), _ptr(d_vals_alt),
+                                                                 m, begin_bit, end_bit, C.byref(side), stream or None))
+        return int(side.value)
+
+    # ---- instrumentation ----------------------------------------------------------------------
+    def set_profiling(self, enabled: bool) -> None:
+        self.lib.check(self.lib.cdll.b200sa_set_profiling(self._ctx, 1 if enabled else 0))
+
+    def profile_reset(self) -> None:
+        self.lib.check(self.lib.cdll.b200sa_profile_reset(self._ctx))
+
+    def profile(self) -> dict:
+        p = _Profile()
+        self.lib.check(self.lib.cdll.b200sa_profile_get(self._ctx, C.byref(p)))
+        out = {"rounds": p.rounds, "sort_passes": p.sort_passes, "sorted_tuples": p.sorted_tuples,
+               "active_tuples": p.active_tuples, "memsets": p.memsets, "phases": {}}
+        for name, i in PHASES.items():
+            out["phases"][name] = {"ms": p.ms[i], "launches": p.launches[i], "alg_bytes": p.alg_bytes[i]}
+        return out
+
+    def launch_count(self) -> int:
+        return int(self.lib.cdll.b200sa_launch_count(self._ctx))
+
+    def release_workspace(self) -> None:
+        self.lib.check(self.lib.cdll.b200sa_release_workspace(self._ctx))
+
+
+# ---- module-level functions with the reference's names ---------------------------------------
+_default_engine: Optional[Engine] = None
+
+
+def _engine() -> Engine:
+    global _default_engine
+    if _default_engine is None:
+        _default_engine = Engine(int(os.environ.get("MSUFSORT_DEVICE", "0")))
+    return _default_engine
+
+
+def make_suffix_array(data, num_threads: int = 1) -> np.ndarray:
+    return _engine().make_suffix_array(data)
+
+
+def forward_burrows_wheeler_transform(data, num_threads: int = 1) -> int:
+    return _engine().forward_burrows_wheeler_transform(data)
+
+
+def reverse_burrows_wheeler_transform(data, sentinel_index: int, num_threads: int = 1) -> None:
+    _engine().reverse_burrows_wheeler_transform(data, sentinel_index)

@@ -1,0 +1,165 @@
+// bwt_kernels.cuh — forward BWT gather and inverse BWT (psi table, walkers, list ranking).
+#pragma once
+#include "common.cuh"
+
+namespace b200sa {
+
+// ---------------------------------------------------------------------------------------------
+// Forward BWT: out[o] = T[SA[row] - 1] with row = o + (o >= s), s = row of suffix 0 = rank[0].
+// Replaces second_stage_its_as_burrows_wheeler_transform (msufsort.cpp:1453-1492) and the serial
+// copy-out loop (:1811-1815).  Row 0 holds SA = n, so it emits T[n-1] without a special case.
+// Each thread produces 4 consecutive output bytes per step (one 32-bit store); SA is read with
+// consecutive lanes on consecutive 16-byte chunks, the text bytes are gathered.
+static const int BW_THREADS = 256;
+static const int BW_STEPS = 4;  // independent 4-byte groups in flight per thread
+
+__global__ void __launch_bounds__(BW_THREADS)
+k_bwt_gather(const u8* __restrict__ text, const i32* __restrict__ sa, const u32* __restrict__ rank,
+             u32 n, u8* __restrict__ out, i32* __restrict__ sentinel_out)
+{
+    const u32 s = rank[0];
+    if (blockIdx.x == 0 && threadIdx.x == 0 && sentinel_out) *sentinel_out = (i32)s;
+    const u32 ngroups = (u32)div_up_u64(n, 4);
+    const bool out_aligned = (((uintptr_t)out) & 3u) == 0;
+    for (u32 g0 = (blockIdx.x * BW_THREADS + threadIdx.x); g0 < ngroups; g0 += gridDim.x * BW_THREADS * BW_STEPS) {
+        u32 packed[BW_STEPS];
+#pragma unroll
+        for (int st = 0; st < BW_STEPS; ++st) {
+            const u32 g = g0 + (u32)st * gridDim.x * BW_THREADS;
+            u32 w = 0;
+            if (g < ngroups) {
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    const u32 o = g * 4u + (u32)b;
+                    if (o < n) {
+                        const u32 row = o + (o >= s ? 1u : 0u);
+                        const u32 v = (u32)sa[row];
+                        w |= (u32)text[v - 1u] << (8 * b);
+                    }
+                }
+            }
+            packed[st] = w;
+        }
+#pragma unroll
+        for (int st = 0; st < BW_STEPS; ++st) {
+            const u32 g = g0 + (u32)st * gridDim.x * BW_THREADS;
+            if (g < ngroups) {
+                const u32 o = g * 4u;
+                if (out_aligned && o + 4u <= n) {
+                    *(u32*)(out + o) = packed[st];
+                } else {
+                    for (u32 b = 0; b < 4u && o + b < n; ++b) out[o + b] = (u8)(packed[st] >> (8 * b));
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Inverse BWT.
+//
+// Rows of the conceptual (n+1)-row matrix: row 0 is the sentinel's row ("" / suffix n), L[row] for
+// row != s is bwt[row - (row > s)], L[s] is the sentinel.  psi[k] = the row r with LF(r) = k, i.e.
+// the row of the suffix one text position to the right of row k's suffix; psi[0] = s.  psi[1..n]
+// is exactly a stable 8-bit counting sort of the rows by their BWT byte — one onesweep pass with
+// generated values (radix_sort.cuh), the reference's phase C (msufsort.cpp:1898-1915).  The first
+// byte of row k's suffix is the symbol whose F-column range contains k (fstart[]), so no symbol is
+// stored next to psi.
+//
+// Decoding follows psi from row s (suffix 0) and emits F[row] at every step.  It is split over
+// walkers seeded at every D-th row plus row s (the reference seeds 256 x threads walkers,
+// :1922-1944): bit 31 of psi[row] marks seed rows.  Pass A measures each walker's segment (length,
+// successor walker); a pointer-jumping list ranking turns the segment chain into text offsets; pass
+// B walks again and writes bytes at their final positions.
+static const u32 UB_MARK = 0x80000000u;
+static const u32 UB_IDX = 0x7fffffffu;
+
+// fstart[c] = first F-row of symbol c (rows 1..n), fstart[256] = n+1.  bins = exclusive byte counts.
+__global__ void k_unbwt_fstart(const u32* __restrict__ bins, u32 n, u32* __restrict__ fstart)
+{
+    const u32 t = threadIdx.x;
+    if (t < 256) fstart[t] = bins[t] + 1u;
+    if (t == 0) fstart[256] = n + 1u;
+}
+
+// walker w < nreg starts at row w*D (walker 0 = row 0 is the terminal, it never walks);
+// walker nreg (only if s % D != 0) starts at row s.
+__device__ __forceinline__ u32 ub_walker_row(u32 w, u32 nreg, u32 D, u32 s) { return w < nreg ? w * D : s; }
+__device__ __forceinline__ u32 ub_row_walker(u32 row, u32 nreg, u32 D, u32 s)
+{
+    return (row % D == 0) ? row / D : nreg;  // only called on marked rows
+}
+
+__global__ void __launch_bounds__(256)
+k_unbwt_mark(u32* __restrict__ psi, u32 nwalkers, u32 nreg, u32 D, u32 s)
+{
+    const u32 w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= nwalkers) return;
+    const u32 row = ub_walker_row(w, nreg, D, s);
+    if (w == 0) psi[0] = s | UB_MARK;
+    else psi[row] |= UB_MARK;
+}
+
+// Pass A: segment length and successor of every walker.
+static const int UW_THREADS = 128;
+
+__global__ void __launch_bounds__(UW_THREADS)
+k_unbwt_measure(const u32* __restrict__ psi, u32 nwalkers, u32 nreg, u32 D, u32 s,
+                u32* __restrict__ seg_len, u32* __restrict__ seg_next)
+{
+    const u32 w = blockIdx.x * UW_THREADS + threadIdx.x;
+    if (w >= nwalkers) return;
+    if (w == 0) { seg_len[0] = 0; seg_next[0] = 0; return; }  // terminal node points to itself
+    u32 cur = ub_walker_row(w, nreg, D, s);
+    u32 e = psi[cur];
+    u32 len = 0;
+    do {
+        ++len;                 // row `cur` emits one byte
+        cur = e & UB_IDX;
+        e = psi[cur];
+    } while (!(e & UB_MARK));
+    seg_len[w] = len;
+    seg_next[w] = ub_row_walker(cur, nreg, D, s);
+}
+
+// Pointer jumping (Wyllie): dist[w] = bytes emitted from walker w to the end of the text.
+// One step: (next, dist) <- (next[next], dist + dist[next]); the terminal has next = itself, dist 0.
+__global__ void __launch_bounds__(256)
+k_unbwt_jump(const u32* __restrict__ next_in, const u32* __restrict__ dist_in,
+             u32* __restrict__ next_out, u32* __restrict__ dist_out, u32 nwalkers)
+{
+    const u32 w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= nwalkers) return;
+    const u32 nx = next_in[w];
+    dist_out[w] = dist_in[w] + dist_in[nx];
+    next_out[w] = next_in[nx];
+}
+
+// Pass B: walk again, emit F[row] at text offset n - dist[w] + step.
+__global__ void __launch_bounds__(UW_THREADS)
+k_unbwt_emit(const u32* __restrict__ psi, const u32* __restrict__ fstart, const u32* __restrict__ dist,
+             u32 nwalkers, u32 nreg, u32 D, u32 s, u32 n, u8* __restrict__ out)
+{
+    __shared__ u32 s_f[257];
+    for (u32 i = threadIdx.x; i < 257; i += UW_THREADS) s_f[i] = fstart[i];
+    __syncthreads();
+    const u32 w = blockIdx.x * UW_THREADS + threadIdx.x;
+    if (w >= nwalkers || w == 0) return;
+    u32 cur = ub_walker_row(w, nreg, D, s);
+    u32 pos = n - dist[w];
+    u32 e = psi[cur];
+    do {
+        // symbol of F-row cur: largest c with s_f[c] <= cur (cur >= 1 here)
+        u32 lo = 0, hi = 256;
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+            const u32 mid = (lo + hi) >> 1;
+            if (s_f[mid] <= cur) lo = mid; else hi = mid;
+        }
+        out[pos++] = (u8)lo;
+        cur = e & UB_IDX;
+        e = psi[cur];
+    } while (!(e & UB_MARK));
+}
+
+}  // namespace b200sa

@@ -1,0 +1,99 @@
+// engine.cuh — host-side orchestration of the suffix-array / BWT / inverse-BWT kernels.
+//
+// One Engine = one CUDA device + one stream + a reusable device workspace (the analogue of one
+// maniscalco::msufsort object, msufsort.h:50-75, whose members hold one job's state).
+#pragma once
+#include "common.cuh"
+#include "radix_sort.cuh"
+#include "sa_kernels.cuh"
+#include "bwt_kernels.cuh"
+#include "../../include/b200sa.h"
+
+#include <string>
+#include <vector>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+namespace b200sa {
+
+int set_error(int code, const char* fmt, ...);
+
+#define B200SA_CU(expr)                                                                                          \
+    do {                                                                                                         \
+        cudaError_t e__ = (expr);                                                                                \
+        if (e__ != cudaSuccess)                                                                                  \
+            return b200sa::set_error(B200SA_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+
+#define B200SA_TRY(expr)           \
+    do {                           \
+        int rc__ = (expr);         \
+        if (rc__ != 0) return rc__; \
+    } while (0)
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes);
+    void release();
+    template <typename T> T* as() const { return (T*)p; }
+};
+
+struct AlphabetPlan {
+    u8 code[256];
+    int sigma;     // distinct byte values
+    int bits;      // bits per dense symbol
+    int k;         // symbols packed into the initial key
+    int len_bits;  // bits of the clamped-length field
+};
+
+AlphabetPlan plan_alphabet(const u32* hist256);
+static inline int bit_length_u64(u64 x) { int b = 0; while (x) { ++b; x >>= 1; } return b; }
+
+struct Engine {
+    int device = 0;
+    cudaStream_t own_stream = nullptr;
+    int num_sms = kNumSMs;
+
+    // workspace (sized for the largest n seen; see DESIGN.md "data layout in HBM")
+    DevBuf keys[2], idx[2], slot[2], gid, rank, sa_ws, sortmeta, agg_cnt, agg_max, misc, text_ws, bwt_ws, walk;
+    u32* h_pinned = nullptr;  // 64 words of pinned host memory for small read-backs
+
+    // instrumentation
+    bool profiling = false;
+    b200sa_profile prof;
+    uint64_t total_launches = 0;
+    struct Span { cudaEvent_t a, b; int phase; };
+    std::vector<Span> spans;
+    std::vector<cudaEvent_t> event_pool;
+    int open_phase = -1;
+    cudaEvent_t open_event = nullptr;
+
+    int init(int dev);
+    void shutdown();
+    int release_workspace();
+
+    cudaStream_t pick(void* s) const { return s ? (cudaStream_t)s : own_stream; }
+
+    // phases / profiling
+    int phase_begin(int phase, cudaStream_t st);
+    int phase_end(cudaStream_t st);
+    int collect_profile();
+    void count_launch(int phase) { prof.launches[phase]++; total_launches++; }
+
+    // building blocks
+    int radix_sort_pairs(u64* keys2[2], u32* vals2[2], bool gen_vals, u32 m, int begin_bit, int end_bit,
+                         int* result_side, cudaStream_t st);
+    int rerank(const u64* keys_sorted, const u32* idx_sorted, const u32* slot_in, u32 m, i32* d_sa,
+               u32* idx_out, u32* slot_out, u32* next_m, u32* next_groups, cudaStream_t st);
+
+    // entry points
+    int ensure_sa_workspace(u64 n);
+    int suffix_array_dev(const u8* d_text, i64 n, i32* d_sa, cudaStream_t st);
+    int bwt_dev(const u8* d_text, i64 n, u8* d_bwt, i32* d_sa_or_null, i32* sentinel_host, cudaStream_t st);
+    int unbwt_dev(const u8* d_bwt, i64 n, i32 sentinel, u8* d_out, cudaStream_t st);
+    int check_sa_dev(const u8* d_text, i64 n, const i32* d_sa, i64* bad_rows, cudaStream_t st);
+};
+
+}  // namespace b200sa

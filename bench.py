@@ -1,0 +1,331 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the SA + BWT hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+
+One "step" = one pass of the hot path over one synthetic text: suffix array (n+1 int32) AND forward
+BWT (n bytes + sentinel index) of the text.
+  * value  : input MB/s, text already resident in HBM, results left in HBM (one sort + one gather per
+             step through b200sa_bwt_dev), CUDA events on the launching stream, max over ranks.
+  * e2e    : the same metric through the reference-facing host entry points with HOST buffers — the
+             two drop-in calls a user of the reference makes (make_suffix_array then
+             forward_burrows_wheeler_transform => b200sa_suffix_array + b200sa_bwt), pinned host
+             memory, H2D and D2H copies inside the timed region.
+  * roofline: the dominant kernel (k_onesweep_pass, radix scatter sweeps): algorithmic bytes (24 B per
+             tuple per sweep, 20 B for the first sweep of round 0 whose values are generated) / summed
+             CUDA-event time of those launches inside the timed region / measured HBM copy peak.
+  * cpu_baseline: the UNMODIFIED reference (oracle/_ref, built from /root/reference) timed on this
+             box's host cores on a bounded prefix of the same text.
+N > 1: every rank sorts its own independent text of the same size (weak scaling, no collective on the
+data path — "batches of independent blocks" in north_star); value = total bytes / max-over-ranks time.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (generator, n, description)
+    "markov3_256MiB": ("markov3", 1 << 28, "256 MiB synthetic order-3 Markov English-like text: SA + BWT (BASELINE.json configs[1])"),
+    "rand_16MiB": ("rand", 1 << 24, "16 MiB synthetic random bytes: SA + BWT (BASELINE.json configs[0])"),
+    "markov3_64MiB": ("markov3", 1 << 26, "64 MiB Markov text (reduced; debugging only)"),
+    "acgt_1GiB": ("acgt_rep", (1 << 30) - 2, "2^30-2 ACGT bases with injected repeats: SA + BWT (BASELINE.json configs[2], single GPU)"),
+}
+CPU_SAMPLE_BYTES = 1 << 26  # reference arm / cpu_baseline: 64 MiB prefix of the workload text
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], None, set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax = float(f[2])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def gen_text(kind: str, n: int, seed_offset: int = 0) -> np.ndarray:
+    from msufsort_b200 import textgen as t
+    if kind == "markov3":
+        return t.markov3(n, t.SEED_MARKOV + seed_offset)
+    if kind == "rand":
+        return t.rand(n, t.SEED_RAND + seed_offset)
+    if kind == "acgt_rep":
+        return t.acgt_rep(n, t.SEED_ACGT + seed_offset)
+    raise ValueError(kind)
+
+
+# ---------------------------------------------------------------------------------------------
+# reference arm: the unmodified reference library on host cores (oracle/_ref)
+
+def load_reference():
+    path = os.path.join(ROOT, "oracle", "_ref", "libmsufsort_ref.so")
+    if not os.path.exists(path):
+        return None
+    lib = C.CDLL(path)
+    P, I64, I32 = C.c_void_p, C.c_int64, C.c_int32
+    lib.ref_make_suffix_array.argtypes = [P, I64, P, I32]
+    lib.ref_forward_bwt.argtypes = [P, I64, I32]
+    lib.ref_forward_bwt.restype = I32
+    lib.ref_hardware_concurrency.restype = C.c_int
+    return lib
+
+
+def reference_step(lib, text: np.ndarray, sa_out: np.ndarray, work: np.ndarray, threads: int) -> float:
+    """one step on the CPU: make_suffix_array + forward_burrows_wheeler_transform (its two public calls)"""
+    np.copyto(work, text)
+    t0 = time.perf_counter()
+    lib.ref_make_suffix_array(text.ctypes.data, text.size, sa_out.ctypes.data, threads)
+    lib.ref_forward_bwt(work.ctypes.data, work.size, threads)
+    return time.perf_counter() - t0
+
+
+def run_reference(args, wl):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    kind, n, desc = WORKLOADS[wl]
+    lib = load_reference()
+    if lib is None:
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libmsufsort_ref.so not built (reference tree absent at build time)"}))
+        return 0
+    threads = lib.ref_hardware_concurrency()
+    ns = min(n, CPU_SAMPLE_BYTES)
+    text = gen_text(kind, n)[:ns].copy() if n <= (1 << 28) else gen_text(kind, ns)
+    sa = np.empty(ns + 1, dtype=np.int32)
+    work = np.empty(ns, dtype=np.uint8)
+    for _ in range(args.warmup):
+        reference_step(lib, text, sa, work, threads)
+    times = [reference_step(lib, text, sa, work, threads) for _ in range(args.steps)]
+    total = sum(times)
+    value = ns * args.steps / total / 1e6
+    sample = f"first {ns} bytes of the workload text, SA + BWT via the reference's two public calls, {threads} threads"
+    line = {
+        "impl": "reference", "metric": "sa_bwt_input_throughput", "value": value, "unit": "MB/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u8/int32", "data": "synthetic",
+        "config": {"workload": wl, "description": desc, "n_bytes": n, "sample_bytes": ns},
+        "cpu_baseline": {"value": value, "unit": "MB/s", "cores": threads, "kind": "reference", "sample": sample},
+        "e2e": {"value": value, "unit": "MB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ---------------------------------------------------------------------------------------------
+# our arm
+
+def run_ours(args, wl):
+    import torch
+    import torch.distributed as dist
+    from msufsort_b200.api import Engine
+
+    kind, n, desc = WORKLOADS[wl]
+    if args.n:
+        n = args.n
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — this framework has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    eng = Engine(local_rank)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    # every rank gets its own text of the same size (rank 0 = the seed the parity tests use)
+    host_text = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+    np.copyto(host_text.numpy(), gen_text(kind, n, seed_offset=rank * 7919))
+    d_text = host_text.cuda(non_blocking=False)
+    d_sa = torch.empty(n + 1, dtype=torch.int32, device="cuda")
+    d_bwt = torch.empty(n, dtype=torch.uint8, device="cuda")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident: value + roofline
+    for _ in range(args.warmup):
+        eng.bwt_dev(d_text, n, d_bwt, d_sa, stream)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    eng.profile_reset()
+    eng.set_profiling(True)
+    launches0 = eng.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        sentinel = eng.bwt_dev(d_text, n, d_bwt, d_sa, stream)
+    ev1.record()
+    barrier()
+    dev_ms = ev0.elapsed_time(ev1)
+    launches = eng.launch_count() - launches0
+    prof = eng.profile()
+    eng.set_profiling(False)
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        tt = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dev_ms = float(tt.item())
+
+    # quick sanity inside the bench (outside the timed region): the GPU validator must accept the SA
+    bad = eng.check_suffix_array_dev(d_text, n, d_sa, stream)
+    if bad != 0:
+        raise SystemExit(f"bench.py: validator found {bad} bad rows — refusing to report a number")
+
+    # ---- end to end through the host entry points (pinned buffers, copies inside the timed region)
+    h_sa = torch.empty(n + 1, dtype=torch.int32, pin_memory=True)
+    h_work = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+    e2e_times = []
+    for it in range(min(args.warmup, 2) + args.steps):
+        h_work.copy_(host_text)  # in-place API: restore the caller's buffer outside the timed region
+        barrier()
+        t0 = time.perf_counter()
+        eng.suffix_array_ptr(host_text.data_ptr(), n, h_sa.data_ptr())
+        s2 = eng.bwt_ptr(h_work.data_ptr(), n)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if it >= min(args.warmup, 2):
+            e2e_times.append(dt)
+    e2e_s = sum(e2e_times) / len(e2e_times)
+    if world > 1:
+        tt = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_s = float(tt.item())
+    assert s2 == sentinel
+    assert int(h_sa[0]) == n
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    peak, peak_src = load_peaks()
+    sp = prof["phases"]["sort_pass"]
+    achieved = sp["alg_bytes"] / (sp["ms"] * 1e-3) / 1e9 if sp["ms"] > 0 else 0.0
+    ms_per_step = dev_ms / args.steps
+    value = world * n / (ms_per_step * 1e-3) / 1e6
+    phases = {k: {"ms_per_step": v["ms"] / args.steps, "launches_per_step": v["launches"] / args.steps,
+                  "alg_GB_per_step": v["alg_bytes"] / args.steps / 1e9} for k, v in prof["phases"].items() if v["launches"]}
+
+    # ---- CPU baseline: the reference itself on a bounded sample (rank 0, N=1 only)
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        lib = load_reference()
+        if lib is not None:
+            threads = lib.ref_hardware_concurrency()
+            ns = min(n, CPU_SAMPLE_BYTES)
+            text = host_text.numpy()[:ns].copy()
+            sa = np.empty(ns + 1, dtype=np.int32)
+            work = np.empty(ns, dtype=np.uint8)
+            t = reference_step(lib, text, sa, work, threads)
+            cpu = {"value": ns / t / 1e6, "unit": "MB/s", "cores": threads, "kind": "reference",
+                   "sample": f"first {ns} bytes of the workload text, SA + BWT via the reference's two public calls, 1 repetition, {threads} threads"}
+
+    line = {
+        "metric": "sa_bwt_input_throughput", "value": value, "unit": "MB/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u8/int32 (u64 sort keys)", "data": "synthetic",
+        "config": {"workload": wl, "description": desc, "n_bytes": n, "per_gpu_bytes": n,
+                   "parallelism": "1 independent text per GPU" if world > 1 else "single GPU",
+                   "l2": "working set (>= 44 n bytes) far larger than the 126 MB L2; no flush needed",
+                   "step": "suffix array (n+1 int32) + forward BWT (n bytes + sentinel index) of the text"},
+        "e2e": {"value": world * n / e2e_s / 1e6, "unit": "MB/s", "h2d_bytes_per_step": 2 * n, "d2h_bytes_per_step": 4 * (n + 1) + n + 4,
+                "ms_per_step": e2e_s * 1e3,
+                "path": "b200sa_suffix_array + b200sa_bwt (the reference's two public calls), pinned host buffers"},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "kernel": "k_onesweep_pass<u64> (radix scatter sweeps)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak if peak else None, "traffic": None, "peak_source": peak_src,
+                     "launches": int(sp["launches"]), "avg_launch_ms": sp["ms"] / sp["launches"] if sp["launches"] else None,
+                     "share_of_step": sp["ms"] / dev_ms if dev_ms else None},
+        "cpu_baseline": cpu,
+        "clocks": clocks,
+        "rounds_per_step": prof["rounds"] / args.steps, "sort_passes_per_step": prof["sort_passes"] / args.steps,
+        "phases": phases,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="markov3_256MiB", choices=sorted(WORKLOADS))
+    ap.add_argument("--n", type=int, default=0, help="override the text size (debugging)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args, args.workload)
+    return run_ours(args, args.workload)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

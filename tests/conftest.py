@@ -75,6 +75,13 @@ class Oracle:
         assert s >= 0
         return buf, int(s)
 
+    def bwt_from_sa(self, text: np.ndarray, sa: np.ndarray):
+        text = np.ascontiguousarray(text, dtype=np.uint8)
+        sa = np.ascontiguousarray(sa, dtype=np.int32)
+        out = np.empty(text.size, dtype=np.uint8)
+        s = self.lib.oracle_bwt_from_sa(text.ctypes.data, text.size, sa.ctypes.data, out.ctypes.data)
+        return out, int(s)
+
     def unbwt(self, bwt: np.ndarray, sentinel: int) -> np.ndarray:
         buf = np.array(bwt, dtype=np.uint8, copy=True)
         assert self.lib.oracle_reverse_bwt(buf.ctypes.data, buf.size, sentinel) == 0

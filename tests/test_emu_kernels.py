@@ -1,0 +1,80 @@
+"""CPU tier: the CUDA sources compiled against the SIMT emulator (tests/emu) — exercises the kernel
+LOGIC (tile indexing, warp ranking, look-back chaining, scans, walkers) through the same C ABI.
+This is test infrastructure: the product never loads the emulator build."""
+import numpy as np
+import pytest
+
+from cases import EDGE_SIZES, FAMILIES, gen, small_alphabet_exhaustive
+
+
+@pytest.mark.parametrize("family", FAMILIES)
+def test_emu_sa_bwt_unbwt_edge_sizes(emu_engine, oracle, family):
+    for n in EDGE_SIZES:
+        x = gen(family, n)
+        want = oracle.sa(x)
+        assert np.array_equal(emu_engine.make_suffix_array(x), want), (family, n)
+        b = x.copy()
+        s = emu_engine.forward_burrows_wheeler_transform(b)
+        wb, ws = oracle.bwt_from_sa(x, want)
+        assert s == ws and np.array_equal(b, wb), (family, n)
+        emu_engine.reverse_burrows_wheeler_transform(b, s)
+        assert np.array_equal(b, x), (family, n)
+
+
+def test_emu_exhaustive_binary_strings(emu_engine, oracle):
+    for x in small_alphabet_exhaustive(7, 2):
+        assert np.array_equal(emu_engine.make_suffix_array(x), oracle.sa_bruteforce(x)), x.tolist()
+
+
+@pytest.mark.parametrize("family", FAMILIES)
+def test_emu_medium(emu_engine, oracle, family):
+    n = 50021
+    x = gen(family, n)
+    sa, bwt, s = emu_engine.suffix_array_and_bwt(x)
+    want = oracle.sa(x)
+    assert np.array_equal(sa, want)
+    wb, ws = oracle.bwt_from_sa(x, want)
+    assert s == ws and np.array_equal(bwt, wb)
+    u = bwt.copy()
+    emu_engine.reverse_burrows_wheeler_transform(u, s)
+    assert np.array_equal(u, x)
+    assert emu_engine.check_suffix_array_dev(x, n, sa) == 0
+
+
+@pytest.mark.parametrize("m,bits", [(1, 64), (7, 8), (4096, 64), (4097, 17), (20000, 64), (70001, 33)])
+def test_emu_radix_sort_pairs(emu_engine, m, bits):
+    rng = np.random.default_rng(m + bits)
+    keys = rng.integers(0, 1 << 63, size=m, dtype=np.uint64)
+    if bits < 64:
+        keys &= np.uint64((1 << bits) - 1)
+    keys[: m // 3] = keys[m // 2]
+    vals = rng.permutation(m).astype(np.uint32)
+    order = np.argsort(keys, kind="stable")
+    k, ka, v, va = keys.copy(), np.empty_like(keys), vals.copy(), np.empty_like(vals)
+    side = emu_engine.radix_sort_pairs_dev(k, ka, v, va, m, 0, bits)
+    assert np.array_equal(ka if side else k, keys[order])
+    assert np.array_equal(va if side else v, vals[order])
+    k = keys.copy()
+    emu_engine.radix_sort_pairs_dev(k, ka, None, va, m, 0, bits)
+    assert np.array_equal(va, order.astype(np.uint32))
+
+
+def test_emu_checker_detects_corruption(emu_engine, oracle):
+    x = gen("markov3", 20000)
+    sa = oracle.sa(x)
+    assert emu_engine.check_suffix_array_dev(x, x.size, sa) == 0
+    bad = sa.copy(); bad[[100, 101]] = bad[[101, 100]]
+    assert emu_engine.check_suffix_array_dev(x, x.size, bad) > 0
+    bad = sa.copy(); bad[3] = bad[4]
+    assert emu_engine.check_suffix_array_dev(x, x.size, bad) > 0
+
+
+def test_emu_profile_accounting(emu_engine):
+    emu_engine.profile_reset()
+    x = gen("markov3", 30000)
+    emu_engine.make_suffix_array(x)
+    p = emu_engine.profile()
+    assert p["rounds"] >= 2
+    assert p["phases"]["sort_pass"]["launches"] == p["sort_passes"]
+    # first sweep of round 0 moves 20 B per tuple (generated values), all others 24 B
+    assert p["phases"]["sort_pass"]["alg_bytes"] == 24 * p["sorted_tuples"] - 4 * x.size

@@ -195,9 +195,9 @@ int Engine::radix_sort_pairs(u64* keys2[2], u32* vals2[2], bool gen_vals, u32 m,
     B200SA_TRY(phase_begin(B200SA_PH_SORT_HIST, st));
     {
         const u32 htiles = (u32)div_up_u64(m, RH_THREADS * RH_IPT);
-        const u32 grid = htiles < (u32)(num_sms * 4) ? htiles : (u32)(num_sms * 4);
+        const u32 grid = htiles < (u32)(num_sms * 6) ? htiles : (u32)(num_sms * 6);
         auto kh = k_radix_hist<u64>;
-        B200SA_LAUNCH(kh, grid, RH_THREADS, 0, st, keys2[0], m, begin_bit, passes, ghist);
+        B200SA_LAUNCH(kh, grid, RH_THREADS, rh_smem_bytes(passes), st, keys2[0], m, begin_bit, passes, ghist);
         count_launch(B200SA_PH_SORT_HIST);
         B200SA_LAUNCH(k_radix_scan_bins, passes, RS_RADIX, 0, st, ghist);
         count_launch(B200SA_PH_SORT_HIST);
@@ -232,18 +232,18 @@ int Engine::radix_sort_pairs(u64* keys2[2], u32* vals2[2], bool gen_vals, u32 m,
 int Engine::rerank(const u64* keys_sorted, const u32* idx_sorted, const u32* slot_in, u32 m, i32* d_sa,
                    u32* idx_out, u32* slot_out, u32* next_m, u32* next_groups, cudaStream_t st)
 {
-    const u32 nblocks = (u32)div_up_u64(m, RR_TILE);
-    B200SA_TRY(agg_cnt.ensure((size_t)nblocks * 8));
-    B200SA_TRY(agg_max.ensure((size_t)nblocks * 4));
+    const u32 ntiles = (u32)div_up_u64(m, RR_TILE);
+    // agg_cnt holds the two descriptor arrays followed by the tile ticket counter
+    const size_t desc_bytes = (size_t)ntiles * 2 * sizeof(u64);
+    B200SA_TRY(agg_cnt.ensure(desc_bytes + 64));
+    u64* desc = agg_cnt.as<u64>();
+    u32* ticket = (u32*)((u8*)agg_cnt.p + desc_bytes);
     u32* d_info = misc.as<u32>() + 512;  // see ensure_sa_workspace for the misc layout
+    B200SA_CU(cudaMemsetAsync(agg_cnt.p, 0, desc_bytes + 64, st));
+    prof.memsets++;
     B200SA_TRY(phase_begin(B200SA_PH_RERANK, st));
-    B200SA_LAUNCH(k_rerank_reduce, nblocks, RR_THREADS, 0, st, keys_sorted, m, agg_cnt.as<u64>(), agg_max.as<u32>());
-    count_launch(B200SA_PH_RERANK);
-    B200SA_LAUNCH(k_rerank_scan_blocks, 1, RS2_THREADS, 0, st, agg_cnt.as<u64>(), agg_max.as<u32>(), nblocks, d_info);
-    count_launch(B200SA_PH_RERANK);
-    B200SA_LAUNCH(k_rerank_apply, nblocks, RR_THREADS, 0, st, keys_sorted, idx_sorted, slot_in, m,
-                  (const u64*)agg_cnt.as<u64>(), (const u32*)agg_max.as<u32>(), rank.as<u32>(), d_sa,
-                  idx_out, slot_out, gid.as<u32>());
+    B200SA_LAUNCH(k_rerank, ntiles, RR_THREADS, 0, st, keys_sorted, idx_sorted, slot_in, m, desc, ntiles, ticket,
+                  rank.as<u32>(), d_sa, idx_out, slot_out, gid.as<u32>(), d_info);
     count_launch(B200SA_PH_RERANK);
     B200SA_TRY(phase_end(st));
     B200SA_CU(cudaGetLastError());
@@ -251,7 +251,7 @@ int Engine::rerank(const u64* keys_sorted, const u32* idx_sorted, const u32* slo
     B200SA_CU(cudaStreamSynchronize(st));
     *next_m = h_pinned[0];
     *next_groups = h_pinned[1];
-    prof.alg_bytes[B200SA_PH_RERANK] += (u64)m * (8 + 8 + 4 + 4 + 4) + (u64)(*next_m) * 12 + (u64)(m - *next_m) * 4;
+    prof.alg_bytes[B200SA_PH_RERANK] += (u64)m * (8 + 4 + 4 + 4) + (u64)(*next_m) * 12 + (u64)(m - *next_m) * 4;
     return 0;
 }
 
@@ -438,9 +438,9 @@ int Engine::unbwt_dev(const u8* d_bwt, i64 n64, i32 sentinel, u8* d_out, cudaStr
     B200SA_TRY(phase_begin(B200SA_PH_UNBWT_BUILD, st));
     {
         const u32 htiles = (u32)div_up_u64(n, RH_THREADS * RH_IPT);
-        const u32 grid = htiles < (u32)(num_sms * 4) ? htiles : (u32)(num_sms * 4);
+        const u32 grid = htiles < (u32)(num_sms * 6) ? htiles : (u32)(num_sms * 6);
         auto kh = k_radix_hist<u8>;
-        B200SA_LAUNCH(kh, grid, RH_THREADS, 0, st, d_bwt, n, 0, 1, ghist);
+        B200SA_LAUNCH(kh, grid, RH_THREADS, rh_smem_bytes(1), st, d_bwt, n, 0, 1, ghist);
         count_launch(B200SA_PH_UNBWT_BUILD);
         B200SA_LAUNCH(k_radix_scan_bins, 1, RS_RADIX, 0, st, ghist);
         count_launch(B200SA_PH_UNBWT_BUILD);

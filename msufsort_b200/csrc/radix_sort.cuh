@@ -8,7 +8,7 @@
 //
 // Per pass and tile (THREADS x IPT consecutive elements, warp-striped so that element order inside
 // a warp is (item, lane)):
-//   1. warp-level ranking: __match_any_sync gives the lanes holding the same digit; the lowest such
+//   1. warp-level ranking: eight ballots give the lanes holding the same digit; the lowest such
 //      lane bumps the warp's private counter in shared memory; rank = old count + #peers below me.
 //   2. per-digit reduction over the warps (thread d owns digit d), published as this tile's PARTIAL
 //      descriptor; look-back over the predecessors' descriptors until an INCLUSIVE one is found;
@@ -49,47 +49,62 @@ __device__ __forceinline__ u32 rs_digit(KeyT key, int shift)
 
 // ---------------------------------------------------------------------------------------------
 // Digit histograms for `npasses` consecutive digits starting at begin_bit: one read of the keys.
-// ghist[p*256 + d] += count.  Counts are warp-aggregated with match_any so that skewed digits (all
-// keys equal in the high bits is the common case here) do not serialise on one shared-memory word.
-static const int RH_THREADS = 512;
+// ghist[p*256 + d] += count.
+//
+// Every warp owns a private [npasses][256] counter table in shared memory and updates it with plain
+// (non-atomic) read-modify-writes: eight ballots group the lanes holding the same digit, the
+// lowest lane of each group adds the group size.  Shared-memory atomics on scattered addresses cost
+// ~2 cycles per lane on this part (B300_MICROARCH.md, "ATOMS spread-addr") — the first version of
+// this kernel used them and took 16 ms for 2^28 keys x 8 digits; plain LDS/STS are bank-limited only.
+static const int RH_THREADS = 128;
+static const int RH_WARPS = RH_THREADS / 32;
 static const int RH_IPT = 8;
+
+__host__ __device__ constexpr size_t rh_smem_bytes(int npasses) { return (size_t)RH_WARPS * npasses * RS_RADIX * 4; }
 
 template <typename KeyT>
 __global__ void __launch_bounds__(RH_THREADS)
 k_radix_hist(const KeyT* __restrict__ keys, u32 m, int begin_bit, int npasses, u32* __restrict__ ghist)
 {
-    __shared__ u32 sh[RS_MAX_PASSES * RS_RADIX];
-    const u32 tid = threadIdx.x, lane = tid & 31u;
-    for (u32 i = tid; i < (u32)(npasses * RS_RADIX); i += RH_THREADS) sh[i] = 0;
+    B200SA_DYN_SMEM(smem);
+    u32* sh = (u32*)smem;  // [RH_WARPS][npasses][256]
+    const u32 tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const u32 per_warp = (u32)npasses * RS_RADIX;
+    for (u32 i = tid; i < RH_WARPS * per_warp; i += RH_THREADS) sh[i] = 0;
     __syncthreads();
-    const u32 tile = RH_THREADS * RH_IPT;
-    const u32 ntiles = (u32)div_up_u64(m, tile);
-    for (u32 t = blockIdx.x; t < ntiles; t += gridDim.x) {
-        const u32 base = t * tile;
+    u32* mine = sh + warp * per_warp;
+    // a warp takes chunks of 32*RH_IPT consecutive keys
+    const u32 chunk = 32u * RH_IPT;
+    const u32 nchunks = (u32)div_up_u64(m, chunk);
+    for (u32 c = blockIdx.x * RH_WARPS + warp; c < nchunks; c += gridDim.x * RH_WARPS) {
+        const u32 base = c * chunk + lane;
         KeyT k[RH_IPT];
         bool ok[RH_IPT];
 #pragma unroll
         for (int i = 0; i < RH_IPT; ++i) {
-            const u32 idx = base + (u32)i * RH_THREADS + tid;
+            const u32 idx = base + (u32)i * 32u;
             ok[i] = idx < m;
             k[i] = ok[i] ? ld_stream(keys + idx) : (KeyT)0;
         }
         for (int p = 0; p < npasses; ++p) {
             const int shift = begin_bit + p * RS_RADIX_BITS;
+            u32* row = mine + p * RS_RADIX;
 #pragma unroll
             for (int i = 0; i < RH_IPT; ++i) {
                 const u32 d = rs_digit<KeyT>(k[i], shift);
-                // invalid lanes get a private pseudo-digit so they match nobody
-                const u32 tag = ok[i] ? d : (0x10000u | lane);
-                const u32 peers = __match_any_sync(B200SA_FULL_MASK, tag);
+                // out-of-range lanes are masked out of everybody's peer set
+                const u32 peers = warp_peers_digit8(d) & __ballot_sync(B200SA_FULL_MASK, ok[i]);
                 const u32 leader = (u32)__ffs((int)peers) - 1u;
-                if (ok[i] && lane == leader) atomicAdd(&sh[p * RS_RADIX + d], (u32)__popc(peers));
+                if (ok[i] && lane == leader) row[d] += (u32)__popc(peers);
+                __syncwarp();
             }
         }
     }
     __syncthreads();
-    for (u32 i = tid; i < (u32)(npasses * RS_RADIX); i += RH_THREADS) {
-        const u32 c = sh[i];
+    for (u32 i = tid; i < per_warp; i += RH_THREADS) {
+        u32 c = 0;
+#pragma unroll
+        for (int w = 0; w < RH_WARPS; ++w) c += sh[w * per_warp + i];
         if (c) atomicAdd(&ghist[i], c);
     }
 }
@@ -164,7 +179,7 @@ k_onesweep_pass(const KeyT* __restrict__ kin, KeyT* __restrict__ kout,
 #pragma unroll
     for (int k = 0; k < IPT; ++k) {
         const u32 d = rs_digit<KeyT>(key[k], shift);
-        const u32 peers = __match_any_sync(B200SA_FULL_MASK, d);
+        const u32 peers = warp_peers_digit8(d);
         const u32 leader = (u32)__ffs((int)peers) - 1u;
         u32 prev = 0;
         if (lane == leader) {
@@ -177,7 +192,8 @@ k_onesweep_pass(const KeyT* __restrict__ kin, KeyT* __restrict__ kout,
     }
     __syncthreads();
 
-    // ---- 2. per-digit: warp-exclusive prefixes, tile count, look-back
+    // ---- 2. per-digit: warp-exclusive prefixes, tile count; publish the PARTIAL descriptor early
+    u32 my_cnt = 0;
     if (tid < (u32)RS_RADIX) {
         u32 acc = 0;
 #pragma unroll
@@ -186,50 +202,55 @@ k_onesweep_pass(const KeyT* __restrict__ kin, KeyT* __restrict__ kout,
             whist[w * RS_RADIX + tid] = acc;
             acc += c;
         }
-        s_cnt[tid] = acc;
-        u64* mine = status + (u64)tile * RS_RADIX + tid;
-        u64 excl = 0;
-        if (tile == 0) {
-            st_relaxed_u64(mine, RS_FLAG_INCLUSIVE | (u64)acc);
-        } else {
-            st_relaxed_u64(mine, RS_FLAG_PARTIAL | (u64)acc);
-            const u64* p = mine - RS_RADIX;
-            for (;;) {
-                u64 v;
-                do { v = ld_relaxed_u64(p); } while ((v >> 62) == 0);
-                excl += v & RS_VALUE_MASK;
-                if (v & RS_FLAG_INCLUSIVE) break;
-                p -= RS_RADIX;
-            }
-            st_relaxed_u64(mine, RS_FLAG_INCLUSIVE | (excl + (u64)acc));
-        }
-        s_gdelta[tid] = bins[tid] + (u32)excl;  // global start of this tile's run of digit tid
-    }
-    __syncthreads();
-
-    // ---- 3. exclusive scan of the 256 tile counts (8 full warps)
-    if (tid < (u32)RS_RADIX) {
-        const u32 c = s_cnt[tid];
-        const u32 incl = warp_incl_scan_u32(c);
+        my_cnt = acc;
+        st_relaxed_u64(status + (u64)tile * RS_RADIX + tid, (tile == 0 ? RS_FLAG_INCLUSIVE : RS_FLAG_PARTIAL) | (u64)acc);
+        // ---- 3a. exclusive scan of the 256 tile counts (8 full warps)
+        const u32 incl = warp_incl_scan_u32(acc);
         if (lane == 31) s_wtot[warp] = incl;
-        s_cnt[tid] = incl - c;  // warp-local exclusive, fixed up below
+        s_cnt[tid] = incl - acc;  // warp-local exclusive, fixed up below
     }
     __syncthreads();
     if (tid < (u32)RS_RADIX) {
         u32 prefix = 0;
         for (u32 w = 0; w < warp; ++w) prefix += s_wtot[w];
-        const u32 off = s_cnt[tid] + prefix;
-        s_coff[tid] = off;
-        s_gdelta[tid] -= off;
+        s_coff[tid] = s_cnt[tid] + prefix;
     }
     __syncthreads();
 
-    // ---- stage keys in digit order
+    // ---- stage keys in digit order (needs only tile-local offsets; predecessors keep publishing meanwhile)
 #pragma unroll
     for (int k = 0; k < IPT; ++k) {
         const u32 d = rs_digit<KeyT>(key[k], shift);
         pos[k] += s_coff[d] + mywh[d];
         skeys[pos[k]] = key[k];
+    }
+
+    // ---- 4. look-back for digit tid: four predecessor descriptors in flight per step
+    if (tid < (u32)RS_RADIX) {
+        u64 excl = 0;
+        if (tile != 0) {
+            const u64* col = status + tid;
+            i64 t = (i64)tile - 1;
+            bool done = false;
+            while (!done) {
+                u64 v[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) v[i] = (t - i >= 0) ? ld_relaxed_u64(col + (u64)(t - i) * RS_RADIX) : 0ull;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    if (!done) {
+                        u64 x = v[i];
+                        while ((x >> 62) == 0) x = ld_relaxed_u64(col + (u64)(t - i) * RS_RADIX);
+                        excl += x & RS_VALUE_MASK;
+                        if (x & RS_FLAG_INCLUSIVE) done = true;
+                    }
+                }
+                t -= 4;
+            }
+            st_relaxed_u64(status + (u64)tile * RS_RADIX + tid, RS_FLAG_INCLUSIVE | (excl + (u64)my_cnt));
+        }
+        // global start of this tile's run of digit tid, minus its slot in shared memory
+        s_gdelta[tid] = bins[tid] + (u32)excl - s_coff[tid];
     }
     __syncthreads();
     if (WRITE_KEYS) {

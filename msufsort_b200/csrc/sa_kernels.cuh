@@ -181,184 +181,187 @@ k_build_keys(const u32* __restrict__ idx, const u32* __restrict__ gid, const u32
 }
 
 // ---------------------------------------------------------------------------------------------
-// Re-ranking after a sort: a three-kernel segmented scan over the m sorted tuples.
+// Re-ranking after a sort: ONE sweep over the m sorted tuples (chained scan, decoupled look-back).
 //   head[j]   = key[j] != key[j-1]            (j == 0 is a head)
 //   single[j] = head[j] && head[j+1]          (j == m-1: head[m] counts as true)
 //   kept[j]   = !single[j]
-// scanned quantities: #kept (compaction slot), #kept heads (new dense group id), max head slot
-// (start of my group).  Block aggregates are combined by one small block; the apply kernel then
-// recomputes the flags and produces all outputs in one sweep.
+// Scanned along j: #kept (compaction slot), #kept heads (new dense group id), last head slot (start
+// of my group -> new rank).  Items are striped over the block (item = q*256 + tid), so flags come
+// from warp ballots, neighbours from shuffles, and every global access is coalesced; a tile's three
+// aggregates travel in two self-validating 64-bit descriptors.
 static const int RR_THREADS = 256;
-static const int RR_IPT = 8;
-static const int RR_TILE = RR_THREADS * RR_IPT;  // 2048 tuples per block
+static const int RR_IPT = 16;
+static const int RR_TILE = RR_THREADS * RR_IPT;  // 4096 tuples per tile
+static const int RR_WARPS = RR_THREADS / 32;
+static const int RR_CHUNKS = RR_IPT * RR_WARPS;  // 128 warp-rows of 32 items per tile
 
-struct RerankFlags {
-    u32 head;    // bit q: item q is a head
-    u32 single;  // bit q: item q is a singleton group
-};
+// descriptor A: flag(2) | kept heads (31) | kept (31);  descriptor B: flag(2) | 1 + last head slot (32)
+static const u64 RR_FLAG_PARTIAL = 1ull << 62;
+static const u64 RR_FLAG_INCLUSIVE = 2ull << 62;
+__device__ __forceinline__ u64 rr_pack_a(u64 flag, u32 kept, u32 kheads) { return flag | ((u64)kheads << 31) | (u64)kept; }
+__device__ __forceinline__ u32 rr_a_kept(u64 a) { return (u32)(a & 0x7fffffffull); }
+__device__ __forceinline__ u32 rr_a_kheads(u64 a) { return (u32)((a >> 31) & 0x7fffffffull); }
 
-// Thread owns items j0 .. j0+RR_IPT-1 (blocked); reads keys j0-1 .. j0+RR_IPT.
-__device__ __forceinline__ RerankFlags rr_flags(const u64* __restrict__ keys, u32 m, u32 j0)
-{
-    RerankFlags f;
-    f.head = 0;
-    f.single = 0;
-    if (j0 >= m) return f;
-    u64 k[RR_IPT + 2];
-#pragma unroll
-    for (int q = 0; q < RR_IPT + 2; ++q) {
-        const i64 j = (i64)j0 + q - 1;
-        k[q] = (j >= 0 && j < (i64)m) ? keys[j] : 0ull;
-    }
-    u32 headx = 0;  // bit q: item j0+q is a head, for q in 0..RR_IPT (one past the end included)
-#pragma unroll
-    for (int q = 0; q <= RR_IPT; ++q) {
-        const u32 j = j0 + (u32)q;
-        const bool h = (j == 0) || (j >= m) || (k[q + 1] != k[q]);
-        headx |= (h ? 1u : 0u) << q;
-    }
-#pragma unroll
-    for (int q = 0; q < RR_IPT; ++q) {
-        if (j0 + (u32)q < m) {
-            const u32 h = (headx >> q) & 1u, hn = (headx >> (q + 1)) & 1u;
-            f.head |= h << q;
-            f.single |= (h & hn) << q;
-        }
-    }
-    return f;
-}
-
-// aggregates: agg_cnt[b] = (#kept heads << 32) | #kept ; agg_max[b] = 1 + max head slot in block (0 = none)
-__global__ void __launch_bounds__(RR_THREADS)
-k_rerank_reduce(const u64* __restrict__ keys, u32 m, u64* __restrict__ agg_cnt, u32* __restrict__ agg_max)
-{
-    __shared__ u64 s_cnt[RR_THREADS / 32];
-    __shared__ u32 s_max[RR_THREADS / 32];
-    const u32 tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    const u32 j0 = blockIdx.x * (u32)RR_TILE + tid * RR_IPT;
-    const RerankFlags f = rr_flags(keys, m, j0);
-    const u32 nvalid = j0 >= m ? 0u : min((u32)RR_IPT, m - j0);
-    const u32 validmask = nvalid >= 32 ? ~0u : ((1u << nvalid) - 1u);
-    const u32 kept = ~f.single & validmask;
-    u64 cnt = (u64)__popc(kept) | ((u64)__popc(kept & f.head) << 32);
-    u32 mx = f.head ? j0 + (31u - (u32)__clz((int)f.head)) + 1u : 0u;
-#pragma unroll
-    for (int d = 16; d >= 1; d >>= 1) {
-        cnt += __shfl_xor_sync(B200SA_FULL_MASK, cnt, d);
-        const u32 o = __shfl_xor_sync(B200SA_FULL_MASK, mx, d);
-        mx = mx > o ? mx : o;
-    }
-    if (lane == 0) { s_cnt[warp] = cnt; s_max[warp] = mx; }
-    __syncthreads();
-    if (tid == 0) {
-        u64 c = 0;
-        u32 x = 0;
-        for (int w = 0; w < RR_THREADS / 32; ++w) { c += s_cnt[w]; x = x > s_max[w] ? x : s_max[w]; }
-        agg_cnt[blockIdx.x] = c;
-        agg_max[blockIdx.x] = x;
-    }
-}
-
-// Exclusive scan of the block aggregates by one block; also publishes the round totals
-// info[0] = #kept (next m), info[1] = #kept heads (next group count).
-static const int RS2_THREADS = 1024;
-
-__global__ void __launch_bounds__(RS2_THREADS)
-k_rerank_scan_blocks(u64* __restrict__ agg_cnt, u32* __restrict__ agg_max, u32 nblocks, u32* __restrict__ info)
-{
-    __shared__ u64 s_wc[RS2_THREADS / 32];
-    __shared__ u32 s_wm[RS2_THREADS / 32];
-    __shared__ u64 s_carry_c;
-    __shared__ u32 s_carry_m;
-    const u32 tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    if (tid == 0) { s_carry_c = 0; s_carry_m = 0; }
-    __syncthreads();
-    for (u32 base = 0; base < nblocks; base += RS2_THREADS) {
-        const u32 b = base + tid;
-        const u64 c = b < nblocks ? agg_cnt[b] : 0ull;
-        const u32 x = b < nblocks ? agg_max[b] : 0u;
-        const u64 ic = warp_incl_scan_u64(c);
-        const u32 ix = warp_incl_scan_max_u32(x);
-        if (lane == 31) { s_wc[warp] = ic; s_wm[warp] = ix; }
-        __syncthreads();
-        u64 pc = s_carry_c;
-        u32 pm = s_carry_m;
-        for (u32 w = 0; w < warp; ++w) { pc += s_wc[w]; pm = pm > s_wm[w] ? pm : s_wm[w]; }
-        // exclusive values: everything before element b
-        const u64 ec = pc + ic - c;
-        u32 ex = pm;
-        {
-            const u32 up = __shfl_up_sync(B200SA_FULL_MASK, ix, 1);
-            if (lane > 0) ex = ex > up ? ex : up;
-        }
-        if (b < nblocks) { agg_cnt[b] = ec; agg_max[b] = ex; }
-        __syncthreads();
-        if (tid == RS2_THREADS - 1) {
-            s_carry_c = pc + ic;
-            s_carry_m = pm > ix ? pm : ix;
-        }
-        __syncthreads();
-    }
-    if (tid == 0) {
-        info[0] = (u32)(s_carry_c & 0xffffffffull);
-        info[1] = (u32)(s_carry_c >> 32);
-    }
-}
-
-// Apply: new ranks into the ISA, final SA entries for singletons, compaction of the rest.
 //   slot_in == nullptr  -> round 0: active slot j is global position j
-__global__ void __launch_bounds__(RR_THREADS)
-k_rerank_apply(const u64* __restrict__ keys, const u32* __restrict__ idx_in, const u32* __restrict__ slot_in, u32 m,
-               const u64* __restrict__ agg_cnt, const u32* __restrict__ agg_max,
-               u32* __restrict__ rank, i32* __restrict__ sa,
-               u32* __restrict__ idx_out, u32* __restrict__ slot_out, u32* __restrict__ gid_out)
+//   info[0] = #kept (next m), info[1] = #kept heads (next group count), written by the last tile
+__global__ void __launch_bounds__(RR_THREADS, 2)
+k_rerank(const u64* __restrict__ keys, const u32* __restrict__ idx_in, const u32* __restrict__ slot_in, u32 m,
+         u64* __restrict__ desc /*[2][ntiles]*/, u32 ntiles, u32* __restrict__ tile_counter,
+         u32* __restrict__ rank, i32* __restrict__ sa,
+         u32* __restrict__ idx_out, u32* __restrict__ slot_out, u32* __restrict__ gid_out, u32* __restrict__ info)
 {
-    __shared__ u64 s_wc[RR_THREADS / 32];
-    __shared__ u32 s_wm[RR_THREADS / 32];
+    __shared__ u32 s_k[RR_CHUNKS], s_kh[RR_CHUNKS], s_lh[RR_CHUNKS];  // per chunk: kept, kept heads, 1+last head (tile-local)
+    __shared__ u32 s_tile, s_pre_k, s_pre_kh, s_pre_lh;
     const u32 tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    const u32 j0 = blockIdx.x * (u32)RR_TILE + tid * RR_IPT;
-    const RerankFlags f = rr_flags(keys, m, j0);
-    const u32 nvalid = j0 >= m ? 0u : min((u32)RR_IPT, m - j0);
-    const u32 validmask = nvalid >= 32 ? ~0u : ((1u << nvalid) - 1u);
-    const u32 kept = ~f.single & validmask;
-    const u64 cnt = (u64)__popc(kept) | ((u64)__popc(kept & f.head) << 32);
-    const u32 mx = f.head ? j0 + (31u - (u32)__clz((int)f.head)) + 1u : 0u;
-
-    const u64 ic = warp_incl_scan_u64(cnt);
-    const u32 ix = warp_incl_scan_max_u32(mx);
-    if (lane == 31) { s_wc[warp] = ic; s_wm[warp] = ix; }
+    if (tid == 0) s_tile = atomicAdd(tile_counter, 1u);
     __syncthreads();
-    u64 pc = agg_cnt[blockIdx.x];
-    u32 pm = agg_max[blockIdx.x];
-    for (u32 w = 0; w < warp; ++w) { pc += s_wc[w]; pm = pm > s_wm[w] ? pm : s_wm[w]; }
-    u64 run_c = pc + ic - cnt;  // exclusive (#kept, #kept heads) before my first item
-    u32 run_m = pm;             // 1 + head slot of the group open before my first item
-    {
-        const u32 up = __shfl_up_sync(B200SA_FULL_MASK, ix, 1);
-        if (lane > 0) run_m = run_m > up ? run_m : up;
-    }
-    if (nvalid == 0) return;
+    const u32 tile = s_tile;
+    const u32 base = tile * (u32)RR_TILE;
 
-    u32 dest = (u32)(run_c & 0xffffffffull);
-    u32 heads = (u32)(run_c >> 32);
+    // ---- flags from coalesced key loads + neighbour shuffles
+    u64 key[RR_IPT];
 #pragma unroll
     for (int q = 0; q < RR_IPT; ++q) {
-        if ((u32)q < nvalid) {
-            const u32 j = j0 + (u32)q;
-            const u32 is_head = (f.head >> q) & 1u, is_single = (f.single >> q) & 1u;
-            if (is_head) run_m = j + 1u;
-            const u32 hs = run_m - 1u;  // head slot of my group (always defined: slot 0 is a head)
+        const u32 j = base + (u32)q * RR_THREADS + tid;
+        key[q] = j < m ? ld_stream(keys + j) : 0ull;
+    }
+    u32 bal_head[RR_IPT], bal_single[RR_IPT];  // warp-uniform ballots per row
+#pragma unroll
+    for (int q = 0; q < RR_IPT; ++q) {
+        const u32 j = base + (u32)q * RR_THREADS + tid;
+        u64 prev = __shfl_up_sync(B200SA_FULL_MASK, key[q], 1);
+        u64 next = __shfl_down_sync(B200SA_FULL_MASK, key[q], 1);
+        const bool valid = j < m;
+        bool head = false, head_next = true;
+        if (valid) {
+            if (lane == 0) prev = j > 0 ? keys[j - 1] : ~key[q];
+            if (lane == 31) next = (j + 1 < m) ? keys[j + 1] : ~key[q];
+            head = (j == 0) || (prev != key[q]);
+            head_next = (j + 1 >= m) || (next != key[q]);
+        }
+        bal_head[q] = __ballot_sync(B200SA_FULL_MASK, head);
+        bal_single[q] = __ballot_sync(B200SA_FULL_MASK, head && head_next);
+    }
+    // ---- chunk aggregates (chunk c = q*8 + warp is item order)
+    if (lane == 0) {
+#pragma unroll
+        for (int q = 0; q < RR_IPT; ++q) {
+            const u32 rowbase = base + (u32)q * RR_THREADS + warp * 32u;
+            const u32 nvalid = rowbase >= m ? 0u : min(32u, m - rowbase);
+            const u32 vmask = nvalid >= 32u ? 0xffffffffu : ((1u << nvalid) - 1u);
+            const u32 kept = ~bal_single[q] & vmask;
+            const u32 c = (u32)q * RR_WARPS + warp;
+            s_k[c] = (u32)__popc(kept);
+            s_kh[c] = (u32)__popc(kept & bal_head[q]);
+            s_lh[c] = bal_head[q] ? ((u32)q * RR_THREADS + warp * 32u + (31u - (u32)__clz((int)bal_head[q])) + 1u) : 0u;
+        }
+    }
+    __syncthreads();
+    // ---- warp 0: exclusive scan of the 128 chunk aggregates, then look-back for the tile prefix
+    if (warp == 0) {
+        u32 k4[4], h4[4], l4[4];
+        u32 sk = 0, sh = 0, sl = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const u32 c = lane * 4u + (u32)i;
+            k4[i] = s_k[c]; h4[i] = s_kh[c]; l4[i] = s_lh[c];
+            sk += k4[i]; sh += h4[i]; sl = sl > l4[i] ? sl : l4[i];
+        }
+        const u32 ik = warp_incl_scan_u32(sk), ih = warp_incl_scan_u32(sh), il = warp_incl_scan_max_u32(sl);
+        u32 ek = ik - sk, eh = ih - sh;
+        u32 el = __shfl_up_sync(B200SA_FULL_MASK, il, 1);
+        if (lane == 0) el = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const u32 c = lane * 4u + (u32)i;
+            s_k[c] = ek; s_kh[c] = eh; s_lh[c] = el;
+            ek += k4[i]; eh += h4[i]; el = el > l4[i] ? el : l4[i];
+        }
+        const u32 tot_k = __shfl_sync(B200SA_FULL_MASK, ik, 31);
+        const u32 tot_kh = __shfl_sync(B200SA_FULL_MASK, ih, 31);
+        const u32 tot_lh_local = __shfl_sync(B200SA_FULL_MASK, il, 31);
+        const u32 tot_lh = tot_lh_local ? base + tot_lh_local : 0u;  // 1 + global slot of the tile's last head
+        u64* da = desc;
+        u64* db = desc + ntiles;
+        u32 pre_k = 0, pre_kh = 0, pre_lh = 0;
+        if (tile == 0) {
+            if (lane == 0) {
+                st_relaxed_u64(da + tile, rr_pack_a(RR_FLAG_INCLUSIVE, tot_k, tot_kh));
+                st_relaxed_u64(db + tile, RR_FLAG_INCLUSIVE | (u64)tot_lh);
+            }
+        } else {
+            if (lane == 0) {
+                st_relaxed_u64(da + tile, rr_pack_a(RR_FLAG_PARTIAL, tot_k, tot_kh));
+                st_relaxed_u64(db + tile, RR_FLAG_PARTIAL | (u64)tot_lh);
+            }
+            // window look-back: lane l inspects tile (t - l)
+            i64 t = (i64)tile - 1;
+            for (;;) {
+                const i64 mine = t - (i64)lane;
+                const bool have = mine >= 0;
+                u64 a = 0, b = 0;
+                if (have) {
+                    do {
+                        a = ld_relaxed_u64(da + mine);
+                        b = ld_relaxed_u64(db + mine);
+                    } while ((a >> 62) == 0 || (a >> 62) != (b >> 62));
+                }
+                const u32 incl = __ballot_sync(B200SA_FULL_MASK, have && (a >> 62) == 2);
+                const u32 cutoff = incl ? (u32)__ffs((int)incl) - 1u : 31u;
+                const bool use = have && lane <= cutoff;
+                u32 ck = use ? rr_a_kept(a) : 0u, ch = use ? rr_a_kheads(a) : 0u;
+                u32 cl = use ? (u32)(b & 0xffffffffull) : 0u;
+#pragma unroll
+                for (int d = 16; d >= 1; d >>= 1) {
+                    ck += __shfl_xor_sync(B200SA_FULL_MASK, ck, d);
+                    ch += __shfl_xor_sync(B200SA_FULL_MASK, ch, d);
+                    const u32 o = __shfl_xor_sync(B200SA_FULL_MASK, cl, d);
+                    cl = cl > o ? cl : o;
+                }
+                pre_k += ck; pre_kh += ch; pre_lh = pre_lh > cl ? pre_lh : cl;
+                if (incl) break;
+                t -= 32;  // no inclusive descriptor in this window: tile 0 is always inclusive, so t stays >= 0
+            }
+            if (lane == 0) {
+                const u32 inc_lh = tot_lh > pre_lh ? tot_lh : pre_lh;
+                st_relaxed_u64(da + tile, rr_pack_a(RR_FLAG_INCLUSIVE, pre_k + tot_k, pre_kh + tot_kh));
+                st_relaxed_u64(db + tile, RR_FLAG_INCLUSIVE | (u64)inc_lh);
+            }
+        }
+        if (lane == 0) {
+            s_pre_k = pre_k; s_pre_kh = pre_kh; s_pre_lh = pre_lh;
+            if (tile == ntiles - 1) { info[0] = pre_k + tot_k; info[1] = pre_kh + tot_kh; }
+        }
+    }
+    __syncthreads();
+    // ---- outputs
+    const u32 pre_k = s_pre_k, pre_kh = s_pre_kh, pre_lh = s_pre_lh;
+    const u32 lt = lanemask_lt(), le = lt | (1u << lane);
+#pragma unroll
+    for (int q = 0; q < RR_IPT; ++q) {
+        const u32 j = base + (u32)q * RR_THREADS + tid;
+        if (j < m) {
+            const u32 c = (u32)q * RR_WARPS + warp;
+            const u32 rowbase = (u32)q * RR_THREADS + warp * 32u;
+            const u32 hb = bal_head[q] & le;
+            u32 hs1;  // 1 + global slot of my group's head
+            if (hb) hs1 = base + rowbase + (31u - (u32)__clz((int)hb)) + 1u;
+            else if (s_lh[c]) hs1 = base + s_lh[c];
+            else hs1 = pre_lh;
+            const u32 hs = hs1 - 1u;
             const u32 gpos = slot_in ? slot_in[hs] : hs;
-            const u32 sfx = idx_in[j];
+            const u32 sfx = ld_stream(idx_in + j);
             rank[sfx] = gpos + 1u;
-            if (is_single) {
+            const bool single = (bal_single[q] >> lane) & 1u;
+            if (single) {
                 sa[gpos + 1u] = (i32)sfx;
             } else {
-                heads += is_head;
-                idx_out[dest] = sfx;
-                slot_out[dest] = slot_in ? slot_in[j] : j;
-                gid_out[dest] = heads - 1u;
-                ++dest;
+                const u32 keptb = ~bal_single[q];
+                const u32 dest = pre_k + s_k[c] + (u32)__popc(keptb & lt);
+                const u32 heads = pre_kh + s_kh[c] + (u32)__popc(keptb & bal_head[q] & le);
+                st_stream(idx_out + dest, sfx);
+                st_stream(slot_out + dest, slot_in ? ld_stream(slot_in + j) : j);
+                st_stream(gid_out + dest, heads - 1u);
             }
         }
     }

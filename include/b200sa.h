@@ -136,6 +136,7 @@ enum {
     B200SA_PH_UNBWT_WALK = 8, /* unBWT: walkers, list ranking, emit                           */
     B200SA_PH_CHECK = 9,      /* validator                                                    */
     B200SA_PH_SEGSORT = 10,   /* in-shared-memory sort of small groups (doubling rounds)      */
+    B200SA_PH_ISA = 11,       /* bucketed ISA update: one radix sweep by suffix index + scatter */
     B200SA_PH_COUNT = 16
 };
 

@@ -96,10 +96,15 @@ int Engine::init(int dev)
     B200SA_CU(cudaStreamCreateWithFlags(&own_stream, cudaStreamNonBlocking));
     B200SA_CU(cudaHostAlloc((void**)&h_pinned, 64 * sizeof(u32), cudaHostAllocDefault));
     memset(&prof, 0, sizeof(prof));
+    // tuning knobs (tests lower them to drive the bucketed ISA update at small n)
+    if (const char* e1 = getenv("B200SA_ISA_DIRECT_BYTES")) isa_direct_bytes = (size_t)strtoull(e1, nullptr, 10);
+    if (const char* e2 = getenv("B200SA_ISA_MIN_UPDATES")) isa_min_updates = (u32)strtoul(e2, nullptr, 10);
     // the scatter kernels use more than the default 48 KB of dynamic shared memory
     {
         auto k64 = k_onesweep_pass<u64, true>;
         auto k8 = k_onesweep_pass<u8, false>;
+        auto k32 = k_onesweep_pass<u32, true>;
+        B200SA_CU(cudaFuncSetAttribute(k32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_pass_smem_bytes<u32>()));
         B200SA_CU(cudaFuncSetAttribute(k64, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_pass_smem_bytes<u64>()));
         B200SA_CU(cudaFuncSetAttribute(k8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_pass_smem_bytes<u8>()));
     }
@@ -229,8 +234,8 @@ int Engine::radix_sort_pairs(u64* keys2[2], u32* vals2[2], bool gen_vals, u32 m,
 // ---------------------------------------------------------------------------------------------
 // rerank driver
 
-int Engine::rerank(const u64* keys_sorted, const u32* idx_sorted, const u32* slot_in, u32 m, i32* d_sa,
-                   u32* idx_out, u32* slot_out, u32* next_m, u32* next_groups, cudaStream_t st)
+int Engine::rerank(const u64* keys_sorted, const u32* idx_sorted, const u32* slot_in, u32 m, u32 n, i32* d_sa,
+                   u32* idx_out, u32* slot_out, u64* free_keys, u32* next_m, u32* next_groups, cudaStream_t st)
 {
     const u32 ntiles = (u32)div_up_u64(m, RR_TILE);
     // agg_cnt holds the two descriptor arrays followed by the tile ticket counter
@@ -241,13 +246,55 @@ int Engine::rerank(const u64* keys_sorted, const u32* idx_sorted, const u32* slo
     u32* d_info = misc.as<u32>() + 512;  // see ensure_sa_workspace for the misc layout
     B200SA_CU(cudaMemsetAsync(agg_cnt.p, 0, desc_bytes + 64, st));
     prof.memsets++;
+    // The ISA (rank[]) is updated by a bucketed scatter when it is too large to live in L2 and there
+    // are enough updates to pay for the extra sweep; otherwise directly from the rerank kernel.
+    const bool bucketed = ((u64)n * 4 > isa_direct_bytes) && (m >= isa_min_updates);
+    u32* newrank = bucketed ? (u32*)free_keys : nullptr;          // [m]
+    u32* bk_val = bucketed ? (u32*)free_keys + m : nullptr;       // [m]
+    u32* bk_key = nullptr;
+    if (bucketed) {
+        B200SA_TRY(agg_max.ensure((size_t)m * 4 + 64));
+        bk_key = agg_max.as<u32>();
+    }
     B200SA_TRY(phase_begin(B200SA_PH_RERANK, st));
     B200SA_LAUNCH(k_rerank, ntiles, RR_THREADS, 0, st, keys_sorted, idx_sorted, slot_in, m, desc, ntiles, ticket,
-                  rank.as<u32>(), d_sa, idx_out, slot_out, gid.as<u32>(), d_info);
+                  rank.as<u32>(), newrank, d_sa, idx_out, slot_out, gid.as<u32>(), d_info);
     count_launch(B200SA_PH_RERANK);
     B200SA_TRY(phase_end(st));
     B200SA_CU(cudaGetLastError());
     B200SA_CU(cudaMemcpyAsync(h_pinned, d_info, 2 * sizeof(u32), cudaMemcpyDeviceToHost, st));
+    if (bucketed) {
+        // one radix sweep of (suffix, new rank) pairs on the top 8 bits of the suffix index ...
+        const int nbits = bit_length_u64((u64)n - 1);
+        const int shift = nbits > RS_RADIX_BITS ? nbits - RS_RADIX_BITS : 0;
+        const u32 tiles = (u32)div_up_u64(m, RS_TILE);
+        const size_t status_bytes = (size_t)tiles * RS_RADIX * sizeof(u64);
+        B200SA_TRY(sortmeta.ensure(kSortMetaHeader + status_bytes));
+        u32* ghist = sortmeta.as<u32>();
+        u32* counters = ghist + RS_MAX_PASSES * RS_RADIX;
+        u64* status = (u64*)((u8*)sortmeta.p + kSortMetaHeader);
+        B200SA_CU(cudaMemsetAsync(sortmeta.p, 0, kSortMetaHeader + status_bytes, st));
+        prof.memsets++;
+        B200SA_TRY(phase_begin(B200SA_PH_ISA, st));
+        const u32 htiles = (u32)div_up_u64(m, RH_THREADS * RH_IPT);
+        const u32 hgrid = htiles < (u32)(num_sms * 6) ? htiles : (u32)(num_sms * 6);
+        auto kh = k_radix_hist<u32>;
+        B200SA_LAUNCH(kh, hgrid, RH_THREADS, rh_smem_bytes(1), st, idx_sorted, m, shift, 1, ghist);
+        count_launch(B200SA_PH_ISA);
+        B200SA_LAUNCH(k_radix_scan_bins, 1, RS_RADIX, 0, st, ghist);
+        count_launch(B200SA_PH_ISA);
+        auto kp = k_onesweep_pass<u32, true>;
+        B200SA_LAUNCH(kp, tiles, RS_THREADS, rs_pass_smem_bytes<u32>(), st, idx_sorted, bk_key, (const u32*)newrank, bk_val,
+                      m, shift, 0xffffffffu, (const u32*)ghist, status, counters);
+        count_launch(B200SA_PH_ISA);
+        // ... then the scatter proper, now confined to an L2-resident window at any moment
+        B200SA_LAUNCH(k_scatter_pairs, (u32)div_up_u64(m, SP_THREADS * SP_IPT), SP_THREADS, 0, st, (const u32*)bk_key,
+                      (const u32*)bk_val, m, rank.as<u32>());
+        count_launch(B200SA_PH_ISA);
+        B200SA_TRY(phase_end(st));
+        B200SA_CU(cudaGetLastError());
+        prof.alg_bytes[B200SA_PH_ISA] += (u64)m * (4 + 8 + 8 + 8 + 4);
+    }
     B200SA_CU(cudaStreamSynchronize(st));
     *next_m = h_pinned[0];
     *next_groups = h_pinned[1];
@@ -331,7 +378,7 @@ int Engine::suffix_array_dev(const u8* d_text, i64 n64, i32* d_sa, cudaStream_t 
     u32 m = 0, groups = 0;
     int cur_slot = 0;  // slot[cur_slot] holds the slot map of the active array
     // sorted tuples are on `side`; the compacted active array goes to the other side
-    B200SA_TRY(rerank(k2[side], v2[side], nullptr, n, d_sa, v2[side ^ 1], slot[cur_slot].as<u32>(), &m, &groups, st));
+    B200SA_TRY(rerank(k2[side], v2[side], nullptr, n, n, d_sa, v2[side ^ 1], slot[cur_slot].as<u32>(), k2[side ^ 1], &m, &groups, st));
     int act = side ^ 1;  // side holding the active idx array
 
     // ---- doubling rounds
@@ -358,8 +405,8 @@ int Engine::suffix_array_dev(const u8* d_text, i64 n64, i32* d_sa, cudaStream_t 
         B200SA_TRY(radix_sort_pairs(kk, vv, false, m, 0, rank_bits + gid_bits, &rs, st));
         const int sorted_side = act ^ rs;
         u32 m2 = 0, g2 = 0;
-        B200SA_TRY(rerank(k2[sorted_side], v2[sorted_side], slot[cur_slot].as<u32>(), m, d_sa, v2[sorted_side ^ 1],
-                          slot[cur_slot ^ 1].as<u32>(), &m2, &g2, st));
+        B200SA_TRY(rerank(k2[sorted_side], v2[sorted_side], slot[cur_slot].as<u32>(), m, n, d_sa, v2[sorted_side ^ 1],
+                          slot[cur_slot ^ 1].as<u32>(), k2[sorted_side ^ 1], &m2, &g2, st));
         prof.rounds++;
         prof.active_tuples += m;
         act = sorted_side ^ 1;

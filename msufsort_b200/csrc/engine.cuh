@@ -14,6 +14,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 
 namespace b200sa {
 
@@ -60,6 +61,11 @@ struct Engine {
     DevBuf keys[2], idx[2], slot[2], gid, rank, sa_ws, sortmeta, agg_cnt, agg_max, misc, text_ws, bwt_ws, walk;
     u32* h_pinned = nullptr;  // 64 words of pinned host memory for small read-backs
 
+    // rank[] arrays up to this size are updated by direct scatter (they stay resident in the 126 MB
+    // L2); larger ones by the bucketed update when a round has at least isa_min_updates tuples
+    size_t isa_direct_bytes = (size_t)48 << 20;
+    u32 isa_min_updates = 1u << 20;
+
     // instrumentation
     bool profiling = false;
     b200sa_profile prof;
@@ -85,8 +91,8 @@ struct Engine {
     // building blocks
     int radix_sort_pairs(u64* keys2[2], u32* vals2[2], bool gen_vals, u32 m, int begin_bit, int end_bit,
                          int* result_side, cudaStream_t st);
-    int rerank(const u64* keys_sorted, const u32* idx_sorted, const u32* slot_in, u32 m, i32* d_sa,
-               u32* idx_out, u32* slot_out, u32* next_m, u32* next_groups, cudaStream_t st);
+    int rerank(const u64* keys_sorted, const u32* idx_sorted, const u32* slot_in, u32 m, u32 n, i32* d_sa,
+               u32* idx_out, u32* slot_out, u64* free_keys, u32* next_m, u32* next_groups, cudaStream_t st);
 
     // entry points
     int ensure_sa_workspace(u64 n);

@@ -203,11 +203,13 @@ __device__ __forceinline__ u32 rr_a_kept(u64 a) { return (u32)(a & 0x7fffffffull
 __device__ __forceinline__ u32 rr_a_kheads(u64 a) { return (u32)((a >> 31) & 0x7fffffffull); }
 
 //   slot_in == nullptr  -> round 0: active slot j is global position j
+//   newrank_out != nullptr -> new ranks are written in slot order (coalesced) instead of being
+//       scattered into rank[]; the caller then runs the bucketed ISA update (k_scatter_pairs)
 //   info[0] = #kept (next m), info[1] = #kept heads (next group count), written by the last tile
 __global__ void __launch_bounds__(RR_THREADS, 2)
 k_rerank(const u64* __restrict__ keys, const u32* __restrict__ idx_in, const u32* __restrict__ slot_in, u32 m,
          u64* __restrict__ desc /*[2][ntiles]*/, u32 ntiles, u32* __restrict__ tile_counter,
-         u32* __restrict__ rank, i32* __restrict__ sa,
+         u32* __restrict__ rank, u32* __restrict__ newrank_out, i32* __restrict__ sa,
          u32* __restrict__ idx_out, u32* __restrict__ slot_out, u32* __restrict__ gid_out, u32* __restrict__ info)
 {
     __shared__ u32 s_k[RR_CHUNKS], s_kh[RR_CHUNKS], s_lh[RR_CHUNKS];  // per chunk: kept, kept heads, 1+last head (tile-local)
@@ -351,7 +353,8 @@ k_rerank(const u64* __restrict__ keys, const u32* __restrict__ idx_in, const u32
             const u32 hs = hs1 - 1u;
             const u32 gpos = slot_in ? slot_in[hs] : hs;
             const u32 sfx = ld_stream(idx_in + j);
-            rank[sfx] = gpos + 1u;
+            if (newrank_out) st_stream(newrank_out + j, gpos + 1u);  // ISA update deferred: bucketed scatter
+            else rank[sfx] = gpos + 1u;
             const bool single = (bal_single[q] >> lane) & 1u;
             if (single) {
                 sa[gpos + 1u] = (i32)sfx;
@@ -364,6 +367,32 @@ k_rerank(const u64* __restrict__ keys, const u32* __restrict__ idx_in, const u32
                 st_stream(gid_out + dest, heads - 1u);
             }
         }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// ISA update, second half: rank[key[j]] = val[j] over pairs that one radix sweep has bucketed by the
+// top 8 bits of the suffix index.  A direct scatter of 2^28 ranks in suffix-array order measured
+// 12.9 ms (every 4-byte write dirties a different 32-byte sector of a 1 GiB array: DRAM
+// read-modify-write); bucketed, all CTAs write into a window of n/256 entries that lives in L2.
+static const int SP_THREADS = 256;
+static const int SP_IPT = 8;
+
+__global__ void __launch_bounds__(SP_THREADS)
+k_scatter_pairs(const u32* __restrict__ key, const u32* __restrict__ val, u32 m, u32* __restrict__ rank)
+{
+    const u32 tile = SP_THREADS * SP_IPT;
+    const u32 base = blockIdx.x * tile + threadIdx.x;
+    u32 k[SP_IPT], v[SP_IPT];
+#pragma unroll
+    for (int q = 0; q < SP_IPT; ++q) {
+        const u32 j = base + (u32)q * SP_THREADS;
+        if (j < m) { k[q] = ld_stream(key + j); v[q] = ld_stream(val + j); }
+    }
+#pragma unroll
+    for (int q = 0; q < SP_IPT; ++q) {
+        const u32 j = base + (u32)q * SP_THREADS;
+        if (j < m) rank[k[q]] = v[q];
     }
 }
 

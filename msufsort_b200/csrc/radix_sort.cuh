@@ -8,8 +8,9 @@
 //
 // Per pass and tile (THREADS x IPT consecutive elements, warp-striped so that element order inside
 // a warp is (item, lane)):
-//   1. warp-level ranking: eight ballots give the lanes holding the same digit; the lowest such
-//      lane bumps the warp's private counter in shared memory; rank = old count + #peers below me.
+//   1. warp-level ranking: the lanes holding the same digit find each other through a shared-memory
+//      mask word (atomicOr + read back); the lowest such lane bumps the warp's private counter;
+//      rank = old count + #peers below me.
 //   2. per-digit reduction over the warps (thread d owns digit d), published as this tile's PARTIAL
 //      descriptor; look-back over the predecessors' descriptors until an INCLUSIVE one is found;
 //      publish INCLUSIVE.  A descriptor is one 64-bit word (2 flag bits | 62-bit count).
@@ -38,7 +39,7 @@ static const u64 RS_VALUE_MASK = (1ull << 62) - 1;
 template <typename KeyT>
 __host__ __device__ constexpr size_t rs_pass_smem_bytes()
 {
-    return (size_t)(RS_THREADS / 32) * RS_RADIX * 4 + 3 * RS_RADIX * 4 + 16 * 4 + (size_t)RS_TILE * sizeof(KeyT) + (size_t)RS_TILE * 4;
+    return (size_t)(RS_THREADS / 32) * RS_RADIX * 4 * 2 + 3 * RS_RADIX * 4 + 16 * 4 + (size_t)RS_TILE * sizeof(KeyT) + (size_t)RS_TILE * 4;
 }
 
 template <typename KeyT>
@@ -51,11 +52,11 @@ __device__ __forceinline__ u32 rs_digit(KeyT key, int shift)
 // Digit histograms for `npasses` consecutive digits starting at begin_bit: one read of the keys.
 // ghist[p*256 + d] += count.
 //
-// Every warp owns a private [npasses][256] counter table in shared memory and updates it with plain
-// (non-atomic) read-modify-writes: eight ballots group the lanes holding the same digit, the
-// lowest lane of each group adds the group size.  Shared-memory atomics on scattered addresses cost
-// ~2 cycles per lane on this part (B300_MICROARCH.md, "ATOMS spread-addr") — the first version of
-// this kernel used them and took 16 ms for 2^28 keys x 8 digits; plain LDS/STS are bank-limited only.
+// Every warp owns a private [npasses][256] counter table in shared memory and bumps it with plain
+// shared-memory atomics.  Measured on B200 (tools/ubench): ATOMS.ADD costs 1.1 (all lanes on one
+// word) to 2.4 (32 random words) SM-cycles per warp instruction, eight VOTE.BALLOTs ~20 and
+// MATCH.ANY ~60 — the first versions of this kernel grouped equal digits with match_any (13.6 ms
+// for 2^28 keys x 8 digits) and then with ballots (7.8 ms).
 static const int RH_THREADS = 128;
 static const int RH_WARPS = RH_THREADS / 32;
 static const int RH_IPT = 8;
@@ -78,25 +79,19 @@ k_radix_hist(const KeyT* __restrict__ keys, u32 m, int begin_bit, int npasses, u
     const u32 nchunks = (u32)div_up_u64(m, chunk);
     for (u32 c = blockIdx.x * RH_WARPS + warp; c < nchunks; c += gridDim.x * RH_WARPS) {
         const u32 base = c * chunk + lane;
+        const bool full = (c + 1u) * chunk <= m;  // warp-uniform
         KeyT k[RH_IPT];
-        bool ok[RH_IPT];
 #pragma unroll
         for (int i = 0; i < RH_IPT; ++i) {
             const u32 idx = base + (u32)i * 32u;
-            ok[i] = idx < m;
-            k[i] = ok[i] ? ld_stream(keys + idx) : (KeyT)0;
+            k[i] = (full || idx < m) ? ld_stream(keys + idx) : (KeyT)0;
         }
-        for (int p = 0; p < npasses; ++p) {
-            const int shift = begin_bit + p * RS_RADIX_BITS;
-            u32* row = mine + p * RS_RADIX;
 #pragma unroll
-            for (int i = 0; i < RH_IPT; ++i) {
-                const u32 d = rs_digit<KeyT>(k[i], shift);
-                // out-of-range lanes are masked out of everybody's peer set
-                const u32 peers = warp_peers_digit8(d) & __ballot_sync(B200SA_FULL_MASK, ok[i]);
-                const u32 leader = (u32)__ffs((int)peers) - 1u;
-                if (ok[i] && lane == leader) row[d] += (u32)__popc(peers);
-                __syncwarp();
+        for (int i = 0; i < RH_IPT; ++i) {
+            const bool ok = full || (base + (u32)i * 32u < m);
+#pragma unroll
+            for (int p = 0; p < RS_MAX_PASSES; ++p) {
+                if (p < npasses && ok) atomicAdd(&mine[p * RS_RADIX + rs_digit<KeyT>(k[i], begin_bit + p * RS_RADIX_BITS)], 1u);
             }
         }
     }
@@ -143,13 +138,14 @@ k_onesweep_pass(const KeyT* __restrict__ kin, KeyT* __restrict__ kout,
     u32* s_coff = s_cnt + RS_RADIX;      // [256] exclusive scan of s_cnt (slot of the digit run in smem)
     u32* s_gdelta = s_coff + RS_RADIX;   // [256] global offset of the digit run minus s_coff
     u32* s_wtot = s_gdelta + RS_RADIX;   // [16]
-    KeyT* skeys = (KeyT*)(s_wtot + 16);  // [TILE]
+    u32* wmask = s_wtot + 16;            // [WARPS][256] per-warp peer masks (all zero between uses)
+    KeyT* skeys = (KeyT*)(wmask + WARPS * RS_RADIX);  // [TILE]
     u32* svals = (u32*)(skeys + TILE);   // [TILE]
     __shared__ u32 s_tile;
 
     const u32 tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     if (tid == 0) s_tile = atomicAdd(tile_counter, 1u);
-    for (u32 i = tid; i < (u32)(WARPS * RS_RADIX); i += THREADS) whist[i] = 0;
+    for (u32 i = tid; i < (u32)(WARPS * RS_RADIX); i += THREADS) { whist[i] = 0; wmask[i] = 0; }
     __syncthreads();
     const u32 tile = s_tile;
     const u32 base = tile * (u32)TILE;
@@ -160,35 +156,65 @@ k_onesweep_pass(const KeyT* __restrict__ kin, KeyT* __restrict__ kout,
     u32 val[IPT];
     u32 pos[IPT];
     const u32 wbase = warp * (32u * IPT) + lane;
+    const bool full = valid == (u32)TILE;  // block-uniform: no bounds checks on the common path
+    if (full) {
+        const KeyT* kp = kin + base + wbase;
 #pragma unroll
-    for (int k = 0; k < IPT; ++k) {
-        const u32 li = wbase + (u32)k * 32u;
-        if (li < valid) {
-            const u32 gi = base + li;
-            key[k] = ld_stream(kin + gi);
-            val[k] = vin ? ld_stream(vin + gi) : gi + (gi >= gen_skip ? 1u : 0u);
-        } else {
-            key[k] = (KeyT)~(KeyT)0;  // digit 255 in every pass: pads sort to the very end of the tile
-            val[k] = 0;
+        for (int k = 0; k < IPT; ++k) key[k] = ld_stream(kp + k * 32);
+    } else {
+#pragma unroll
+        for (int k = 0; k < IPT; ++k) {
+            const u32 li = wbase + (u32)k * 32u;
+            // pads get digit 255 in every pass: they sort to the very end of the tile
+            key[k] = li < valid ? ld_stream(kin + base + li) : (KeyT)~(KeyT)0;
         }
     }
 
-    // ---- 1. rank inside the warp
+    // ---- 1. rank inside the warp.  Peers (lanes with my digit) are found through shared memory:
+    // every lane ORs its bit into the warp's mask word for its digit and reads the word back
+    // (7.4 SM-cycles per 32 keys on B200 against 20.7 for eight ballots and 60 for MATCH.ANY,
+    // tools/ubench).  All peers then read the warp's running count for the digit (one broadcast word);
+    // the lowest peer clears the mask and bumps the count by the group size.
     u32* mywh = whist + warp * RS_RADIX;
+    u32* mymask = wmask + warp * RS_RADIX;
     const u32 lt = lanemask_lt();
+    const u32 mybit = 1u << lane;
 #pragma unroll
     for (int k = 0; k < IPT; ++k) {
         const u32 d = rs_digit<KeyT>(key[k], shift);
-        const u32 peers = warp_peers_digit8(d);
-        const u32 leader = (u32)__ffs((int)peers) - 1u;
-        u32 prev = 0;
-        if (lane == leader) {
-            prev = mywh[d];
+        atomicOr(&mymask[d], mybit);
+        __syncwarp();
+        const u32 peers = mymask[d];
+        const u32 prev = mywh[d];
+        __syncwarp();
+        const u32 below = (u32)__popc(peers & lt);
+        if (below == 0) {
+            mymask[d] = 0;
             mywh[d] = prev + (u32)__popc(peers);
         }
-        prev = __shfl_sync(B200SA_FULL_MASK, prev, (int)leader);
-        pos[k] = prev + (u32)__popc(peers & lt);
         __syncwarp();
+        pos[k] = prev + below;
+    }
+    // values are fetched only now: during ranking they would cost 16 more live registers (spills at
+    // the 80-register budget of 3 CTAs/SM); their latency overlaps the tile-level scan below
+    if (vin) {
+        if (full) {
+            const u32* vp = vin + base + wbase;
+#pragma unroll
+            for (int k = 0; k < IPT; ++k) val[k] = ld_stream(vp + k * 32);
+        } else {
+#pragma unroll
+            for (int k = 0; k < IPT; ++k) {
+                const u32 li = wbase + (u32)k * 32u;
+                val[k] = li < valid ? ld_stream(vin + base + li) : 0u;
+            }
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < IPT; ++k) {
+            const u32 gi = base + wbase + (u32)k * 32u;
+            val[k] = gi + (gi >= gen_skip ? 1u : 0u);
+        }
     }
     __syncthreads();
 
@@ -217,12 +243,14 @@ k_onesweep_pass(const KeyT* __restrict__ kin, KeyT* __restrict__ kout,
     }
     __syncthreads();
 
-    // ---- stage keys in digit order (needs only tile-local offsets; predecessors keep publishing meanwhile)
+    // ---- stage keys and values in digit order (needs only tile-local offsets; predecessors keep
+    // publishing their descriptors meanwhile)
 #pragma unroll
     for (int k = 0; k < IPT; ++k) {
         const u32 d = rs_digit<KeyT>(key[k], shift);
-        pos[k] += s_coff[d] + mywh[d];
-        skeys[pos[k]] = key[k];
+        const u32 p = pos[k] + s_coff[d] + mywh[d];
+        skeys[p] = key[k];
+        svals[p] = val[k];
     }
 
     // ---- 4. look-back for digit tid: four predecessor descriptors in flight per step
@@ -253,22 +281,23 @@ k_onesweep_pass(const KeyT* __restrict__ kin, KeyT* __restrict__ kout,
         s_gdelta[tid] = bins[tid] + (u32)excl - s_coff[tid];
     }
     __syncthreads();
-    if (WRITE_KEYS) {
-#pragma unroll 4
+    // ---- write out: consecutive threads take consecutive slots, i.e. consecutive addresses inside a digit run
+    if (full) {
+#pragma unroll
+        for (int i = 0; i < IPT; ++i) {
+            const u32 j = tid + (u32)i * THREADS;
+            const KeyT kk = skeys[j];
+            const u32 g = s_gdelta[rs_digit<KeyT>(kk, shift)] + j;
+            if (WRITE_KEYS) st_stream(kout + g, kk);
+            st_stream(vout + g, svals[j]);
+        }
+    } else {
         for (u32 j = tid; j < valid; j += THREADS) {
             const KeyT kk = skeys[j];
-            const u32 d = rs_digit<KeyT>(kk, shift);
-            st_stream(kout + (s_gdelta[d] + j), kk);
+            const u32 g = s_gdelta[rs_digit<KeyT>(kk, shift)] + j;
+            if (WRITE_KEYS) st_stream(kout + g, kk);
+            st_stream(vout + g, svals[j]);
         }
-    }
-    // ---- stage and write values
-#pragma unroll
-    for (int k = 0; k < IPT; ++k) svals[pos[k]] = val[k];
-    __syncthreads();
-#pragma unroll 4
-    for (u32 j = tid; j < valid; j += THREADS) {
-        const u32 d = rs_digit<KeyT>(skeys[j], shift);
-        st_stream(vout + (s_gdelta[d] + j), svals[j]);
     }
 }
 

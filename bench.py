@@ -66,7 +66,7 @@ class ClockSampler:
         q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "20", "-i", str(self.index)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -205,12 +205,14 @@ def run_ours(args, wl):
         torch.cuda.synchronize()
 
     # ---- device-resident: value + roofline
-    for _ in range(args.warmup):
-        eng.bwt_dev(d_text, n, d_bwt, d_sa, stream)
-    barrier()
+    # the clock sampler starts before the warm-up steps (nvidia-smi needs ~100 ms to come up) and
+    # stops right after the timed region: every sample is taken under the same load
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    for _ in range(args.warmup):
+        eng.bwt_dev(d_text, n, d_bwt, d_sa, stream)
+    barrier()
     eng.profile_reset()
     eng.set_profiling(True)
     launches0 = eng.launch_count()

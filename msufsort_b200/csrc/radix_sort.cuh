@@ -8,9 +8,8 @@
 //
 // Per pass and tile (THREADS x IPT consecutive elements, warp-striped so that element order inside
 // a warp is (item, lane)):
-//   1. warp-level ranking: the lanes holding the same digit find each other through a shared-memory
-//      mask word (atomicOr + read back); the lowest such lane bumps the warp's private counter;
-//      rank = old count + #peers below me.
+//   1. warp-level ranking: eight ballots give the lanes holding the same digit; the lowest such
+//      lane bumps the warp's private counter in shared memory; rank = old count + #peers below me.
 //   2. per-digit reduction over the warps (thread d owns digit d), published as this tile's PARTIAL
 //      descriptor; look-back over the predecessors' descriptors until an INCLUSIVE one is found;
 //      publish INCLUSIVE.  A descriptor is one 64-bit word (2 flag bits | 62-bit count).
@@ -26,10 +25,20 @@ namespace b200sa {
 
 static const int RS_RADIX_BITS = 8;
 static const int RS_RADIX = 256;
+// Tuning knobs (overridable at compile time for experiments: make NVCC_DEFS="-DB200SA_RS_IPT=8 ...").
+#ifndef B200SA_RS_IPT
+#define B200SA_RS_IPT 16
+#endif
+#ifndef B200SA_RS_MIN_BLOCKS
+#define B200SA_RS_MIN_BLOCKS 3
+#endif
+#ifndef B200SA_RS_PEERS_ATOMIC_OR
+#define B200SA_RS_PEERS_ATOMIC_OR 0
+#endif
 static const int RS_THREADS = 256;
-static const int RS_IPT = 16;
+static const int RS_IPT = B200SA_RS_IPT;
 static const int RS_TILE = RS_THREADS * RS_IPT;  // 4096 pairs per tile
-static const int RS_MIN_BLOCKS = 3;              // 3 CTAs/SM -> <= 85 registers per thread
+static const int RS_MIN_BLOCKS = B200SA_RS_MIN_BLOCKS;  // 3 CTAs/SM -> <= 85 registers per thread
 static const int RS_MAX_PASSES = 8;
 
 static const u64 RS_FLAG_PARTIAL = 1ull << 62;
@@ -39,7 +48,8 @@ static const u64 RS_VALUE_MASK = (1ull << 62) - 1;
 template <typename KeyT>
 __host__ __device__ constexpr size_t rs_pass_smem_bytes()
 {
-    return (size_t)(RS_THREADS / 32) * RS_RADIX * 4 * 2 + 3 * RS_RADIX * 4 + 16 * 4 + (size_t)RS_TILE * sizeof(KeyT) + (size_t)RS_TILE * 4;
+    return (size_t)(RS_THREADS / 32) * RS_RADIX * 4 * (B200SA_RS_PEERS_ATOMIC_OR ? 2 : 1) + 3 * RS_RADIX * 4 + 16 * 4 +
+           (size_t)RS_TILE * sizeof(KeyT) + (size_t)RS_TILE * 4;
 }
 
 template <typename KeyT>
@@ -138,14 +148,23 @@ k_onesweep_pass(const KeyT* __restrict__ kin, KeyT* __restrict__ kout,
     u32* s_coff = s_cnt + RS_RADIX;      // [256] exclusive scan of s_cnt (slot of the digit run in smem)
     u32* s_gdelta = s_coff + RS_RADIX;   // [256] global offset of the digit run minus s_coff
     u32* s_wtot = s_gdelta + RS_RADIX;   // [16]
+#if B200SA_RS_PEERS_ATOMIC_OR
     u32* wmask = s_wtot + 16;            // [WARPS][256] per-warp peer masks (all zero between uses)
     KeyT* skeys = (KeyT*)(wmask + WARPS * RS_RADIX);  // [TILE]
+#else
+    KeyT* skeys = (KeyT*)(s_wtot + 16);  // [TILE]
+#endif
     u32* svals = (u32*)(skeys + TILE);   // [TILE]
     __shared__ u32 s_tile;
 
     const u32 tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     if (tid == 0) s_tile = atomicAdd(tile_counter, 1u);
-    for (u32 i = tid; i < (u32)(WARPS * RS_RADIX); i += THREADS) { whist[i] = 0; wmask[i] = 0; }
+    for (u32 i = tid; i < (u32)(WARPS * RS_RADIX); i += THREADS) {
+        whist[i] = 0;
+#if B200SA_RS_PEERS_ATOMIC_OR
+        wmask[i] = 0;
+#endif
+    }
     __syncthreads();
     const u32 tile = s_tile;
     const u32 base = tile * (u32)TILE;
@@ -170,26 +189,36 @@ k_onesweep_pass(const KeyT* __restrict__ kin, KeyT* __restrict__ kout,
         }
     }
 
-    // ---- 1. rank inside the warp.  Peers (lanes with my digit) are found through shared memory:
-    // every lane ORs its bit into the warp's mask word for its digit and reads the word back
-    // (7.4 SM-cycles per 32 keys on B200 against 20.7 for eight ballots and 60 for MATCH.ANY,
-    // tools/ubench).  All peers then read the warp's running count for the digit (one broadcast word);
-    // the lowest peer clears the mask and bumps the count by the group size.
+    // ---- 1. rank inside the warp.  Peers = lanes holding my digit.  Two interchangeable ways to find
+    // them (tools/ubench on B200, SM-cycles per 32 keys at full occupancy): eight ballots 20.7,
+    // atomicOr into a shared mask word + read back 7.4, MATCH.ANY 60.  Inside this kernel the shared
+    // memory pipe is the scarcer resource (staging + counters already need ~25 wavefronts per 32
+    // keys), so the ballot form is faster in situ (R0 sweep 2.0 ms vs 2.4 ms) and is the default.
+    // All peers then read the warp's running count for the digit (one broadcast word) and the lowest
+    // peer bumps it by the group size.
     u32* mywh = whist + warp * RS_RADIX;
-    u32* mymask = wmask + warp * RS_RADIX;
     const u32 lt = lanemask_lt();
+#if B200SA_RS_PEERS_ATOMIC_OR
+    u32* mymask = wmask + warp * RS_RADIX;
     const u32 mybit = 1u << lane;
+#endif
 #pragma unroll
     for (int k = 0; k < IPT; ++k) {
         const u32 d = rs_digit<KeyT>(key[k], shift);
+#if B200SA_RS_PEERS_ATOMIC_OR
         atomicOr(&mymask[d], mybit);
         __syncwarp();
         const u32 peers = mymask[d];
+#else
+        const u32 peers = warp_peers_digit8(d);
+#endif
         const u32 prev = mywh[d];
         __syncwarp();
         const u32 below = (u32)__popc(peers & lt);
         if (below == 0) {
+#if B200SA_RS_PEERS_ATOMIC_OR
             mymask[d] = 0;
+#endif
             mywh[d] = prev + (u32)__popc(peers);
         }
         __syncwarp();
@@ -239,7 +268,11 @@ k_onesweep_pass(const KeyT* __restrict__ kin, KeyT* __restrict__ kout,
     if (tid < (u32)RS_RADIX) {
         u32 prefix = 0;
         for (u32 w = 0; w < warp; ++w) prefix += s_wtot[w];
-        s_coff[tid] = s_cnt[tid] + prefix;
+        const u32 off = s_cnt[tid] + prefix;
+        s_coff[tid] = off;
+        // fold the digit's slot into every warp's exclusive prefix: staging then needs one lookup per key
+#pragma unroll
+        for (int w = 0; w < WARPS; ++w) whist[w * RS_RADIX + tid] += off;
     }
     __syncthreads();
 
@@ -248,7 +281,7 @@ k_onesweep_pass(const KeyT* __restrict__ kin, KeyT* __restrict__ kout,
 #pragma unroll
     for (int k = 0; k < IPT; ++k) {
         const u32 d = rs_digit<KeyT>(key[k], shift);
-        const u32 p = pos[k] + s_coff[d] + mywh[d];
+        const u32 p = pos[k] + mywh[d];
         skeys[p] = key[k];
         svals[p] = val[k];
     }

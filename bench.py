@@ -314,6 +314,74 @@ def run_ours(args, wl):
     return 0
 
 
+def run_sharded(args, wl):
+    """ONE text sharded over all ranks (strong scaling): value = n / max-over-ranks time."""
+    import torch
+    import torch.distributed as dist
+    from msufsort_b200.api import Engine
+    from msufsort_b200.sharded import ShardedSorter
+
+    kind, n, desc = WORKLOADS[wl]
+    if args.n:
+        n = args.n
+    world = int(os.environ["WORLD_SIZE"]); rank = int(os.environ["RANK"]); local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    eng = Engine(local_rank)
+    text = gen_text(kind, n)                      # the same text on every rank
+    d_text = torch.from_numpy(text).cuda()
+    sorter = ShardedSorter(eng)
+    for _ in range(args.warmup):
+        res = sorter.suffix_array_bwt(d_text)
+    dist.barrier(); torch.cuda.synchronize()
+    eng.profile_reset(); eng.set_profiling(True)
+    launches0 = eng.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    dist.barrier(); torch.cuda.synchronize()
+    ev0.record()
+    for _ in range(args.steps):
+        res = sorter.suffix_array_bwt(d_text)
+    ev1.record()
+    dist.barrier(); torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1)
+    tt = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ms = float(tt.item())
+    clocks = sampler.stop() if rank == 0 else None
+    prof = eng.profile(); eng.set_profiling(False)
+    launches = eng.launch_count() - launches0
+    # correctness outside the timed region: assemble the SA and let the GPU validator judge it
+    full_sa = sorter.gather_sa(res)
+    bad = eng.check_suffix_array_dev(d_text, n, full_sa, torch.cuda.current_stream().cuda_stream)
+    if bad != 0:
+        raise SystemExit(f"bench.py: sharded SA has {bad} bad rows")
+    if rank == 0:
+        peak, peak_src = load_peaks()
+        sp = prof["phases"]["sort_pass"]
+        achieved = sp["alg_bytes"] / (sp["ms"] * 1e-3) / 1e9 if sp["ms"] > 0 else 0.0
+        ms_per_step = ms / args.steps
+        line = {
+            "metric": "sa_bwt_input_throughput", "value": n / (ms_per_step * 1e-3) / 1e6, "unit": "MB/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "u8/int32 (u64 sort keys)", "data": "synthetic",
+            "config": {"workload": wl, "description": desc, "n_bytes": n, "parallelism": f"one text sharded by key range over {world} GPUs",
+                       "owned_suffixes_per_rank": res.counts, "rounds": res.rounds,
+                       "nccl_bytes_received_per_rank_per_step": res.exchanged_bytes},
+            "e2e": None, "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": "k_onesweep_pass<u64> (rank 0)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak if peak else None, "traffic": None, "peak_source": peak_src},
+            "cpu_baseline": None, "clocks": clocks,
+            "phases_rank0": {k: {"ms_per_step": v["ms"] / args.steps, "launches_per_step": v["launches"] / args.steps}
+                             for k, v in prof["phases"].items() if v["launches"]},
+        }
+        print(json.dumps(line))
+    dist.destroy_process_group()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -323,9 +391,15 @@ def main():
     ap.add_argument("--workload", default="markov3_256MiB", choices=sorted(WORKLOADS))
     ap.add_argument("--n", type=int, default=0, help="override the text size (debugging)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mode", default="independent", choices=["independent", "sharded"],
+                    help="N>1 only. independent (default): one text per GPU, no data-path collective, weak scaling. "
+                         "sharded: ONE text partitioned by key range over the N GPUs, ISA updates all-gathered over NCCL "
+                         "after every doubling round, strong scaling (north_star item 4)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args, args.workload)
+    if args.mode == "sharded" and int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        return run_sharded(args, args.workload)
     return run_ours(args, args.workload)
 
 

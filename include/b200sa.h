@@ -122,6 +122,40 @@ B200SA_API int b200sa_unbwt_dev(b200sa_ctx* ctx, const uint8_t* d_bwt, int64_t n
 B200SA_API int b200sa_check_suffix_array_dev(b200sa_ctx* ctx, const uint8_t* d_text, int64_t n,
                                              const int32_t* d_sa, int64_t* bad_rows_out, void* stream);
 
+/* ---- sharded (multi-GPU) building blocks --------------------------------------------------
+ *
+ * One text, G GPUs, one process and one context per GPU (msufsort_b200/sharded.py drives these over
+ * torch.distributed / NCCL).  Every GPU holds the whole text and a replica of the ISA.  Round 0 is
+ * partitioned by key range: each context packs all n initial keys, derives the same G-1 splitters
+ * from a sorted regular sample (no communication) and sorts only the suffixes of its own range.
+ * A range consists of whole groups, so every later doubling round sorts locally; what travels
+ * between GPUs after each round is the list of (suffix, new rank) ISA updates (all-gather), which
+ * every context applies to its replica.  The reference has no counterpart (single address space);
+ * this is north_star item (4).                                                                   */
+
+/* Alphabet, keys, splitters, key-range filter and first sort for part `part` of `nparts`.
+ * d_sa: n+1 int32 (only this part's rows are written).  *n_local_out = suffixes owned. */
+B200SA_API int b200sa_shard_begin(b200sa_ctx* ctx, const uint8_t* d_text, int64_t n, int32_t* d_sa,
+                                  int part, int nparts, int64_t* n_local_out, void* stream);
+/* Round-0 ranking.  slot_base = number of suffixes owned by lower parts (exclusive scan of the
+ * n_local values, exchanged by the caller).  *m_local_out = suffixes of this part still active. */
+B200SA_API int b200sa_shard_round0(b200sa_ctx* ctx, int64_t slot_base, int64_t* m_local_out, void* stream);
+/* One doubling round on this part's active suffixes (a no-op when none are left). */
+B200SA_API int b200sa_shard_round(b200sa_ctx* ctx, int64_t* m_local_out, void* stream);
+/* ISA updates produced by the last round0/round call: device arrays valid until the next step. */
+B200SA_API int b200sa_shard_updates(b200sa_ctx* ctx, const uint32_t** d_idx_out, const uint32_t** d_rank_out,
+                                    int64_t* count_out);
+/* Copies those updates into caller-owned device buffers (e.g. the send buffer of an all-gather). */
+B200SA_API int b200sa_shard_copy_updates(b200sa_ctx* ctx, uint32_t* d_idx_dst, uint32_t* d_rank_dst,
+                                         int64_t capacity, void* stream);
+/* rank[d_idx[j]] = d_rank[j] on this context's ISA replica (own and peers' updates alike). */
+B200SA_API int b200sa_shard_apply_updates(b200sa_ctx* ctx, const uint32_t* d_idx, const uint32_t* d_rank,
+                                          int64_t count, void* stream);
+/* BWT bytes of SA rows [row_begin,row_end) into d_bwt (an n-byte buffer; bytes
+ * [*out_begin,*out_end) are written). */
+B200SA_API int b200sa_shard_bwt(b200sa_ctx* ctx, int64_t row_begin, int64_t row_end, uint8_t* d_bwt,
+                                int64_t* out_begin, int64_t* out_end, int32_t* sentinel_index_out, void* stream);
+
 /* ---- instrumentation --------------------------------------------------------------------- */
 
 enum {

@@ -64,6 +64,13 @@ ABI = [
     ("b200sa_bwt_dev", C.c_int, [_P, _P, C.c_int64, _P, _P, C.POINTER(C.c_int32), _P]),
     ("b200sa_unbwt_dev", C.c_int, [_P, _P, C.c_int64, C.c_int32, _P, _P]),
     ("b200sa_check_suffix_array_dev", C.c_int, [_P, _P, C.c_int64, _P, C.POINTER(C.c_int64), _P]),
+    ("b200sa_shard_begin", C.c_int, [_P, _P, C.c_int64, _P, C.c_int, C.c_int, C.POINTER(C.c_int64), _P]),
+    ("b200sa_shard_round0", C.c_int, [_P, C.c_int64, C.POINTER(C.c_int64), _P]),
+    ("b200sa_shard_round", C.c_int, [_P, C.POINTER(C.c_int64), _P]),
+    ("b200sa_shard_updates", C.c_int, [_P, C.POINTER(_P), C.POINTER(_P), C.POINTER(C.c_int64)]),
+    ("b200sa_shard_copy_updates", C.c_int, [_P, _P, _P, C.c_int64, _P]),
+    ("b200sa_shard_apply_updates", C.c_int, [_P, _P, _P, C.c_int64, _P]),
+    ("b200sa_shard_bwt", C.c_int, [_P, C.c_int64, C.c_int64, _P, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int32), _P]),
     ("b200sa_set_profiling", C.c_int, [_P, C.c_int]),
     ("b200sa_profile_reset", C.c_int, [_P]),
     ("b200sa_profile_get", C.c_int, [_P, C.POINTER(_Profile)]),
@@ -224,6 +231,39 @@ class Engine:
         self.lib.check(self.lib.cdll.b200sa_radix_sort_pairs_dev(self._ctx, _ptr(d_keys), _ptr(d_keys_alt), _ptr(d_vals), _ptr(d_vals_alt),
                                                                  m, begin_bit, end_bit, C.byref(side), stream or None))
         return int(side.value)
+
+    # ---- sharded building blocks (see msufsort_b200/sharded.py) ----------------------------------
+    def shard_begin(self, d_text, n: int, d_sa, part: int, nparts: int, stream: int = 0) -> int:
+        out = C.c_int64(0)
+        self.lib.check(self.lib.cdll.b200sa_shard_begin(self._ctx, _ptr(d_text), n, _ptr(d_sa), part, nparts, C.byref(out), stream or None))
+        return int(out.value)
+
+    def shard_round0(self, slot_base: int, stream: int = 0) -> int:
+        out = C.c_int64(0)
+        self.lib.check(self.lib.cdll.b200sa_shard_round0(self._ctx, slot_base, C.byref(out), stream or None))
+        return int(out.value)
+
+    def shard_round(self, stream: int = 0) -> int:
+        out = C.c_int64(0)
+        self.lib.check(self.lib.cdll.b200sa_shard_round(self._ctx, C.byref(out), stream or None))
+        return int(out.value)
+
+    def shard_updates(self):
+        """(idx_ptr, rank_ptr, count) of the ISA updates produced by the last step"""
+        pi, pr, cnt = _P(), _P(), C.c_int64(0)
+        self.lib.check(self.lib.cdll.b200sa_shard_updates(self._ctx, C.byref(pi), C.byref(pr), C.byref(cnt)))
+        return (pi.value or 0), (pr.value or 0), int(cnt.value)
+
+    def shard_copy_updates(self, d_idx_dst, d_rank_dst, capacity: int, stream: int = 0) -> None:
+        self.lib.check(self.lib.cdll.b200sa_shard_copy_updates(self._ctx, _ptr(d_idx_dst), _ptr(d_rank_dst), capacity, stream or None))
+
+    def shard_apply_updates(self, d_idx, d_rank, count: int, stream: int = 0) -> None:
+        self.lib.check(self.lib.cdll.b200sa_shard_apply_updates(self._ctx, _ptr(d_idx), _ptr(d_rank), count, stream or None))
+
+    def shard_bwt(self, row_begin: int, row_end: int, d_bwt, stream: int = 0):
+        ob, oe, s = C.c_int64(0), C.c_int64(0), C.c_int32(0)
+        self.lib.check(self.lib.cdll.b200sa_shard_bwt(self._ctx, row_begin, row_end, _ptr(d_bwt), C.byref(ob), C.byref(oe), C.byref(s), stream or None))
+        return int(ob.value), int(oe.value), int(s.value)
 
     # ---- instrumentation ----------------------------------------------------------------------
     def set_profiling(self, enabled: bool) -> None:

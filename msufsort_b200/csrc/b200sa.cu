@@ -234,9 +234,59 @@ int Engine::radix_sort_pairs(u64* keys2[2], u32* vals2[2], bool gen_vals, u32 m,
 // ---------------------------------------------------------------------------------------------
 // rerank driver
 
-int Engine::rerank(const u64* keys_sorted, const u32* idx_sorted, const u32* slot_in, u32 m, u32 n, i32* d_sa,
-                   u32* idx_out, u32* slot_out, u64* free_keys, u32* next_m, u32* next_groups, cudaStream_t st)
+// ISA update rank[idx[j]] = val[j] for `count` pairs.  Large arrays go through one radix sweep on the
+// top 8 bits of the suffix index so that the scatter proper works inside an L2-resident window.
+int Engine::isa_update(const u32* d_idx, const u32* d_val, u32 count, u32 n, u32* bk_key, u32* bk_val, cudaStream_t st)
 {
+    if (count == 0) return 0;
+    const bool bucketed = ((u64)n * 4 > isa_direct_bytes) && (count >= isa_min_updates) && bk_key && bk_val;
+    B200SA_TRY(phase_begin(B200SA_PH_ISA, st));
+    if (bucketed) {
+        const int nbits = bit_length_u64((u64)n - 1);
+        const int shift = nbits > RS_RADIX_BITS ? nbits - RS_RADIX_BITS : 0;
+        const u32 tiles = (u32)div_up_u64(count, RS_TILE);
+        const size_t status_bytes = (size_t)tiles * RS_RADIX * sizeof(u64);
+        B200SA_TRY(sortmeta.ensure(kSortMetaHeader + status_bytes));
+        u32* ghist = sortmeta.as<u32>();
+        u32* counters = ghist + RS_MAX_PASSES * RS_RADIX;
+        u64* status = (u64*)((u8*)sortmeta.p + kSortMetaHeader);
+        B200SA_CU(cudaMemsetAsync(sortmeta.p, 0, kSortMetaHeader + status_bytes, st));
+        prof.memsets++;
+        const u32 htiles = (u32)div_up_u64(count, RH_THREADS * RH_IPT);
+        const u32 hgrid = htiles < (u32)(num_sms * 6) ? htiles : (u32)(num_sms * 6);
+        auto kh = k_radix_hist<u32>;
+        B200SA_LAUNCH(kh, hgrid, RH_THREADS, rh_smem_bytes(1), st, d_idx, count, shift, 1, ghist);
+        count_launch(B200SA_PH_ISA);
+        B200SA_LAUNCH(k_radix_scan_bins, 1, RS_RADIX, 0, st, ghist);
+        count_launch(B200SA_PH_ISA);
+        auto kp = k_onesweep_pass<u32, true>;
+        B200SA_LAUNCH(kp, tiles, RS_THREADS, rs_pass_smem_bytes<u32>(), st, d_idx, bk_key, d_val, bk_val,
+                      count, shift, 0xffffffffu, (const u32*)ghist, status, counters);
+        count_launch(B200SA_PH_ISA);
+        B200SA_LAUNCH(k_scatter_pairs, (u32)div_up_u64(count, SP_THREADS * SP_IPT), SP_THREADS, 0, st, (const u32*)bk_key,
+                      (const u32*)bk_val, count, rank.as<u32>());
+        count_launch(B200SA_PH_ISA);
+        prof.alg_bytes[B200SA_PH_ISA] += (u64)count * (4 + 8 + 8 + 8 + 4);
+    } else {
+        B200SA_LAUNCH(k_scatter_pairs, (u32)div_up_u64(count, SP_THREADS * SP_IPT), SP_THREADS, 0, st, d_idx, d_val, count,
+                      rank.as<u32>());
+        count_launch(B200SA_PH_ISA);
+        prof.alg_bytes[B200SA_PH_ISA] += (u64)count * 12;
+    }
+    B200SA_TRY(phase_end(st));
+    B200SA_CU(cudaGetLastError());
+    return 0;
+}
+
+// Rerank driver.  mode: 0 = the kernel scatters new ranks into rank[] itself (small ISA);
+// 1 = new ranks are written in slot order and applied here through isa_update(); 2 = written in slot
+// order and left for the caller (sharded runs exchange them between GPUs first).
+int Engine::rerank(const u64* keys_sorted, const u32* idx_sorted, const u32* slot_in, u32 slot_base, u32 m, u32 n, i32* d_sa,
+                   u32* idx_out, u32* slot_out, u64* free_keys, int mode, u32* next_m, u32* next_groups, cudaStream_t st)
+{
+    *next_m = 0;
+    *next_groups = 0;
+    if (m == 0) return 0;
     const u32 ntiles = (u32)div_up_u64(m, RR_TILE);
     // agg_cnt holds the two descriptor arrays followed by the tile ticket counter
     const size_t desc_bytes = (size_t)ntiles * 2 * sizeof(u64);
@@ -246,54 +296,18 @@ int Engine::rerank(const u64* keys_sorted, const u32* idx_sorted, const u32* slo
     u32* d_info = misc.as<u32>() + 512;  // see ensure_sa_workspace for the misc layout
     B200SA_CU(cudaMemsetAsync(agg_cnt.p, 0, desc_bytes + 64, st));
     prof.memsets++;
-    // The ISA (rank[]) is updated by a bucketed scatter when it is too large to live in L2 and there
-    // are enough updates to pay for the extra sweep; otherwise directly from the rerank kernel.
-    const bool bucketed = ((u64)n * 4 > isa_direct_bytes) && (m >= isa_min_updates);
-    u32* newrank = bucketed ? (u32*)free_keys : nullptr;          // [m]
-    u32* bk_val = bucketed ? (u32*)free_keys + m : nullptr;       // [m]
-    u32* bk_key = nullptr;
-    if (bucketed) {
-        B200SA_TRY(agg_max.ensure((size_t)m * 4 + 64));
-        bk_key = agg_max.as<u32>();
-    }
+    if (mode == 1 && !(((u64)n * 4 > isa_direct_bytes) && (m >= isa_min_updates))) mode = 0;
+    u32* newrank = mode ? (u32*)free_keys : nullptr;  // [m]
     B200SA_TRY(phase_begin(B200SA_PH_RERANK, st));
-    B200SA_LAUNCH(k_rerank, ntiles, RR_THREADS, 0, st, keys_sorted, idx_sorted, slot_in, m, desc, ntiles, ticket,
+    B200SA_LAUNCH(k_rerank, ntiles, RR_THREADS, 0, st, keys_sorted, idx_sorted, slot_in, slot_base, m, desc, ntiles, ticket,
                   rank.as<u32>(), newrank, d_sa, idx_out, slot_out, gid.as<u32>(), d_info);
     count_launch(B200SA_PH_RERANK);
     B200SA_TRY(phase_end(st));
     B200SA_CU(cudaGetLastError());
     B200SA_CU(cudaMemcpyAsync(h_pinned, d_info, 2 * sizeof(u32), cudaMemcpyDeviceToHost, st));
-    if (bucketed) {
-        // one radix sweep of (suffix, new rank) pairs on the top 8 bits of the suffix index ...
-        const int nbits = bit_length_u64((u64)n - 1);
-        const int shift = nbits > RS_RADIX_BITS ? nbits - RS_RADIX_BITS : 0;
-        const u32 tiles = (u32)div_up_u64(m, RS_TILE);
-        const size_t status_bytes = (size_t)tiles * RS_RADIX * sizeof(u64);
-        B200SA_TRY(sortmeta.ensure(kSortMetaHeader + status_bytes));
-        u32* ghist = sortmeta.as<u32>();
-        u32* counters = ghist + RS_MAX_PASSES * RS_RADIX;
-        u64* status = (u64*)((u8*)sortmeta.p + kSortMetaHeader);
-        B200SA_CU(cudaMemsetAsync(sortmeta.p, 0, kSortMetaHeader + status_bytes, st));
-        prof.memsets++;
-        B200SA_TRY(phase_begin(B200SA_PH_ISA, st));
-        const u32 htiles = (u32)div_up_u64(m, RH_THREADS * RH_IPT);
-        const u32 hgrid = htiles < (u32)(num_sms * 6) ? htiles : (u32)(num_sms * 6);
-        auto kh = k_radix_hist<u32>;
-        B200SA_LAUNCH(kh, hgrid, RH_THREADS, rh_smem_bytes(1), st, idx_sorted, m, shift, 1, ghist);
-        count_launch(B200SA_PH_ISA);
-        B200SA_LAUNCH(k_radix_scan_bins, 1, RS_RADIX, 0, st, ghist);
-        count_launch(B200SA_PH_ISA);
-        auto kp = k_onesweep_pass<u32, true>;
-        B200SA_LAUNCH(kp, tiles, RS_THREADS, rs_pass_smem_bytes<u32>(), st, idx_sorted, bk_key, (const u32*)newrank, bk_val,
-                      m, shift, 0xffffffffu, (const u32*)ghist, status, counters);
-        count_launch(B200SA_PH_ISA);
-        // ... then the scatter proper, now confined to an L2-resident window at any moment
-        B200SA_LAUNCH(k_scatter_pairs, (u32)div_up_u64(m, SP_THREADS * SP_IPT), SP_THREADS, 0, st, (const u32*)bk_key,
-                      (const u32*)bk_val, m, rank.as<u32>());
-        count_launch(B200SA_PH_ISA);
-        B200SA_TRY(phase_end(st));
-        B200SA_CU(cudaGetLastError());
-        prof.alg_bytes[B200SA_PH_ISA] += (u64)m * (4 + 8 + 8 + 8 + 4);
+    if (mode == 1) {
+        B200SA_TRY(agg_max.ensure((size_t)m * 4 + 64));
+        B200SA_TRY(isa_update(idx_sorted, newrank, m, n, agg_max.as<u32>(), (u32*)free_keys + m, st));
     }
     B200SA_CU(cudaStreamSynchronize(st));
     *next_m = h_pinned[0];
@@ -320,18 +334,16 @@ int Engine::ensure_sa_workspace(u64 n)
     return 0;
 }
 
-int Engine::suffix_array_dev(const u8* d_text, i64 n64, i32* d_sa, cudaStream_t st)
+// The sort is a small state machine so that the single-GPU entry point and the sharded (multi-GPU)
+// driver share every step: begin (alphabet, keys, optional key-range filter, first sort) ->
+// round 0 ranking -> doubling rounds.  With nparts > 1 a context sorts only the suffixes whose
+// initial key falls into its splitter range; those form whole groups, so every later sort is local
+// and only ISA updates travel between GPUs (msufsort_b200/sharded.py).
+int Engine::sort_begin(const u8* d_text, u32 n, i32* d_sa, int part, int nparts, u32* n_local, cudaStream_t st)
 {
-    if (n64 < 0 || n64 > B200SA_MAX_N_INT32) return set_error(B200SA_EINVAL, "n = %lld outside [0, 2^31-2]", (long long)n64);
-    if (!d_sa || (n64 > 0 && !d_text)) return set_error(B200SA_EINVAL, "null pointer");
-    B200SA_CU(cudaSetDevice(device));
-    const u32 n = (u32)n64;
-    if (n == 0) {
-        B200SA_CU(cudaMemsetAsync(d_sa, 0, sizeof(i32), st));
-        B200SA_CU(cudaStreamSynchronize(st));
-        return 0;
-    }
     B200SA_TRY(ensure_sa_workspace(n));
+    ss = SortState();
+    ss.d_text = d_text; ss.n = n; ss.d_sa = d_sa; ss.part = part; ss.nparts = nparts;
     u32* d_hist = misc.as<u32>();
     u8* d_code = (u8*)(misc.as<u32>() + 256);
 
@@ -350,10 +362,11 @@ int Engine::suffix_array_dev(const u8* d_text, i64 n64, i32* d_sa, cudaStream_t 
     u32 h_hist[256];
     B200SA_CU(cudaMemcpyAsync(h_hist, d_hist, sizeof(h_hist), cudaMemcpyDeviceToHost, st));
     B200SA_CU(cudaStreamSynchronize(st));
-    const AlphabetPlan plan = plan_alphabet(h_hist);
+    ss.plan = plan_alphabet(h_hist);
+    const AlphabetPlan& plan = ss.plan;
     B200SA_CU(cudaMemcpyAsync(d_code, plan.code, 256, cudaMemcpyHostToDevice, st));
 
-    // ---- round 0: pack, sort, rank
+    // ---- initial keys for every suffix
     B200SA_LAUNCH(k_sa_init, 1, 32, 0, st, rank.as<u32>(), d_sa, n);
     count_launch(B200SA_PH_PACK);
     B200SA_TRY(phase_begin(B200SA_PH_PACK, st));
@@ -370,57 +383,170 @@ int Engine::suffix_array_dev(const u8* d_text, i64 n64, i32* d_sa, cudaStream_t 
 
     u64* k2[2] = {keys[0].as<u64>(), keys[1].as<u64>()};
     u32* v2[2] = {idx[0].as<u32>(), idx[1].as<u32>()};
+    const int key_bits = plan.bits * plan.k + plan.len_bits;
     int side = 0;
-    B200SA_TRY(radix_sort_pairs(k2, v2, true, n, 0, plan.bits * plan.k + plan.len_bits, &side, st));
-    prof.rounds++;
-    prof.active_tuples += n;
-
-    u32 m = 0, groups = 0;
-    int cur_slot = 0;  // slot[cur_slot] holds the slot map of the active array
-    // sorted tuples are on `side`; the compacted active array goes to the other side
-    B200SA_TRY(rerank(k2[side], v2[side], nullptr, n, n, d_sa, v2[side ^ 1], slot[cur_slot].as<u32>(), k2[side ^ 1], &m, &groups, st));
-    int act = side ^ 1;  // side holding the active idx array
-
-    // ---- doubling rounds
-    const int rank_bits = bit_length_u64(n);
-    u64 h = (u64)plan.k;
-    int guard = 0;
-    while (m > 0) {
-        if (++guard > 64) return set_error(B200SA_EINTERNAL, "prefix doubling did not converge (m=%u, h=%llu)", m, (unsigned long long)h);
-        if (groups == 0 || h > (u64)n) return set_error(B200SA_EINTERNAL, "inconsistent round state (m=%u groups=%u h=%llu)", m, groups, (unsigned long long)h);
-        const int gid_bits = groups <= 1 ? 0 : bit_length_u64((u64)groups - 1);
-        B200SA_TRY(phase_begin(B200SA_PH_BUILD, st));
-        {
-            const u32 tiles = (u32)div_up_u64(m, BK_THREADS * BK_IPT);
-            const u32 grid = tiles < (u32)(num_sms * 8) ? tiles : (u32)(num_sms * 8);
-            B200SA_LAUNCH(k_build_keys, grid, BK_THREADS, 0, st, (const u32*)v2[act], (const u32*)gid.as<u32>(),
-                          (const u32*)rank.as<u32>(), m, n, (u32)h, rank_bits, k2[act]);
-            count_launch(B200SA_PH_BUILD);
-        }
+    u32 count = n;
+    if (nparts > 1) {
+        // ---- splitters from a sorted sample of the keys (same text + same kernels on every GPU =>
+        // identical splitters everywhere, no communication), then keep only this part's key range
+        u32 nsample = n < (1u << 18) ? n : (1u << 18);
+        const u32 stride = n / nsample;
+        u64* smp[2] = {(u64*)slot[0].p, (u64*)slot[1].p};  // the slot maps are not in use yet (8 * 2^18 bytes each fits: n >= nsample)
+        B200SA_TRY(slot[0].ensure((size_t)nsample * 8 + 64));
+        B200SA_TRY(slot[1].ensure((size_t)nsample * 8 + 64));
+        smp[0] = (u64*)slot[0].p; smp[1] = (u64*)slot[1].p;
+        B200SA_TRY(agg_max.ensure((size_t)nsample * 8 + 64));
+        u32* sv[2] = {agg_max.as<u32>(), agg_max.as<u32>() + nsample};
+        B200SA_LAUNCH(k_sample_keys, (u32)div_up_u64(nsample, 256), 256, 0, st, (const u64*)k2[0], nsample, stride, smp[0]);
+        count_launch(B200SA_PH_PACK);
+        int sside = 0;
+        B200SA_TRY(radix_sort_pairs(smp, sv, true, nsample, 0, key_bits, &sside, st));
+        std::vector<u64> h_sample(nsample);
+        B200SA_CU(cudaMemcpyAsync(h_sample.data(), smp[sside], (size_t)nsample * 8, cudaMemcpyDeviceToHost, st));
+        B200SA_CU(cudaStreamSynchronize(st));
+        const u64 lo = part == 0 ? 0ull : h_sample[(size_t)((u64)part * nsample / nparts)];
+        const u64 hi = part == nparts - 1 ? ~0ull : h_sample[(size_t)((u64)(part + 1) * nsample / nparts)];
+        const bool hi_inclusive = part == nparts - 1;
+        u32* d_count = misc.as<u32>() + 536;
+        B200SA_CU(cudaMemsetAsync(d_count, 0, 4, st));
+        prof.memsets++;
+        B200SA_TRY(phase_begin(B200SA_PH_PACK, st));
+        B200SA_LAUNCH(k_filter_range, (u32)div_up_u64(n, FR_THREADS * FR_IPT), FR_THREADS, 0, st, (const u64*)k2[0], n, lo, hi,
+                      hi_inclusive ? 1 : 0, k2[1], v2[1], d_count);
+        count_launch(B200SA_PH_PACK);
         B200SA_TRY(phase_end(st));
-        prof.alg_bytes[B200SA_PH_BUILD] += (u64)m * 20;
-        u64* kk[2] = {k2[act], k2[act ^ 1]};
-        u32* vv[2] = {v2[act], v2[act ^ 1]};
+        B200SA_CU(cudaMemcpyAsync(h_pinned + 16, d_count, 4, cudaMemcpyDeviceToHost, st));
+        B200SA_CU(cudaStreamSynchronize(st));
+        count = h_pinned[16];
+        prof.alg_bytes[B200SA_PH_PACK] += (u64)n * 8 + (u64)count * 12;
+        // sort this part: input on side 1
+        u64* kk[2] = {k2[1], k2[0]};
+        u32* vv[2] = {v2[1], v2[0]};
         int rs = 0;
-        B200SA_TRY(radix_sort_pairs(kk, vv, false, m, 0, rank_bits + gid_bits, &rs, st));
-        const int sorted_side = act ^ rs;
-        u32 m2 = 0, g2 = 0;
-        B200SA_TRY(rerank(k2[sorted_side], v2[sorted_side], slot[cur_slot].as<u32>(), m, n, d_sa, v2[sorted_side ^ 1],
-                          slot[cur_slot ^ 1].as<u32>(), k2[sorted_side ^ 1], &m2, &g2, st));
-        prof.rounds++;
-        prof.active_tuples += m;
-        act = sorted_side ^ 1;
-        cur_slot ^= 1;
-        m = m2;
-        groups = g2;
-        h *= 2;
+        B200SA_TRY(radix_sort_pairs(kk, vv, false, count, 0, key_bits, &rs, st));
+        side = 1 ^ rs;
+    } else {
+        B200SA_TRY(radix_sort_pairs(k2, v2, true, n, 0, key_bits, &side, st));
     }
+    prof.rounds++;
+    prof.active_tuples += count;
+    ss.n_local = count;
+    ss.sorted_side = side;
+    ss.stage = 1;
+    *n_local = count;
+    return 0;
+}
+
+int Engine::sort_round0(u32 slot_base, u32* m_local, cudaStream_t st)
+{
+    if (ss.stage != 1) return set_error(B200SA_EINVAL, "sort_round0 called out of order");
+    u64* k2[2] = {keys[0].as<u64>(), keys[1].as<u64>()};
+    u32* v2[2] = {idx[0].as<u32>(), idx[1].as<u32>()};
+    const int side = ss.sorted_side;
+    ss.cur_slot = 0;
+    // sorted tuples are on `side`; the compacted active array goes to the other side
+    B200SA_TRY(rerank(k2[side], v2[side], nullptr, slot_base, ss.n_local, ss.n, ss.d_sa, v2[side ^ 1], slot[0].as<u32>(),
+                      k2[side ^ 1], ss.nparts > 1 ? 2 : 1, &ss.m, &ss.groups, st));
+    ss.upd_idx = v2[side];
+    ss.upd_rank = (const u32*)k2[side ^ 1];
+    ss.upd_count = ss.nparts > 1 ? ss.n_local : 0;
+    ss.act = side ^ 1;
+    ss.rank_bits = bit_length_u64(ss.n);
+    ss.h = (u64)ss.plan.k;
+    ss.stage = 2;
+    ss.guard = 0;
+    *m_local = ss.m;
+    return 0;
+}
+
+int Engine::sort_round(u32* m_local, cudaStream_t st)
+{
+    if (ss.stage != 2) return set_error(B200SA_EINVAL, "sort_round called out of order");
+    ss.upd_count = 0;
+    if (ss.m == 0) { *m_local = 0; ss.h *= 2; return 0; }  // nothing left here; peers may still be working
+    const u32 m = ss.m, n = ss.n;
+    if (++ss.guard > 64) return set_error(B200SA_EINTERNAL, "prefix doubling did not converge (m=%u, h=%llu)", m, (unsigned long long)ss.h);
+    if (ss.groups == 0 || ss.h > (u64)n) return set_error(B200SA_EINTERNAL, "inconsistent round state (m=%u groups=%u h=%llu)", m, ss.groups, (unsigned long long)ss.h);
+    u64* k2[2] = {keys[0].as<u64>(), keys[1].as<u64>()};
+    u32* v2[2] = {idx[0].as<u32>(), idx[1].as<u32>()};
+    const int act = ss.act;
+    const int gid_bits = ss.groups <= 1 ? 0 : bit_length_u64((u64)ss.groups - 1);
+    B200SA_TRY(phase_begin(B200SA_PH_BUILD, st));
+    {
+        const u32 tiles = (u32)div_up_u64(m, BK_THREADS * BK_IPT);
+        const u32 grid = tiles < (u32)(num_sms * 8) ? tiles : (u32)(num_sms * 8);
+        B200SA_LAUNCH(k_build_keys, grid, BK_THREADS, 0, st, (const u32*)v2[act], (const u32*)gid.as<u32>(),
+                      (const u32*)rank.as<u32>(), m, n, (u32)ss.h, ss.rank_bits, k2[act]);
+        count_launch(B200SA_PH_BUILD);
+    }
+    B200SA_TRY(phase_end(st));
+    prof.alg_bytes[B200SA_PH_BUILD] += (u64)m * 20;
+    u64* kk[2] = {k2[act], k2[act ^ 1]};
+    u32* vv[2] = {v2[act], v2[act ^ 1]};
+    int rs = 0;
+    B200SA_TRY(radix_sort_pairs(kk, vv, false, m, 0, ss.rank_bits + gid_bits, &rs, st));
+    const int sorted_side = act ^ rs;
+    u32 m2 = 0, g2 = 0;
+    B200SA_TRY(rerank(k2[sorted_side], v2[sorted_side], slot[ss.cur_slot].as<u32>(), 0, m, n, ss.d_sa, v2[sorted_side ^ 1],
+                      slot[ss.cur_slot ^ 1].as<u32>(), k2[sorted_side ^ 1], ss.nparts > 1 ? 2 : 1, &m2, &g2, st));
+    prof.rounds++;
+    prof.active_tuples += m;
+    ss.upd_idx = v2[sorted_side];
+    ss.upd_rank = (const u32*)k2[sorted_side ^ 1];
+    ss.upd_count = ss.nparts > 1 ? m : 0;
+    ss.act = sorted_side ^ 1;
+    ss.cur_slot ^= 1;
+    ss.m = m2;
+    ss.groups = g2;
+    ss.h *= 2;
+    *m_local = m2;
+    return 0;
+}
+
+int Engine::suffix_array_dev(const u8* d_text, i64 n64, i32* d_sa, cudaStream_t st)
+{
+    if (n64 < 0 || n64 > B200SA_MAX_N_INT32) return set_error(B200SA_EINVAL, "n = %lld outside [0, 2^31-2]", (long long)n64);
+    if (!d_sa || (n64 > 0 && !d_text)) return set_error(B200SA_EINVAL, "null pointer");
+    B200SA_CU(cudaSetDevice(device));
+    const u32 n = (u32)n64;
+    if (n == 0) {
+        B200SA_CU(cudaMemsetAsync(d_sa, 0, sizeof(i32), st));
+        B200SA_CU(cudaStreamSynchronize(st));
+        return 0;
+    }
+    u32 n_local = 0, m = 0;
+    B200SA_TRY(sort_begin(d_text, n, d_sa, 0, 1, &n_local, st));
+    B200SA_TRY(sort_round0(0, &m, st));
+    while (m > 0) B200SA_TRY(sort_round(&m, st));
+    ss.stage = 3;
     if (profiling) B200SA_TRY(collect_profile());
     return 0;
 }
 
 // ---------------------------------------------------------------------------------------------
 // forward BWT
+
+// output bytes [o_begin, o_end) from a finished SA (+ rank[0] = sentinel row); the sentinel row lands
+// in h_pinned[8]
+int Engine::bwt_rows(const u8* d_text, u32 n, const i32* d_sa, u32 o_begin, u32 o_end, u8* d_bwt, cudaStream_t st)
+{
+    i32* d_sent = (i32*)(misc.as<u32>() + 528);
+    B200SA_TRY(phase_begin(B200SA_PH_BWT, st));
+    {
+        const u32 groups = (u32)div_up_u64(o_end - o_begin, 4);
+        const u32 want = (u32)div_up_u64(groups, BW_THREADS * BW_STEPS);
+        const u32 grid = want < (u32)(num_sms * 16) ? (want ? want : 1u) : (u32)(num_sms * 16);
+        B200SA_LAUNCH(k_bwt_gather, grid, BW_THREADS, 0, st, d_text, d_sa, (const u32*)rank.as<u32>(), o_begin, o_end, d_bwt, d_sent);
+        count_launch(B200SA_PH_BWT);
+    }
+    B200SA_TRY(phase_end(st));
+    prof.alg_bytes[B200SA_PH_BWT] += (u64)(o_end - o_begin) * 6;
+    B200SA_CU(cudaGetLastError());
+    B200SA_CU(cudaMemcpyAsync(h_pinned + 8, d_sent, sizeof(i32), cudaMemcpyDeviceToHost, st));
+    B200SA_CU(cudaStreamSynchronize(st));
+    (void)n;
+    return 0;
+}
 
 int Engine::bwt_dev(const u8* d_text, i64 n64, u8* d_bwt, i32* d_sa_or_null, i32* sentinel_host, cudaStream_t st)
 {
@@ -438,20 +564,7 @@ int Engine::bwt_dev(const u8* d_text, i64 n64, u8* d_bwt, i32* d_sa_or_null, i32
         d_sa = sa_ws.as<i32>();
     }
     B200SA_TRY(suffix_array_dev(d_text, n64, d_sa, st));
-    i32* d_sent = (i32*)(misc.as<u32>() + 528);
-    B200SA_TRY(phase_begin(B200SA_PH_BWT, st));
-    {
-        const u32 groups = (u32)div_up_u64(n, 4);
-        const u32 want = (u32)div_up_u64(groups, BW_THREADS * BW_STEPS);
-        const u32 grid = want < (u32)(num_sms * 16) ? (want ? want : 1u) : (u32)(num_sms * 16);
-        B200SA_LAUNCH(k_bwt_gather, grid, BW_THREADS, 0, st, d_text, (const i32*)d_sa, (const u32*)rank.as<u32>(), n, d_bwt, d_sent);
-        count_launch(B200SA_PH_BWT);
-    }
-    B200SA_TRY(phase_end(st));
-    prof.alg_bytes[B200SA_PH_BWT] += (u64)n * 6;
-    B200SA_CU(cudaGetLastError());
-    B200SA_CU(cudaMemcpyAsync(h_pinned + 8, d_sent, sizeof(i32), cudaMemcpyDeviceToHost, st));
-    B200SA_CU(cudaStreamSynchronize(st));
+    B200SA_TRY(bwt_rows(d_text, n, d_sa, 0, n, d_bwt, st));
     if (sentinel_host) *sentinel_host = (i32)h_pinned[8];
     if (profiling) B200SA_TRY(collect_profile());
     return 0;
@@ -712,6 +825,104 @@ int b200sa_unbwt(b200sa_ctx* ctx, uint8_t* bwt_inout, int64_t n, int32_t sentine
     B200SA_TRY(e.unbwt_dev(e.bwt_ws.as<u8>(), n, sentinel_index, e.text_ws.as<u8>(), st));
     B200SA_CU(cudaMemcpyAsync(bwt_inout, e.text_ws.p, (size_t)n, cudaMemcpyDeviceToHost, st));
     B200SA_CU(cudaStreamSynchronize(st));
+    return 0;
+}
+
+// ---- sharded (multi-GPU) building blocks ---------------------------------------------------------
+
+int b200sa_shard_begin(b200sa_ctx* ctx, const uint8_t* d_text, int64_t n, int32_t* d_sa, int part, int nparts,
+                       int64_t* n_local_out, void* stream)
+{
+    B200SA_NEED_CTX(ctx);
+    if (n <= 0 || n > B200SA_MAX_N_INT32 || !d_text || !d_sa || !n_local_out || nparts < 1 || part < 0 || part >= nparts)
+        return b200sa::set_error(B200SA_EINVAL, "bad argument");
+    Engine& e = ctx->eng;
+    B200SA_CU(cudaSetDevice(e.device));
+    u32 nl = 0;
+    B200SA_TRY(e.sort_begin(d_text, (u32)n, d_sa, part, nparts, &nl, e.pick(stream)));
+    *n_local_out = nl;
+    return 0;
+}
+
+int b200sa_shard_round0(b200sa_ctx* ctx, int64_t slot_base, int64_t* m_local_out, void* stream)
+{
+    B200SA_NEED_CTX(ctx);
+    if (!m_local_out || slot_base < 0) return b200sa::set_error(B200SA_EINVAL, "bad argument");
+    u32 m = 0;
+    B200SA_TRY(ctx->eng.sort_round0((u32)slot_base, &m, ctx->eng.pick(stream)));
+    *m_local_out = m;
+    return 0;
+}
+
+int b200sa_shard_round(b200sa_ctx* ctx, int64_t* m_local_out, void* stream)
+{
+    B200SA_NEED_CTX(ctx);
+    if (!m_local_out) return b200sa::set_error(B200SA_EINVAL, "bad argument");
+    u32 m = 0;
+    B200SA_TRY(ctx->eng.sort_round(&m, ctx->eng.pick(stream)));
+    *m_local_out = m;
+    return 0;
+}
+
+int b200sa_shard_updates(b200sa_ctx* ctx, const uint32_t** d_idx_out, const uint32_t** d_rank_out, int64_t* count_out)
+{
+    B200SA_NEED_CTX(ctx);
+    if (!d_idx_out || !d_rank_out || !count_out) return b200sa::set_error(B200SA_EINVAL, "bad argument");
+    *d_idx_out = ctx->eng.ss.upd_idx;
+    *d_rank_out = ctx->eng.ss.upd_rank;
+    *count_out = ctx->eng.ss.upd_count;
+    return 0;
+}
+
+int b200sa_shard_copy_updates(b200sa_ctx* ctx, uint32_t* d_idx_dst, uint32_t* d_rank_dst, int64_t capacity, void* stream)
+{
+    B200SA_NEED_CTX(ctx);
+    Engine& e = ctx->eng;
+    const int64_t count = e.ss.upd_count;
+    if (count > capacity || (count > 0 && (!d_idx_dst || !d_rank_dst))) return b200sa::set_error(B200SA_EINVAL, "destination too small");
+    if (count == 0) return 0;
+    cudaStream_t st = e.pick(stream);
+    B200SA_CU(cudaMemcpyAsync(d_idx_dst, e.ss.upd_idx, (size_t)count * 4, cudaMemcpyDeviceToDevice, st));
+    B200SA_CU(cudaMemcpyAsync(d_rank_dst, e.ss.upd_rank, (size_t)count * 4, cudaMemcpyDeviceToDevice, st));
+    B200SA_CU(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int b200sa_shard_apply_updates(b200sa_ctx* ctx, const uint32_t* d_idx, const uint32_t* d_rank, int64_t count, void* stream)
+{
+    B200SA_NEED_CTX(ctx);
+    Engine& e = ctx->eng;
+    if (count < 0 || (count > 0 && (!d_idx || !d_rank))) return b200sa::set_error(B200SA_EINVAL, "bad argument");
+    if (e.ss.stage < 1) return b200sa::set_error(B200SA_EINVAL, "no sharded sort in progress");
+    if (count == 0) return 0;
+    cudaStream_t st = e.pick(stream);
+    B200SA_TRY(e.agg_max.ensure((size_t)count * 4 + 64));
+    B200SA_TRY(e.walk.ensure((size_t)count * 4 + 64));
+    B200SA_TRY(e.isa_update(d_idx, d_rank, (u32)count, e.ss.n, e.agg_max.as<u32>(), e.walk.as<u32>(), st));
+    B200SA_CU(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int b200sa_shard_bwt(b200sa_ctx* ctx, int64_t row_begin, int64_t row_end, uint8_t* d_bwt, int64_t* out_begin, int64_t* out_end,
+                     int32_t* sentinel_index_out, void* stream)
+{
+    B200SA_NEED_CTX(ctx);
+    Engine& e = ctx->eng;
+    if (e.ss.stage < 2) return b200sa::set_error(B200SA_EINVAL, "no finished sharded sort");
+    const int64_t n = e.ss.n;
+    if (row_begin < 0 || row_end < row_begin || row_end > n + 1 || !d_bwt || !out_begin || !out_end)
+        return b200sa::set_error(B200SA_EINVAL, "bad argument");
+    cudaStream_t st = e.pick(stream);
+    // sentinel row s = rank[0]; rows [row_begin,row_end) minus row s map to bytes [rb - (rb > s), re - (re > s))
+    B200SA_CU(cudaMemcpyAsync(e.h_pinned + 9, e.rank.as<u32>(), 4, cudaMemcpyDeviceToHost, st));
+    B200SA_CU(cudaStreamSynchronize(st));
+    const int64_t s = e.h_pinned[9];
+    const int64_t ob = row_begin - (row_begin > s ? 1 : 0), oe = row_end - (row_end > s ? 1 : 0);
+    if (oe > ob) B200SA_TRY(e.bwt_rows(e.ss.d_text, (u32)n, e.ss.d_sa, (u32)ob, (u32)oe, d_bwt, st));
+    *out_begin = ob;
+    *out_end = oe;
+    if (sentinel_index_out) *sentinel_index_out = (int32_t)s;
+    if (e.profiling) B200SA_TRY(e.collect_profile());
     return 0;
 }
 

@@ -13,14 +13,17 @@ namespace b200sa {
 static const int BW_THREADS = 256;
 static const int BW_STEPS = 4;  // independent 4-byte groups in flight per thread
 
+// Produces output bytes [o_begin, o_end) (the whole transform: 0 and n; a sharded run: the bytes
+// of the rows this GPU owns).
 __global__ void __launch_bounds__(BW_THREADS)
 k_bwt_gather(const u8* __restrict__ text, const i32* __restrict__ sa, const u32* __restrict__ rank,
-             u32 n, u8* __restrict__ out, i32* __restrict__ sentinel_out)
+             u32 o_begin, u32 o_end, u8* __restrict__ out, i32* __restrict__ sentinel_out)
 {
     const u32 s = rank[0];
     if (blockIdx.x == 0 && threadIdx.x == 0 && sentinel_out) *sentinel_out = (i32)s;
-    const u32 ngroups = (u32)div_up_u64(n, 4);
-    const bool out_aligned = (((uintptr_t)out) & 3u) == 0;
+    const u32 span = o_end - o_begin;
+    const u32 ngroups = (u32)div_up_u64(span, 4);
+    const bool out_aligned = (((uintptr_t)(out + o_begin)) & 3u) == 0;
     for (u32 g0 = (blockIdx.x * BW_THREADS + threadIdx.x); g0 < ngroups; g0 += gridDim.x * BW_THREADS * BW_STEPS) {
         u32 packed[BW_STEPS];
 #pragma unroll
@@ -30,8 +33,8 @@ k_bwt_gather(const u8* __restrict__ text, const i32* __restrict__ sa, const u32*
             if (g < ngroups) {
 #pragma unroll
                 for (int b = 0; b < 4; ++b) {
-                    const u32 o = g * 4u + (u32)b;
-                    if (o < n) {
+                    const u32 o = o_begin + g * 4u + (u32)b;
+                    if (o < o_end) {
                         const u32 row = o + (o >= s ? 1u : 0u);
                         const u32 v = (u32)sa[row];
                         w |= (u32)text[v - 1u] << (8 * b);
@@ -44,11 +47,11 @@ k_bwt_gather(const u8* __restrict__ text, const i32* __restrict__ sa, const u32*
         for (int st = 0; st < BW_STEPS; ++st) {
             const u32 g = g0 + (u32)st * gridDim.x * BW_THREADS;
             if (g < ngroups) {
-                const u32 o = g * 4u;
-                if (out_aligned && o + 4u <= n) {
+                const u32 o = o_begin + g * 4u;
+                if (out_aligned && o + 4u <= o_end) {
                     *(u32*)(out + o) = packed[st];
                 } else {
-                    for (u32 b = 0; b < 4u && o + b < n; ++b) out[o + b] = (u8)(packed[st] >> (8 * b));
+                    for (u32 b = 0; b < 4u && o + b < o_end; ++b) out[o + b] = (u8)(packed[st] >> (8 * b));
                 }
             }
         }

@@ -91,12 +91,33 @@ struct Engine {
     // building blocks
     int radix_sort_pairs(u64* keys2[2], u32* vals2[2], bool gen_vals, u32 m, int begin_bit, int end_bit,
                          int* result_side, cudaStream_t st);
-    int rerank(const u64* keys_sorted, const u32* idx_sorted, const u32* slot_in, u32 m, u32 n, i32* d_sa,
-               u32* idx_out, u32* slot_out, u64* free_keys, u32* next_m, u32* next_groups, cudaStream_t st);
+    int isa_update(const u32* d_idx, const u32* d_val, u32 count, u32 n, u32* bk_key, u32* bk_val, cudaStream_t st);
+    int rerank(const u64* keys_sorted, const u32* idx_sorted, const u32* slot_in, u32 slot_base, u32 m, u32 n, i32* d_sa,
+               u32* idx_out, u32* slot_out, u64* free_keys, int mode, u32* next_m, u32* next_groups, cudaStream_t st);
+
+    // suffix sort as resumable steps (shared by the single-GPU entry point and the sharded driver)
+    struct SortState {
+        int stage = 0;  // 0 idle, 1 first sort done, 2 ranking rounds, 3 finished
+        const u8* d_text = nullptr;
+        u32 n = 0;
+        i32* d_sa = nullptr;
+        int part = 0, nparts = 1;
+        AlphabetPlan plan;
+        u32 n_local = 0, m = 0, groups = 0;
+        int sorted_side = 0, act = 0, cur_slot = 0, rank_bits = 0, guard = 0;
+        u64 h = 0;
+        const u32* upd_idx = nullptr;   // ISA updates produced by the last step (sharded runs)
+        const u32* upd_rank = nullptr;
+        u32 upd_count = 0;
+    } ss;
+    int sort_begin(const u8* d_text, u32 n, i32* d_sa, int part, int nparts, u32* n_local, cudaStream_t st);
+    int sort_round0(u32 slot_base, u32* m_local, cudaStream_t st);
+    int sort_round(u32* m_local, cudaStream_t st);
 
     // entry points
     int ensure_sa_workspace(u64 n);
     int suffix_array_dev(const u8* d_text, i64 n, i32* d_sa, cudaStream_t st);
+    int bwt_rows(const u8* d_text, u32 n, const i32* d_sa, u32 o_begin, u32 o_end, u8* d_bwt, cudaStream_t st);
     int bwt_dev(const u8* d_text, i64 n, u8* d_bwt, i32* d_sa_or_null, i32* sentinel_host, cudaStream_t st);
     int unbwt_dev(const u8* d_bwt, i64 n, i32 sentinel, u8* d_out, cudaStream_t st);
     int check_sa_dev(const u8* d_text, i64 n, const i32* d_sa, i64* bad_rows, cudaStream_t st);

@@ -137,6 +137,47 @@ k_pack_keys(const u8* __restrict__ text, u32 n, const u8* __restrict__ code, int
 }
 
 // ---------------------------------------------------------------------------------------------
+// Sharded runs: every GPU packs all n keys, sorts a regular sample of them to pick splitters, and
+// keeps the (key, suffix) pairs of its own key range.  Output order is irrelevant (equal keys form
+// one group whatever their order), so the compaction uses a warp-aggregated atomic cursor.
+__global__ void __launch_bounds__(256)
+k_sample_keys(const u64* __restrict__ keys, u32 nsample, u32 stride, u64* __restrict__ out)
+{
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nsample) out[i] = keys[(u64)i * stride];
+}
+
+static const int FR_THREADS = 256;
+static const int FR_IPT = 8;
+
+__global__ void __launch_bounds__(FR_THREADS)
+k_filter_range(const u64* __restrict__ keys, u32 n, u64 lo, u64 hi, int hi_inclusive,
+               u64* __restrict__ out_keys, u32* __restrict__ out_idx, u32* __restrict__ cursor)
+{
+    const u32 lane = threadIdx.x & 31u;
+    const u32 base = blockIdx.x * (u32)(FR_THREADS * FR_IPT) + threadIdx.x;
+#pragma unroll
+    for (int q = 0; q < FR_IPT; ++q) {
+        const u32 i = base + (u32)q * FR_THREADS;
+        u64 k = 0;
+        bool keep = false;
+        if (i < n) {
+            k = ld_stream(keys + i);
+            keep = k >= lo && (hi_inclusive ? k <= hi : k < hi);
+        }
+        const u32 bal = __ballot_sync(B200SA_FULL_MASK, keep);
+        u32 pos = 0;
+        if (lane == 0 && bal) pos = atomicAdd(cursor, (u32)__popc(bal));
+        pos = __shfl_sync(B200SA_FULL_MASK, pos, 0);
+        if (keep) {
+            const u32 d = pos + (u32)__popc(bal & lanemask_lt());
+            out_keys[d] = k;
+            out_idx[d] = i;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // rank[n] = 0 (sentinel row), SA[0] = n.
 __global__ void k_sa_init(u32* __restrict__ rank, i32* __restrict__ sa, u32 n)
 {
@@ -202,12 +243,13 @@ __device__ __forceinline__ u64 rr_pack_a(u64 flag, u32 kept, u32 kheads) { retur
 __device__ __forceinline__ u32 rr_a_kept(u64 a) { return (u32)(a & 0x7fffffffull); }
 __device__ __forceinline__ u32 rr_a_kheads(u64 a) { return (u32)((a >> 31) & 0x7fffffffull); }
 
-//   slot_in == nullptr  -> round 0: active slot j is global position j
+//   slot_in == nullptr  -> round 0: active slot j is global position slot_base + j (slot_base = number
+//       of suffixes owned by lower-numbered parts in a sharded run, else 0)
 //   newrank_out != nullptr -> new ranks are written in slot order (coalesced) instead of being
 //       scattered into rank[]; the caller then runs the bucketed ISA update (k_scatter_pairs)
 //   info[0] = #kept (next m), info[1] = #kept heads (next group count), written by the last tile
 __global__ void __launch_bounds__(RR_THREADS, 2)
-k_rerank(const u64* __restrict__ keys, const u32* __restrict__ idx_in, const u32* __restrict__ slot_in, u32 m,
+k_rerank(const u64* __restrict__ keys, const u32* __restrict__ idx_in, const u32* __restrict__ slot_in, u32 slot_base, u32 m,
          u64* __restrict__ desc /*[2][ntiles]*/, u32 ntiles, u32* __restrict__ tile_counter,
          u32* __restrict__ rank, u32* __restrict__ newrank_out, i32* __restrict__ sa,
          u32* __restrict__ idx_out, u32* __restrict__ slot_out, u32* __restrict__ gid_out, u32* __restrict__ info)
@@ -351,7 +393,7 @@ k_rerank(const u64* __restrict__ keys, const u32* __restrict__ idx_in, const u32
             else if (s_lh[c]) hs1 = base + s_lh[c];
             else hs1 = pre_lh;
             const u32 hs = hs1 - 1u;
-            const u32 gpos = slot_in ? slot_in[hs] : hs;
+            const u32 gpos = slot_in ? slot_in[hs] : slot_base + hs;
             const u32 sfx = ld_stream(idx_in + j);
             if (newrank_out) st_stream(newrank_out + j, gpos + 1u);  // ISA update deferred: bucketed scatter
             else rank[sfx] = gpos + 1u;
@@ -363,7 +405,7 @@ k_rerank(const u64* __restrict__ keys, const u32* __restrict__ idx_in, const u32
                 const u32 dest = pre_k + s_k[c] + (u32)__popc(keptb & lt);
                 const u32 heads = pre_kh + s_kh[c] + (u32)__popc(keptb & bal_head[q] & le);
                 st_stream(idx_out + dest, sfx);
-                st_stream(slot_out + dest, slot_in ? ld_stream(slot_in + j) : j);
+                st_stream(slot_out + dest, slot_in ? ld_stream(slot_in + j) : slot_base + j);
                 st_stream(gid_out + dest, heads - 1u);
             }
         }

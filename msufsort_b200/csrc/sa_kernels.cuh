@@ -154,26 +154,44 @@ __global__ void __launch_bounds__(FR_THREADS)
 k_filter_range(const u64* __restrict__ keys, u32 n, u64 lo, u64 hi, int hi_inclusive,
                u64* __restrict__ out_keys, u32* __restrict__ out_idx, u32* __restrict__ cursor)
 {
-    const u32 lane = threadIdx.x & 31u;
+    __shared__ u32 s_wcnt[FR_THREADS / 32];
+    __shared__ u32 s_base;
+    const u32 lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const u32 base = blockIdx.x * (u32)(FR_THREADS * FR_IPT) + threadIdx.x;
+    u64 k[FR_IPT];
+    u32 bal[FR_IPT];
+    u32 wtotal = 0;
 #pragma unroll
     for (int q = 0; q < FR_IPT; ++q) {
         const u32 i = base + (u32)q * FR_THREADS;
-        u64 k = 0;
         bool keep = false;
+        k[q] = 0;
         if (i < n) {
-            k = ld_stream(keys + i);
-            keep = k >= lo && (hi_inclusive ? k <= hi : k < hi);
+            k[q] = ld_stream(keys + i);
+            keep = k[q] >= lo && (hi_inclusive ? k[q] <= hi : k[q] < hi);
         }
-        const u32 bal = __ballot_sync(B200SA_FULL_MASK, keep);
-        u32 pos = 0;
-        if (lane == 0 && bal) pos = atomicAdd(cursor, (u32)__popc(bal));
-        pos = __shfl_sync(B200SA_FULL_MASK, pos, 0);
-        if (keep) {
-            const u32 d = pos + (u32)__popc(bal & lanemask_lt());
-            out_keys[d] = k;
-            out_idx[d] = i;
+        bal[q] = __ballot_sync(B200SA_FULL_MASK, keep);
+        wtotal += (u32)__popc(bal[q]);
+    }
+    // one cursor bump per block (a bump per warp made 8.4 M same-address atomics: 6 ms for 2^28 keys)
+    if (lane == 0) s_wcnt[warp] = wtotal;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        u32 tot = 0;
+        for (int w = 0; w < FR_THREADS / 32; ++w) { const u32 c = s_wcnt[w]; s_wcnt[w] = tot; tot += c; }
+        s_base = tot ? atomicAdd(cursor, tot) : 0u;
+    }
+    __syncthreads();
+    u32 pos = s_base + s_wcnt[warp];
+    const u32 lt = lanemask_lt();
+#pragma unroll
+    for (int q = 0; q < FR_IPT; ++q) {
+        if ((bal[q] >> lane) & 1u) {
+            const u32 d = pos + (u32)__popc(bal[q] & lt);
+            out_keys[d] = k[q];
+            out_idx[d] = base + (u32)q * FR_THREADS;
         }
+        pos += (u32)__popc(bal[q]);
     }
 }
 

@@ -253,6 +253,10 @@ static const int RR_IPT = 16;
 static const int RR_TILE = RR_THREADS * RR_IPT;  // 4096 tuples per tile
 static const int RR_WARPS = RR_THREADS / 32;
 static const int RR_CHUNKS = RR_IPT * RR_WARPS;  // 128 warp-rows of 32 items per tile
+#ifndef B200SA_RR_MIN_BLOCKS
+#define B200SA_RR_MIN_BLOCKS 6
+#endif
+static const int RR_MIN_BLOCKS = B200SA_RR_MIN_BLOCKS;
 
 // descriptor A: flag(2) | kept heads (31) | kept (31);  descriptor B: flag(2) | 1 + last head slot (32)
 static const u64 RR_FLAG_PARTIAL = 1ull << 62;
@@ -266,7 +270,7 @@ __device__ __forceinline__ u32 rr_a_kheads(u64 a) { return (u32)((a >> 31) & 0x7
 //   newrank_out != nullptr -> new ranks are written in slot order (coalesced) instead of being
 //       scattered into rank[]; the caller then runs the bucketed ISA update (k_scatter_pairs)
 //   info[0] = #kept (next m), info[1] = #kept heads (next group count), written by the last tile
-__global__ void __launch_bounds__(RR_THREADS, 2)
+__global__ void __launch_bounds__(RR_THREADS, RR_MIN_BLOCKS)
 k_rerank(const u64* __restrict__ keys, const u32* __restrict__ idx_in, const u32* __restrict__ slot_in, u32 slot_base, u32 m,
          u64* __restrict__ desc /*[2][ntiles]*/, u32 ntiles, u32* __restrict__ tile_counter,
          u32* __restrict__ rank, u32* __restrict__ newrank_out, i32* __restrict__ sa,

@@ -268,6 +268,15 @@ def run_ours(args, wl):
     peak, peak_src = load_peaks()
     sp = prof["phases"]["sort_pass"]
     achieved = sp["alg_bytes"] / (sp["ms"] * 1e-3) / 1e9 if sp["ms"] > 0 else 0.0
+    # DRAM traffic per launch from the committed ncu --set full capture (profiles/r01_traffic.json), scaled to
+    # this run's average launch: traffic / algorithmic bytes was measured on the round-0 sweep (m = 2^28)
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            tr = json.load(f)
+        traffic = tr["dram_bytes_per_launch"] / tr["algorithmic_bytes_per_launch"] * sp["alg_bytes"] / sp["launches"]
+    except Exception:
+        pass
     ms_per_step = dev_ms / args.steps
     value = world * n / (ms_per_step * 1e-3) / 1e6
     phases = {k: {"ms_per_step": v["ms"] / args.steps, "launches_per_step": v["launches"] / args.steps,
@@ -300,7 +309,9 @@ def run_ours(args, wl):
                 "path": "b200sa_suffix_array + b200sa_bwt (the reference's two public calls), pinned host buffers"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": "k_onesweep_pass<u64> (radix scatter sweeps)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak if peak else None, "traffic": None, "peak_source": peak_src,
+                     "frac": achieved / peak if peak else None, "traffic": traffic, "peak_source": peak_src,
+                     "traffic_note": "bytes per average launch; ncu-measured DRAM/algorithmic ratio of the m=2^28 sweep (profiles/r01_traffic.json) x this run's algorithmic bytes per launch",
+                     "algorithmic_bytes_per_launch": sp["alg_bytes"] / sp["launches"] if sp["launches"] else None,
                      "launches": int(sp["launches"]), "avg_launch_ms": sp["ms"] / sp["launches"] if sp["launches"] else None,
                      "share_of_step": sp["ms"] / dev_ms if dev_ms else None},
         "cpu_baseline": cpu,

@@ -99,6 +99,11 @@ int Engine::init(int dev)
     // tuning knobs (tests lower them to drive the bucketed ISA update at small n)
     if (const char* e1 = getenv("B200SA_ISA_DIRECT_BYTES")) isa_direct_bytes = (size_t)strtoull(e1, nullptr, 10);
     if (const char* e2 = getenv("B200SA_ISA_MIN_UPDATES")) isa_min_updates = (u32)strtoul(e2, nullptr, 10);
+    if (const char* e3 = getenv("B200SA_GROUPSORT_AVG")) groupsort_max_avg = (u32)strtoul(e3, nullptr, 10);
+    if (const char* e4 = getenv("B200SA_GROUPSORT_TINY")) groupsort_tiny = (u32)strtoul(e4, nullptr, 10);
+    if (const char* e5 = getenv("B200SA_GROUPSORT_MEDIUM")) groupsort_medium = (u32)strtoul(e5, nullptr, 10);
+    if (groupsort_tiny > (u32)GS_TINY) groupsort_tiny = GS_TINY;
+    if (groupsort_medium > (u32)GS_MEDIUM) groupsort_medium = GS_MEDIUM;
     // the scatter kernels use more than the default 48 KB of dynamic shared memory
     {
         auto k64 = k_onesweep_pass<u64, true>;
@@ -114,7 +119,7 @@ int Engine::init(int dev)
 int Engine::release_workspace()
 {
     for (int i = 0; i < 2; ++i) { keys[i].release(); idx[i].release(); slot[i].release(); }
-    gid.release(); rank.release(); sa_ws.release(); sortmeta.release(); agg_cnt.release(); agg_max.release();
+    gid.release(); gstart.release(); glist.release(); rank.release(); sa_ws.release(); sortmeta.release(); agg_cnt.release(); agg_max.release();
     misc.release(); text_ws.release(); bwt_ws.release(); walk.release();
     return 0;
 }
@@ -300,7 +305,7 @@ int Engine::rerank(const u64* keys_sorted, const u32* idx_sorted, const u32* slo
     u32* newrank = mode ? (u32*)free_keys : nullptr;  // [m]
     B200SA_TRY(phase_begin(B200SA_PH_RERANK, st));
     B200SA_LAUNCH(k_rerank, ntiles, RR_THREADS, 0, st, keys_sorted, idx_sorted, slot_in, slot_base, m, desc, ntiles, ticket,
-                  rank.as<u32>(), newrank, d_sa, idx_out, slot_out, gid.as<u32>(), d_info);
+                  rank.as<u32>(), newrank, d_sa, idx_out, slot_out, gid.as<u32>(), gstart.as<u32>(), d_info);
     count_launch(B200SA_PH_RERANK);
     B200SA_TRY(phase_end(st));
     B200SA_CU(cudaGetLastError());
@@ -327,6 +332,7 @@ int Engine::ensure_sa_workspace(u64 n)
         B200SA_TRY(slot[i].ensure((size_t)n * 4 + 64));
     }
     B200SA_TRY(gid.ensure((size_t)n * 4 + 64));
+    B200SA_TRY(gstart.ensure(((size_t)n / 2 + 2) * 4 + 64));  // a kept group has >= 2 members
     B200SA_TRY(rank.ensure(((size_t)n + 1) * 4 + 64));
     // misc: [0..255] byte histogram u32, [256..319] symbol codes (256 bytes), [512..] round info,
     // [520..521] validator counter (u64), [528] sentinel row
@@ -471,21 +477,86 @@ int Engine::sort_round(u32* m_local, cudaStream_t st)
     u32* v2[2] = {idx[0].as<u32>(), idx[1].as<u32>()};
     const int act = ss.act;
     const int gid_bits = ss.groups <= 1 ? 0 : bit_length_u64((u64)ss.groups - 1);
-    B200SA_TRY(phase_begin(B200SA_PH_BUILD, st));
-    {
-        const u32 tiles = (u32)div_up_u64(m, BK_THREADS * BK_IPT);
-        const u32 grid = tiles < (u32)(num_sms * 8) ? tiles : (u32)(num_sms * 8);
-        B200SA_LAUNCH(k_build_keys, grid, BK_THREADS, 0, st, (const u32*)v2[act], (const u32*)gid.as<u32>(),
-                      (const u32*)rank.as<u32>(), m, n, (u32)ss.h, ss.rank_bits, k2[act]);
-        count_launch(B200SA_PH_BUILD);
+    int sorted_side = -1;
+
+    // ---- small groups: sort every group where it lies (no radix sweeps)
+    if (groupsort_max_avg > 0 && (u64)m <= (u64)ss.groups * groupsort_max_avg) {
+        const u32 G = ss.groups;
+        B200SA_TRY(glist.ensure(((size_t)G * 2 + 16) * 4));
+        u32* medium_list = glist.as<u32>();
+        u32* huge_list = glist.as<u32>() + G;
+        u32* d_cnt = misc.as<u32>() + 540;  // 4 counters
+        B200SA_CU(cudaMemsetAsync(d_cnt, 0, 16, st));
+        prof.memsets++;
+        B200SA_TRY(phase_begin(B200SA_PH_SEGSORT, st));
+        B200SA_LAUNCH(k_group_sort_tiny, (u32)div_up_u64(G, GS_THREADS), GS_THREADS, 0, st, (const u32*)gstart.as<u32>(), G, v2[act],
+                      (const u32*)rank.as<u32>(), n, (u32)ss.h, ss.rank_bits, k2[act], groupsort_tiny, groupsort_medium,
+                      medium_list, huge_list, d_cnt);
+        count_launch(B200SA_PH_SEGSORT);
+        B200SA_CU(cudaMemcpyAsync(h_pinned + 20, d_cnt, 16, cudaMemcpyDeviceToHost, st));
+        B200SA_CU(cudaStreamSynchronize(st));
+        const u32 nmedium = h_pinned[20], nhuge = h_pinned[21];
+        prof.alg_bytes[B200SA_PH_SEGSORT] += (u64)G * 4 + (u64)m * 20;
+        if (nhuge <= 64) {
+            if (nmedium) {
+                B200SA_LAUNCH(k_group_sort_medium, nmedium, GM_THREADS, 0, st, (const u32*)medium_list, (const u32*)gstart.as<u32>(),
+                              v2[act], (const u32*)rank.as<u32>(), n, (u32)ss.h, ss.rank_bits, k2[act]);
+                count_launch(B200SA_PH_SEGSORT);
+            }
+            B200SA_TRY(phase_end(st));
+            B200SA_CU(cudaGetLastError());
+            if (nhuge) {
+                // the few groups too large for one CTA: radix-sort their slot ranges one by one on the second key
+                std::vector<u32> hl(nhuge), gs((size_t)2 * nhuge);
+                B200SA_CU(cudaMemcpyAsync(hl.data(), huge_list, (size_t)nhuge * 4, cudaMemcpyDeviceToHost, st));
+                B200SA_CU(cudaStreamSynchronize(st));
+                for (u32 q = 0; q < nhuge; ++q)
+                    B200SA_CU(cudaMemcpyAsync(&gs[2 * q], gstart.as<u32>() + hl[q], 8, cudaMemcpyDeviceToHost, st));
+                B200SA_CU(cudaStreamSynchronize(st));
+                for (u32 q = 0; q < nhuge; ++q) {
+                    const u32 s0 = gs[2 * q], sz = gs[2 * q + 1] - s0;
+                    B200SA_TRY(phase_begin(B200SA_PH_BUILD, st));
+                    const u32 tiles = (u32)div_up_u64(sz, BK_THREADS * BK_IPT);
+                    const u32 grid = tiles < (u32)(num_sms * 8) ? tiles : (u32)(num_sms * 8);
+                    B200SA_LAUNCH(k_build_keys, grid, BK_THREADS, 0, st, (const u32*)(v2[act] + s0), (const u32*)(gid.as<u32>() + s0),
+                                  (const u32*)rank.as<u32>(), sz, n, (u32)ss.h, ss.rank_bits, k2[act] + s0);
+                    count_launch(B200SA_PH_BUILD);
+                    B200SA_TRY(phase_end(st));
+                    u64* kk[2] = {k2[act] + s0, k2[act ^ 1] + s0};
+                    u32* vv[2] = {v2[act] + s0, v2[act ^ 1] + s0};
+                    int rs = 0;
+                    B200SA_TRY(radix_sort_pairs(kk, vv, false, sz, 0, ss.rank_bits, &rs, st));
+                    if (rs) {
+                        B200SA_CU(cudaMemcpyAsync(kk[0], kk[1], (size_t)sz * 8, cudaMemcpyDeviceToDevice, st));
+                        B200SA_CU(cudaMemcpyAsync(vv[0], vv[1], (size_t)sz * 4, cudaMemcpyDeviceToDevice, st));
+                    }
+                }
+            }
+            sorted_side = act;
+        } else {
+            // too many large groups for per-group launches: fall through to the radix path, which
+            // rebuilds the keys (the in-place work done so far only permuted members inside groups)
+            B200SA_TRY(phase_end(st));
+        }
     }
-    B200SA_TRY(phase_end(st));
-    prof.alg_bytes[B200SA_PH_BUILD] += (u64)m * 20;
-    u64* kk[2] = {k2[act], k2[act ^ 1]};
-    u32* vv[2] = {v2[act], v2[act ^ 1]};
-    int rs = 0;
-    B200SA_TRY(radix_sort_pairs(kk, vv, false, m, 0, ss.rank_bits + gid_bits, &rs, st));
-    const int sorted_side = act ^ rs;
+
+    if (sorted_side < 0) {
+        B200SA_TRY(phase_begin(B200SA_PH_BUILD, st));
+        {
+            const u32 tiles = (u32)div_up_u64(m, BK_THREADS * BK_IPT);
+            const u32 grid = tiles < (u32)(num_sms * 8) ? tiles : (u32)(num_sms * 8);
+            B200SA_LAUNCH(k_build_keys, grid, BK_THREADS, 0, st, (const u32*)v2[act], (const u32*)gid.as<u32>(),
+                          (const u32*)rank.as<u32>(), m, n, (u32)ss.h, ss.rank_bits, k2[act]);
+            count_launch(B200SA_PH_BUILD);
+        }
+        B200SA_TRY(phase_end(st));
+        prof.alg_bytes[B200SA_PH_BUILD] += (u64)m * 20;
+        u64* kk[2] = {k2[act], k2[act ^ 1]};
+        u32* vv[2] = {v2[act], v2[act ^ 1]};
+        int rs = 0;
+        B200SA_TRY(radix_sort_pairs(kk, vv, false, m, 0, ss.rank_bits + gid_bits, &rs, st));
+        sorted_side = act ^ rs;
+    }
     u32 m2 = 0, g2 = 0;
     B200SA_TRY(rerank(k2[sorted_side], v2[sorted_side], slot[ss.cur_slot].as<u32>(), 0, m, n, ss.d_sa, v2[sorted_side ^ 1],
                       slot[ss.cur_slot ^ 1].as<u32>(), k2[sorted_side ^ 1], ss.nparts > 1 ? 2 : 1, &m2, &g2, st));

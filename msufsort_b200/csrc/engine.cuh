@@ -58,13 +58,19 @@ struct Engine {
     int num_sms = kNumSMs;
 
     // workspace (sized for the largest n seen; see DESIGN.md "data layout in HBM")
-    DevBuf keys[2], idx[2], slot[2], gid, rank, sa_ws, sortmeta, agg_cnt, agg_max, misc, text_ws, bwt_ws, walk;
+    DevBuf keys[2], idx[2], slot[2], gid, gstart, glist, rank, sa_ws, sortmeta, agg_cnt, agg_max, misc, text_ws, bwt_ws, walk;
     u32* h_pinned = nullptr;  // 64 words of pinned host memory for small read-backs
 
     // rank[] arrays up to this size are updated by direct scatter (they stay resident in the 126 MB
     // L2); larger ones by the bucketed update when a round has at least isa_min_updates tuples
     size_t isa_direct_bytes = (size_t)48 << 20;
     u32 isa_min_updates = 1u << 20;
+
+    // rounds >= 1 sort every group where it lies when the average group has at most this many members
+    // (0 disables the path); tiny groups go to one thread, medium ones to one CTA
+    u32 groupsort_max_avg = 16;
+    u32 groupsort_tiny = GS_TINY;
+    u32 groupsort_medium = GS_MEDIUM;
 
     // instrumentation
     bool profiling = false;

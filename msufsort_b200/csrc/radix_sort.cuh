@@ -35,7 +35,10 @@ static const int RS_RADIX = 256;
 #ifndef B200SA_RS_PEERS_ATOMIC_OR
 #define B200SA_RS_PEERS_ATOMIC_OR 0
 #endif
-static const int RS_THREADS = 256;
+#ifndef B200SA_RS_THREADS
+#define B200SA_RS_THREADS 256
+#endif
+static const int RS_THREADS = B200SA_RS_THREADS;
 static const int RS_IPT = B200SA_RS_IPT;
 static const int RS_TILE = RS_THREADS * RS_IPT;  // 4096 pairs per tile
 static const int RS_MIN_BLOCKS = B200SA_RS_MIN_BLOCKS;  // 3 CTAs/SM -> <= 85 registers per thread
@@ -209,6 +212,8 @@ k_onesweep_pass(const KeyT* __restrict__ kin, KeyT* __restrict__ kout,
         atomicOr(&mymask[d], mybit);
         __syncwarp();
         const u32 peers = mymask[d];
+#elif defined(B200SA_ABLATE_BALLOTS)
+        const u32 peers = 1u << lane;  // timing experiment only: wrong ranks
 #else
         const u32 peers = warp_peers_digit8(d);
 #endif
@@ -289,7 +294,11 @@ k_onesweep_pass(const KeyT* __restrict__ kin, KeyT* __restrict__ kout,
     // ---- 4. look-back for digit tid: four predecessor descriptors in flight per step
     if (tid < (u32)RS_RADIX) {
         u64 excl = 0;
+#ifdef B200SA_ABLATE_LOOKBACK
+        if (false) {
+#else
         if (tile != 0) {
+#endif
             const u64* col = status + tid;
             i64 t = (i64)tile - 1;
             bool done = false;

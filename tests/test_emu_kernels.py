@@ -78,3 +78,27 @@ def test_emu_profile_accounting(emu_engine):
     assert p["phases"]["sort_pass"]["launches"] == p["sort_passes"]
     # first sweep of round 0 moves 20 B per tuple (generated values), all others 24 B
     assert p["phases"]["sort_pass"]["alg_bytes"] == 24 * p["sorted_tuples"] - 4 * x.size
+
+
+@pytest.mark.parametrize("env", [
+    {"B200SA_GROUPSORT_TINY": "2", "B200SA_GROUPSORT_MEDIUM": "8", "B200SA_GROUPSORT_AVG": "1000000"},   # tiny/medium/huge + fallback
+    {"B200SA_GROUPSORT_TINY": "3", "B200SA_GROUPSORT_MEDIUM": "4096", "B200SA_GROUPSORT_AVG": "1000000"},  # CTA bitonic path
+    {"B200SA_GROUPSORT_AVG": "0"},                                                                        # radix rounds only
+    {"B200SA_ISA_DIRECT_BYTES": "0", "B200SA_ISA_MIN_UPDATES": "1"},                                      # bucketed ISA update
+], ids=["groups-small-thresholds", "groups-cta", "radix-only", "bucketed-isa"])
+def test_emu_round_variants(oracle, env, monkeypatch):
+    """every way a doubling round can run (in-place group sort: thread / CTA / per-group radix / fallback; radix
+    rounds; direct and bucketed ISA update) gives the oracle's suffix array"""
+    import os
+    from conftest import ROOT
+    from msufsort_b200.api import Engine, Library
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    eng = Engine(0, library=Library(os.path.join(ROOT, "tests", "emu", "libb200sa_emu.so")))
+    try:
+        for family, n in [("markov3", 30011), ("acgt_rep", 20000), ("zeros", 3000), ("abcabca", 5000), ("fib", 6000),
+                          ("sigma2", 4097), ("periodic1009", 9000), ("zero_tail", 777)]:
+            x = gen(family, n)
+            assert np.array_equal(eng.make_suffix_array(x), oracle.sa(x)), (family, n, env)
+    finally:
+        eng.close()

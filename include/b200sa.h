@@ -156,6 +156,18 @@ B200SA_API int b200sa_shard_apply_updates(b200sa_ctx* ctx, const uint32_t* d_idx
 B200SA_API int b200sa_shard_bwt(b200sa_ctx* ctx, int64_t row_begin, int64_t row_end, uint8_t* d_bwt,
                                 int64_t* out_begin, int64_t* out_end, int32_t* sentinel_index_out, void* stream);
 
+/* Inverse BWT over several GPUs: the psi table is built on every GPU (replicated), the walkers are
+ * split.  build -> measure(my walker slice) -> exchange the (length, successor) entries of all slices
+ * (segments, direction 0 = export mine, 1 = import a peer's) -> finish(my slice) writes my segments'
+ * bytes into d_text_out (caller zero-fills it; the slices of all GPUs are disjoint, a sum all-reduce
+ * assembles the text).  Single GPU: b200sa_unbwt_dev does build + measure(all) + finish(all).        */
+B200SA_API int b200sa_unbwt_shard_build(b200sa_ctx* ctx, const uint8_t* d_bwt, int64_t n, int32_t sentinel_index,
+                                        int64_t* nwalkers_out, void* stream);
+B200SA_API int b200sa_unbwt_shard_measure(b200sa_ctx* ctx, int64_t w_begin, int64_t w_end, void* stream);
+B200SA_API int b200sa_unbwt_shard_segments(b200sa_ctx* ctx, int direction, int64_t w_begin, int64_t w_end,
+                                           uint32_t* d_len, uint32_t* d_next, void* stream);
+B200SA_API int b200sa_unbwt_shard_finish(b200sa_ctx* ctx, int64_t w_begin, int64_t w_end, uint8_t* d_text_out, void* stream);
+
 /* ---- instrumentation --------------------------------------------------------------------- */
 
 enum {

@@ -71,6 +71,10 @@ ABI = [
     ("b200sa_shard_copy_updates", C.c_int, [_P, _P, _P, C.c_int64, _P]),
     ("b200sa_shard_apply_updates", C.c_int, [_P, _P, _P, C.c_int64, _P]),
     ("b200sa_shard_bwt", C.c_int, [_P, C.c_int64, C.c_int64, _P, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int32), _P]),
+    ("b200sa_unbwt_shard_build", C.c_int, [_P, _P, C.c_int64, C.c_int32, C.POINTER(C.c_int64), _P]),
+    ("b200sa_unbwt_shard_measure", C.c_int, [_P, C.c_int64, C.c_int64, _P]),
+    ("b200sa_unbwt_shard_segments", C.c_int, [_P, C.c_int, C.c_int64, C.c_int64, _P, _P, _P]),
+    ("b200sa_unbwt_shard_finish", C.c_int, [_P, C.c_int64, C.c_int64, _P, _P]),
     ("b200sa_set_profiling", C.c_int, [_P, C.c_int]),
     ("b200sa_profile_reset", C.c_int, [_P]),
     ("b200sa_profile_get", C.c_int, [_P, C.POINTER(_Profile)]),
@@ -264,6 +268,20 @@ class Engine:
         ob, oe, s = C.c_int64(0), C.c_int64(0), C.c_int32(0)
         self.lib.check(self.lib.cdll.b200sa_shard_bwt(self._ctx, row_begin, row_end, _ptr(d_bwt), C.byref(ob), C.byref(oe), C.byref(s), stream or None))
         return int(ob.value), int(oe.value), int(s.value)
+
+    def unbwt_shard_build(self, d_bwt, n: int, sentinel_index: int, stream: int = 0) -> int:
+        w = C.c_int64(0)
+        self.lib.check(self.lib.cdll.b200sa_unbwt_shard_build(self._ctx, _ptr(d_bwt), n, int(sentinel_index), C.byref(w), stream or None))
+        return int(w.value)
+
+    def unbwt_shard_measure(self, w_begin: int, w_end: int, stream: int = 0) -> None:
+        self.lib.check(self.lib.cdll.b200sa_unbwt_shard_measure(self._ctx, w_begin, w_end, stream or None))
+
+    def unbwt_shard_segments(self, direction: int, w_begin: int, w_end: int, d_len, d_next, stream: int = 0) -> None:
+        self.lib.check(self.lib.cdll.b200sa_unbwt_shard_segments(self._ctx, direction, w_begin, w_end, _ptr(d_len), _ptr(d_next), stream or None))
+
+    def unbwt_shard_finish(self, w_begin: int, w_end: int, d_text_out, stream: int = 0) -> None:
+        self.lib.check(self.lib.cdll.b200sa_unbwt_shard_finish(self._ctx, w_begin, w_end, _ptr(d_text_out), stream or None))
 
     # ---- instrumentation ----------------------------------------------------------------------
     def set_profiling(self, enabled: bool) -> None:

@@ -94,7 +94,7 @@ int Engine::init(int dev)
     B200SA_CU(cudaGetDeviceProperties(&prop, dev));
     num_sms = prop.multiProcessorCount > 0 ? prop.multiProcessorCount : kNumSMs;
     B200SA_CU(cudaStreamCreateWithFlags(&own_stream, cudaStreamNonBlocking));
-    B200SA_CU(cudaHostAlloc((void**)&h_pinned, 64 * sizeof(u32), cudaHostAllocDefault));
+    B200SA_CU(cudaHostAlloc((void**)&h_pinned, 512 * sizeof(u32), cudaHostAllocDefault));
     memset(&prof, 0, sizeof(prof));
     // tuning knobs (tests lower them to drive the bucketed ISA update at small n)
     if (const char* e1 = getenv("B200SA_ISA_DIRECT_BYTES")) isa_direct_bytes = (size_t)strtoull(e1, nullptr, 10);
@@ -241,7 +241,7 @@ int Engine::radix_sort_pairs(u64* keys2[2], u32* vals2[2], bool gen_vals, u32 m,
 
 // ISA update rank[idx[j]] = val[j] for `count` pairs.  Large arrays go through one radix sweep on the
 // top 8 bits of the suffix index so that the scatter proper works inside an L2-resident window.
-int Engine::isa_update(const u32* d_idx, const u32* d_val, u32 count, u32 n, u32* bk_key, u32* bk_val, cudaStream_t st)
+int Engine::isa_update(const u32* d_idx, const u32* d_val, u32 count, u32 n, u32* bk_key, u32* bk_val, bool all_suffixes, cudaStream_t st)
 {
     if (count == 0) return 0;
     const bool bucketed = ((u64)n * 4 > isa_direct_bytes) && (count >= isa_min_updates) && bk_key && bk_val;
@@ -257,13 +257,23 @@ int Engine::isa_update(const u32* d_idx, const u32* d_val, u32 count, u32 n, u32
         u64* status = (u64*)((u8*)sortmeta.p + kSortMetaHeader);
         B200SA_CU(cudaMemsetAsync(sortmeta.p, 0, kSortMetaHeader + status_bytes, st));
         prof.memsets++;
-        const u32 htiles = (u32)div_up_u64(count, RH_THREADS * RH_IPT);
-        const u32 hgrid = htiles < (u32)(num_sms * 6) ? htiles : (u32)(num_sms * 6);
-        auto kh = k_radix_hist<u32>;
-        B200SA_LAUNCH(kh, hgrid, RH_THREADS, rh_smem_bytes(1), st, d_idx, count, shift, 1, ghist);
-        count_launch(B200SA_PH_ISA);
-        B200SA_LAUNCH(k_radix_scan_bins, 1, RS_RADIX, 0, st, ghist);
-        count_launch(B200SA_PH_ISA);
+        if (all_suffixes && count == n) {
+            // every suffix 0..n-1 appears exactly once (round 0 on one GPU): bucket b starts at min(b << shift, n)
+            u32* h_bins = h_pinned + 64;
+            for (u32 b = 0; b < 256; ++b) {
+                const u64 lo = (u64)b << shift;
+                h_bins[b] = (u32)(lo < n ? lo : n);
+            }
+            B200SA_CU(cudaMemcpyAsync(ghist, h_bins, 256 * 4, cudaMemcpyHostToDevice, st));
+        } else {
+            const u32 htiles = (u32)div_up_u64(count, RH_THREADS * RH_IPT);
+            const u32 hgrid = htiles < (u32)(num_sms * 6) ? htiles : (u32)(num_sms * 6);
+            auto kh = k_radix_hist<u32>;
+            B200SA_LAUNCH(kh, hgrid, RH_THREADS, rh_smem_bytes(1), st, d_idx, count, shift, 1, ghist);
+            count_launch(B200SA_PH_ISA);
+            B200SA_LAUNCH(k_radix_scan_bins, 1, RS_RADIX, 0, st, ghist);
+            count_launch(B200SA_PH_ISA);
+        }
         auto kp = k_onesweep_pass<u32, true>;
         B200SA_LAUNCH(kp, tiles, RS_THREADS, rs_pass_smem_bytes<u32>(), st, d_idx, bk_key, d_val, bk_val,
                       count, shift, 0xffffffffu, (const u32*)ghist, status, counters);
@@ -312,7 +322,7 @@ int Engine::rerank(const u64* keys_sorted, const u32* idx_sorted, const u32* slo
     B200SA_CU(cudaMemcpyAsync(h_pinned, d_info, 2 * sizeof(u32), cudaMemcpyDeviceToHost, st));
     if (mode == 1) {
         B200SA_TRY(agg_max.ensure((size_t)m * 4 + 64));
-        B200SA_TRY(isa_update(idx_sorted, newrank, m, n, agg_max.as<u32>(), (u32*)free_keys + m, st));
+        B200SA_TRY(isa_update(idx_sorted, newrank, m, n, agg_max.as<u32>(), (u32*)free_keys + m, slot_in == nullptr && m == n, st));
     }
     B200SA_CU(cudaStreamSynchronize(st));
     *next_m = h_pinned[0];
@@ -644,16 +654,15 @@ int Engine::bwt_dev(const u8* d_text, i64 n64, u8* d_bwt, i32* d_sa_or_null, i32
 // ---------------------------------------------------------------------------------------------
 // inverse BWT
 
-int Engine::unbwt_dev(const u8* d_bwt, i64 n64, i32 sentinel, u8* d_out, cudaStream_t st)
+// Three steps so that a sharded run can split the walkers over GPUs: build (psi table, F-column table,
+// seed marks: replicated), measure (a slice of the walkers), finish (list ranking over all walkers, then
+// emit the slice's bytes).
+int Engine::unbwt_build(const u8* d_bwt, u32 n, u32 s, u32* nwalkers_out, cudaStream_t st)
 {
-    if (n64 < 0 || n64 > B200SA_MAX_N_INT32) return set_error(B200SA_EINVAL, "n = %lld outside [0, 2^31-2]", (long long)n64);
-    if (n64 == 0) return 0;
-    if (!d_bwt || !d_out) return set_error(B200SA_EINVAL, "null pointer");
-    if (sentinel < 1 || (i64)sentinel > n64) return set_error(B200SA_EINVAL, "sentinel index %d outside [1, n]", sentinel);
-    B200SA_CU(cudaSetDevice(device));
-    const u32 n = (u32)n64, s = (u32)sentinel;
     B200SA_TRY(keys[0].ensure(((size_t)n + 1) * 4 + 64));
-    B200SA_TRY(misc.ensure(4096));
+    B200SA_TRY(misc.ensure(8192));
+    us = UnbwtState();
+    us.n = n; us.s = s;
     u32* psi = keys[0].as<u32>();
     u32* fstart = misc.as<u32>() + 600;  // 257 words
 
@@ -682,41 +691,79 @@ int Engine::unbwt_dev(const u8* d_bwt, i64 n64, i32 sentinel, u8* d_out, cudaStr
                       n, 0, s, (const u32*)ghist, status, counters);
         count_launch(B200SA_PH_UNBWT_BUILD);
     }
+    // ---- walkers: every D-th row plus row s
+    u32 D = (u32)div_up_u64((u64)n + 1, (u64)1 << 21);
+    if (D < 64) D = 64;
+    us.D = D;
+    us.nreg = (u32)div_up_u64((u64)n + 1, D);
+    us.nwalkers = us.nreg + ((s % D) != 0 ? 1u : 0u);
+    B200SA_TRY(walk.ensure((size_t)us.nwalkers * 4 * 4 + 64));
+    B200SA_LAUNCH(k_unbwt_mark, (u32)div_up_u64(us.nwalkers, 256), 256, 0, st, psi, us.nwalkers, us.nreg, D, s);
+    count_launch(B200SA_PH_UNBWT_BUILD);
     B200SA_TRY(phase_end(st));
     prof.alg_bytes[B200SA_PH_UNBWT_BUILD] += (u64)n * 6;
     B200SA_CU(cudaGetLastError());
+    us.stage = 1;
+    *nwalkers_out = us.nwalkers;
+    return 0;
+}
 
-    // ---- walkers
-    u32 D = (u32)div_up_u64((u64)n + 1, (u64)1 << 21);
-    if (D < 64) D = 64;
-    const u32 nreg = (u32)div_up_u64((u64)n + 1, D);
-    const u32 nwalkers = nreg + ((s % D) != 0 ? 1u : 0u);
-    B200SA_TRY(walk.ensure((size_t)nwalkers * 4 * 4 + 64));
-    u32* nx[2] = {walk.as<u32>(), walk.as<u32>() + (size_t)nwalkers};
-    u32* ds[2] = {walk.as<u32>() + 2 * (size_t)nwalkers, walk.as<u32>() + 3 * (size_t)nwalkers};
+int Engine::unbwt_measure(u32 w_begin, u32 w_end, cudaStream_t st)
+{
+    if (us.stage < 1 || w_begin > w_end || w_end > us.nwalkers) return set_error(B200SA_EINVAL, "unbwt_measure: bad state or range");
+    if (w_end == w_begin) return 0;
+    const size_t W = us.nwalkers;
+    u32* nx0 = walk.as<u32>();
+    u32* ds0 = walk.as<u32>() + 2 * W;
     B200SA_TRY(phase_begin(B200SA_PH_UNBWT_WALK, st));
-    {
-        const u32 g256 = (u32)div_up_u64(nwalkers, 256);
-        const u32 gw = (u32)div_up_u64(nwalkers, UW_THREADS);
-        B200SA_LAUNCH(k_unbwt_mark, g256, 256, 0, st, psi, nwalkers, nreg, D, s);
+    B200SA_LAUNCH(k_unbwt_measure, (u32)div_up_u64(w_end - w_begin, UW_THREADS), UW_THREADS, 0, st, (const u32*)keys[0].as<u32>(),
+                  w_begin, w_end, us.nreg, us.D, us.s, ds0, nx0);
+    count_launch(B200SA_PH_UNBWT_WALK);
+    B200SA_TRY(phase_end(st));
+    B200SA_CU(cudaGetLastError());
+    return 0;
+}
+
+int Engine::unbwt_finish(u32 w_begin, u32 w_end, u8* d_out, cudaStream_t st)
+{
+    if (us.stage < 1 || w_begin > w_end || w_end > us.nwalkers) return set_error(B200SA_EINVAL, "unbwt_finish: bad state or range");
+    const size_t W = us.nwalkers;
+    u32* nx[2] = {walk.as<u32>(), walk.as<u32>() + W};
+    u32* ds[2] = {walk.as<u32>() + 2 * W, walk.as<u32>() + 3 * W};
+    B200SA_TRY(phase_begin(B200SA_PH_UNBWT_WALK, st));
+    const u32 g256 = (u32)div_up_u64(W, 256);
+    int cur = 0;
+    const int jumps = bit_length_u64(W);
+    for (int it = 0; it < jumps; ++it) {
+        B200SA_LAUNCH(k_unbwt_jump, g256, 256, 0, st, (const u32*)nx[cur], (const u32*)ds[cur], nx[cur ^ 1], ds[cur ^ 1], (u32)W);
         count_launch(B200SA_PH_UNBWT_WALK);
-        B200SA_LAUNCH(k_unbwt_measure, gw, UW_THREADS, 0, st, (const u32*)psi, nwalkers, nreg, D, s, ds[0], nx[0]);
-        count_launch(B200SA_PH_UNBWT_WALK);
-        int cur = 0;
-        const int jumps = bit_length_u64(nwalkers);
-        for (int it = 0; it < jumps; ++it) {
-            B200SA_LAUNCH(k_unbwt_jump, g256, 256, 0, st, (const u32*)nx[cur], (const u32*)ds[cur], nx[cur ^ 1], ds[cur ^ 1], nwalkers);
-            count_launch(B200SA_PH_UNBWT_WALK);
-            cur ^= 1;
-        }
-        B200SA_LAUNCH(k_unbwt_emit, gw, UW_THREADS, 0, st, (const u32*)psi, (const u32*)fstart, (const u32*)ds[cur],
-                      nwalkers, nreg, D, s, n, d_out);
+        cur ^= 1;
+    }
+    if (w_end > w_begin) {
+        B200SA_LAUNCH(k_unbwt_emit, (u32)div_up_u64(w_end - w_begin, UW_THREADS), UW_THREADS, 0, st, (const u32*)keys[0].as<u32>(),
+                      (const u32*)(misc.as<u32>() + 600), (const u32*)ds[cur], w_begin, w_end, us.nreg, us.D, us.s, us.n, d_out);
         count_launch(B200SA_PH_UNBWT_WALK);
     }
     B200SA_TRY(phase_end(st));
-    prof.alg_bytes[B200SA_PH_UNBWT_WALK] += (u64)n * 9;
+    prof.alg_bytes[B200SA_PH_UNBWT_WALK] += (u64)us.n * 9;
     B200SA_CU(cudaGetLastError());
     B200SA_CU(cudaStreamSynchronize(st));
+    // the jumps consumed the measured segments: a second finish needs a new measure pass
+    us.stage = 0;
+    return 0;
+}
+
+int Engine::unbwt_dev(const u8* d_bwt, i64 n64, i32 sentinel, u8* d_out, cudaStream_t st)
+{
+    if (n64 < 0 || n64 > B200SA_MAX_N_INT32) return set_error(B200SA_EINVAL, "n = %lld outside [0, 2^31-2]", (long long)n64);
+    if (n64 == 0) return 0;
+    if (!d_bwt || !d_out) return set_error(B200SA_EINVAL, "null pointer");
+    if (sentinel < 1 || (i64)sentinel > n64) return set_error(B200SA_EINVAL, "sentinel index %d outside [1, n]", sentinel);
+    B200SA_CU(cudaSetDevice(device));
+    u32 W = 0;
+    B200SA_TRY(unbwt_build(d_bwt, (u32)n64, (u32)sentinel, &W, st));
+    B200SA_TRY(unbwt_measure(0, W, st));
+    B200SA_TRY(unbwt_finish(0, W, d_out, st));
     if (profiling) B200SA_TRY(collect_profile());
     return 0;
 }
@@ -969,7 +1016,7 @@ int b200sa_shard_apply_updates(b200sa_ctx* ctx, const uint32_t* d_idx, const uin
     cudaStream_t st = e.pick(stream);
     B200SA_TRY(e.agg_max.ensure((size_t)count * 4 + 64));
     B200SA_TRY(e.walk.ensure((size_t)count * 4 + 64));
-    B200SA_TRY(e.isa_update(d_idx, d_rank, (u32)count, e.ss.n, e.agg_max.as<u32>(), e.walk.as<u32>(), st));
+    B200SA_TRY(e.isa_update(d_idx, d_rank, (u32)count, e.ss.n, e.agg_max.as<u32>(), e.walk.as<u32>(), false, st));
     B200SA_CU(cudaStreamSynchronize(st));
     return 0;
 }
@@ -993,6 +1040,63 @@ int b200sa_shard_bwt(b200sa_ctx* ctx, int64_t row_begin, int64_t row_end, uint8_
     *out_begin = ob;
     *out_end = oe;
     if (sentinel_index_out) *sentinel_index_out = (int32_t)s;
+    if (e.profiling) B200SA_TRY(e.collect_profile());
+    return 0;
+}
+
+int b200sa_unbwt_shard_build(b200sa_ctx* ctx, const uint8_t* d_bwt, int64_t n, int32_t sentinel_index, int64_t* nwalkers_out, void* stream)
+{
+    B200SA_NEED_CTX(ctx);
+    if (n <= 0 || n > B200SA_MAX_N_INT32 || !d_bwt || !nwalkers_out) return b200sa::set_error(B200SA_EINVAL, "bad argument");
+    if (sentinel_index < 1 || (int64_t)sentinel_index > n) return b200sa::set_error(B200SA_EINVAL, "sentinel index %d outside [1, n]", sentinel_index);
+    Engine& e = ctx->eng;
+    B200SA_CU(cudaSetDevice(e.device));
+    u32 W = 0;
+    B200SA_TRY(e.unbwt_build(d_bwt, (u32)n, (u32)sentinel_index, &W, e.pick(stream)));
+    *nwalkers_out = W;
+    return 0;
+}
+
+int b200sa_unbwt_shard_measure(b200sa_ctx* ctx, int64_t w_begin, int64_t w_end, void* stream)
+{
+    B200SA_NEED_CTX(ctx);
+    if (w_begin < 0 || w_end < w_begin) return b200sa::set_error(B200SA_EINVAL, "bad range");
+    Engine& e = ctx->eng;
+    B200SA_TRY(e.unbwt_measure((u32)w_begin, (u32)w_end, e.pick(stream)));
+    B200SA_CU(cudaStreamSynchronize(e.pick(stream)));
+    return 0;
+}
+
+// direction 0: copy this context's measured (length, successor) entries [w_begin,w_end) OUT to caller buffers;
+// direction 1: copy a peer's entries IN
+int b200sa_unbwt_shard_segments(b200sa_ctx* ctx, int direction, int64_t w_begin, int64_t w_end, uint32_t* d_len, uint32_t* d_next, void* stream)
+{
+    B200SA_NEED_CTX(ctx);
+    Engine& e = ctx->eng;
+    if (e.us.stage < 1 || w_begin < 0 || w_end < w_begin || w_end > (int64_t)e.us.nwalkers || !d_len || !d_next)
+        return b200sa::set_error(B200SA_EINVAL, "bad state or argument");
+    const size_t W = e.us.nwalkers, cnt = (size_t)(w_end - w_begin);
+    if (cnt == 0) return 0;
+    u32* nx0 = e.walk.as<u32>() + w_begin;
+    u32* ds0 = e.walk.as<u32>() + 2 * W + w_begin;
+    cudaStream_t st = e.pick(stream);
+    if (direction == 0) {
+        B200SA_CU(cudaMemcpyAsync(d_len, ds0, cnt * 4, cudaMemcpyDeviceToDevice, st));
+        B200SA_CU(cudaMemcpyAsync(d_next, nx0, cnt * 4, cudaMemcpyDeviceToDevice, st));
+    } else {
+        B200SA_CU(cudaMemcpyAsync(ds0, d_len, cnt * 4, cudaMemcpyDeviceToDevice, st));
+        B200SA_CU(cudaMemcpyAsync(nx0, d_next, cnt * 4, cudaMemcpyDeviceToDevice, st));
+    }
+    B200SA_CU(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int b200sa_unbwt_shard_finish(b200sa_ctx* ctx, int64_t w_begin, int64_t w_end, uint8_t* d_text_out, void* stream)
+{
+    B200SA_NEED_CTX(ctx);
+    if (w_begin < 0 || w_end < w_begin || !d_text_out) return b200sa::set_error(B200SA_EINVAL, "bad argument");
+    Engine& e = ctx->eng;
+    B200SA_TRY(e.unbwt_finish((u32)w_begin, (u32)w_end, d_text_out, e.pick(stream)));
     if (e.profiling) B200SA_TRY(e.collect_profile());
     return 0;
 }

@@ -103,15 +103,16 @@ k_unbwt_mark(u32* __restrict__ psi, u32 nwalkers, u32 nreg, u32 D, u32 s)
     else psi[row] |= UB_MARK;
 }
 
-// Pass A: segment length and successor of every walker.
+// Pass A: segment length and successor of the walkers [w_begin, w_end) (a sharded run gives every GPU
+// a slice of the walkers; the psi table is replicated).
 static const int UW_THREADS = 128;
 
 __global__ void __launch_bounds__(UW_THREADS)
-k_unbwt_measure(const u32* __restrict__ psi, u32 nwalkers, u32 nreg, u32 D, u32 s,
+k_unbwt_measure(const u32* __restrict__ psi, u32 w_begin, u32 w_end, u32 nreg, u32 D, u32 s,
                 u32* __restrict__ seg_len, u32* __restrict__ seg_next)
 {
-    const u32 w = blockIdx.x * UW_THREADS + threadIdx.x;
-    if (w >= nwalkers) return;
+    const u32 w = w_begin + blockIdx.x * UW_THREADS + threadIdx.x;
+    if (w >= w_end) return;
     if (w == 0) { seg_len[0] = 0; seg_next[0] = 0; return; }  // terminal node points to itself
     u32 cur = ub_walker_row(w, nreg, D, s);
     u32 e = psi[cur];
@@ -141,13 +142,13 @@ k_unbwt_jump(const u32* __restrict__ next_in, const u32* __restrict__ dist_in,
 // Pass B: walk again, emit F[row] at text offset n - dist[w] + step.
 __global__ void __launch_bounds__(UW_THREADS)
 k_unbwt_emit(const u32* __restrict__ psi, const u32* __restrict__ fstart, const u32* __restrict__ dist,
-             u32 nwalkers, u32 nreg, u32 D, u32 s, u32 n, u8* __restrict__ out)
+             u32 w_begin, u32 w_end, u32 nreg, u32 D, u32 s, u32 n, u8* __restrict__ out)
 {
     __shared__ u32 s_f[257];
     for (u32 i = threadIdx.x; i < 257; i += UW_THREADS) s_f[i] = fstart[i];
     __syncthreads();
-    const u32 w = blockIdx.x * UW_THREADS + threadIdx.x;
-    if (w >= nwalkers || w == 0) return;
+    const u32 w = w_begin + blockIdx.x * UW_THREADS + threadIdx.x;
+    if (w >= w_end || w == 0) return;
     u32 cur = ub_walker_row(w, nreg, D, s);
     u32 pos = n - dist[w];
     u32 e = psi[cur];

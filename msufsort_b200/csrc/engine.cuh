@@ -97,7 +97,7 @@ struct Engine {
     // building blocks
     int radix_sort_pairs(u64* keys2[2], u32* vals2[2], bool gen_vals, u32 m, int begin_bit, int end_bit,
                          int* result_side, cudaStream_t st);
-    int isa_update(const u32* d_idx, const u32* d_val, u32 count, u32 n, u32* bk_key, u32* bk_val, cudaStream_t st);
+    int isa_update(const u32* d_idx, const u32* d_val, u32 count, u32 n, u32* bk_key, u32* bk_val, bool all_suffixes, cudaStream_t st);
     int rerank(const u64* keys_sorted, const u32* idx_sorted, const u32* slot_in, u32 slot_base, u32 m, u32 n, i32* d_sa,
                u32* idx_out, u32* slot_out, u64* free_keys, int mode, u32* next_m, u32* next_groups, cudaStream_t st);
 
@@ -125,6 +125,10 @@ struct Engine {
     int suffix_array_dev(const u8* d_text, i64 n, i32* d_sa, cudaStream_t st);
     int bwt_rows(const u8* d_text, u32 n, const i32* d_sa, u32 o_begin, u32 o_end, u8* d_bwt, cudaStream_t st);
     int bwt_dev(const u8* d_text, i64 n, u8* d_bwt, i32* d_sa_or_null, i32* sentinel_host, cudaStream_t st);
+    struct UnbwtState { int stage = 0; u32 n = 0, s = 0, D = 0, nreg = 0, nwalkers = 0; } us;
+    int unbwt_build(const u8* d_bwt, u32 n, u32 s, u32* nwalkers_out, cudaStream_t st);
+    int unbwt_measure(u32 w_begin, u32 w_end, cudaStream_t st);
+    int unbwt_finish(u32 w_begin, u32 w_end, u8* d_out, cudaStream_t st);
     int unbwt_dev(const u8* d_bwt, i64 n, i32 sentinel, u8* d_out, cudaStream_t st);
     int check_sa_dev(const u8* d_text, i64 n, const i32* d_sa, i64* bad_rows, cudaStream_t st);
 };

@@ -96,6 +96,34 @@ class ShardedSorter:
             res.out_begin, res.out_end, res.sentinel = self.eng.shard_bwt(res.row_begin, res.row_end, res.bwt, stream)
         return res
 
+    # -- the sharded inverse BWT ------------------------------------------------------------------------
+    def inverse_bwt(self, d_bwt: torch.Tensor, sentinel_index: int) -> torch.Tensor:
+        """psi table replicated, walkers partitioned: every rank measures and emits the segments of its slice
+        of the walkers; the (length, successor) entries are all-gathered for the list ranking and the disjoint
+        output slices are combined with a sum all-reduce.  Returns the whole text on every rank."""
+        n = d_bwt.numel()
+        device = d_bwt.device
+        stream = torch.cuda.current_stream().cuda_stream if device.type == "cuda" else 0
+        W = self.eng.unbwt_shard_build(d_bwt, n, sentinel_index, stream)
+        per = (W + self.world - 1) // self.world
+        spans = [(min(W, p * per), min(W, (p + 1) * per)) for p in range(self.world)]
+        wb, we = spans[self.rank]
+        self.eng.unbwt_shard_measure(wb, we, stream)
+        send = torch.zeros((2, per), dtype=torch.int32, device=device)
+        if we > wb:
+            self.eng.unbwt_shard_segments(0, wb, we, send[0], send[1], stream)
+        recv = torch.empty((self.world, 2, per), dtype=torch.int32, device=device)
+        dist.all_gather_into_tensor(recv.view(-1), send.view(-1), group=self.group)
+        if device.type == "cuda":
+            torch.cuda.current_stream().synchronize()
+        for p, (b, e) in enumerate(spans):
+            if p != self.rank and e > b:
+                self.eng.unbwt_shard_segments(1, b, e, recv[p, 0], recv[p, 1], stream)
+        out = torch.zeros(n, dtype=torch.uint8, device=device)
+        self.eng.unbwt_shard_finish(wb, we, out, stream)
+        dist.all_reduce(out, op=dist.ReduceOp.SUM, group=self.group)
+        return out
+
     # -- helpers for callers that want the whole result on every rank -------------------------------
     def gather_sa(self, res: ShardedResult) -> torch.Tensor:
         n1 = res.sa.numel()

@@ -37,6 +37,8 @@ def _worker(rank, world, port, family, n, q):
         res = sorter.suffix_array_bwt(d_text)
         sa = sorter.gather_sa(res).numpy()
         bwt = sorter.gather_bwt(res).numpy()
+        back = sorter.inverse_bwt(sorter.gather_bwt(res), res.sentinel)
+        assert bool((back.cpu() == d_text.cpu()).all()), "sharded inverse BWT did not restore the text"
         if rank == 0:
             q.put((sa, bwt, res.sentinel, res.counts, res.rounds))
         dist.barrier()

@@ -49,22 +49,27 @@ class ShardedSorter:
         dist.all_gather_into_tensor(out, t, group=self.group)
         return [int(x) for x in out.cpu().tolist()]
 
-    def _exchange_updates(self, device, stream: int, res: ShardedResult) -> None:
+    def _exchange_updates(self, device, stream: int, res: ShardedResult, n: int) -> None:
         _, _, cnt = self.eng.shard_updates()
         counts = self._gather_int(cnt, device)
         maxc = max(counts)
         if maxc == 0:
             return
-        send = torch.empty((2, maxc), dtype=torch.int32, device=device)
-        self.eng.shard_copy_updates(send[0], send[1], maxc, stream)
-        recv = torch.empty((self.world, 2, maxc), dtype=torch.int32, device=device)
-        dist.all_gather_into_tensor(recv.view(-1), send.view(-1), group=self.group)
+        # Every rank contributes maxc pairs: its own updates padded with (suffix = n, rank = 0) — writing
+        # rank[n] = 0 is a no-op (the sentinel row is 0 by definition) — so the gathered arrays can be applied
+        # to the ISA replica with ONE bucketed update instead of one per peer.
+        send_idx = torch.full((maxc,), n, dtype=torch.int32, device=device)  # n <= 2^31-2 fits int32
+        send_rank = torch.zeros(maxc, dtype=torch.int32, device=device)
+        if cnt:
+            self.eng.shard_copy_updates(send_idx, send_rank, maxc, stream)
+        recv_idx = torch.empty(self.world * maxc, dtype=torch.int32, device=device)
+        recv_rank = torch.empty(self.world * maxc, dtype=torch.int32, device=device)
+        dist.all_gather_into_tensor(recv_idx, send_idx, group=self.group)
+        dist.all_gather_into_tensor(recv_rank, send_rank, group=self.group)
         if device.type == "cuda":
             torch.cuda.current_stream().synchronize()
         res.exchanged_bytes += (self.world - 1) * 2 * 4 * maxc
-        for p in range(self.world):
-            if counts[p]:
-                self.eng.shard_apply_updates(recv[p, 0], recv[p, 1], counts[p], stream)
+        self.eng.shard_apply_updates(recv_idx, recv_rank, self.world * maxc, stream)
 
     # -- the sharded SA + BWT ----------------------------------------------------------------------
     def suffix_array_bwt(self, d_text: torch.Tensor, want_bwt: bool = True) -> ShardedResult:
@@ -78,7 +83,7 @@ class ShardedSorter:
         assert sum(res.counts) == n, "key-range parts do not cover the text"
         slot_base = sum(res.counts[: self.rank])
         m_local = self.eng.shard_round0(slot_base, stream)
-        self._exchange_updates(device, stream, res)
+        self._exchange_updates(device, stream, res, n)
         res.rounds = 1
         while True:
             t = torch.tensor([m_local], dtype=torch.int64, device=device)
@@ -86,7 +91,7 @@ class ShardedSorter:
             if int(t.item()) == 0:
                 break
             m_local = self.eng.shard_round(stream)
-            self._exchange_updates(device, stream, res)
+            self._exchange_updates(device, stream, res, n)
             res.rounds += 1
         # rows of the (n+1)-row suffix array owned here; row 0 (the empty suffix) belongs to rank 0
         res.row_begin = 0 if self.rank == 0 else slot_base + 1

@@ -102,6 +102,8 @@ int Engine::init(int dev)
     if (const char* e3 = getenv("B200SA_GROUPSORT_AVG")) groupsort_max_avg = (u32)strtoul(e3, nullptr, 10);
     if (const char* e4 = getenv("B200SA_GROUPSORT_TINY")) groupsort_tiny = (u32)strtoul(e4, nullptr, 10);
     if (const char* e5 = getenv("B200SA_GROUPSORT_MEDIUM")) groupsort_medium = (u32)strtoul(e5, nullptr, 10);
+    if (const char* e6 = getenv("B200SA_UNBWT_CAP_MULT")) unbwt_cap_mult = (u32)strtoul(e6, nullptr, 10);
+    if (unbwt_cap_mult < 1) unbwt_cap_mult = 1;
     if (groupsort_tiny > (u32)GS_TINY) groupsort_tiny = GS_TINY;
     if (groupsort_medium > (u32)GS_MEDIUM) groupsort_medium = GS_MEDIUM;
     // the scatter kernels use more than the default 48 KB of dynamic shared memory
@@ -697,7 +699,8 @@ int Engine::unbwt_build(const u8* d_bwt, u32 n, u32 s, u32* nwalkers_out, cudaSt
     us.D = D;
     us.nreg = (u32)div_up_u64((u64)n + 1, D);
     us.nwalkers = us.nreg + ((s % D) != 0 ? 1u : 0u);
-    B200SA_TRY(walk.ensure((size_t)us.nwalkers * 4 * 4 + 64));
+    B200SA_TRY(walk.ensure((size_t)us.nwalkers * 5 * 4 + 64));
+    us.cap = unbwt_cap_mult * D;  // window bytes per walker (multiple of 8: D >= 64)
     B200SA_LAUNCH(k_unbwt_mark, (u32)div_up_u64(us.nwalkers, 256), 256, 0, st, psi, us.nwalkers, us.nreg, D, s);
     count_launch(B200SA_PH_UNBWT_BUILD);
     B200SA_TRY(phase_end(st));
@@ -715,10 +718,16 @@ int Engine::unbwt_measure(u32 w_begin, u32 w_end, cudaStream_t st)
     const size_t W = us.nwalkers;
     u32* nx0 = walk.as<u32>();
     u32* ds0 = walk.as<u32>() + 2 * W;
+    u32* ovf = walk.as<u32>() + 4 * W;
+    // decode windows: cap bytes per walker of this slice, addressed by the global walker number
+    B200SA_TRY(keys[1].ensure((size_t)W * us.cap + 256));
+    B200SA_TRY(idx[0].ensure((size_t)W * 4 + 64));
     B200SA_TRY(phase_begin(B200SA_PH_UNBWT_WALK, st));
-    B200SA_LAUNCH(k_unbwt_measure, (u32)div_up_u64(w_end - w_begin, UW_THREADS), UW_THREADS, 0, st, (const u32*)keys[0].as<u32>(),
-                  w_begin, w_end, us.nreg, us.D, us.s, ds0, nx0);
+    B200SA_LAUNCH(k_unbwt_walk, (u32)div_up_u64(w_end - w_begin, UW_THREADS), UW_THREADS, 0, st, (const u32*)keys[0].as<u32>(),
+                  (const u32*)(misc.as<u32>() + 600), w_begin, w_end, us.nreg, us.D, us.s, us.cap, keys[1].as<u8>(), ds0, nx0, ovf);
     count_launch(B200SA_PH_UNBWT_WALK);
+    // the list ranking below overwrites the lengths: keep a copy for the placement pass
+    B200SA_CU(cudaMemcpyAsync(idx[0].as<u32>() + w_begin, ds0 + w_begin, (size_t)(w_end - w_begin) * 4, cudaMemcpyDeviceToDevice, st));
     B200SA_TRY(phase_end(st));
     B200SA_CU(cudaGetLastError());
     return 0;
@@ -730,6 +739,7 @@ int Engine::unbwt_finish(u32 w_begin, u32 w_end, u8* d_out, cudaStream_t st)
     const size_t W = us.nwalkers;
     u32* nx[2] = {walk.as<u32>(), walk.as<u32>() + W};
     u32* ds[2] = {walk.as<u32>() + 2 * W, walk.as<u32>() + 3 * W};
+    u32* ovf = walk.as<u32>() + 4 * W;
     B200SA_TRY(phase_begin(B200SA_PH_UNBWT_WALK, st));
     const u32 g256 = (u32)div_up_u64(W, 256);
     int cur = 0;
@@ -740,12 +750,13 @@ int Engine::unbwt_finish(u32 w_begin, u32 w_end, u8* d_out, cudaStream_t st)
         cur ^= 1;
     }
     if (w_end > w_begin) {
-        B200SA_LAUNCH(k_unbwt_emit, (u32)div_up_u64(w_end - w_begin, UW_THREADS), UW_THREADS, 0, st, (const u32*)keys[0].as<u32>(),
-                      (const u32*)(misc.as<u32>() + 600), (const u32*)ds[cur], w_begin, w_end, us.nreg, us.D, us.s, us.n, d_out);
+        B200SA_LAUNCH(k_unbwt_place, (u32)div_up_u64(w_end - w_begin, UP_THREADS / 32), UP_THREADS, 0, st, (const u32*)keys[0].as<u32>(),
+                      (const u32*)(misc.as<u32>() + 600), (const u32*)ds[cur], (const u32*)idx[0].as<u32>(), (const u32*)ovf,
+                      (const u8*)keys[1].as<u8>(), us.cap, w_begin, w_end, us.n, d_out);
         count_launch(B200SA_PH_UNBWT_WALK);
     }
     B200SA_TRY(phase_end(st));
-    prof.alg_bytes[B200SA_PH_UNBWT_WALK] += (u64)us.n * 9;
+    prof.alg_bytes[B200SA_PH_UNBWT_WALK] += (u64)us.n * 7;
     B200SA_CU(cudaGetLastError());
     B200SA_CU(cudaStreamSynchronize(st));
     // the jumps consumed the measured segments: a second finish needs a new measure pass

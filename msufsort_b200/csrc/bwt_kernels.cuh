@@ -73,7 +73,7 @@ k_bwt_gather(const u8* __restrict__ text, const i32* __restrict__ sa, const u32*
 // walkers seeded at every D-th row plus row s (the reference seeds 256 x threads walkers,
 // :1922-1944): bit 31 of psi[row] marks seed rows.  Pass A measures each walker's segment (length,
 // successor walker); a pointer-jumping list ranking turns the segment chain into text offsets; pass
-// B walks again and writes bytes at their final positions.
+// B copies the decoded windows to their final positions (and finishes the few overlong segments).
 static const u32 UB_MARK = 0x80000000u;
 static const u32 UB_IDX = 0x7fffffffu;
 
@@ -103,27 +103,62 @@ k_unbwt_mark(u32* __restrict__ psi, u32 nwalkers, u32 nreg, u32 D, u32 s)
     else psi[row] |= UB_MARK;
 }
 
-// Pass A: segment length and successor of the walkers [w_begin, w_end) (a sharded run gives every GPU
-// a slice of the walkers; the psi table is replicated).
+// symbol of F-row `row` (row >= 1): the largest c with f[c] <= row; f = 257-entry table in shared memory
+__device__ __forceinline__ u32 ub_row_symbol(const u32* f, u32 row)
+{
+    u32 lo = 0, hi = 256;
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+        const u32 mid = (lo + hi) >> 1;
+        if (f[mid] <= row) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+// Pass A: walkers [w_begin, w_end) (a sharded run gives every GPU a slice; the psi table is replicated)
+// follow psi until the next seed row, record segment length and successor, and decode on the way: the
+// bytes go to the walker's private window of `cap` bytes in `scratch` (8 bytes per store); a walker
+// whose segment is longer than its window remembers the row where it stopped storing (ovf_row) and only
+// counts from there.  Segment lengths are close to exponentially distributed with mean D, so with
+// cap = 4 D about 2 % of the bytes are decoded a second time by k_unbwt_place instead of 100 % in the
+// first version (measure pass + emit pass).  The next psi load is issued before the symbol search of
+// the current row, so the 8-step search hides under the DRAM latency of the dependent load.
 static const int UW_THREADS = 128;
+static const u32 UB_NO_OVERFLOW = 0xffffffffu;
 
 __global__ void __launch_bounds__(UW_THREADS)
-k_unbwt_measure(const u32* __restrict__ psi, u32 w_begin, u32 w_end, u32 nreg, u32 D, u32 s,
-                u32* __restrict__ seg_len, u32* __restrict__ seg_next)
+k_unbwt_walk(const u32* __restrict__ psi, const u32* __restrict__ fstart, u32 w_begin, u32 w_end, u32 nreg, u32 D, u32 s,
+             u32 cap, u8* __restrict__ scratch, u32* __restrict__ seg_len, u32* __restrict__ seg_next, u32* __restrict__ ovf_row)
 {
+    __shared__ u32 s_f[257];
+    for (u32 i = threadIdx.x; i < 257; i += UW_THREADS) s_f[i] = fstart[i];
+    __syncthreads();
     const u32 w = w_begin + blockIdx.x * UW_THREADS + threadIdx.x;
     if (w >= w_end) return;
-    if (w == 0) { seg_len[0] = 0; seg_next[0] = 0; return; }  // terminal node points to itself
+    if (w == 0) { seg_len[0] = 0; seg_next[0] = 0; ovf_row[0] = UB_NO_OVERFLOW; return; }  // terminal node points to itself
+    u64* win = (u64*)(scratch + (u64)w * cap);  // cap is a multiple of 8 and scratch is 256-byte aligned
     u32 cur = ub_walker_row(w, nreg, D, s);
     u32 e = psi[cur];
-    u32 len = 0;
+    u32 len = 0, ovf = UB_NO_OVERFLOW;
+    u64 acc = 0;
     do {
-        ++len;                 // row `cur` emits one byte
-        cur = e & UB_IDX;
-        e = psi[cur];
+        const u32 nxt = e & UB_IDX;
+        const u32 e2 = psi[nxt];                      // dependent load first ...
+        if (len < cap) {
+            const u64 c = ub_row_symbol(s_f, cur);    // ... symbol search while it is in flight
+            acc |= c << (8 * (len & 7u));
+            if ((len & 7u) == 7u) { win[len >> 3] = acc; acc = 0; }
+        } else if (len == cap) {
+            ovf = cur;                                // first row whose byte did not fit
+        }
+        ++len;
+        cur = nxt;
+        e = e2;
     } while (!(e & UB_MARK));
+    if (len < cap && (len & 7u)) win[len >> 3] = acc;  // partial last word (inside the window: cap % 8 == 0)
     seg_len[w] = len;
     seg_next[w] = ub_row_walker(cur, nreg, D, s);
+    ovf_row[w] = ovf;
 }
 
 // Pointer jumping (Wyllie): dist[w] = bytes emitted from walker w to the end of the text.
@@ -139,31 +174,38 @@ k_unbwt_jump(const u32* __restrict__ next_in, const u32* __restrict__ dist_in,
     next_out[w] = next_in[nx];
 }
 
-// Pass B: walk again, emit F[row] at text offset n - dist[w] + step.
-__global__ void __launch_bounds__(UW_THREADS)
-k_unbwt_emit(const u32* __restrict__ psi, const u32* __restrict__ fstart, const u32* __restrict__ dist,
-             u32 w_begin, u32 w_end, u32 nreg, u32 D, u32 s, u32 n, u8* __restrict__ out)
+// Pass B: one warp per walker copies the decoded window to its final place (text offset n - dist[w]);
+// the few walkers that outgrew their window continue decoding from ovf_row straight into the text.
+static const int UP_THREADS = 256;
+
+__global__ void __launch_bounds__(UP_THREADS)
+k_unbwt_place(const u32* __restrict__ psi, const u32* __restrict__ fstart, const u32* __restrict__ dist,
+              const u32* __restrict__ seg_len, const u32* __restrict__ ovf_row, const u8* __restrict__ scratch, u32 cap,
+              u32 w_begin, u32 w_end, u32 n, u8* __restrict__ out)
 {
     __shared__ u32 s_f[257];
-    for (u32 i = threadIdx.x; i < 257; i += UW_THREADS) s_f[i] = fstart[i];
+    for (u32 i = threadIdx.x; i < 257; i += UP_THREADS) s_f[i] = fstart[i];
     __syncthreads();
-    const u32 w = w_begin + blockIdx.x * UW_THREADS + threadIdx.x;
+    const u32 lane = threadIdx.x & 31u;
+    const u32 w = w_begin + blockIdx.x * (UP_THREADS / 32) + (threadIdx.x >> 5);
     if (w >= w_end || w == 0) return;
-    u32 cur = ub_walker_row(w, nreg, D, s);
-    u32 pos = n - dist[w];
-    u32 e = psi[cur];
-    do {
-        // symbol of F-row cur: largest c with s_f[c] <= cur (cur >= 1 here)
-        u32 lo = 0, hi = 256;
-#pragma unroll
-        for (int it = 0; it < 8; ++it) {
-            const u32 mid = (lo + hi) >> 1;
-            if (s_f[mid] <= cur) lo = mid; else hi = mid;
+    const u32 len = seg_len[w];
+    const u32 pos = n - dist[w];
+    const u32 stored = len < cap ? len : cap;
+    const u8* src = scratch + (u64)w * cap;
+    for (u32 i = lane; i < stored; i += 32u) out[pos + i] = src[i];
+    if (len > cap && lane == 0) {
+        u32 cur = ovf_row[w];
+        u32 e = psi[cur];
+        u32 o = pos + cap;
+        for (u32 k = cap; k < len; ++k) {
+            const u32 nxt = e & UB_IDX;
+            const u32 e2 = psi[nxt];
+            out[o++] = (u8)ub_row_symbol(s_f, cur);
+            cur = nxt;
+            e = e2;
         }
-        out[pos++] = (u8)lo;
-        cur = e & UB_IDX;
-        e = psi[cur];
-    } while (!(e & UB_MARK));
+    }
 }
 
 }  // namespace b200sa

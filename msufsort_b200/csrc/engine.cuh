@@ -72,6 +72,9 @@ struct Engine {
     u32 groupsort_tiny = GS_TINY;
     u32 groupsort_medium = GS_MEDIUM;
 
+    // inverse BWT: bytes of decode window per walker = unbwt_cap_mult * D (D = mean segment length)
+    u32 unbwt_cap_mult = 4;
+
     // instrumentation
     bool profiling = false;
     b200sa_profile prof;
@@ -125,7 +128,7 @@ struct Engine {
     int suffix_array_dev(const u8* d_text, i64 n, i32* d_sa, cudaStream_t st);
     int bwt_rows(const u8* d_text, u32 n, const i32* d_sa, u32 o_begin, u32 o_end, u8* d_bwt, cudaStream_t st);
     int bwt_dev(const u8* d_text, i64 n, u8* d_bwt, i32* d_sa_or_null, i32* sentinel_host, cudaStream_t st);
-    struct UnbwtState { int stage = 0; u32 n = 0, s = 0, D = 0, nreg = 0, nwalkers = 0; } us;
+    struct UnbwtState { int stage = 0; u32 n = 0, s = 0, D = 0, nreg = 0, nwalkers = 0, cap = 0; } us;
     int unbwt_build(const u8* d_bwt, u32 n, u32 s, u32* nwalkers_out, cudaStream_t st);
     int unbwt_measure(u32 w_begin, u32 w_end, cudaStream_t st);
     int unbwt_finish(u32 w_begin, u32 w_end, u8* d_out, cudaStream_t st);

@@ -102,3 +102,22 @@ def test_emu_round_variants(oracle, env, monkeypatch):
             assert np.array_equal(eng.make_suffix_array(x), oracle.sa(x)), (family, n, env)
     finally:
         eng.close()
+
+
+@pytest.mark.parametrize("cap_mult", ["1", "4"])
+def test_emu_inverse_bwt_window_overflow(oracle, cap_mult, monkeypatch):
+    """inverse BWT with small decode windows (many walkers outgrow them and finish in the placement pass)"""
+    import os
+    from conftest import ROOT
+    from msufsort_b200.api import Engine, Library
+    monkeypatch.setenv("B200SA_UNBWT_CAP_MULT", cap_mult)
+    eng = Engine(0, library=Library(os.path.join(ROOT, "tests", "emu", "libb200sa_emu.so")))
+    try:
+        for family, n in [("markov3", 100003), ("zeros", 20000), ("abcabca", 30000), ("rand", 70000), ("fib", 50000), ("rand", 5)]:
+            x = gen(family, n)
+            bwt, s = oracle.bwt(x)
+            b = bwt.copy()
+            eng.reverse_burrows_wheeler_transform(b, s)
+            assert np.array_equal(b, x), (family, n, cap_mult)
+    finally:
+        eng.close()

@@ -700,7 +700,7 @@ int Engine::unbwt_build(const u8* d_bwt, u32 n, u32 s, u32* nwalkers_out, cudaSt
     us.nreg = (u32)div_up_u64((u64)n + 1, D);
     us.nwalkers = us.nreg + ((s % D) != 0 ? 1u : 0u);
     B200SA_TRY(walk.ensure((size_t)us.nwalkers * 5 * 4 + 64));
-    us.cap = unbwt_cap_mult * D;  // window bytes per walker (multiple of 8: D >= 64)
+    us.cap = (unbwt_cap_mult * D + 7u) & ~7u;  // window bytes per walker, 8-byte granular (64-bit stores)
     B200SA_LAUNCH(k_unbwt_mark, (u32)div_up_u64(us.nwalkers, 256), 256, 0, st, psi, us.nwalkers, us.nreg, D, s);
     count_launch(B200SA_PH_UNBWT_BUILD);
     B200SA_TRY(phase_end(st));

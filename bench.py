@@ -341,7 +341,7 @@ def run_sharded(args, wl):
     eng = Engine(local_rank)
     text = gen_text(kind, n)                      # the same text on every rank
     d_text = torch.from_numpy(text).cuda()
-    sorter = ShardedSorter(eng)
+    sorter = ShardedSorter(eng, isa=args.isa)
     for _ in range(args.warmup):
         res = sorter.suffix_array_bwt(d_text)
     dist.barrier(); torch.cuda.synchronize()
@@ -378,7 +378,7 @@ def run_sharded(args, wl):
             "metric": "sa_bwt_input_throughput", "value": n / (ms_per_step * 1e-3) / 1e6, "unit": "MB/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "u8/int32 (u64 sort keys)", "data": "synthetic",
-            "config": {"workload": wl, "description": desc, "n_bytes": n, "parallelism": f"one text sharded by key range over {world} GPUs",
+            "config": {"workload": wl, "description": desc, "n_bytes": n, "parallelism": f"one text sharded by key range over {world} GPUs, ISA {args.isa}",
                        "owned_suffixes_per_rank": res.counts, "rounds": res.rounds,
                        "nccl_bytes_received_per_rank_per_step": res.exchanged_bytes},
             "e2e": None, "gpu_launches": int(launches),
@@ -402,6 +402,7 @@ def main():
     ap.add_argument("--workload", default="markov3_256MiB", choices=sorted(WORKLOADS))
     ap.add_argument("--n", type=int, default=0, help="override the text size (debugging)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--isa", default="owner", choices=["owner", "replicated"], help="sharded mode: how the ISA travels (see msufsort_b200/sharded.py)")
     ap.add_argument("--mode", default="independent", choices=["independent", "sharded"],
                     help="N>1 only. independent (default): one text per GPU, no data-path collective, weak scaling. "
                          "sharded: ONE text partitioned by key range over the N GPUs, ISA updates all-gathered over NCCL "

@@ -151,6 +151,17 @@ B200SA_API int b200sa_shard_copy_updates(b200sa_ctx* ctx, uint32_t* d_idx_dst, u
 /* rank[d_idx[j]] = d_rank[j] on this context's ISA replica (own and peers' updates alike). */
 B200SA_API int b200sa_shard_apply_updates(b200sa_ctx* ctx, const uint32_t* d_idx, const uint32_t* d_rank,
                                           int64_t count, void* stream);
+/* Owner-sharded ISA (the scalable variant): GPU g is the authority for rank[] of the text positions
+ * [g*B, (g+1)*B), B a power of two.  After a round the producer of a new rank sends it to the owner of
+ * that suffix (all-to-all), and before the next round every GPU asks the owners for the ranks it is
+ * about to read (all-to-all of positions, all-to-all of values) and drops the replies into its own
+ * rank[] as a cache.  shard_partition routes pairs by owner (bucket = (key >> shift) & 255, stable),
+ * shard_requests lists the positions the next round reads, shard_gather_ranks serves a request list. */
+B200SA_API int b200sa_shard_partition(b200sa_ctx* ctx, const uint32_t* d_keys, const uint32_t* d_vals, int64_t count,
+                                      int shift, uint32_t* d_keys_out, uint32_t* d_vals_out, uint32_t* counts_out /*256, host*/,
+                                      void* stream);
+B200SA_API int b200sa_shard_requests(b200sa_ctx* ctx, uint32_t* d_pos_out, int64_t capacity, int64_t* count_out, void* stream);
+B200SA_API int b200sa_shard_gather_ranks(b200sa_ctx* ctx, const uint32_t* d_pos, int64_t count, uint32_t* d_out, void* stream);
 /* BWT bytes of SA rows [row_begin,row_end) into d_bwt (an n-byte buffer; bytes
  * [*out_begin,*out_end) are written). */
 B200SA_API int b200sa_shard_bwt(b200sa_ctx* ctx, int64_t row_begin, int64_t row_end, uint8_t* d_bwt,

@@ -70,6 +70,9 @@ ABI = [
     ("b200sa_shard_updates", C.c_int, [_P, C.POINTER(_P), C.POINTER(_P), C.POINTER(C.c_int64)]),
     ("b200sa_shard_copy_updates", C.c_int, [_P, _P, _P, C.c_int64, _P]),
     ("b200sa_shard_apply_updates", C.c_int, [_P, _P, _P, C.c_int64, _P]),
+    ("b200sa_shard_partition", C.c_int, [_P, _P, _P, C.c_int64, C.c_int, _P, _P, C.POINTER(C.c_uint32), _P]),
+    ("b200sa_shard_requests", C.c_int, [_P, _P, C.c_int64, C.POINTER(C.c_int64), _P]),
+    ("b200sa_shard_gather_ranks", C.c_int, [_P, _P, C.c_int64, _P, _P]),
     ("b200sa_shard_bwt", C.c_int, [_P, C.c_int64, C.c_int64, _P, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int32), _P]),
     ("b200sa_unbwt_shard_build", C.c_int, [_P, _P, C.c_int64, C.c_int32, C.POINTER(C.c_int64), _P]),
     ("b200sa_unbwt_shard_measure", C.c_int, [_P, C.c_int64, C.c_int64, _P]),
@@ -263,6 +266,20 @@ class Engine:
 
     def shard_apply_updates(self, d_idx, d_rank, count: int, stream: int = 0) -> None:
         self.lib.check(self.lib.cdll.b200sa_shard_apply_updates(self._ctx, _ptr(d_idx), _ptr(d_rank), count, stream or None))
+
+    def shard_partition(self, d_keys, d_vals, count: int, shift: int, d_keys_out, d_vals_out, stream: int = 0) -> list:
+        counts = (C.c_uint32 * 256)()
+        self.lib.check(self.lib.cdll.b200sa_shard_partition(self._ctx, _ptr(d_keys), _ptr(d_vals), count, shift, _ptr(d_keys_out),
+                                                            _ptr(d_vals_out), counts, stream or None))
+        return list(counts)
+
+    def shard_requests(self, d_pos_out, capacity: int, stream: int = 0) -> int:
+        cnt = C.c_int64(0)
+        self.lib.check(self.lib.cdll.b200sa_shard_requests(self._ctx, _ptr(d_pos_out), capacity, C.byref(cnt), stream or None))
+        return int(cnt.value)
+
+    def shard_gather_ranks(self, d_pos, count: int, d_out, stream: int = 0) -> None:
+        self.lib.check(self.lib.cdll.b200sa_shard_gather_ranks(self._ctx, _ptr(d_pos), count, _ptr(d_out), stream or None))
 
     def shard_bwt(self, row_begin: int, row_end: int, d_bwt, stream: int = 0):
         ob, oe, s = C.c_int64(0), C.c_int64(0), C.c_int32(0)

@@ -1055,6 +1055,85 @@ int b200sa_shard_bwt(b200sa_ctx* ctx, int64_t row_begin, int64_t row_end, uint8_
     return 0;
 }
 
+// Stable partition of (key, value) pairs by (key >> shift) & 255 — the routing step of every all-to-all of the
+// owner-sharded ISA (bucket = owning GPU).  counts_out: 256 host words.  d_vals may be NULL.
+int b200sa_shard_partition(b200sa_ctx* ctx, const uint32_t* d_keys, const uint32_t* d_vals, int64_t count, int shift,
+                           uint32_t* d_keys_out, uint32_t* d_vals_out, uint32_t* counts_out, void* stream)
+{
+    B200SA_NEED_CTX(ctx);
+    Engine& e = ctx->eng;
+    if (count < 0 || shift < 0 || shift > 31 || !counts_out || (count > 0 && (!d_keys || !d_keys_out || !d_vals_out)))
+        return b200sa::set_error(B200SA_EINVAL, "bad argument");
+    for (int i = 0; i < 256; ++i) counts_out[i] = 0;
+    if (count == 0) return 0;
+    B200SA_CU(cudaSetDevice(e.device));
+    cudaStream_t st = e.pick(stream);
+    const u32 m = (u32)count;
+    const u32 tiles = (u32)b200sa::div_up_u64(m, b200sa::RS_TILE);
+    const size_t status_bytes = (size_t)tiles * b200sa::RS_RADIX * sizeof(u64);
+    B200SA_TRY(e.sortmeta.ensure(b200sa::kSortMetaHeader + status_bytes));
+    u32* ghist = e.sortmeta.as<u32>();
+    u32* counters = ghist + b200sa::RS_MAX_PASSES * b200sa::RS_RADIX;
+    u64* status = (u64*)((u8*)e.sortmeta.p + b200sa::kSortMetaHeader);
+    B200SA_CU(cudaMemsetAsync(e.sortmeta.p, 0, b200sa::kSortMetaHeader + status_bytes, st));
+    e.prof.memsets++;
+    B200SA_TRY(e.phase_begin(B200SA_PH_ISA, st));
+    const u32 htiles = (u32)b200sa::div_up_u64(m, b200sa::RH_THREADS * b200sa::RH_IPT);
+    const u32 hgrid = htiles < (u32)(e.num_sms * 6) ? htiles : (u32)(e.num_sms * 6);
+    auto kh = b200sa::k_radix_hist<u32>;
+    B200SA_LAUNCH(kh, hgrid, b200sa::RH_THREADS, b200sa::rh_smem_bytes(1), st, d_keys, m, shift, 1, ghist);
+    e.count_launch(B200SA_PH_ISA);
+    B200SA_CU(cudaMemcpyAsync(counts_out, ghist, 256 * 4, cudaMemcpyDeviceToHost, st));
+    B200SA_CU(cudaStreamSynchronize(st));
+    B200SA_LAUNCH(b200sa::k_radix_scan_bins, 1, b200sa::RS_RADIX, 0, st, ghist);
+    e.count_launch(B200SA_PH_ISA);
+    auto kp = b200sa::k_onesweep_pass<u32, true>;
+    B200SA_LAUNCH(kp, tiles, b200sa::RS_THREADS, b200sa::rs_pass_smem_bytes<u32>(), st, d_keys, d_keys_out, d_vals, d_vals_out,
+                  m, shift, 0xffffffffu, (const u32*)ghist, status, counters);
+    e.count_launch(B200SA_PH_ISA);
+    B200SA_TRY(e.phase_end(st));
+    B200SA_CU(cudaGetLastError());
+    B200SA_CU(cudaStreamSynchronize(st));
+    return 0;
+}
+
+// Positions (suffix + h, clamped to n) whose ranks the next doubling round of this part will read.
+int b200sa_shard_requests(b200sa_ctx* ctx, uint32_t* d_pos_out, int64_t capacity, int64_t* count_out, void* stream)
+{
+    B200SA_NEED_CTX(ctx);
+    Engine& e = ctx->eng;
+    if (e.ss.stage != 2 || !count_out) return b200sa::set_error(B200SA_EINVAL, "no sharded sort in its ranking rounds");
+    const u32 m = e.ss.m;
+    *count_out = m;
+    if (m == 0) return 0;
+    if ((int64_t)m > capacity || !d_pos_out) return b200sa::set_error(B200SA_EINVAL, "destination too small");
+    cudaStream_t st = e.pick(stream);
+    const u32 grid = (u32)b200sa::div_up_u64(m, 256) < (u32)(e.num_sms * 8) ? (u32)b200sa::div_up_u64(m, 256) : (u32)(e.num_sms * 8);
+    B200SA_LAUNCH(b200sa::k_make_requests, grid, 256, 0, st, (const u32*)e.idx[e.ss.act].as<u32>(), m, (u32)e.ss.h, e.ss.n, d_pos_out);
+    e.count_launch(B200SA_PH_BUILD);
+    B200SA_CU(cudaGetLastError());
+    B200SA_CU(cudaStreamSynchronize(st));
+    return 0;
+}
+
+// out[j] = rank[pos[j]] — serves the lookups of other GPUs from this context's ISA shard.
+int b200sa_shard_gather_ranks(b200sa_ctx* ctx, const uint32_t* d_pos, int64_t count, uint32_t* d_out, void* stream)
+{
+    B200SA_NEED_CTX(ctx);
+    Engine& e = ctx->eng;
+    if (count < 0 || (count > 0 && (!d_pos || !d_out))) return b200sa::set_error(B200SA_EINVAL, "bad argument");
+    if (e.ss.stage < 1) return b200sa::set_error(B200SA_EINVAL, "no sharded sort in progress");
+    if (count == 0) return 0;
+    cudaStream_t st = e.pick(stream);
+    const u32 c = (u32)count;
+    const u32 grid = (u32)b200sa::div_up_u64(c, 256) < (u32)(e.num_sms * 8) ? (u32)b200sa::div_up_u64(c, 256) : (u32)(e.num_sms * 8);
+    B200SA_LAUNCH(b200sa::k_gather_u32, grid, 256, 0, st, d_pos, c, (const u32*)e.rank.as<u32>(), d_out);
+    e.count_launch(B200SA_PH_ISA);
+    B200SA_CU(cudaGetLastError());
+    B200SA_CU(cudaStreamSynchronize(st));
+    return 0;
+}
+
 int b200sa_unbwt_shard_build(b200sa_ctx* ctx, const uint8_t* d_bwt, int64_t n, int32_t sentinel_index, int64_t* nwalkers_out, void* stream)
 {
     B200SA_NEED_CTX(ctx);

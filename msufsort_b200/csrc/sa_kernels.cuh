@@ -147,6 +147,22 @@ k_sample_keys(const u64* __restrict__ keys, u32 nsample, u32 stride, u64* __rest
     if (i < nsample) out[i] = keys[(u64)i * stride];
 }
 
+// owner-sharded ISA (multi-GPU): positions whose ranks the next round will read, and the serving gather
+__global__ void __launch_bounds__(256)
+k_make_requests(const u32* __restrict__ idx, u32 m, u32 h, u32 n, u32* __restrict__ pos_out)
+{
+    for (u32 j = blockIdx.x * blockDim.x + threadIdx.x; j < m; j += gridDim.x * blockDim.x) {
+        const u64 p = (u64)idx[j] + h;
+        pos_out[j] = (u32)(p < n ? p : n);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_gather_u32(const u32* __restrict__ pos, u32 count, const u32* __restrict__ table, u32* __restrict__ out)
+{
+    for (u32 j = blockIdx.x * blockDim.x + threadIdx.x; j < count; j += gridDim.x * blockDim.x) out[j] = table[pos[j]];
+}
+
 static const int FR_THREADS = 256;
 static const int FR_IPT = 8;
 

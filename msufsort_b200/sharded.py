@@ -7,11 +7,15 @@ Scheme (north_star item 4; include/b200sa.h "sharded building blocks"):
   * round 0 is partitioned by key range — each rank packs all n initial keys, derives the same
     G-1 splitters from a sorted regular sample (identical on all ranks, no communication) and
     radix-sorts only the suffixes whose key falls into its range;
-  * a range consists of whole groups, so every doubling round sorts locally; after each round the
-    ranks all-gather their (suffix, new rank) ISA updates and apply them to their replicas;
+  * a range consists of whole groups, so every doubling round sorts locally;
+  * the ISA is what travels.  ``isa="owner"`` (default): rank g is the authority for the ranks of the text
+    positions [g*B, (g+1)*B); after a round every new (suffix, rank) pair is routed to the owner of the suffix
+    (one radix sweep by owner + all-to-all), and before the next round every rank asks the owners for the
+    ranks it is about to read (all-to-all of positions, all-to-all of values) and caches the replies in its
+    own array — all three exchanges and all ISA work scale with 1/G.  ``isa="replicated"``: the pairs are
+    all-gathered and every rank applies all of them (simpler, but the ISA update is replicated work);
   * a rank ends up owning a contiguous slice of the suffix array and of the BWT.
-The exchange step is the only collective on the data path; counts and the termination test are
-tiny all-gathers / all-reduces.
+The exchanges are the only collectives on the data path; counts and the termination test are tiny.
 """
 from __future__ import annotations
 
@@ -36,11 +40,66 @@ class ShardedResult:
 
 
 class ShardedSorter:
-    def __init__(self, engine, group: Optional[dist.ProcessGroup] = None):
+    def __init__(self, engine, group: Optional[dist.ProcessGroup] = None, isa: str = "owner"):
+        assert isa in ("owner", "replicated")
         self.eng = engine
         self.group = group
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
+        self.isa = isa
+        assert self.world <= 256, "the owner routing sweep has 256 buckets"
+
+    # -- owner-sharded ISA ---------------------------------------------------------------------------
+    def _owner_shift(self, n: int) -> int:
+        per = (n + 1 + self.world - 1) // self.world
+        return max(0, (per - 1).bit_length())        # B = 2^shift >= ceil((n+1)/G): owner(p) = p >> shift < G
+
+    def _a2a(self, send: torch.Tensor, send_counts: list, recv_counts: list) -> torch.Tensor:
+        out = torch.empty(sum(recv_counts), dtype=send.dtype, device=send.device)
+        dist.all_to_all_single(out, send, recv_counts, send_counts, group=self.group)
+        return out
+
+    def _exchange_counts(self, counts: list, device) -> list:
+        sc = torch.tensor(counts, dtype=torch.int64, device=device)
+        rc = torch.empty(self.world, dtype=torch.int64, device=device)
+        dist.all_to_all_single(rc, sc, group=self.group)
+        return [int(x) for x in rc.cpu().tolist()]
+
+    def _route_updates(self, device, stream: int, res: "ShardedResult", shift: int) -> None:
+        """new (suffix, rank) pairs -> the owners of the suffixes"""
+        pi, pr, cnt = self.eng.shard_updates()
+        kout = torch.empty(max(cnt, 1), dtype=torch.int32, device=device)
+        vout = torch.empty(max(cnt, 1), dtype=torch.int32, device=device)
+        counts = self.eng.shard_partition(pi, pr, cnt, shift, kout, vout, stream)[: self.world]
+        rcounts = self._exchange_counts(counts, device)
+        ridx = self._a2a(kout[:cnt], counts, rcounts)
+        rrank = self._a2a(vout[:cnt], counts, rcounts)
+        if device.type == "cuda":
+            torch.cuda.current_stream().synchronize()
+        res.exchanged_bytes += 8 * (sum(rcounts) - rcounts[self.rank])
+        if ridx.numel():
+            self.eng.shard_apply_updates(ridx, rrank, ridx.numel(), stream)
+
+    def _fetch_lookups(self, m_local: int, device, stream: int, res: "ShardedResult", shift: int) -> None:
+        """ranks the next round reads: ask the owners, cache the replies in the local array"""
+        pos = torch.empty(max(m_local, 1), dtype=torch.int32, device=device)
+        cnt = self.eng.shard_requests(pos, m_local, stream) if m_local else 0
+        kout = torch.empty(max(cnt, 1), dtype=torch.int32, device=device)
+        vout = torch.empty(max(cnt, 1), dtype=torch.int32, device=device)
+        counts = self.eng.shard_partition(pos, None, cnt, shift, kout, vout, stream)[: self.world]
+        rcounts = self._exchange_counts(counts, device)
+        rpos = self._a2a(kout[:cnt], counts, rcounts)                 # positions other ranks want from my shard
+        vals = torch.empty(max(rpos.numel(), 1), dtype=torch.int32, device=device)
+        if device.type == "cuda":
+            torch.cuda.current_stream().synchronize()
+        if rpos.numel():
+            self.eng.shard_gather_ranks(rpos, rpos.numel(), vals, stream)
+        replies = self._a2a(vals[: rpos.numel()], rcounts, counts)    # come back in the order of kout
+        if device.type == "cuda":
+            torch.cuda.current_stream().synchronize()
+        res.exchanged_bytes += 4 * (sum(rcounts) - rcounts[self.rank]) + 4 * (cnt - counts[self.rank])
+        if cnt:
+            self.eng.shard_apply_updates(kout[:cnt], replies, cnt, stream)
 
     # -- tiny collectives ------------------------------------------------------------------------
     def _gather_int(self, value: int, device) -> list:
@@ -82,17 +141,31 @@ class ShardedSorter:
         res.counts = self._gather_int(n_local, device)
         assert sum(res.counts) == n, "key-range parts do not cover the text"
         slot_base = sum(res.counts[: self.rank])
+        shift = self._owner_shift(n)
         m_local = self.eng.shard_round0(slot_base, stream)
-        self._exchange_updates(device, stream, res, n)
         res.rounds = 1
         while True:
+            if self.isa == "owner":
+                self._route_updates(device, stream, res, shift)
+            else:
+                self._exchange_updates(device, stream, res, n)
             t = torch.tensor([m_local], dtype=torch.int64, device=device)
             dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
             if int(t.item()) == 0:
                 break
+            if self.isa == "owner":
+                self._fetch_lookups(m_local, device, stream, res, shift)
             m_local = self.eng.shard_round(stream)
-            self._exchange_updates(device, stream, res, n)
             res.rounds += 1
+        if self.isa == "owner":
+            # the sentinel row s = rank[0] lives on the owner of position 0
+            t = torch.zeros(1, dtype=torch.int32, device=device)
+            if self.rank == 0:
+                self.eng.shard_gather_ranks(torch.zeros(1, dtype=torch.int32, device=device), 1, t, stream)
+            src = dist.get_global_rank(self.group, 0) if self.group is not None else 0
+            dist.broadcast(t, src=src, group=self.group)
+            if self.rank != 0:
+                self.eng.shard_apply_updates(torch.zeros(1, dtype=torch.int32, device=device), t, 1, stream)
         # rows of the (n+1)-row suffix array owned here; row 0 (the empty suffix) belongs to rank 0
         res.row_begin = 0 if self.rank == 0 else slot_base + 1
         res.row_end = slot_base + n_local + 1

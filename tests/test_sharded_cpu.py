@@ -18,7 +18,7 @@ def _free_port():
     s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
 
 
-def _worker(rank, world, port, family, n, q):
+def _worker(rank, world, port, family, n, q, isa="owner"):
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -33,7 +33,7 @@ def _worker(rank, world, port, family, n, q):
         eng = Engine(0, library=Library(os.path.join(ROOT, "tests", "emu", "libb200sa_emu.so")))
         x = gen(family, n)
         d_text = torch.from_numpy(x.copy())
-        sorter = ShardedSorter(eng)
+        sorter = ShardedSorter(eng, isa=isa)
         res = sorter.suffix_array_bwt(d_text)
         sa = sorter.gather_sa(res).numpy()
         bwt = sorter.gather_bwt(res).numpy()
@@ -47,15 +47,16 @@ def _worker(rank, world, port, family, n, q):
         dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("isa", ["owner", "replicated"])
 @pytest.mark.parametrize("world", [2, 3])
 @pytest.mark.parametrize("family,n", [("markov3", 40000), ("acgt_rep", 30011), ("rand", 5000), ("abcabca", 9000),
                                       ("zeros", 3000), ("fib", 10000), ("sigma2", 257), ("rand", 3)])
-def test_sharded_matches_oracle(oracle, world, family, n):
+def test_sharded_matches_oracle(oracle, world, family, n, isa):
     from cases import gen
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, family, n, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, family, n, q, isa)) for r in range(world)]
     for p in procs:
         p.start()
     sa, bwt, sentinel, counts, rounds = q.get(timeout=300)

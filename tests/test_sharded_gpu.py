@@ -20,7 +20,7 @@ def _free_port():
     s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
 
 
-def _worker(rank, world, port, family, n, q):
+def _worker(rank, world, port, family, n, q, isa="owner"):
     import torch
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -34,7 +34,7 @@ def _worker(rank, world, port, family, n, q):
         eng = Engine(rank)
         x = gen(family, n)
         d_text = torch.from_numpy(x.copy()).cuda()
-        sorter = ShardedSorter(eng)
+        sorter = ShardedSorter(eng, isa=isa)
         res = sorter.suffix_array_bwt(d_text)
         sa = sorter.gather_sa(res).cpu().numpy()
         bwt = sorter.gather_bwt(res).cpu().numpy()
@@ -49,16 +49,17 @@ def _worker(rank, world, port, family, n, q):
 
 
 @pytest.mark.skipif(_ngpus() < 2, reason="needs at least 2 GPUs")
+@pytest.mark.parametrize("isa", ["owner", "replicated"])
 @pytest.mark.parametrize("family,n", [("markov3", (1 << 22) + 5), ("acgt_rep", 1 << 22), ("rand", 1 << 20), ("abcabca", 1 << 20),
                                       ("fib", 1 << 19), ("zeros", 1 << 18)])
-def test_sharded_nccl_matches_oracle(oracle, family, n):
+def test_sharded_nccl_matches_oracle(oracle, family, n, isa):
     import torch.multiprocessing as mp
     from cases import gen
     world = min(_ngpus(), 8)
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, family, n, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, family, n, q, isa)) for r in range(world)]
     for p in procs:
         p.start()
     sa, bwt, sentinel, counts, rounds = q.get(timeout=600)

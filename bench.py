@@ -175,7 +175,7 @@ def run_reference(args, wl):
 def run_ours(args, wl):
     import torch
     import torch.distributed as dist
-    from msufsort_b200.api import Engine
+    from msufsort_b200.api import torch_stream_handle, Engine
 
     kind, n, desc = WORKLOADS[wl]
     if args.n:
@@ -190,7 +190,7 @@ def run_ours(args, wl):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     eng = Engine(local_rank)
-    stream = torch.cuda.current_stream().cuda_stream
+    stream = torch_stream_handle()
 
     # every rank gets its own text of the same size (rank 0 = the seed the parity tests use)
     host_text = torch.empty(n, dtype=torch.uint8, pin_memory=True)
@@ -329,7 +329,7 @@ def run_sharded(args, wl):
     """ONE text sharded over all ranks (strong scaling): value = n / max-over-ranks time."""
     import torch
     import torch.distributed as dist
-    from msufsort_b200.api import Engine
+    from msufsort_b200.api import Engine, torch_stream_handle
     from msufsort_b200.sharded import ShardedSorter
 
     kind, n, desc = WORKLOADS[wl]
@@ -366,7 +366,7 @@ def run_sharded(args, wl):
     launches = eng.launch_count() - launches0
     # correctness outside the timed region: assemble the SA and let the GPU validator judge it
     full_sa = sorter.gather_sa(res)
-    bad = eng.check_suffix_array_dev(d_text, n, full_sa, torch.cuda.current_stream().cuda_stream)
+    bad = eng.check_suffix_array_dev(d_text, n, full_sa, torch_stream_handle())
     if bad != 0:
         raise SystemExit(f"bench.py: sharded SA has {bad} bad rows")
     if rank == 0:

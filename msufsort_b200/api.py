@@ -123,6 +123,18 @@ def load_library() -> Library:
         return _lib
 
 
+CUDA_STREAM_LEGACY = 1  # cudaStreamLegacy: the explicit handle of the legacy default stream
+
+
+def torch_stream_handle() -> int:
+    """cudaStream_t of torch's current stream, suitable for the `stream` argument of the *_dev entry points.
+    torch reports the default stream as handle 0, which this ABI reads as "use the context's own stream" (a
+    non-blocking stream that is NOT ordered with torch's work); the explicit legacy handle keeps the kernels on
+    the stream torch is using, so torch fills, NCCL collectives and torch.cuda.Event timings are ordered with them."""
+    import torch
+    return int(torch.cuda.current_stream().cuda_stream) or CUDA_STREAM_LEGACY
+
+
 def _ptr(x) -> Optional[int]:
     """Address of a numpy array / bytearray / torch tensor / raw int."""
     if x is None:
@@ -147,6 +159,22 @@ class Engine:
         self._ctx = _P()
         self.lib.check(self.lib.cdll.b200sa_create(C.byref(self._ctx), device))
         self.device = device
+
+    def _st(self, stream: Optional[int]):
+        """stream argument for the C ABI: an explicit handle is passed through; None means "the stream torch is
+        currently using" when torch has a CUDA context (so torch fills, copies, collectives and events stay ordered
+        with the kernels), else the context's own stream (NULL)"""
+        if stream is not None:
+            return stream or None
+        import sys
+        torch = sys.modules.get("torch")
+        if torch is not None and os.path.basename(str(self.lib.path)) == "libb200sa.so":
+            try:
+                if torch.cuda.is_available() and torch.cuda.is_initialized():
+                    return torch_stream_handle()
+            except Exception:
+                pass
+        return None
 
     def close(self) -> None:
         if getattr(self, "_ctx", None) is not None and self._ctx:
@@ -217,42 +245,42 @@ class Engine:
         self.lib.check(self.lib.cdll.b200sa_unbwt(self._ctx, bwt_ptr, n, int(sentinel_index)))
 
     # ---- device-resident entry points ---------------------------------------------------------
-    def suffix_array_dev(self, d_text, n: int, d_sa, stream: int = 0) -> None:
-        self.lib.check(self.lib.cdll.b200sa_suffix_array_dev(self._ctx, _ptr(d_text), n, _ptr(d_sa), stream or None))
+    def suffix_array_dev(self, d_text, n: int, d_sa, stream: Optional[int] = None) -> None:
+        self.lib.check(self.lib.cdll.b200sa_suffix_array_dev(self._ctx, _ptr(d_text), n, _ptr(d_sa), self._st(stream)))
 
-    def bwt_dev(self, d_text, n: int, d_bwt, d_sa=None, stream: int = 0) -> int:
+    def bwt_dev(self, d_text, n: int, d_bwt, d_sa=None, stream: Optional[int] = None) -> int:
         s = C.c_int32(0)
-        self.lib.check(self.lib.cdll.b200sa_bwt_dev(self._ctx, _ptr(d_text), n, _ptr(d_bwt), _ptr(d_sa), C.byref(s), stream or None))
+        self.lib.check(self.lib.cdll.b200sa_bwt_dev(self._ctx, _ptr(d_text), n, _ptr(d_bwt), _ptr(d_sa), C.byref(s), self._st(stream)))
         return int(s.value)
 
-    def unbwt_dev(self, d_bwt, n: int, sentinel_index: int, d_out, stream: int = 0) -> None:
-        self.lib.check(self.lib.cdll.b200sa_unbwt_dev(self._ctx, _ptr(d_bwt), n, int(sentinel_index), _ptr(d_out), stream or None))
+    def unbwt_dev(self, d_bwt, n: int, sentinel_index: int, d_out, stream: Optional[int] = None) -> None:
+        self.lib.check(self.lib.cdll.b200sa_unbwt_dev(self._ctx, _ptr(d_bwt), n, int(sentinel_index), _ptr(d_out), self._st(stream)))
 
-    def check_suffix_array_dev(self, d_text, n: int, d_sa, stream: int = 0) -> int:
+    def check_suffix_array_dev(self, d_text, n: int, d_sa, stream: Optional[int] = None) -> int:
         bad = C.c_int64(-1)
-        self.lib.check(self.lib.cdll.b200sa_check_suffix_array_dev(self._ctx, _ptr(d_text), n, _ptr(d_sa), C.byref(bad), stream or None))
+        self.lib.check(self.lib.cdll.b200sa_check_suffix_array_dev(self._ctx, _ptr(d_text), n, _ptr(d_sa), C.byref(bad), self._st(stream)))
         return int(bad.value)
 
-    def radix_sort_pairs_dev(self, d_keys, d_keys_alt, d_vals, d_vals_alt, m: int, begin_bit: int, end_bit: int, stream: int = 0) -> int:
+    def radix_sort_pairs_dev(self, d_keys, d_keys_alt, d_vals, d_vals_alt, m: int, begin_bit: int, end_bit: int, stream: Optional[int] = None) -> int:
         side = C.c_int(0)
         self.lib.check(self.lib.cdll.b200sa_radix_sort_pairs_dev(self._ctx, _ptr(d_keys), _ptr(d_keys_alt), _ptr(d_vals), _ptr(d_vals_alt),
-                                                                 m, begin_bit, end_bit, C.byref(side), stream or None))
+                                                                 m, begin_bit, end_bit, C.byref(side), self._st(stream)))
         return int(side.value)
 
     # ---- sharded building blocks (see msufsort_b200/sharded.py) ----------------------------------
-    def shard_begin(self, d_text, n: int, d_sa, part: int, nparts: int, stream: int = 0) -> int:
+    def shard_begin(self, d_text, n: int, d_sa, part: int, nparts: int, stream: Optional[int] = None) -> int:
         out = C.c_int64(0)
-        self.lib.check(self.lib.cdll.b200sa_shard_begin(self._ctx, _ptr(d_text), n, _ptr(d_sa), part, nparts, C.byref(out), stream or None))
+        self.lib.check(self.lib.cdll.b200sa_shard_begin(self._ctx, _ptr(d_text), n, _ptr(d_sa), part, nparts, C.byref(out), self._st(stream)))
         return int(out.value)
 
-    def shard_round0(self, slot_base: int, stream: int = 0) -> int:
+    def shard_round0(self, slot_base: int, stream: Optional[int] = None) -> int:
         out = C.c_int64(0)
-        self.lib.check(self.lib.cdll.b200sa_shard_round0(self._ctx, slot_base, C.byref(out), stream or None))
+        self.lib.check(self.lib.cdll.b200sa_shard_round0(self._ctx, slot_base, C.byref(out), self._st(stream)))
         return int(out.value)
 
-    def shard_round(self, stream: int = 0) -> int:
+    def shard_round(self, stream: Optional[int] = None) -> int:
         out = C.c_int64(0)
-        self.lib.check(self.lib.cdll.b200sa_shard_round(self._ctx, C.byref(out), stream or None))
+        self.lib.check(self.lib.cdll.b200sa_shard_round(self._ctx, C.byref(out), self._st(stream)))
         return int(out.value)
 
     def shard_updates(self):
@@ -261,44 +289,44 @@ class Engine:
         self.lib.check(self.lib.cdll.b200sa_shard_updates(self._ctx, C.byref(pi), C.byref(pr), C.byref(cnt)))
         return (pi.value or 0), (pr.value or 0), int(cnt.value)
 
-    def shard_copy_updates(self, d_idx_dst, d_rank_dst, capacity: int, stream: int = 0) -> None:
-        self.lib.check(self.lib.cdll.b200sa_shard_copy_updates(self._ctx, _ptr(d_idx_dst), _ptr(d_rank_dst), capacity, stream or None))
+    def shard_copy_updates(self, d_idx_dst, d_rank_dst, capacity: int, stream: Optional[int] = None) -> None:
+        self.lib.check(self.lib.cdll.b200sa_shard_copy_updates(self._ctx, _ptr(d_idx_dst), _ptr(d_rank_dst), capacity, self._st(stream)))
 
-    def shard_apply_updates(self, d_idx, d_rank, count: int, stream: int = 0) -> None:
-        self.lib.check(self.lib.cdll.b200sa_shard_apply_updates(self._ctx, _ptr(d_idx), _ptr(d_rank), count, stream or None))
+    def shard_apply_updates(self, d_idx, d_rank, count: int, stream: Optional[int] = None) -> None:
+        self.lib.check(self.lib.cdll.b200sa_shard_apply_updates(self._ctx, _ptr(d_idx), _ptr(d_rank), count, self._st(stream)))
 
-    def shard_partition(self, d_keys, d_vals, count: int, shift: int, d_keys_out, d_vals_out, stream: int = 0) -> list:
+    def shard_partition(self, d_keys, d_vals, count: int, shift: int, d_keys_out, d_vals_out, stream: Optional[int] = None) -> list:
         counts = (C.c_uint32 * 256)()
         self.lib.check(self.lib.cdll.b200sa_shard_partition(self._ctx, _ptr(d_keys), _ptr(d_vals), count, shift, _ptr(d_keys_out),
-                                                            _ptr(d_vals_out), counts, stream or None))
+                                                            _ptr(d_vals_out), counts, self._st(stream)))
         return list(counts)
 
-    def shard_requests(self, d_pos_out, capacity: int, stream: int = 0) -> int:
+    def shard_requests(self, d_pos_out, capacity: int, stream: Optional[int] = None) -> int:
         cnt = C.c_int64(0)
-        self.lib.check(self.lib.cdll.b200sa_shard_requests(self._ctx, _ptr(d_pos_out), capacity, C.byref(cnt), stream or None))
+        self.lib.check(self.lib.cdll.b200sa_shard_requests(self._ctx, _ptr(d_pos_out), capacity, C.byref(cnt), self._st(stream)))
         return int(cnt.value)
 
-    def shard_gather_ranks(self, d_pos, count: int, d_out, stream: int = 0) -> None:
-        self.lib.check(self.lib.cdll.b200sa_shard_gather_ranks(self._ctx, _ptr(d_pos), count, _ptr(d_out), stream or None))
+    def shard_gather_ranks(self, d_pos, count: int, d_out, stream: Optional[int] = None) -> None:
+        self.lib.check(self.lib.cdll.b200sa_shard_gather_ranks(self._ctx, _ptr(d_pos), count, _ptr(d_out), self._st(stream)))
 
-    def shard_bwt(self, row_begin: int, row_end: int, d_bwt, stream: int = 0):
+    def shard_bwt(self, row_begin: int, row_end: int, d_bwt, stream: Optional[int] = None):
         ob, oe, s = C.c_int64(0), C.c_int64(0), C.c_int32(0)
-        self.lib.check(self.lib.cdll.b200sa_shard_bwt(self._ctx, row_begin, row_end, _ptr(d_bwt), C.byref(ob), C.byref(oe), C.byref(s), stream or None))
+        self.lib.check(self.lib.cdll.b200sa_shard_bwt(self._ctx, row_begin, row_end, _ptr(d_bwt), C.byref(ob), C.byref(oe), C.byref(s), self._st(stream)))
         return int(ob.value), int(oe.value), int(s.value)
 
-    def unbwt_shard_build(self, d_bwt, n: int, sentinel_index: int, stream: int = 0) -> int:
+    def unbwt_shard_build(self, d_bwt, n: int, sentinel_index: int, stream: Optional[int] = None) -> int:
         w = C.c_int64(0)
-        self.lib.check(self.lib.cdll.b200sa_unbwt_shard_build(self._ctx, _ptr(d_bwt), n, int(sentinel_index), C.byref(w), stream or None))
+        self.lib.check(self.lib.cdll.b200sa_unbwt_shard_build(self._ctx, _ptr(d_bwt), n, int(sentinel_index), C.byref(w), self._st(stream)))
         return int(w.value)
 
-    def unbwt_shard_measure(self, w_begin: int, w_end: int, stream: int = 0) -> None:
-        self.lib.check(self.lib.cdll.b200sa_unbwt_shard_measure(self._ctx, w_begin, w_end, stream or None))
+    def unbwt_shard_measure(self, w_begin: int, w_end: int, stream: Optional[int] = None) -> None:
+        self.lib.check(self.lib.cdll.b200sa_unbwt_shard_measure(self._ctx, w_begin, w_end, self._st(stream)))
 
-    def unbwt_shard_segments(self, direction: int, w_begin: int, w_end: int, d_len, d_next, stream: int = 0) -> None:
-        self.lib.check(self.lib.cdll.b200sa_unbwt_shard_segments(self._ctx, direction, w_begin, w_end, _ptr(d_len), _ptr(d_next), stream or None))
+    def unbwt_shard_segments(self, direction: int, w_begin: int, w_end: int, d_len, d_next, stream: Optional[int] = None) -> None:
+        self.lib.check(self.lib.cdll.b200sa_unbwt_shard_segments(self._ctx, direction, w_begin, w_end, _ptr(d_len), _ptr(d_next), self._st(stream)))
 
-    def unbwt_shard_finish(self, w_begin: int, w_end: int, d_text_out, stream: int = 0) -> None:
-        self.lib.check(self.lib.cdll.b200sa_unbwt_shard_finish(self._ctx, w_begin, w_end, _ptr(d_text_out), stream or None))
+    def unbwt_shard_finish(self, w_begin: int, w_end: int, d_text_out, stream: Optional[int] = None) -> None:
+        self.lib.check(self.lib.cdll.b200sa_unbwt_shard_finish(self._ctx, w_begin, w_end, _ptr(d_text_out), self._st(stream)))
 
     # ---- instrumentation ----------------------------------------------------------------------
     def set_profiling(self, enabled: bool) -> None:

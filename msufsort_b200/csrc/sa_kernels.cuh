@@ -152,8 +152,11 @@ __global__ void __launch_bounds__(256)
 k_make_requests(const u32* __restrict__ idx, u32 m, u32 h, u32 n, u32* __restrict__ pos_out)
 {
     for (u32 j = blockIdx.x * blockDim.x + threadIdx.x; j < m; j += gridDim.x * blockDim.x) {
-        const u64 p = (u64)idx[j] + h;
-        pos_out[j] = (u32)(p < n ? p : n);
+        // rank[n] = 0 is known everywhere: a read past the end needs no lookup; ask for the suffix's own rank
+        // instead (harmless, keeps every request below n so that position >> shift is a valid owner)
+        const u32 i = idx[j];
+        const u64 p = (u64)i + h;
+        pos_out[j] = p < n ? (u32)p : i;
     }
 }
 

@@ -24,6 +24,8 @@ from typing import Optional
 import torch
 import torch.distributed as dist
 
+from .api import torch_stream_handle
+
 
 class ShardedResult:
     def __init__(self):
@@ -51,8 +53,8 @@ class ShardedSorter:
 
     # -- owner-sharded ISA ---------------------------------------------------------------------------
     def _owner_shift(self, n: int) -> int:
-        per = (n + 1 + self.world - 1) // self.world
-        return max(0, (per - 1).bit_length())        # B = 2^shift >= ceil((n+1)/G): owner(p) = p >> shift < G
+        per = (n + self.world - 1) // self.world
+        return max(0, (per - 1).bit_length())        # B = 2^shift >= ceil(n/G): owner(p) = p >> shift < G for p < n
 
     def _a2a(self, send: torch.Tensor, send_counts: list, recv_counts: list) -> torch.Tensor:
         out = torch.empty(sum(recv_counts), dtype=send.dtype, device=send.device)
@@ -134,7 +136,7 @@ class ShardedSorter:
     def suffix_array_bwt(self, d_text: torch.Tensor, want_bwt: bool = True) -> ShardedResult:
         n = d_text.numel()
         device = d_text.device
-        stream = torch.cuda.current_stream().cuda_stream if device.type == "cuda" else 0
+        stream = torch_stream_handle() if device.type == "cuda" else 0
         res = ShardedResult()
         res.sa = torch.empty(n + 1, dtype=torch.int32, device=device)
         n_local = self.eng.shard_begin(d_text, n, res.sa, self.rank, self.world, stream)
@@ -181,7 +183,7 @@ class ShardedSorter:
         output slices are combined with a sum all-reduce.  Returns the whole text on every rank."""
         n = d_bwt.numel()
         device = d_bwt.device
-        stream = torch.cuda.current_stream().cuda_stream if device.type == "cuda" else 0
+        stream = torch_stream_handle() if device.type == "cuda" else 0
         W = self.eng.unbwt_shard_build(d_bwt, n, sentinel_index, stream)
         per = (W + self.world - 1) // self.world
         spans = [(min(W, p * per), min(W, (p + 1) * per)) for p in range(self.world)]

@@ -4,12 +4,12 @@ O(n) GPU validator (no CPU oracle at these sizes) and the round trip.  usage: bi
 import json, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
-from msufsort_b200.api import Engine
+from msufsort_b200.api import torch_stream_handle, Engine
 from msufsort_b200 import textgen
 
 family = sys.argv[1]; n = int(sys.argv[2])
 eng = Engine(0)
-stream = torch.cuda.current_stream().cuda_stream
+stream = torch_stream_handle()
 t0 = time.time(); x = textgen.GENERATORS[family](n); tg = time.time() - t0
 d_text = torch.from_numpy(x).cuda()
 d_sa = torch.empty(n + 1, dtype=torch.int32, device="cuda")

@@ -4,7 +4,7 @@ usage: python tools/sort_bench.py [log2_m] [bits] [kind]"""
 import json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from msufsort_b200.api import Engine
+from msufsort_b200.api import torch_stream_handle, Engine
 
 lg = int(sys.argv[1]) if len(sys.argv) > 1 else 28
 bits = int(sys.argv[2]) if len(sys.argv) > 2 else 64
@@ -18,7 +18,7 @@ if bits < 64:
 if kind == "skew":      # few distinct values per digit
     keys0 &= 0x0303030303030303
 ka = torch.empty_like(keys0); v = torch.empty(m, dtype=torch.int32, device="cuda"); va = torch.empty_like(v)
-stream = torch.cuda.current_stream().cuda_stream
+stream = torch_stream_handle()
 peak = 6547.2
 try:
     peak = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))["hbm_gbs"]

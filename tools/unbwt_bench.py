@@ -4,13 +4,13 @@ usage: python tools/unbwt_bench.py [n] [steps]"""
 import json, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
-from msufsort_b200.api import Engine
+from msufsort_b200.api import torch_stream_handle, Engine
 from msufsort_b200 import textgen
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else (1 << 28)
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 eng = Engine(0)
-stream = torch.cuda.current_stream().cuda_stream
+stream = torch_stream_handle()
 x = textgen.markov3(n)
 d_text = torch.from_numpy(x).cuda()
 d_bwt = torch.empty(n, dtype=torch.uint8, device="cuda")

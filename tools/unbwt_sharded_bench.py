@@ -4,7 +4,7 @@ usage: torchrun --nproc-per-node N tools/unbwt_sharded_bench.py [n] [steps]"""
 import json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, torch.distributed as dist
-from msufsort_b200.api import Engine
+from msufsort_b200.api import torch_stream_handle, Engine
 from msufsort_b200.sharded import ShardedSorter
 from msufsort_b200 import textgen
 
@@ -14,7 +14,7 @@ rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os
 torch.cuda.set_device(lr)
 dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
 eng = Engine(lr)
-stream = torch.cuda.current_stream().cuda_stream
+stream = torch_stream_handle()
 d_text = torch.from_numpy(textgen.markov3(n)).cuda()
 d_bwt = torch.empty(n, dtype=torch.uint8, device="cuda")
 s = eng.bwt_dev(d_text, n, d_bwt, None, stream)

@@ -1,0 +1,47 @@
+"""GPU tier at BASELINE.json's full sizes.  No CPU oracle finishes in seconds here, so correctness is judged by
+size-independent properties: the O(n) GPU validator (SA[0]=n, permutation, order of neighbouring rows via the ISA —
+which, the SA being unique, proves bit-exactness with the reference), the sentinel index being the row of suffix 0,
+and the BWT -> inverse BWT round trip reproducing the text byte for byte."""
+import os
+
+import numpy as np
+import pytest
+
+from cases import gen
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(gpu_engine, family, n):
+    import torch
+    x = gen(family, n)
+    d_text = torch.from_numpy(x).cuda()
+    d_sa = torch.empty(n + 1, dtype=torch.int32, device="cuda")
+    d_bwt = torch.empty(n, dtype=torch.uint8, device="cuda")
+    s = gpu_engine.bwt_dev(d_text, n, d_bwt, d_sa)
+    assert gpu_engine.check_suffix_array_dev(d_text, n, d_sa) == 0
+    assert int(d_sa[s]) == 0 and int(d_sa[0]) == n                     # sentinel index = row of suffix 0
+    # spot-check the BWT definition on a sample of rows
+    rows = torch.randint(1, n + 1, (4096,), device="cuda")
+    rows = rows[rows != s]
+    out_idx = rows - (rows > s).long()
+    assert bool((d_bwt[out_idx] == d_text[(d_sa[rows].long() - 1)]).all())
+    del d_sa
+    gpu_engine.release_workspace()
+    d_back = torch.empty(n, dtype=torch.uint8, device="cuda")
+    gpu_engine.unbwt_dev(d_bwt, n, s, d_back)
+    assert bool(torch.equal(d_back, d_text))
+    gpu_engine.release_workspace()
+
+
+def test_config2_markov_256mib(gpu_engine):
+    _run(gpu_engine, "markov3", 1 << 28)
+
+
+def test_config3_and_4_acgt_repeats_1gib(gpu_engine):
+    _run(gpu_engine, "acgt_rep", (1 << 30) - 2)          # the largest n the reference itself handles correctly
+
+
+@pytest.mark.skipif(os.environ.get("B200SA_TEST_HUGE") != "1", reason="2 GiB deep-doubling run (≈130 GB of HBM, ≈10 s): set B200SA_TEST_HUGE=1")
+def test_config5_periodic_2gib(gpu_engine):
+    _run(gpu_engine, "periodic7", (1 << 31) - 2)

@@ -1218,6 +1218,15 @@ int b200sa_profile_get(b200sa_ctx* ctx, b200sa_profile* out)
 
 uint64_t b200sa_launch_count(b200sa_ctx* ctx) { return ctx ? ctx->eng.total_launches : 0; }
 
+#ifdef B200SA_PHASE_TIMING
+extern "C" __attribute__((visibility("default"))) int b200sa_debug_phase_cycles(unsigned long long* out8, int reset)
+{
+    if (cudaMemcpyFromSymbol(out8, b200sa::g_phase_cycles, 64) != cudaSuccess) return 1;
+    if (reset) { unsigned long long z[8] = {0}; cudaMemcpyToSymbol(b200sa::g_phase_cycles, z, 64); }
+    return 0;
+}
+#endif
+
 // ---- building blocks ---------------------------------------------------------------------------
 
 int b200sa_radix_sort_pairs_dev(b200sa_ctx* ctx, uint64_t* d_keys, uint64_t* d_keys_alt, uint32_t* d_vals, uint32_t* d_vals_alt,

@@ -32,6 +32,9 @@ static const int RS_RADIX = 256;
 #ifndef B200SA_RS_MIN_BLOCKS
 #define B200SA_RS_MIN_BLOCKS 3
 #endif
+#ifndef B200SA_RS_LOOKBACK_DEPTH
+#define B200SA_RS_LOOKBACK_DEPTH 4
+#endif
 #ifndef B200SA_RS_PEERS_ATOMIC_OR
 #define B200SA_RS_PEERS_ATOMIC_OR 0
 #endif
@@ -137,6 +140,14 @@ k_radix_scan_bins(u32* __restrict__ ghist)
 // One scatter sweep on digit (key >> shift) & 255.
 //   vin == nullptr  -> the value of element i is i + (i >= gen_skip)   (element indices / BWT rows)
 //   WRITE_KEYS=false-> only the permuted values are written (psi table of the inverse BWT)
+#ifdef B200SA_PHASE_TIMING
+// debug build only: cycles spent per phase of the sweep, summed over warp 0 of every 16th tile
+__device__ unsigned long long g_phase_cycles[8];
+#define PT_MARK(i) do { if (pt_on) { const long long now_ = clock64(); atomicAdd(&g_phase_cycles[i], (unsigned long long)(now_ - pt_t)); pt_t = now_; } } while (0)
+#else
+#define PT_MARK(i) do { } while (0)
+#endif
+
 template <typename KeyT, bool WRITE_KEYS>
 __global__ void __launch_bounds__(RS_THREADS, RS_MIN_BLOCKS)
 k_onesweep_pass(const KeyT* __restrict__ kin, KeyT* __restrict__ kout,
@@ -172,6 +183,11 @@ k_onesweep_pass(const KeyT* __restrict__ kin, KeyT* __restrict__ kout,
     const u32 tile = s_tile;
     const u32 base = tile * (u32)TILE;
     const u32 valid = min((u32)TILE, m - base);
+#ifdef B200SA_PHASE_TIMING
+    const bool pt_on = (tid == 0) && ((tile & 15u) == 0) && sizeof(KeyT) == 8;
+    long long pt_t = clock64();
+    if (pt_on) atomicAdd(&g_phase_cycles[7], 1ull);
+#endif
 
     // ---- load (warp-striped): element order inside the tile is (warp, item, lane)
     KeyT key[IPT];
@@ -192,6 +208,8 @@ k_onesweep_pass(const KeyT* __restrict__ kin, KeyT* __restrict__ kout,
         }
     }
 
+    if (sizeof(KeyT) == 8) { volatile u32 sink = (u32)key[IPT - 1]; (void)sink; }
+    PT_MARK(0);  // keys arrived
     // ---- 1. rank inside the warp.  Peers = lanes holding my digit.  Two interchangeable ways to find
     // them (tools/ubench on B200, SM-cycles per 32 keys at full occupancy): eight ballots 20.7,
     // atomicOr into a shared mask word + read back 7.4, MATCH.ANY 60.  Inside this kernel the shared
@@ -229,6 +247,7 @@ k_onesweep_pass(const KeyT* __restrict__ kin, KeyT* __restrict__ kout,
         __syncwarp();
         pos[k] = prev + below;
     }
+    PT_MARK(1);  // ranking
     // values are fetched only now: during ranking they would cost 16 more live registers (spills at
     // the 80-register budget of 3 CTAs/SM); their latency overlaps the tile-level scan below
     if (vin) {
@@ -281,6 +300,7 @@ k_onesweep_pass(const KeyT* __restrict__ kin, KeyT* __restrict__ kout,
     }
     __syncthreads();
 
+    PT_MARK(2);  // tile-level combine + scan (incl. barrier waits)
     // ---- stage keys and values in digit order (needs only tile-local offsets; predecessors keep
     // publishing their descriptors meanwhile)
 #pragma unroll
@@ -291,7 +311,8 @@ k_onesweep_pass(const KeyT* __restrict__ kin, KeyT* __restrict__ kout,
         svals[p] = val[k];
     }
 
-    // ---- 4. look-back for digit tid: four predecessor descriptors in flight per step
+    PT_MARK(3);  // staging
+    // ---- 4. look-back for digit tid: B200SA_RS_LOOKBACK_DEPTH predecessor descriptors in flight per step
     if (tid < (u32)RS_RADIX) {
         u64 excl = 0;
 #ifdef B200SA_ABLATE_LOOKBACK
@@ -303,11 +324,15 @@ k_onesweep_pass(const KeyT* __restrict__ kin, KeyT* __restrict__ kout,
             i64 t = (i64)tile - 1;
             bool done = false;
             while (!done) {
-                u64 v[4];
+                // LB descriptors in flight per step: the inclusive frontier trails a running tile by some
+                // tens of tiles (clock64 phase timing: with 4 in flight the walk back cost 6.3 k of the 25 k
+                // cycles of a tile's life); keys/values/ranks are dead by now, so registers are free
+                constexpr int LB = B200SA_RS_LOOKBACK_DEPTH;
+                u64 v[LB];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) v[i] = (t - i >= 0) ? ld_relaxed_u64(col + (u64)(t - i) * RS_RADIX) : 0ull;
+                for (int i = 0; i < LB; ++i) v[i] = (t - i >= 0) ? ld_relaxed_u64(col + (u64)(t - i) * RS_RADIX) : 0ull;
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
+                for (int i = 0; i < LB; ++i) {
                     if (!done) {
                         u64 x = v[i];
                         while ((x >> 62) == 0) x = ld_relaxed_u64(col + (u64)(t - i) * RS_RADIX);
@@ -315,14 +340,16 @@ k_onesweep_pass(const KeyT* __restrict__ kin, KeyT* __restrict__ kout,
                         if (x & RS_FLAG_INCLUSIVE) done = true;
                     }
                 }
-                t -= 4;
+                t -= LB;
             }
             st_relaxed_u64(status + (u64)tile * RS_RADIX + tid, RS_FLAG_INCLUSIVE | (excl + (u64)my_cnt));
         }
         // global start of this tile's run of digit tid, minus its slot in shared memory
         s_gdelta[tid] = bins[tid] + (u32)excl - s_coff[tid];
     }
+    PT_MARK(4);  // look-back
     __syncthreads();
+    PT_MARK(5);  // barrier after look-back
     // ---- write out: consecutive threads take consecutive slots, i.e. consecutive addresses inside a digit run
     if (full) {
 #pragma unroll
@@ -341,6 +368,7 @@ k_onesweep_pass(const KeyT* __restrict__ kin, KeyT* __restrict__ kout,
             st_stream(vout + g, svals[j]);
         }
     }
+    PT_MARK(6);  // write-out (issue only; stores retire asynchronously)
 }
 
 }  // namespace b200sa

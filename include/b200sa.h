@@ -122,6 +122,20 @@ B200SA_API int b200sa_unbwt_dev(b200sa_ctx* ctx, const uint8_t* d_bwt, int64_t n
 B200SA_API int b200sa_check_suffix_array_dev(b200sa_ctx* ctx, const uint8_t* d_text, int64_t n,
                                              const int32_t* d_sa, int64_t* bad_rows_out, void* stream);
 
+/* LCP array.  Replaces the demo's LCP construction (src/executable/msufsort/main.cpp:16-105:
+ * match_length, lcp, lcp_multithreaded), which is the only LCP code the reference ships.  Convention:
+ * n+1 int32 entries aligned with the suffix array, lcp[0] = 0 and lcp[r] = length of the longest common
+ * prefix of suffixes SA[r-1] and SA[r] (so lcp[1] = 0: SA[0] is the empty suffix).  The reference's
+ * output[i] (main.cpp:150-153, i = 0..n-2) is lcp[i+2]; its last entry reads past its suffix array.
+ * d_sa must be the correct suffix array of d_text (e.g. from b200sa_suffix_array_dev); work is
+ * O(n log n) text probes in the worst case and independent of the text's repetitiveness. */
+B200SA_API int b200sa_lcp_dev(b200sa_ctx* ctx, const uint8_t* d_text, int64_t n, const int32_t* d_sa,
+                              int32_t* d_lcp_out, void* stream);
+/* Host buffers.  sa == NULL: the suffix array is computed first (and returned through sa_out when that
+ * is not NULL); otherwise sa must be the n+1-entry suffix array of text.  lcp_out: n+1 int32. */
+B200SA_API int b200sa_lcp(b200sa_ctx* ctx, const uint8_t* text, int64_t n, const int32_t* sa,
+                          int32_t* sa_out, int32_t* lcp_out);
+
 /* ---- sharded (multi-GPU) building blocks --------------------------------------------------
  *
  * One text, G GPUs, one process and one context per GPU (msufsort_b200/sharded.py drives these over
@@ -194,6 +208,7 @@ enum {
     B200SA_PH_CHECK = 9,      /* validator                                                    */
     B200SA_PH_SEGSORT = 10,   /* in-shared-memory sort of small groups (doubling rounds)      */
     B200SA_PH_ISA = 11,       /* bucketed ISA update: one radix sweep by suffix index + scatter */
+    B200SA_PH_LCP = 12,       /* LCP array: PLCP levels + gather (the phi scatter is counted under ISA) */
     B200SA_PH_COUNT = 16
 };
 

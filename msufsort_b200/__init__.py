@@ -14,11 +14,12 @@ from .api import (  # noqa: F401
     make_suffix_array,
     forward_burrows_wheeler_transform,
     reverse_burrows_wheeler_transform,
+    make_lcp_array,
     PHASES,
 )
 from . import textgen  # noqa: F401
 
 __all__ = [
     "B200SAError", "Library", "Engine", "load_library", "make_suffix_array",
-    "forward_burrows_wheeler_transform", "reverse_burrows_wheeler_transform", "textgen", "PHASES",
+    "forward_burrows_wheeler_transform", "reverse_burrows_wheeler_transform", "make_lcp_array", "textgen", "PHASES",
 ]

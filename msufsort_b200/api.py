@@ -21,7 +21,7 @@ PRODUCT_LIB = os.path.join(_HERE, "lib", "libb200sa.so")
 
 PHASES = {
     "alphabet": 0, "pack": 1, "sort_hist": 2, "sort_pass": 3, "build": 4, "rerank": 5,
-    "bwt": 6, "unbwt_build": 7, "unbwt_walk": 8, "check": 9, "segsort": 10, "isa": 11,
+    "bwt": 6, "unbwt_build": 7, "unbwt_walk": 8, "check": 9, "segsort": 10, "isa": 11, "lcp": 12,
 }
 _PH_COUNT = 16
 
@@ -64,6 +64,8 @@ ABI = [
     ("b200sa_bwt_dev", C.c_int, [_P, _P, C.c_int64, _P, _P, C.POINTER(C.c_int32), _P]),
     ("b200sa_unbwt_dev", C.c_int, [_P, _P, C.c_int64, C.c_int32, _P, _P]),
     ("b200sa_check_suffix_array_dev", C.c_int, [_P, _P, C.c_int64, _P, C.POINTER(C.c_int64), _P]),
+    ("b200sa_lcp_dev", C.c_int, [_P, _P, C.c_int64, _P, _P, _P]),
+    ("b200sa_lcp", C.c_int, [_P, _P, C.c_int64, _P, _P, _P]),
     ("b200sa_shard_begin", C.c_int, [_P, _P, C.c_int64, _P, C.c_int, C.c_int, C.POINTER(C.c_int64), _P]),
     ("b200sa_shard_round0", C.c_int, [_P, C.c_int64, C.POINTER(C.c_int64), _P]),
     ("b200sa_shard_round", C.c_int, [_P, C.POINTER(C.c_int64), _P]),
@@ -232,6 +234,26 @@ class Engine:
                                                              _ptr(bwt) if n else None, C.byref(s)))
         return sa, bwt, int(s.value)
 
+    def make_lcp_array(self, data, sa: Optional[np.ndarray] = None, return_sa: bool = False):
+        """LCP array (int32, len(data)+1 entries aligned with the suffix array: lcp[0] = lcp[1] = 0,
+        lcp[r] = lcp(SA[r-1], SA[r])) — the demo's ``make_lcp_array`` (main.cpp:141-159; its output[i] is lcp[i+2]).
+        ``sa`` is the suffix array of ``data``; when omitted it is computed first."""
+        buf = np.ascontiguousarray(np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else data)
+        if buf.dtype.itemsize != 1:
+            raise TypeError("input must be a 1-byte element buffer")
+        n = buf.size
+        lcp = np.empty(n + 1, dtype=np.int32)
+        sa_in = None
+        if sa is not None:
+            sa_in = np.ascontiguousarray(sa, dtype=np.int32)
+            if sa_in.size != n + 1:
+                raise ValueError("suffix array must have len(data)+1 entries")
+        sa_out = np.empty(n + 1, dtype=np.int32) if (return_sa and sa_in is None) else None
+        self.lib.check(self.lib.cdll.b200sa_lcp(self._ctx, _ptr(buf) if n else None, n, _ptr(sa_in), _ptr(sa_out), _ptr(lcp)))
+        if return_sa:
+            return lcp, (sa_in if sa_in is not None else sa_out)
+        return lcp
+
     # ---- raw-pointer variants of the host entry points (pinned buffers in bench.py) ----------
     def suffix_array_ptr(self, text_ptr: int, n: int, sa_ptr: int) -> None:
         self.lib.check(self.lib.cdll.b200sa_suffix_array(self._ctx, text_ptr, n, sa_ptr))
@@ -255,6 +277,9 @@ class Engine:
 
     def unbwt_dev(self, d_bwt, n: int, sentinel_index: int, d_out, stream: Optional[int] = None) -> None:
         self.lib.check(self.lib.cdll.b200sa_unbwt_dev(self._ctx, _ptr(d_bwt), n, int(sentinel_index), _ptr(d_out), self._st(stream)))
+
+    def lcp_dev(self, d_text, n: int, d_sa, d_lcp, stream: Optional[int] = None) -> None:
+        self.lib.check(self.lib.cdll.b200sa_lcp_dev(self._ctx, _ptr(d_text), n, _ptr(d_sa), _ptr(d_lcp), self._st(stream)))
 
     def check_suffix_array_dev(self, d_text, n: int, d_sa, stream: Optional[int] = None) -> int:
         bad = C.c_int64(-1)
@@ -372,3 +397,7 @@ def forward_burrows_wheeler_transform(data, num_threads: int = 1) -> int:
 
 def reverse_burrows_wheeler_transform(data, sentinel_index: int, num_threads: int = 1) -> None:
     _engine().reverse_burrows_wheeler_transform(data, sentinel_index)
+
+
+def make_lcp_array(data, suffix_array=None, num_threads: int = 1) -> np.ndarray:
+    return _engine().make_lcp_array(data, suffix_array)

@@ -243,9 +243,11 @@ int Engine::radix_sort_pairs(u64* keys2[2], u32* vals2[2], bool gen_vals, u32 m,
 
 // ISA update rank[idx[j]] = val[j] for `count` pairs.  Large arrays go through one radix sweep on the
 // top 8 bits of the suffix index so that the scatter proper works inside an L2-resident window.
-int Engine::isa_update(const u32* d_idx, const u32* d_val, u32 count, u32 n, u32* bk_key, u32* bk_val, bool all_suffixes, cudaStream_t st)
+int Engine::isa_update(const u32* d_idx, const u32* d_val, u32 count, u32 n, u32* bk_key, u32* bk_val, bool all_suffixes, cudaStream_t st,
+                       u32* target)
 {
     if (count == 0) return 0;
+    if (!target) target = rank.as<u32>();
     const bool bucketed = ((u64)n * 4 > isa_direct_bytes) && (count >= isa_min_updates) && bk_key && bk_val;
     B200SA_TRY(phase_begin(B200SA_PH_ISA, st));
     if (bucketed) {
@@ -281,12 +283,12 @@ int Engine::isa_update(const u32* d_idx, const u32* d_val, u32 count, u32 n, u32
                       count, shift, 0xffffffffu, (const u32*)ghist, status, counters);
         count_launch(B200SA_PH_ISA);
         B200SA_LAUNCH(k_scatter_pairs, (u32)div_up_u64(count, SP_THREADS * SP_IPT), SP_THREADS, 0, st, (const u32*)bk_key,
-                      (const u32*)bk_val, count, rank.as<u32>());
+                      (const u32*)bk_val, count, target);
         count_launch(B200SA_PH_ISA);
         prof.alg_bytes[B200SA_PH_ISA] += (u64)count * (4 + 8 + 8 + 8 + 4);
     } else {
         B200SA_LAUNCH(k_scatter_pairs, (u32)div_up_u64(count, SP_THREADS * SP_IPT), SP_THREADS, 0, st, d_idx, d_val, count,
-                      rank.as<u32>());
+                      target);
         count_launch(B200SA_PH_ISA);
         prof.alg_bytes[B200SA_PH_ISA] += (u64)count * 12;
     }
@@ -812,6 +814,79 @@ int Engine::check_sa_dev(const u8* d_text, i64 n64, const i32* d_sa, i64* bad_ro
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------------
+// LCP array (lcp_kernels.cuh): phi scatter, hierarchical PLCP levels, gather through the SA
+
+int Engine::lcp_dev(const u8* d_text, i64 n64, const i32* d_sa, i32* d_lcp, cudaStream_t st)
+{
+    if (n64 < 0 || n64 > B200SA_MAX_N_INT32) return set_error(B200SA_EINVAL, "n = %lld outside [0, 2^31-2]", (long long)n64);
+    if (!d_sa || !d_lcp || (n64 > 0 && !d_text)) return set_error(B200SA_EINVAL, "null pointer");
+    B200SA_CU(cudaSetDevice(device));
+    const u32 n = (u32)n64;
+    if (n == 0) {
+        B200SA_CU(cudaMemsetAsync(d_lcp, 0, sizeof(i32), st));
+        B200SA_CU(cudaStreamSynchronize(st));
+        return 0;
+    }
+    // workspace: phi -> gid, plcp -> slot[0], overflow list -> slot[1], bucketed scatter scratch -> agg_max / keys[0]
+    B200SA_TRY(gid.ensure((size_t)n * 4 + 64));
+    B200SA_TRY(slot[0].ensure((size_t)n * 4 + 64));
+    B200SA_TRY(slot[1].ensure(((size_t)n / 2 + 1024 + 2) * 8 + 64));
+    B200SA_TRY(agg_max.ensure((size_t)n * 4 + 64));
+    B200SA_TRY(keys[0].ensure((size_t)n * 4 + 64));
+    B200SA_TRY(misc.ensure(4096));
+    u32* phi = gid.as<u32>();
+    u32* plcp = slot[0].as<u32>();
+    const size_t ovf_cap = (size_t)n / 2 + 1024 + 2;
+    u32* ovf_pos = slot[1].as<u32>();
+    u32* ovf_len = slot[1].as<u32>() + ovf_cap;
+    u32* d_cnt = misc.as<u32>() + 960;  // one overflow counter per level (<= 33 levels)
+    B200SA_CU(cudaMemsetAsync(d_cnt, 0, 40 * sizeof(u32), st));
+    prof.memsets++;
+
+    // ---- phi[SA[r]] = SA[r-1]: the pairs are two shifted views of the suffix array itself
+    B200SA_TRY(isa_update((const u32*)d_sa + 1, (const u32*)d_sa, n, n, agg_max.as<u32>(), keys[0].as<u32>(), true, st, phi));
+
+    // ---- PLCP, coarse to fine
+    B200SA_TRY(phase_begin(B200SA_PH_LCP, st));
+    u64 top = 1;
+    while (div_up_u64(n, top) > 1024) top <<= 1;
+    int level = 0;
+    auto run_level = [&](u32 first, u64 step, u32 back, u32 ns) -> int {
+        if (ns == 0) return 0;
+        const u32 want = (u32)div_up_u64(ns, LC_THREADS);
+        const u32 grid = want < (u32)(num_sms * 8) ? want : (u32)(num_sms * 8);
+        B200SA_LAUNCH(k_plcp_level, grid, LC_THREADS, 0, st, d_text, n, (const u32*)phi, plcp, first, (u32)step, back, ns, ovf_pos, ovf_len,
+                      d_cnt + level);
+        count_launch(B200SA_PH_LCP);
+        B200SA_LAUNCH(k_plcp_overflow, (u32)(num_sms * 4), LC_THREADS, 0, st, d_text, n, (const u32*)phi, plcp, (const u32*)ovf_pos,
+                      (const u32*)ovf_len, (const u32*)(d_cnt + level));
+        count_launch(B200SA_PH_LCP);
+        ++level;
+        return 0;
+    };
+    B200SA_TRY(run_level(0, top, 0, (u32)div_up_u64(n, top)));
+    for (u64 S = top >> 1; S >= 1; S >>= 1) {
+        const u32 ns = (u64)n > S ? (u32)(((u64)n - S - 1) / (2 * S) + 1) : 0u;
+        B200SA_TRY(run_level((u32)S, 2 * S, (u32)S, ns));
+    }
+    // ---- lcp[r] = plcp[SA[r]]
+    {
+        const u64 quads = div_up_u64((u64)n + 1, 4);
+        const u32 want = (u32)div_up_u64(quads, 256);
+        const u32 grid = want < (u32)(num_sms * 16) ? (want ? want : 1u) : (u32)(num_sms * 16);
+        B200SA_LAUNCH(k_lcp_gather, grid, 256, 0, st, d_sa, n, (const u32*)plcp, d_lcp);
+        count_launch(B200SA_PH_LCP);
+    }
+    B200SA_TRY(phase_end(st));
+    // phi read + plcp write + text probes (one sector-sized access per position, counted as 8 bytes) + SA/plcp/lcp of the gather
+    prof.alg_bytes[B200SA_PH_LCP] += (u64)n * (4 + 4 + 8 + 4 + 4 + 4);
+    B200SA_CU(cudaGetLastError());
+    B200SA_CU(cudaStreamSynchronize(st));
+    if (profiling) B200SA_TRY(collect_profile());
+    return 0;
+}
+
 }  // namespace b200sa
 
 // =============================================================================================
@@ -892,6 +967,12 @@ int b200sa_check_suffix_array_dev(b200sa_ctx* ctx, const uint8_t* d_text, int64_
     return ctx->eng.check_sa_dev(d_text, n, d_sa, bad_rows_out, ctx->eng.pick(stream));
 }
 
+int b200sa_lcp_dev(b200sa_ctx* ctx, const uint8_t* d_text, int64_t n, const int32_t* d_sa, int32_t* d_lcp_out, void* stream)
+{
+    B200SA_NEED_CTX(ctx);
+    return ctx->eng.lcp_dev(d_text, n, d_sa, d_lcp_out, ctx->eng.pick(stream));
+}
+
 // ---- host-buffer entry points ----------------------------------------------------------------
 
 int b200sa_suffix_array_bwt(b200sa_ctx* ctx, const uint8_t* text, int64_t n, int32_t* sa_out, uint8_t* bwt_out,
@@ -953,6 +1034,32 @@ int b200sa_unbwt(b200sa_ctx* ctx, uint8_t* bwt_inout, int64_t n, int32_t sentine
     B200SA_CU(cudaMemcpyAsync(e.bwt_ws.p, bwt_inout, (size_t)n, cudaMemcpyHostToDevice, st));
     B200SA_TRY(e.unbwt_dev(e.bwt_ws.as<u8>(), n, sentinel_index, e.text_ws.as<u8>(), st));
     B200SA_CU(cudaMemcpyAsync(bwt_inout, e.text_ws.p, (size_t)n, cudaMemcpyDeviceToHost, st));
+    B200SA_CU(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int b200sa_lcp(b200sa_ctx* ctx, const uint8_t* text, int64_t n, const int32_t* sa, int32_t* sa_out, int32_t* lcp_out)
+{
+    B200SA_NEED_CTX(ctx);
+    Engine& e = ctx->eng;
+    if (n < 0 || n > B200SA_MAX_N_INT32) return b200sa::set_error(B200SA_EINVAL, "n = %lld outside [0, 2^31-2]", (long long)n);
+    if (!lcp_out || (n > 0 && !text)) return b200sa::set_error(B200SA_EINVAL, "null pointer");
+    if (n == 0) {
+        lcp_out[0] = 0;
+        if (sa_out) sa_out[0] = 0;
+        return 0;
+    }
+    B200SA_CU(cudaSetDevice(e.device));
+    cudaStream_t st = e.own_stream;
+    B200SA_TRY(e.text_ws.ensure((size_t)n));
+    B200SA_TRY(e.sa_ws.ensure(((size_t)n + 1) * 4));
+    B200SA_TRY(e.keys[1].ensure(((size_t)n + 1) * 4 + 64));  // LCP staging: keys[1] is not used by lcp_dev
+    B200SA_CU(cudaMemcpyAsync(e.text_ws.p, text, (size_t)n, cudaMemcpyHostToDevice, st));
+    if (sa) B200SA_CU(cudaMemcpyAsync(e.sa_ws.p, sa, ((size_t)n + 1) * 4, cudaMemcpyHostToDevice, st));
+    else B200SA_TRY(e.suffix_array_dev(e.text_ws.as<u8>(), n, e.sa_ws.as<i32>(), st));
+    if (sa_out) B200SA_CU(cudaMemcpyAsync(sa_out, e.sa_ws.p, ((size_t)n + 1) * 4, cudaMemcpyDeviceToHost, st));
+    B200SA_TRY(e.lcp_dev(e.text_ws.as<u8>(), n, e.sa_ws.as<i32>(), e.keys[1].as<i32>(), st));
+    B200SA_CU(cudaMemcpyAsync(lcp_out, e.keys[1].p, ((size_t)n + 1) * 4, cudaMemcpyDeviceToHost, st));
     B200SA_CU(cudaStreamSynchronize(st));
     return 0;
 }

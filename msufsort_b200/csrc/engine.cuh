@@ -7,6 +7,7 @@
 #include "radix_sort.cuh"
 #include "sa_kernels.cuh"
 #include "bwt_kernels.cuh"
+#include "lcp_kernels.cuh"
 #include "../../include/b200sa.h"
 
 #include <string>
@@ -100,7 +101,9 @@ struct Engine {
     // building blocks
     int radix_sort_pairs(u64* keys2[2], u32* vals2[2], bool gen_vals, u32 m, int begin_bit, int end_bit,
                          int* result_side, cudaStream_t st);
-    int isa_update(const u32* d_idx, const u32* d_val, u32 count, u32 n, u32* bk_key, u32* bk_val, bool all_suffixes, cudaStream_t st);
+    // target == nullptr: the engine's rank[] (ISA); the LCP path scatters phi[] with the same machinery
+    int isa_update(const u32* d_idx, const u32* d_val, u32 count, u32 n, u32* bk_key, u32* bk_val, bool all_suffixes, cudaStream_t st,
+                   u32* target = nullptr);
     int rerank(const u64* keys_sorted, const u32* idx_sorted, const u32* slot_in, u32 slot_base, u32 m, u32 n, i32* d_sa,
                u32* idx_out, u32* slot_out, u64* free_keys, int mode, u32* next_m, u32* next_groups, cudaStream_t st);
 
@@ -134,6 +137,7 @@ struct Engine {
     int unbwt_finish(u32 w_begin, u32 w_end, u8* d_out, cudaStream_t st);
     int unbwt_dev(const u8* d_bwt, i64 n, i32 sentinel, u8* d_out, cudaStream_t st);
     int check_sa_dev(const u8* d_text, i64 n, const i32* d_sa, i64* bad_rows, cudaStream_t st);
+    int lcp_dev(const u8* d_text, i64 n, const i32* d_sa, i32* d_lcp, cudaStream_t st);
 };
 
 }  // namespace b200sa

@@ -295,6 +295,66 @@ int64_t oracle_check_suffix_array(const uint8_t* text, int64_t n, const int32_t*
     return bad;
 }
 
+/* ---------------------------------------------------------------------------------------------
+ * LCP array.  Two restatements:
+ *  (1) oracle_make_lcp_array: the reference demo's construction (main.cpp:16-64): match_length()
+ *      compares from a known common-prefix length; lcp() halves a range of the suffix array, using
+ *      the match length of its two end points as the starting length for the left half.
+ *  (2) oracle_lcp_kasai: Kasai et al.'s linear-time algorithm (different family, cross-check).
+ * Output convention of this repository (include/b200sa.h): n+1 entries aligned with the SA,
+ * lcp[0] = lcp[1] = 0, lcp[r] = lcp(SA[r-1], SA[r]).  The reference's output[i] is lcp[i+2]. */
+static int32_t match_length_(const uint8_t* t, int64_t n, int32_t a, int32_t b, int32_t len)
+{
+    if (a > b) { int32_t x = a; a = b; b = x; }
+    while ((int64_t)b + len < n && t[a + len] == t[b + len]) ++len;  /* main.cpp:27-37, byte-wise */
+    return len;
+}
+
+static void lcp_range_(const uint8_t* t, int64_t n, const int32_t* sa, int32_t* out, int64_t lo, int64_t size, int32_t cur)
+{
+    /* out[lo+i] = lcp(sa[lo+i], sa[lo+i+1]) for i < size, every pair shares at least `cur` bytes (main.cpp:42-64) */
+    while (size > 4) {
+        const int64_t mid = size / 2;
+        const int32_t next = match_length_(t, n, sa[lo], sa[lo + mid], cur);
+        lcp_range_(t, n, sa, out, lo, mid, next);
+        lo += mid;
+        size -= mid;
+    }
+    for (int64_t i = 0; i < size; ++i) out[lo + i] = match_length_(t, n, sa[lo + i], sa[lo + i + 1], cur);
+}
+
+int oracle_make_lcp_array(const uint8_t* text, int64_t n, const int32_t* sa, int32_t* lcp_out)
+{
+    if (n < 0 || !sa || !lcp_out) return -1;
+    lcp_out[0] = 0;
+    if (n >= 1) lcp_out[1] = 0;
+    if (n >= 2) {
+        /* rows 1..n hold real suffixes; pair (r, r+1) goes to lcp_out[r+1]: shift the output by one */
+        lcp_range_(text, n, sa + 1, lcp_out + 2, 0, n - 1, 0);
+    }
+    return 0;
+}
+
+int oracle_lcp_kasai(const uint8_t* text, int64_t n, const int32_t* sa, int32_t* lcp_out)
+{
+    if (n < 0 || !sa || !lcp_out) return -1;
+    int32_t* isa = (int32_t*)malloc(((size_t)n + 1) * sizeof(int32_t));
+    if (!isa) return -1;
+    for (int64_t r = 0; r <= n; ++r) isa[sa[r]] = (int32_t)r;
+    lcp_out[0] = 0;
+    int64_t l = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        const int64_t r = isa[i];          /* r >= 1: row 0 is the empty suffix */
+        const int64_t j = sa[r - 1];
+        if (j == n) l = 0;
+        else while (i + l < n && j + l < n && text[i + l] == text[j + l]) ++l;
+        lcp_out[r] = (int32_t)l;
+        if (l > 0) --l;
+    }
+    free(isa);
+    return 0;
+}
+
 uint64_t oracle_fnv1a64(const void* data, int64_t nbytes)
 {
     const uint8_t* p = (const uint8_t*)data;

@@ -42,6 +42,12 @@ int oracle_reverse_bwt(uint8_t* bwt_inout, int64_t n, int32_t sentinel_index);
  * number of offending rows (0 = correct), or -1 on allocation failure. */
 int64_t oracle_check_suffix_array(const uint8_t* text, int64_t n, const int32_t* sa);
 
+/* LCP array, n+1 entries aligned with the SA: lcp[0] = lcp[1] = 0, lcp[r] = lcp(SA[r-1], SA[r]).
+ * oracle_make_lcp_array restates the reference demo (main.cpp:16-64; its output[i] = lcp[i+2]);
+ * oracle_lcp_kasai is an independent linear-time cross-check.  Return 0 / -1. */
+int oracle_make_lcp_array(const uint8_t* text, int64_t n, const int32_t* sa, int32_t* lcp_out);
+int oracle_lcp_kasai(const uint8_t* text, int64_t n, const int32_t* sa, int32_t* lcp_out);
+
 /* FNV-1a-64 (h=0xcbf29ce484222325; h^=b; h*=0x100000001b3) over raw bytes. */
 uint64_t oracle_fnv1a64(const void* data, int64_t nbytes);
 

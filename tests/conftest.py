@@ -45,6 +45,8 @@ class Oracle:
         self.lib.oracle_reverse_bwt.argtypes = [P, I64, I32]
         self.lib.oracle_check_suffix_array.argtypes = [P, I64, P]
         self.lib.oracle_check_suffix_array.restype = I64
+        self.lib.oracle_make_lcp_array.argtypes = [P, I64, P, P]
+        self.lib.oracle_lcp_kasai.argtypes = [P, I64, P, P]
         self.lib.oracle_fnv1a64.argtypes = [P, I64]
         self.lib.oracle_fnv1a64.restype = C.c_uint64
         ref_path = os.path.join(ROOT, "oracle", "_ref", "libmsufsort_ref.so")
@@ -55,6 +57,7 @@ class Oracle:
             self.ref.ref_forward_bwt.argtypes = [P, I64, I32]
             self.ref.ref_forward_bwt.restype = I32
             self.ref.ref_reverse_bwt.argtypes = [P, I64, I32, I32]
+            self.ref.ref_lcp.argtypes = [P, I64, P, P, I32]
 
     # --- restatement
     def sa(self, text: np.ndarray) -> np.ndarray:
@@ -92,6 +95,15 @@ class Oracle:
         sa = np.ascontiguousarray(sa, dtype=np.int32)
         return int(self.lib.oracle_check_suffix_array(text.ctypes.data, text.size, sa.ctypes.data))
 
+    def lcp(self, text: np.ndarray, sa: np.ndarray, kasai: bool = False) -> np.ndarray:
+        """n+1 entries aligned with the SA (lcp[0] = lcp[1] = 0); the reference demo's recursion or Kasai"""
+        text = np.ascontiguousarray(text, dtype=np.uint8)
+        sa = np.ascontiguousarray(sa, dtype=np.int32)
+        out = np.empty(text.size + 1, dtype=np.int32)
+        fn = self.lib.oracle_lcp_kasai if kasai else self.lib.oracle_make_lcp_array
+        assert fn(text.ctypes.data, text.size, sa.ctypes.data, out.ctypes.data) == 0
+        return out
+
     def fnv(self, arr: np.ndarray) -> int:
         a = np.ascontiguousarray(arr)
         return int(self.lib.oracle_fnv1a64(a.ctypes.data, a.nbytes))
@@ -107,6 +119,17 @@ class Oracle:
         buf = np.array(text, dtype=np.uint8, copy=True)
         s = self.ref.ref_forward_bwt(buf.ctypes.data, buf.size, threads)
         return buf, int(s)
+
+    def ref_lcp(self, text: np.ndarray, sa: np.ndarray, threads: int = 1) -> np.ndarray:
+        """the reference demo's lcp_multithreaded, mapped to this repository's convention (n+1 entries)"""
+        text = np.ascontiguousarray(text, dtype=np.uint8)
+        sa = np.ascontiguousarray(sa, dtype=np.int32)
+        out = np.zeros(text.size + 1, dtype=np.int32)
+        if text.size >= 2:
+            tail = np.empty(text.size - 1, dtype=np.int32)
+            assert self.ref.ref_lcp(text.ctypes.data, text.size, sa.ctypes.data, tail.ctypes.data, threads) == 0
+            out[2:] = tail
+        return out
 
     def ref_unbwt(self, bwt: np.ndarray, sentinel: int, threads: int = 1) -> np.ndarray:
         buf = np.array(bwt, dtype=np.uint8, copy=True)

@@ -1,0 +1,130 @@
+"""LCP array: oracle pinned against the reference demo's own LCP code, kernel logic
+under the emulator (CPU tier) and bit-exact parity on the GPU through the C ABI (GPU tier)."""
+import os
+
+import numpy as np
+import pytest
+
+from cases import EDGE_SIZES, FAMILIES, gen
+
+LCP_FAMILIES = ["rand", "markov3", "acgt_rep", "periodic7", "periodic1009", "fib", "zeros", "abcabca", "sigma2", "zero_tail"]
+
+
+# ---- oracle -----------------------------------------------------------------------------------
+@pytest.mark.parametrize("family", FAMILIES)
+def test_oracle_lcp_pinned_to_reference_demo(ref, family):
+    """restated recursion == Kasai == the unmodified main.cpp:16-105 compiled into oracle/_ref"""
+    for n in [1, 2, 3, 5, 17, 257, 4097, 30011]:
+        x = gen(family, n)
+        sa = ref.sa(x)
+        a = ref.lcp(x, sa)
+        assert np.array_equal(a, ref.lcp(x, sa, kasai=True)), (family, n)
+        assert np.array_equal(a, ref.ref_lcp(x, sa)), (family, n)
+        if n >= 4:
+            assert np.array_equal(a, ref.ref_lcp(x, sa, threads=3)), (family, n)
+
+
+def test_oracle_lcp_bruteforce_small(oracle):
+    rng = np.random.default_rng(5)
+    for n in range(1, 40):
+        x = rng.integers(0, 3, size=n, dtype=np.uint8)
+        sa = oracle.sa(x)
+        lcp = oracle.lcp(x, sa)
+        assert lcp[0] == 0 and lcp[1] == 0
+        for r in range(2, n + 1):
+            a, b = bytes(x[sa[r - 1]:]), bytes(x[sa[r]:])
+            l = 0
+            while l < min(len(a), len(b)) and a[l] == b[l]:
+                l += 1
+            assert lcp[r] == l
+
+
+# ---- emulator ---------------------------------------------------------------------------------
+@pytest.mark.parametrize("family", LCP_FAMILIES)
+def test_emu_lcp(emu_engine, oracle, family):
+    for n in EDGE_SIZES + [20011]:
+        x = gen(family, n)
+        sa = oracle.sa(x)
+        assert np.array_equal(emu_engine.make_lcp_array(x, sa), oracle.lcp(x, sa, kasai=True)), (family, n)
+
+
+def test_emu_lcp_long_matches_and_unaligned_text(emu_engine, oracle):
+    """matches far beyond the per-thread budget (CTA compare), text pointer at every alignment mod 4"""
+    for family, n in [("zeros", 70001), ("periodic7", 40000), ("fib", 46368), ("abcabca", 33333)]:
+        buf = gen(family, n + 3)
+        for shift in range(4):
+            x = buf[shift:shift + n]
+            sa = oracle.sa(x)
+            lcp, sa2 = emu_engine.make_lcp_array(x, return_sa=True)
+            assert np.array_equal(sa2, sa)
+            assert np.array_equal(lcp, oracle.lcp(x, sa, kasai=True)), (family, shift)
+            # device-pointer entry point straight on the (unaligned) view
+            out = np.empty(n + 1, dtype=np.int32)
+            emu_engine.lcp_dev(x, n, sa, out)
+            assert np.array_equal(out, lcp), (family, shift)
+
+
+def test_emu_lcp_bucketed_phi(oracle, monkeypatch):
+    from conftest import ROOT
+    from msufsort_b200.api import Engine, Library
+    monkeypatch.setenv("B200SA_ISA_DIRECT_BYTES", "0")
+    monkeypatch.setenv("B200SA_ISA_MIN_UPDATES", "1")
+    eng = Engine(0, library=Library(os.path.join(ROOT, "tests", "emu", "libb200sa_emu.so")))
+    try:
+        for family, n in [("markov3", 30011), ("acgt_rep", 9000), ("zeros", 5000), ("rand", 1)]:
+            x = gen(family, n)
+            sa = oracle.sa(x)
+            assert np.array_equal(eng.make_lcp_array(x, sa), oracle.lcp(x, sa, kasai=True)), (family, n)
+    finally:
+        eng.close()
+
+
+def test_emu_lcp_empty_and_errors(emu_engine):
+    from msufsort_b200.api import B200SAError
+    assert emu_engine.make_lcp_array(np.empty(0, dtype=np.uint8)).tolist() == [0]
+    with pytest.raises(ValueError):
+        emu_engine.make_lcp_array(np.zeros(4, dtype=np.uint8), np.zeros(3, dtype=np.int32))
+    with pytest.raises(B200SAError):
+        emu_engine.lcp_dev(None, 5, None, None)
+
+
+# ---- GPU --------------------------------------------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("family", FAMILIES)
+def test_gpu_lcp_parity(gpu_engine, oracle, family):
+    for n in EDGE_SIZES + [65536, 1 << 20]:
+        x = gen(family, n)
+        lcp, sa = gpu_engine.make_lcp_array(x, return_sa=True)
+        want_sa = oracle.sa(x)
+        assert np.array_equal(sa, want_sa), (family, n)
+        assert np.array_equal(lcp, oracle.lcp(x, want_sa, kasai=True)), (family, n)
+
+
+@pytest.mark.gpu
+def test_gpu_lcp_16MiB_device_resident(gpu_engine, oracle):
+    """device-resident entry point at 16 MiB (above the direct-scatter threshold: bucketed phi), unaligned text"""
+    import torch
+    n = 1 << 24
+    for family in ["markov3", "acgt_rep"]:
+        buf = gen(family, n + 1)
+        x = buf[1:]
+        d_buf = torch.from_numpy(buf).cuda()
+        d_text = d_buf[1:]
+        d_sa = torch.empty(n + 1, dtype=torch.int32, device="cuda")
+        d_lcp = torch.empty(n + 1, dtype=torch.int32, device="cuda")
+        gpu_engine.suffix_array_dev(d_text, n, d_sa)
+        gpu_engine.lcp_dev(d_text, n, d_sa, d_lcp)
+        torch.cuda.synchronize()
+        sa = d_sa.cpu().numpy()
+        want_sa = oracle.sa(x)
+        assert np.array_equal(sa, want_sa)
+        assert np.array_equal(d_lcp.cpu().numpy(), oracle.lcp(x, want_sa, kasai=True)), family
+
+
+@pytest.mark.gpu
+def test_gpu_lcp_deep_repeats(gpu_engine, oracle):
+    """lcp ~ n inputs: the CTA-wide compare keeps these at a few streaming passes"""
+    for family, n in [("zeros", 1 << 22), ("fib", 1 << 22), ("periodic1009", 1 << 23), ("abcabca", 1 << 22)]:
+        x = gen(family, n)
+        lcp, sa = gpu_engine.make_lcp_array(x, return_sa=True)
+        assert np.array_equal(lcp, oracle.lcp(x, sa, kasai=True)), family

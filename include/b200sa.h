@@ -136,6 +136,31 @@ B200SA_API int b200sa_lcp_dev(b200sa_ctx* ctx, const uint8_t* d_text, int64_t n,
 B200SA_API int b200sa_lcp(b200sa_ctx* ctx, const uint8_t* text, int64_t n, const int32_t* sa,
                           int32_t* sa_out, int32_t* lcp_out);
 
+/* ---- batches of independent blocks (north_star "batches of independent blocks") ----
+ *
+ * The reference transforms a batch by calling forward_/reverse_burrows_wheeler_transform once per block
+ * (msufsort.h:63-75; the demo's round trip main.cpp:466-487).  Here `count` blocks are handed over packed back
+ * to back: block b is bytes [offsets[b], offsets[b+1]) of `blocks`, offsets[0] = 0, empty blocks allowed,
+ * offsets[count] + count <= 2^31-2.  All blocks are suffix-sorted TOGETHER by one launch sequence (block
+ * number as the most significant key part, one separator slot per block), so thousands of small blocks cost
+ * the same as one text of their total size; results are bit-identical to per-block calls.
+ *   - suffix arrays: sa_out has offsets[count] + count entries; block b's n_b+1 entries (SA_b[0] = n_b)
+ *     start at offsets[b] + b, values are block-local;
+ *   - BWT: in place, packed like the input; sentinel_index_out[b] in [1, n_b] (0 for an empty block);
+ *   - inverse: in place from (BWT bytes, sentinel indices); the blocks share one upload and one download
+ *     and are decoded one after the other on the device.                                               */
+B200SA_API int b200sa_suffix_array_batch(b200sa_ctx* ctx, const uint8_t* blocks, const int64_t* offsets, int64_t count,
+                                         int32_t* sa_out);
+B200SA_API int b200sa_bwt_batch(b200sa_ctx* ctx, uint8_t* blocks_inout, const int64_t* offsets, int64_t count,
+                                int32_t* sentinel_index_out);
+B200SA_API int b200sa_unbwt_batch(b200sa_ctx* ctx, uint8_t* blocks_inout, const int64_t* offsets, int64_t count,
+                                  const int32_t* sentinel_index);
+/* Device-resident form: d_blocks packed as above (device), offsets and sentinel_index_out in host memory.
+ * d_bwt_out (offsets[count] bytes, must not alias d_blocks), d_sa_out (offsets[count] + count int32) and
+ * sentinel_index_out may each be NULL. */
+B200SA_API int b200sa_batch_dev(b200sa_ctx* ctx, const uint8_t* d_blocks, const int64_t* offsets, int64_t count,
+                                uint8_t* d_bwt_out, int32_t* d_sa_out, int32_t* sentinel_index_out, void* stream);
+
 /* ---- sharded (multi-GPU) building blocks --------------------------------------------------
  *
  * One text, G GPUs, one process and one context per GPU (msufsort_b200/sharded.py drives these over

@@ -66,6 +66,10 @@ ABI = [
     ("b200sa_check_suffix_array_dev", C.c_int, [_P, _P, C.c_int64, _P, C.POINTER(C.c_int64), _P]),
     ("b200sa_lcp_dev", C.c_int, [_P, _P, C.c_int64, _P, _P, _P]),
     ("b200sa_lcp", C.c_int, [_P, _P, C.c_int64, _P, _P, _P]),
+    ("b200sa_suffix_array_batch", C.c_int, [_P, _P, _P, C.c_int64, _P]),
+    ("b200sa_bwt_batch", C.c_int, [_P, _P, _P, C.c_int64, _P]),
+    ("b200sa_unbwt_batch", C.c_int, [_P, _P, _P, C.c_int64, _P]),
+    ("b200sa_batch_dev", C.c_int, [_P, _P, _P, C.c_int64, _P, _P, _P, _P]),
     ("b200sa_shard_begin", C.c_int, [_P, _P, C.c_int64, _P, C.c_int, C.c_int, C.POINTER(C.c_int64), _P]),
     ("b200sa_shard_round0", C.c_int, [_P, C.c_int64, C.POINTER(C.c_int64), _P]),
     ("b200sa_shard_round", C.c_int, [_P, C.POINTER(C.c_int64), _P]),
@@ -253,6 +257,54 @@ class Engine:
         if return_sa:
             return lcp, (sa_in if sa_in is not None else sa_out)
         return lcp
+
+    # ---- batches of independent blocks (one launch sequence for all of them) ------------------
+    @staticmethod
+    def _pack_blocks(blocks):
+        arrs = [np.ascontiguousarray(np.frombuffer(b, dtype=np.uint8) if not isinstance(b, np.ndarray) else b).view(np.uint8).ravel()
+                for b in blocks]
+        offsets = np.zeros(len(arrs) + 1, dtype=np.int64)
+        if arrs:
+            np.cumsum([a.size for a in arrs], out=offsets[1:])
+        packed = np.concatenate(arrs) if arrs else np.empty(0, dtype=np.uint8)
+        return np.ascontiguousarray(packed), offsets
+
+    def suffix_array_batch(self, blocks) -> list:
+        """Suffix arrays of independent blocks: a list of int32 arrays, block b's has len(block)+1 entries."""
+        packed, offsets = self._pack_blocks(blocks)
+        count = len(offsets) - 1
+        sa = np.empty(int(offsets[-1]) + count, dtype=np.int32)
+        self.lib.check(self.lib.cdll.b200sa_suffix_array_batch(self._ctx, _ptr(packed) if packed.size else None, _ptr(offsets), count, _ptr(sa)))
+        return [sa[int(offsets[b]) + b: int(offsets[b + 1]) + b + 1] for b in range(count)]
+
+    def bwt_batch(self, blocks):
+        """Forward BWT of independent blocks: (list of uint8 arrays, list of sentinel indices)."""
+        packed, offsets = self._pack_blocks(blocks)
+        count = len(offsets) - 1
+        sent = np.zeros(max(count, 1), dtype=np.int32)
+        packed = packed.copy()
+        self.lib.check(self.lib.cdll.b200sa_bwt_batch(self._ctx, _ptr(packed) if packed.size else None, _ptr(offsets), count, _ptr(sent)))
+        return [packed[int(offsets[b]): int(offsets[b + 1])] for b in range(count)], [int(v) for v in sent[:count]]
+
+    def unbwt_batch(self, blocks, sentinel_indices) -> list:
+        """Inverse BWT of independent blocks."""
+        packed, offsets = self._pack_blocks(blocks)
+        count = len(offsets) - 1
+        sent = np.ascontiguousarray(np.asarray(list(sentinel_indices) + [0], dtype=np.int32))
+        if sent.size != count + 1:
+            raise ValueError("one sentinel index per block")
+        packed = packed.copy()
+        self.lib.check(self.lib.cdll.b200sa_unbwt_batch(self._ctx, _ptr(packed) if packed.size else None, _ptr(offsets), count, _ptr(sent)))
+        return [packed[int(offsets[b]): int(offsets[b + 1])] for b in range(count)]
+
+    def batch_dev(self, d_blocks, offsets: np.ndarray, d_bwt=None, d_sa=None, stream: Optional[int] = None) -> np.ndarray:
+        """Device-resident batch: returns the sentinel indices (host int32 array)."""
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        count = offsets.size - 1
+        sent = np.zeros(max(count, 1), dtype=np.int32)
+        self.lib.check(self.lib.cdll.b200sa_batch_dev(self._ctx, _ptr(d_blocks), _ptr(offsets), count, _ptr(d_bwt), _ptr(d_sa), _ptr(sent),
+                                                      self._st(stream)))
+        return sent[:count]
 
     # ---- raw-pointer variants of the host entry points (pinned buffers in bench.py) ----------
     def suffix_array_ptr(self, text_ptr: int, n: int, sa_ptr: int) -> None:

@@ -53,7 +53,7 @@ void DevBuf::release()
 // ---------------------------------------------------------------------------------------------
 // alphabet plan: dense symbol codes; as many symbols as fit next to the clamped-length field
 
-AlphabetPlan plan_alphabet(const u32* hist)
+AlphabetPlan plan_alphabet(const u32* hist, int reserved_bits)
 {
     AlphabetPlan a;
     int sigma = 0;
@@ -69,7 +69,7 @@ AlphabetPlan plan_alphabet(const u32* hist)
     a.bits = bits;
     int k = 1;
     for (int cand = 1; cand <= 58; ++cand)
-        if (cand * bits + bit_length_u64((u64)cand) <= 64) k = cand;
+        if (cand * bits + bit_length_u64((u64)cand) <= 64 - reserved_bits) k = cand;
     a.k = k;
     a.len_bits = bit_length_u64((u64)k);
     return a;
@@ -123,6 +123,7 @@ int Engine::release_workspace()
     for (int i = 0; i < 2; ++i) { keys[i].release(); idx[i].release(); slot[i].release(); }
     gid.release(); gstart.release(); glist.release(); rank.release(); sa_ws.release(); sortmeta.release(); agg_cnt.release(); agg_max.release();
     misc.release(); text_ws.release(); bwt_ws.release(); walk.release();
+    batch_text.release(); batch_meta.release(); batch_out.release();
     return 0;
 }
 
@@ -364,6 +365,13 @@ int Engine::sort_begin(const u8* d_text, u32 n, i32* d_sa, int part, int nparts,
     B200SA_TRY(ensure_sa_workspace(n));
     ss = SortState();
     ss.d_text = d_text; ss.n = n; ss.d_sa = d_sa; ss.part = part; ss.nparts = nparts;
+    if (next_batch.count) {
+        if (nparts != 1) return set_error(B200SA_EINVAL, "a batched sort cannot be sharded");
+        ss.batch_ends = next_batch.d_ends;
+        ss.batch_count = next_batch.count;
+        ss.batch_bits = bit_length_u64((u64)next_batch.count - 1);
+        next_batch = BatchDesc();
+    }
     u32* d_hist = misc.as<u32>();
     u8* d_code = (u8*)(misc.as<u32>() + 256);
 
@@ -382,7 +390,8 @@ int Engine::sort_begin(const u8* d_text, u32 n, i32* d_sa, int part, int nparts,
     u32 h_hist[256];
     B200SA_CU(cudaMemcpyAsync(h_hist, d_hist, sizeof(h_hist), cudaMemcpyDeviceToHost, st));
     B200SA_CU(cudaStreamSynchronize(st));
-    ss.plan = plan_alphabet(h_hist);
+    if (ss.batch_count) h_hist[0] -= ss.batch_count;  // the separator slots of a batch are not symbols
+    ss.plan = plan_alphabet(h_hist, ss.batch_bits);
     const AlphabetPlan& plan = ss.plan;
     B200SA_CU(cudaMemcpyAsync(d_code, plan.code, 256, cudaMemcpyHostToDevice, st));
 
@@ -393,8 +402,12 @@ int Engine::sort_begin(const u8* d_text, u32 n, i32* d_sa, int part, int nparts,
     {
         const u32 tiles = (u32)div_up_u64(n, PK_TILE);
         const u32 grid = tiles < (u32)(num_sms * 4) ? tiles : (u32)(num_sms * 4);
-        B200SA_LAUNCH(k_pack_keys, grid, PK_THREADS, 0, st, d_text, n, (const u8*)d_code, plan.bits, plan.k, plan.len_bits,
-                      keys[0].as<u64>());
+        if (ss.batch_count)
+            B200SA_LAUNCH(k_pack_keys_batch, grid, PK_THREADS, 0, st, d_text, n, (const u8*)d_code, plan.bits, plan.k, plan.len_bits,
+                          ss.batch_ends, ss.batch_count, keys[0].as<u64>());
+        else
+            B200SA_LAUNCH(k_pack_keys, grid, PK_THREADS, 0, st, d_text, n, (const u8*)d_code, plan.bits, plan.k, plan.len_bits,
+                          keys[0].as<u64>());
         count_launch(B200SA_PH_PACK);
     }
     B200SA_TRY(phase_end(st));
@@ -403,7 +416,7 @@ int Engine::sort_begin(const u8* d_text, u32 n, i32* d_sa, int part, int nparts,
 
     u64* k2[2] = {keys[0].as<u64>(), keys[1].as<u64>()};
     u32* v2[2] = {idx[0].as<u32>(), idx[1].as<u32>()};
-    const int key_bits = plan.bits * plan.k + plan.len_bits;
+    const int key_bits = plan.bits * plan.k + plan.len_bits + ss.batch_bits;
     int side = 0;
     u32 count = n;
     if (nparts > 1) {
@@ -887,6 +900,89 @@ int Engine::lcp_dev(const u8* d_text, i64 n64, const i32* d_sa, i32* d_lcp, cuda
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------------
+// batch of independent blocks (batch_kernels.cuh)
+
+int Engine::batch_dev(const u8* d_packed, const i64* offsets, i64 count64, u8* d_bwt_out, i32* d_sa_out, i32* sentinels_host, cudaStream_t st)
+{
+    if (count64 < 0 || count64 > ((i64)1 << 24) || (count64 > 0 && !offsets))
+        return set_error(B200SA_EINVAL, "block count %lld outside [0, 2^24] or null offsets", (long long)count64);
+    if (count64 == 0) return 0;
+    const u32 count = (u32)count64;
+    if (offsets[0] != 0) return set_error(B200SA_EINVAL, "offsets[0] must be 0");
+    for (u32 b = 0; b < count; ++b)
+        if (offsets[b + 1] < offsets[b]) return set_error(B200SA_EINVAL, "offsets must be non-decreasing (block %u)", b);
+    const i64 total64 = offsets[count];
+    if (total64 + count64 > B200SA_MAX_N_INT32)
+        return set_error(B200SA_EINVAL, "batch of %lld bytes in %u blocks exceeds 2^31-2 suffixes", (long long)total64, count);
+    if (total64 > 0 && !d_packed) return set_error(B200SA_EINVAL, "null pointer");
+    B200SA_CU(cudaSetDevice(device));
+    const u32 total = (u32)total64, N = total + count;
+    // block tables: [ends u32 count][offs u32 count+1][sent i32 count]
+    const size_t meta_words = (size_t)count * 3 + 1;
+    B200SA_TRY(batch_meta.ensure(meta_words * 4 + 64));
+    u32* d_ends = batch_meta.as<u32>();
+    u32* d_offs = d_ends + count;
+    i32* d_sent = (i32*)(d_offs + count + 1);
+    {
+        std::vector<u32> h((size_t)count * 2 + 1);
+        for (u32 b = 0; b < count; ++b) h[b] = (u32)offsets[b + 1] + b;
+        for (u32 b = 0; b <= count; ++b) h[count + b] = (u32)offsets[b];
+        B200SA_CU(cudaMemcpyAsync(d_ends, h.data(), h.size() * 4, cudaMemcpyHostToDevice, st));
+        B200SA_CU(cudaStreamSynchronize(st));  // h goes out of scope
+    }
+    B200SA_TRY(batch_text.ensure((size_t)N + 64));
+    B200SA_TRY(sa_ws.ensure(((size_t)N + 1) * 4));
+    u8* d_text = batch_text.as<u8>();
+    i32* d_sa = sa_ws.as<i32>();
+    B200SA_TRY(phase_begin(B200SA_PH_PACK, st));
+    {
+        const u32 want = (u32)div_up_u64(div_up_u64(N, BE_IPT), BE_THREADS);
+        const u32 grid = want < (u32)(num_sms * 8) ? want : (u32)(num_sms * 8);
+        B200SA_LAUNCH(k_batch_expand, grid, BE_THREADS, 0, st, d_packed, (const u32*)d_ends, count, N, d_text);
+        count_launch(B200SA_PH_PACK);
+    }
+    B200SA_TRY(phase_end(st));
+    prof.alg_bytes[B200SA_PH_PACK] += (u64)total + N;
+
+    next_batch.d_ends = d_ends;
+    next_batch.count = count;
+    u32 n_local = 0, m = 0;
+    B200SA_TRY(sort_begin(d_text, N, d_sa, 0, 1, &n_local, st));
+    B200SA_TRY(sort_round0(0, &m, st));
+    while (m > 0) B200SA_TRY(sort_round(&m, st));
+    ss.stage = 3;
+
+    if (d_sa_out) {
+        B200SA_TRY(phase_begin(B200SA_PH_BWT, st));
+        const u32 want = (u32)div_up_u64(div_up_u64(N, BL_IPT), BL_THREADS);
+        const u32 grid = want < (u32)(num_sms * 8) ? want : (u32)(num_sms * 8);
+        B200SA_LAUNCH(k_batch_localize, grid, BL_THREADS, 0, st, (const i32*)d_sa, (const u32*)d_ends, count, N, d_sa_out);
+        count_launch(B200SA_PH_BWT);
+        B200SA_TRY(phase_end(st));
+        prof.alg_bytes[B200SA_PH_BWT] += (u64)N * 8;
+    }
+    if (d_bwt_out || sentinels_host) {
+        B200SA_TRY(phase_begin(B200SA_PH_BWT, st));
+        B200SA_LAUNCH(k_batch_sentinels, (u32)div_up_u64(count, 256), 256, 0, st, (const u32*)rank.as<u32>(), (const u32*)d_ends, count, d_sent);
+        count_launch(B200SA_PH_BWT);
+        if (d_bwt_out && total) {
+            const u32 want = (u32)div_up_u64(div_up_u64(total, 4), BW_THREADS);
+            const u32 grid = want < (u32)(num_sms * 16) ? want : (u32)(num_sms * 16);
+            B200SA_LAUNCH(k_bwt_gather_batch, grid, BW_THREADS, 0, st, (const u8*)d_text, (const i32*)d_sa, (const u32*)d_offs,
+                          (const u32*)d_ends, (const i32*)d_sent, count, total, d_bwt_out);
+            count_launch(B200SA_PH_BWT);
+            prof.alg_bytes[B200SA_PH_BWT] += (u64)total * 6;
+        }
+        B200SA_TRY(phase_end(st));
+        if (sentinels_host) B200SA_CU(cudaMemcpyAsync(sentinels_host, d_sent, (size_t)count * 4, cudaMemcpyDeviceToHost, st));
+    }
+    B200SA_CU(cudaGetLastError());
+    B200SA_CU(cudaStreamSynchronize(st));
+    if (profiling) B200SA_TRY(collect_profile());
+    return 0;
+}
+
 }  // namespace b200sa
 
 // =============================================================================================
@@ -1060,6 +1156,84 @@ int b200sa_lcp(b200sa_ctx* ctx, const uint8_t* text, int64_t n, const int32_t* s
     if (sa_out) B200SA_CU(cudaMemcpyAsync(sa_out, e.sa_ws.p, ((size_t)n + 1) * 4, cudaMemcpyDeviceToHost, st));
     B200SA_TRY(e.lcp_dev(e.text_ws.as<u8>(), n, e.sa_ws.as<i32>(), e.keys[1].as<i32>(), st));
     B200SA_CU(cudaMemcpyAsync(lcp_out, e.keys[1].p, ((size_t)n + 1) * 4, cudaMemcpyDeviceToHost, st));
+    B200SA_CU(cudaStreamSynchronize(st));
+    return 0;
+}
+
+// ---- batches of independent blocks ------------------------------------------------------------------
+
+int b200sa_batch_dev(b200sa_ctx* ctx, const uint8_t* d_blocks, const int64_t* offsets, int64_t count, uint8_t* d_bwt_out,
+                     int32_t* d_sa_out, int32_t* sentinel_index_out, void* stream)
+{
+    B200SA_NEED_CTX(ctx);
+    if (d_bwt_out && d_bwt_out == d_blocks) return b200sa::set_error(B200SA_EINVAL, "d_bwt_out must not alias d_blocks");
+    return ctx->eng.batch_dev(d_blocks, offsets, count, d_bwt_out, d_sa_out, sentinel_index_out, ctx->eng.pick(stream));
+}
+
+static int batch_host(b200sa_ctx* ctx, const uint8_t* blocks, const int64_t* offsets, int64_t count, uint8_t* bwt_out, int32_t* sa_out,
+                      int32_t* sentinel_index_out)
+{
+    B200SA_NEED_CTX(ctx);
+    Engine& e = ctx->eng;
+    if (count < 0 || (count > 0 && !offsets)) return b200sa::set_error(B200SA_EINVAL, "bad block table");
+    if (count == 0) return 0;
+    const int64_t total = offsets[count];
+    if (total < 0 || total + count > B200SA_MAX_N_INT32) return b200sa::set_error(B200SA_EINVAL, "batch too large for 32-bit suffix indices");
+    if (total > 0 && !blocks) return b200sa::set_error(B200SA_EINVAL, "null blocks");
+    B200SA_CU(cudaSetDevice(e.device));
+    cudaStream_t st = e.own_stream;
+    B200SA_TRY(e.text_ws.ensure((size_t)total + 64));
+    if (total) B200SA_CU(cudaMemcpyAsync(e.text_ws.p, blocks, (size_t)total, cudaMemcpyHostToDevice, st));
+    u8* d_bwt = nullptr;
+    i32* d_sa = nullptr;
+    if (bwt_out) { B200SA_TRY(e.bwt_ws.ensure((size_t)total + 64)); d_bwt = e.bwt_ws.as<u8>(); }
+    if (sa_out) { B200SA_TRY(e.batch_out.ensure(((size_t)total + (size_t)count) * 4 + 64)); d_sa = e.batch_out.as<i32>(); }
+    B200SA_TRY(e.batch_dev(e.text_ws.as<u8>(), offsets, count, d_bwt, d_sa, sentinel_index_out, st));
+    if (bwt_out && total) B200SA_CU(cudaMemcpyAsync(bwt_out, d_bwt, (size_t)total, cudaMemcpyDeviceToHost, st));
+    if (sa_out) B200SA_CU(cudaMemcpyAsync(sa_out, d_sa, ((size_t)total + (size_t)count) * 4, cudaMemcpyDeviceToHost, st));
+    B200SA_CU(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int b200sa_suffix_array_batch(b200sa_ctx* ctx, const uint8_t* blocks, const int64_t* offsets, int64_t count, int32_t* sa_out)
+{
+    if (count > 0 && !sa_out) return b200sa::set_error(B200SA_EINVAL, "null sa_out");
+    return batch_host(ctx, blocks, offsets, count, nullptr, sa_out, nullptr);
+}
+
+int b200sa_bwt_batch(b200sa_ctx* ctx, uint8_t* blocks_inout, const int64_t* offsets, int64_t count, int32_t* sentinel_index_out)
+{
+    if (count > 0 && !sentinel_index_out) return b200sa::set_error(B200SA_EINVAL, "null sentinel_index_out");
+    return batch_host(ctx, blocks_inout, offsets, count, blocks_inout, nullptr, sentinel_index_out);
+}
+
+int b200sa_unbwt_batch(b200sa_ctx* ctx, uint8_t* blocks_inout, const int64_t* offsets, int64_t count, const int32_t* sentinel_index)
+{
+    B200SA_NEED_CTX(ctx);
+    Engine& e = ctx->eng;
+    if (count < 0 || (count > 0 && (!offsets || !sentinel_index))) return b200sa::set_error(B200SA_EINVAL, "bad block table");
+    if (count == 0) return 0;
+    if (offsets[0] != 0) return b200sa::set_error(B200SA_EINVAL, "offsets[0] must be 0");
+    const int64_t total = offsets[count];
+    for (int64_t b = 0; b < count; ++b) {
+        const int64_t nb = offsets[b + 1] - offsets[b];
+        if (nb < 0 || nb > B200SA_MAX_N_INT32) return b200sa::set_error(B200SA_EINVAL, "bad size of block %lld", (long long)b);
+        if (nb > 0 && (sentinel_index[b] < 1 || (int64_t)sentinel_index[b] > nb))
+            return b200sa::set_error(B200SA_EINVAL, "sentinel index %d of block %lld outside [1, %lld]", sentinel_index[b], (long long)b, (long long)nb);
+    }
+    if (total > 0 && !blocks_inout) return b200sa::set_error(B200SA_EINVAL, "null blocks");
+    B200SA_CU(cudaSetDevice(e.device));
+    cudaStream_t st = e.own_stream;
+    // one upload, one download; the blocks are decoded one after the other on the device
+    B200SA_TRY(e.bwt_ws.ensure((size_t)total + 64));
+    B200SA_TRY(e.text_ws.ensure((size_t)total + 64));
+    if (total) B200SA_CU(cudaMemcpyAsync(e.bwt_ws.p, blocks_inout, (size_t)total, cudaMemcpyHostToDevice, st));
+    for (int64_t b = 0; b < count; ++b) {
+        const int64_t nb = offsets[b + 1] - offsets[b];
+        if (nb == 0) continue;
+        B200SA_TRY(e.unbwt_dev(e.bwt_ws.as<u8>() + offsets[b], nb, sentinel_index[b], e.text_ws.as<u8>() + offsets[b], st));
+    }
+    if (total) B200SA_CU(cudaMemcpyAsync(blocks_inout, e.text_ws.p, (size_t)total, cudaMemcpyDeviceToHost, st));
     B200SA_CU(cudaStreamSynchronize(st));
     return 0;
 }

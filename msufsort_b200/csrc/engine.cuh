@@ -8,6 +8,7 @@
 #include "sa_kernels.cuh"
 #include "bwt_kernels.cuh"
 #include "lcp_kernels.cuh"
+#include "batch_kernels.cuh"
 #include "../../include/b200sa.h"
 
 #include <string>
@@ -50,7 +51,8 @@ struct AlphabetPlan {
     int len_bits;  // bits of the clamped-length field
 };
 
-AlphabetPlan plan_alphabet(const u32* hist256);
+// reserved_bits: key bits kept free above the symbols (the block number of a batched sort)
+AlphabetPlan plan_alphabet(const u32* hist256, int reserved_bits = 0);
 static inline int bit_length_u64(u64 x) { int b = 0; while (x) { ++b; x >>= 1; } return b; }
 
 struct Engine {
@@ -60,6 +62,7 @@ struct Engine {
 
     // workspace (sized for the largest n seen; see DESIGN.md "data layout in HBM")
     DevBuf keys[2], idx[2], slot[2], gid, gstart, glist, rank, sa_ws, sortmeta, agg_cnt, agg_max, misc, text_ws, bwt_ws, walk;
+    DevBuf batch_text, batch_meta, batch_out;  // batched sort: expanded text, block tables, staging of packed results
     u32* h_pinned = nullptr;  // 64 words of pinned host memory for small read-backs
 
     // rank[] arrays up to this size are updated by direct scatter (they stay resident in the 126 MB
@@ -121,7 +124,12 @@ struct Engine {
         const u32* upd_idx = nullptr;   // ISA updates produced by the last step (sharded runs)
         const u32* upd_rank = nullptr;
         u32 upd_count = 0;
+        // batched sort (batch_kernels.cuh): separator positions of the blocks in expanded coordinates
+        const u32* batch_ends = nullptr;
+        u32 batch_count = 0;
+        int batch_bits = 0;
     } ss;
+    struct BatchDesc { const u32* d_ends = nullptr; u32 count = 0; } next_batch;  // consumed by the next sort_begin
     int sort_begin(const u8* d_text, u32 n, i32* d_sa, int part, int nparts, u32* n_local, cudaStream_t st);
     int sort_round0(u32 slot_base, u32* m_local, cudaStream_t st);
     int sort_round(u32* m_local, cudaStream_t st);
@@ -138,6 +146,8 @@ struct Engine {
     int unbwt_dev(const u8* d_bwt, i64 n, i32 sentinel, u8* d_out, cudaStream_t st);
     int check_sa_dev(const u8* d_text, i64 n, const i32* d_sa, i64* bad_rows, cudaStream_t st);
     int lcp_dev(const u8* d_text, i64 n, const i32* d_sa, i32* d_lcp, cudaStream_t st);
+    // batch of independent blocks, packed back to back at offsets[0..count]; any of the outputs may be null
+    int batch_dev(const u8* d_packed, const i64* offsets, i64 count, u8* d_bwt_out, i32* d_sa_out, i32* sentinels_host, cudaStream_t st);
 };
 
 }  // namespace b200sa

@@ -1,0 +1,101 @@
+"""Batches of independent blocks: all blocks are suffix-sorted together by one launch
+sequence; every block's SA / BWT / sentinel index must equal what a per-block call (= the oracle = the
+reference) gives, whatever the other blocks of the batch contain."""
+import numpy as np
+import pytest
+
+from cases import FAMILIES, gen
+
+
+def _check(eng, oracle, blocks):
+    sas = eng.suffix_array_batch(blocks)
+    bw, sent = eng.bwt_batch(blocks)
+    assert len(sas) == len(bw) == len(sent) == len(blocks)
+    for b, x in enumerate(blocks):
+        x = np.asarray(x, dtype=np.uint8)
+        if x.size == 0:
+            assert sas[b].tolist() == [0] and sent[b] == 0 and bw[b].size == 0
+            continue
+        want = oracle.sa(x)
+        assert np.array_equal(sas[b], want), (b, x.size)
+        wb, ws = oracle.bwt_from_sa(x, want)
+        assert sent[b] == ws and np.array_equal(bw[b], wb), (b, x.size)
+    back = eng.unbwt_batch(bw, sent)
+    for b, x in enumerate(blocks):
+        assert np.array_equal(back[b], np.asarray(x, dtype=np.uint8)), b
+
+
+def _cases(scale):
+    rng = np.random.default_rng(11)
+    yield "single", [gen("markov3", 1000 * scale)]
+    yield "mixed", [gen("markov3", 1000 * scale), gen("rand", 17), gen("zeros", 300), np.empty(0, np.uint8), gen("fib", 4097),
+                    gen("acgt_rep", 5000 * scale), gen("zeros", 1), np.empty(0, np.uint8)]
+    x = gen("markov3", 3000 * scale)
+    yield "identical-blocks", [x] * 9                      # cross-block repeats must not deepen the rounds
+    yield "identical-runs", [gen("zeros", 50)] * 40
+    yield "tiny", [rng.integers(0, 3, size=int(rng.integers(0, 12)), dtype=np.uint8) for _ in range(700)]
+    yield "families", [gen(f, int(rng.integers(1, 9000 * scale))) for f in FAMILIES for _ in range(3)]
+    yield "two-random", [gen("rand", 30000 * scale), gen("rand", 20000 * scale)]
+    yield "zero-bytes", [np.zeros(5, np.uint8), np.array([0, 0, 1, 0], np.uint8), np.array([1, 0, 0], np.uint8)]
+
+
+@pytest.mark.parametrize("name", [n for n, _ in _cases(1)])
+def test_emu_batch(emu_engine, oracle, name):
+    _check(emu_engine, oracle, dict(_cases(1))[name])
+
+
+def test_emu_batch_profile_one_sort(emu_engine):
+    """the whole batch is ONE sort: launches do not grow with the number of blocks"""
+    a = [gen("markov3", 2000)] * 4
+    b = [gen("markov3", 250)] * 32
+    counts = []
+    for blocks in (a, b):
+        before = emu_engine.launch_count()
+        emu_engine.bwt_batch(blocks)
+        counts.append(emu_engine.launch_count() - before)
+    assert counts[1] <= counts[0] + 40, counts
+
+
+def test_emu_batch_errors(emu_engine):
+    from msufsort_b200.api import B200SAError
+    assert emu_engine.suffix_array_batch([]) == []
+    with pytest.raises(ValueError):
+        emu_engine.unbwt_batch([np.zeros(3, np.uint8)], [1, 2])
+    with pytest.raises(B200SAError):
+        emu_engine.unbwt_batch([np.zeros(3, np.uint8)], [7])  # sentinel outside [1, n]
+    with pytest.raises(B200SAError):
+        emu_engine.batch_dev(np.zeros(4, np.uint8), np.array([0, 3, 2], dtype=np.int64))  # decreasing offsets
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", [n for n, _ in _cases(8)])
+def test_gpu_batch(gpu_engine, oracle, name):
+    _check(gpu_engine, oracle, dict(_cases(8))[name])
+
+
+@pytest.mark.gpu
+def test_gpu_batch_many_blocks_device_resident(gpu_engine, oracle):
+    """4096 blocks of 16 KiB .. 48 KiB through the device-resident entry point; spot-checked against the oracle,
+    all blocks round-tripped through the inverse"""
+    import torch
+    rng = np.random.default_rng(3)
+    sizes = rng.integers(16 << 10, 48 << 10, size=4096)
+    text = gen("markov3", int(sizes.sum()))
+    offsets = np.zeros(sizes.size + 1, dtype=np.int64)
+    np.cumsum(sizes, out=offsets[1:])
+    total, count = int(offsets[-1]), sizes.size
+    d_blocks = torch.from_numpy(text).cuda()
+    d_bwt = torch.empty(total, dtype=torch.uint8, device="cuda")
+    d_sa = torch.empty(total + count, dtype=torch.int32, device="cuda")
+    sent = gpu_engine.batch_dev(d_blocks, offsets, d_bwt, d_sa)
+    torch.cuda.synchronize()
+    bwt, sa = d_bwt.cpu().numpy(), d_sa.cpu().numpy()
+    for b in list(range(0, count, 257)) + [count - 1]:
+        x = text[offsets[b]:offsets[b + 1]]
+        want = oracle.sa(x)
+        assert np.array_equal(sa[offsets[b] + b: offsets[b + 1] + b + 1], want), b
+        wb, ws = oracle.bwt_from_sa(x, want)
+        assert int(sent[b]) == ws and np.array_equal(bwt[offsets[b]:offsets[b + 1]], wb), b
+    back = gpu_engine.unbwt_batch([bwt[offsets[b]:offsets[b + 1]] for b in range(0, count, 64)], [int(sent[b]) for b in range(0, count, 64)])
+    for i, b in enumerate(range(0, count, 64)):
+        assert np.array_equal(back[i], text[offsets[b]:offsets[b + 1]]), b

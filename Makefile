@@ -3,6 +3,7 @@
 #   lib      msufsort_b200/lib/libb200sa.so          hand-written CUDA kernels + C ABI (sm_100a only)
 #   textgen  msufsort_b200/lib/libb200sa_textgen.so  synthetic input generators (host C)
 #   facade   msufsort_b200/lib/libmsufsort.so        the reference-shaped C++ facade (src/library)
+#   cli      msufsort_b200/lib/msufsort              command line tool with the reference demo's modes (src/executable)
 #   oracle   oracle/liboracle.so (+ oracle/_ref/ when /root/reference exists)   TEST INFRASTRUCTURE
 #   emu      tests/emu/libb200sa_emu.so              kernel logic under a CPU SIMT emulator (tests only)
 NVCC      ?= nvcc
@@ -15,7 +16,7 @@ CSRC      := msufsort_b200/csrc
 LIBDIR    := msufsort_b200/lib
 KSRC      := $(CSRC)/b200sa.cu $(CSRC)/engine.cuh $(CSRC)/common.cuh $(CSRC)/radix_sort.cuh $(CSRC)/sa_kernels.cuh $(CSRC)/bwt_kernels.cuh $(CSRC)/lcp_kernels.cuh $(CSRC)/batch_kernels.cuh include/b200sa.h
 
-all: lib textgen facade oracle emu
+all: lib textgen facade cli oracle emu
 
 lib: $(LIBDIR)/libb200sa.so
 $(LIBDIR)/libb200sa.so: $(KSRC)
@@ -32,6 +33,10 @@ facade: $(LIBDIR)/libmsufsort.so
 $(LIBDIR)/libmsufsort.so: src/library/msufsort/msufsort.cpp src/library/msufsort/msufsort.h src/library/msufsort.h include/b200sa.h $(LIBDIR)/libb200sa.so
 	$(CXX) -O2 -std=c++17 -fPIC -shared -Isrc -Iinclude -o $@ src/library/msufsort/msufsort.cpp -L$(LIBDIR) -lb200sa -Wl,-rpath,'$$ORIGIN'
 
+cli: $(LIBDIR)/msufsort
+$(LIBDIR)/msufsort: src/executable/msufsort/main.cpp $(LIBDIR)/libmsufsort.so
+	$(CXX) -O2 -std=c++17 -Isrc -Iinclude -o $@ $< -L$(LIBDIR) -lmsufsort -lb200sa -Wl,-rpath,'$$ORIGIN'
+
 oracle:
 	$(MAKE) -C oracle
 
@@ -40,7 +45,7 @@ tests/emu/libb200sa_emu.so: $(KSRC) tests/emu/cuda_emu.h
 	$(CXX) -O2 -g -std=c++17 -fPIC -shared -DB200SA_EMU -x c++ -Itests/emu -I$(CSRC) -Wno-unused-function -o $@ $(CSRC)/b200sa.cu
 
 clean:
-	rm -f $(LIBDIR)/*.so $(LIBDIR)/ptxas.log tests/emu/*.so
+	rm -f $(LIBDIR)/*.so $(LIBDIR)/msufsort $(LIBDIR)/ptxas.log tests/emu/*.so
 	$(MAKE) -C oracle clean
 
-.PHONY: all lib textgen facade oracle emu clean
+.PHONY: all lib textgen facade cli oracle emu clean

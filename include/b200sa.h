@@ -147,8 +147,8 @@ B200SA_API int b200sa_lcp(b200sa_ctx* ctx, const uint8_t* text, int64_t n, const
  *   - suffix arrays: sa_out has offsets[count] + count entries; block b's n_b+1 entries (SA_b[0] = n_b)
  *     start at offsets[b] + b, values are block-local;
  *   - BWT: in place, packed like the input; sentinel_index_out[b] in [1, n_b] (0 for an empty block);
- *   - inverse: in place from (BWT bytes, sentinel indices); the blocks share one upload and one download
- *     and are decoded one after the other on the device.                                               */
+ *   - inverse: in place from (BWT bytes, sentinel indices); one sort of (block, byte) pairs builds the LF
+ *     tables of all blocks, one walk decodes all blocks.                                                */
 B200SA_API int b200sa_suffix_array_batch(b200sa_ctx* ctx, const uint8_t* blocks, const int64_t* offsets, int64_t count,
                                          int32_t* sa_out);
 B200SA_API int b200sa_bwt_batch(b200sa_ctx* ctx, uint8_t* blocks_inout, const int64_t* offsets, int64_t count,
@@ -160,6 +160,9 @@ B200SA_API int b200sa_unbwt_batch(b200sa_ctx* ctx, uint8_t* blocks_inout, const 
  * sentinel_index_out may each be NULL. */
 B200SA_API int b200sa_batch_dev(b200sa_ctx* ctx, const uint8_t* d_blocks, const int64_t* offsets, int64_t count,
                                 uint8_t* d_bwt_out, int32_t* d_sa_out, int32_t* sentinel_index_out, void* stream);
+
+B200SA_API int b200sa_unbwt_batch_dev(b200sa_ctx* ctx, const uint8_t* d_bwt, const int64_t* offsets, int64_t count,
+                                      const int32_t* sentinel_index, uint8_t* d_text_out, void* stream);
 
 /* ---- sharded (multi-GPU) building blocks --------------------------------------------------
  *

@@ -70,6 +70,7 @@ ABI = [
     ("b200sa_bwt_batch", C.c_int, [_P, _P, _P, C.c_int64, _P]),
     ("b200sa_unbwt_batch", C.c_int, [_P, _P, _P, C.c_int64, _P]),
     ("b200sa_batch_dev", C.c_int, [_P, _P, _P, C.c_int64, _P, _P, _P, _P]),
+    ("b200sa_unbwt_batch_dev", C.c_int, [_P, _P, _P, C.c_int64, _P, _P, _P]),
     ("b200sa_shard_begin", C.c_int, [_P, _P, C.c_int64, _P, C.c_int, C.c_int, C.POINTER(C.c_int64), _P]),
     ("b200sa_shard_round0", C.c_int, [_P, C.c_int64, C.POINTER(C.c_int64), _P]),
     ("b200sa_shard_round", C.c_int, [_P, C.POINTER(C.c_int64), _P]),
@@ -305,6 +306,12 @@ class Engine:
         self.lib.check(self.lib.cdll.b200sa_batch_dev(self._ctx, _ptr(d_blocks), _ptr(offsets), count, _ptr(d_bwt), _ptr(d_sa), _ptr(sent),
                                                       self._st(stream)))
         return sent[:count]
+
+    def unbwt_batch_dev(self, d_bwt, offsets: np.ndarray, sentinel_indices, d_out, stream: Optional[int] = None) -> None:
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        sent = np.ascontiguousarray(np.asarray(sentinel_indices, dtype=np.int32))
+        self.lib.check(self.lib.cdll.b200sa_unbwt_batch_dev(self._ctx, _ptr(d_bwt), _ptr(offsets), offsets.size - 1, _ptr(sent), _ptr(d_out),
+                                                            self._st(stream)))
 
     # ---- raw-pointer variants of the host entry points (pinned buffers in bench.py) ----------
     def suffix_array_ptr(self, text_ptr: int, n: int, sa_ptr: int) -> None:

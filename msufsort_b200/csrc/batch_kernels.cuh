@@ -18,6 +18,7 @@
 #pragma once
 #include "common.cuh"
 #include "sa_kernels.cuh"
+#include "bwt_kernels.cuh"
 
 namespace b200sa {
 
@@ -192,6 +193,175 @@ k_bwt_gather_batch(const u8* __restrict__ text, const i32* __restrict__ sa, cons
         }
     }
     (void)ends;
+}
+
+
+// =============================================================================================
+// Inverse BWT of a batch.  Rows live in the same expanded coordinates as the forward transform: block b owns
+// rows [start_b, end_b], local row 0 (= start_b) is the row of the block's empty suffix, the block's text
+// starts at local row s_b (its sentinel index).  One table entry per row, 8 bytes:
+//     bits 0..30  psi''[row]  (the row of the suffix one text position to the right; same block)
+//     bit  31     the row is a walker seed / a terminal
+//     bits 32..39 first byte of the row's suffix (what the walker emits when it stands on the row)
+// psi and the symbols of all blocks come from ONE stable sort of the BWT bytes by (block << 8 | byte) with the
+// rows as values — the batched form of the reference's phase C (msufsort.cpp:1898-1915) — so no per-block
+// F-column table is needed.  Walkers: every D-th row, every block's start row and every block's row 0
+// (terminal); walker ids are [0, nreg) regular, [nreg, nreg + count) block starts, [nreg + count, nreg + 2 count)
+// terminals.  A regular walker whose row is also a start or a terminal row is dead (the special walker owns it).
+static const u64 UBB_SYM_SHIFT = 32;
+
+__device__ __forceinline__ u32 ubb_block_start(const u32* __restrict__ ends, u32 b) { return b ? ends[b - 1u] + 1u : 0u; }
+
+// sort input: key = block << 8 | byte, value = global row of the byte
+__global__ void __launch_bounds__(256)
+k_ubb_gen(const u8* __restrict__ bwt, const u32* __restrict__ offs, const i32* __restrict__ sent, u32 count, u32 total,
+          u32* __restrict__ keys, u32* __restrict__ vals)
+{
+    const u32 ngroups = (u32)div_up_u64(total, 4);
+    for (u32 g = blockIdx.x * blockDim.x + threadIdx.x; g < ngroups; g += gridDim.x * blockDim.x) {
+        const u32 x0 = g * 4u;
+        u32 lo = 0, hi = count - 1u;
+        while (lo < hi) {
+            const u32 mid = (lo + hi) >> 1;
+            if (offs[mid + 1u] > x0) hi = mid; else lo = mid + 1u;
+        }
+        u32 b = lo, ob = offs[b], oe = offs[b + 1u], s = (u32)sent[b];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const u32 x = x0 + (u32)i;
+            if (x < total) {
+                while (x >= oe) { ++b; ob = oe; oe = offs[b + 1u]; s = (u32)sent[b]; }
+                const u32 o = x - ob;
+                keys[x] = (b << 8) | (u32)bwt[x];
+                vals[x] = ob + b + o + (o >= s ? 1u : 0u);
+            }
+        }
+    }
+}
+
+// table rows 1..n_b of every block from the sorted pairs; sorted position x of block b is row x + b + 1
+__global__ void __launch_bounds__(256)
+k_ubb_table(const u32* __restrict__ keys, const u32* __restrict__ vals, u32 total, u64* __restrict__ table)
+{
+    for (u32 x = blockIdx.x * blockDim.x + threadIdx.x; x < total; x += gridDim.x * blockDim.x) {
+        const u32 k = ld_stream(keys + x);
+        table[x + (k >> 8) + 1u] = ((u64)(k & 255u) << UBB_SYM_SHIFT) | (u64)ld_stream(vals + x);
+    }
+}
+
+__device__ __forceinline__ u32 ubb_row_walker(u32 row, const u32* __restrict__ ends, const i32* __restrict__ sent, u32 count, u32 nreg, u32 D)
+{
+    const u32 b = bt_block_of(ends, count, row);
+    const u32 start = ubb_block_start(ends, b);
+    if (row == start) return nreg + count + b;
+    if (row == start + (u32)sent[b]) return nreg + b;
+    return row / D;
+}
+
+// seed row of walker w; returns false for walkers that do not walk (terminals, dead duplicates, empty blocks)
+__device__ __forceinline__ bool ubb_walker_seed(u32 w, const u32* __restrict__ ends, const i32* __restrict__ sent, u32 count, u32 nreg, u32 D,
+                                                u32 N, u32* row_out, u32* block_out)
+{
+    if (w < nreg) {
+        const u32 row = w * D;
+        if (row >= N) return false;
+        const u32 b = bt_block_of(ends, count, row);
+        const u32 start = ubb_block_start(ends, b);
+        *row_out = row; *block_out = b;
+        return row != start && row != start + (u32)sent[b];
+    }
+    if (w < nreg + count) {
+        const u32 b = w - nreg;
+        const u32 start = ubb_block_start(ends, b);
+        *row_out = start + (u32)sent[b]; *block_out = b;
+        return ends[b] > start;  // empty block: nothing to decode
+    }
+    const u32 b = w - nreg - count;
+    *row_out = ubb_block_start(ends, b); *block_out = b;
+    return false;
+}
+
+// row 0 of every block: psi = the block's start row; then the seed / terminal marks
+__global__ void __launch_bounds__(256)
+k_ubb_rows0(const u32* __restrict__ ends, const i32* __restrict__ sent, u32 count, u64* __restrict__ table)
+{
+    const u32 b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= count) return;
+    const u32 start = ubb_block_start(ends, b);
+    table[start] = (u64)(start + (u32)sent[b]) | UB_MARK;
+}
+
+__global__ void __launch_bounds__(256)
+k_ubb_mark(u64* __restrict__ table, const u32* __restrict__ ends, const i32* __restrict__ sent, u32 count, u32 nreg, u32 D, u32 N)
+{
+    const u32 w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= nreg + count) return;  // terminals are marked by k_ubb_rows0
+    u32 row = 0, b = 0;
+    if (ubb_walker_seed(w, ends, sent, count, nreg, D, N, &row, &b)) atomicOr((u32*)(table + row), UB_MARK);  // low word = psi | mark
+}
+
+__global__ void __launch_bounds__(UW_THREADS)
+k_ubb_walk(const u64* __restrict__ table, const u32* __restrict__ ends, const i32* __restrict__ sent, u32 count, u32 nreg, u32 D, u32 N,
+           u32 nwalkers, u32 cap, u8* __restrict__ scratch, u32* __restrict__ seg_len, u32* __restrict__ seg_next, u32* __restrict__ ovf_row)
+{
+    const u32 w = blockIdx.x * UW_THREADS + threadIdx.x;
+    if (w >= nwalkers) return;
+    u32 cur = 0, blk = 0;
+    if (!ubb_walker_seed(w, ends, sent, count, nreg, D, N, &cur, &blk)) {
+        seg_len[w] = 0; seg_next[w] = w; ovf_row[w] = UB_NO_OVERFLOW;  // terminal / dead: points to itself
+        return;
+    }
+    u64* win = (u64*)(scratch + (u64)w * cap);
+    u64 e = table[cur];
+    u32 len = 0, ovf = UB_NO_OVERFLOW;
+    u64 acc = 0;
+    do {
+        const u32 nxt = (u32)e & UB_IDX;
+        const u64 e2 = table[nxt];
+        if (len < cap) {
+            acc |= ((e >> UBB_SYM_SHIFT) & 255ull) << (8 * (len & 7u));
+            if ((len & 7u) == 7u) { win[len >> 3] = acc; acc = 0; }
+        } else if (len == cap) {
+            ovf = cur;
+        }
+        ++len;
+        cur = nxt;
+        e = e2;
+    } while (!((u32)e & UB_MARK));
+    if (len < cap && (len & 7u)) win[len >> 3] = acc;
+    seg_len[w] = len;
+    seg_next[w] = ubb_row_walker(cur, ends, sent, count, nreg, D);
+    ovf_row[w] = ovf;
+}
+
+// one warp per walker: window -> offs[block + 1] - dist[w] in the packed output
+__global__ void __launch_bounds__(UP_THREADS)
+k_ubb_place(const u64* __restrict__ table, const u32* __restrict__ ends, const u32* __restrict__ offs, const i32* __restrict__ sent, u32 count,
+            u32 nreg, u32 D, u32 N, u32 nwalkers, const u32* __restrict__ dist, const u32* __restrict__ seg_len,
+            const u32* __restrict__ ovf_row, const u8* __restrict__ scratch, u32 cap, u8* __restrict__ out)
+{
+    const u32 lane = threadIdx.x & 31u;
+    const u32 w = blockIdx.x * (UP_THREADS / 32) + (threadIdx.x >> 5);
+    if (w >= nwalkers) return;
+    u32 row = 0, blk = 0;
+    if (!ubb_walker_seed(w, ends, sent, count, nreg, D, N, &row, &blk)) return;
+    const u32 len = seg_len[w];
+    const u32 pos = offs[blk + 1u] - dist[w];
+    const u32 stored = len < cap ? len : cap;
+    const u8* src = scratch + (u64)w * cap;
+    for (u32 i = lane; i < stored; i += 32u) out[pos + i] = src[i];
+    if (len > cap && lane == 0) {
+        u32 cur = ovf_row[w];
+        u64 e = table[cur];
+        u32 o = pos + cap;
+        for (u32 k = cap; k < len; ++k) {
+            const u32 nxt = (u32)e & UB_IDX;
+            const u64 e2 = table[nxt];
+            out[o++] = (u8)(e >> UBB_SYM_SHIFT);
+            cur = nxt;
+            e = e2;
+        }
+    }
 }
 
 }  // namespace b200sa

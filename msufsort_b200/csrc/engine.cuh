@@ -148,6 +148,8 @@ struct Engine {
     int lcp_dev(const u8* d_text, i64 n, const i32* d_sa, i32* d_lcp, cudaStream_t st);
     // batch of independent blocks, packed back to back at offsets[0..count]; any of the outputs may be null
     int batch_dev(const u8* d_packed, const i64* offsets, i64 count, u8* d_bwt_out, i32* d_sa_out, i32* sentinels_host, cudaStream_t st);
+    int batch_tables(const i64* offsets, u32 count, const i32* sentinels_or_null, u32** d_ends, u32** d_offs, i32** d_sent, cudaStream_t st);
+    int unbwt_batch_dev(const u8* d_bwt_packed, const i64* offsets, i64 count, const i32* sentinels_host, u8* d_out_packed, cudaStream_t st);
 };
 
 }  // namespace b200sa

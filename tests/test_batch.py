@@ -56,6 +56,34 @@ def test_emu_batch_profile_one_sort(emu_engine):
     assert counts[1] <= counts[0] + 40, counts
 
 
+@pytest.mark.parametrize("cap_mult", ["1", "4"])
+def test_emu_batch_inverse_window_overflow(oracle, cap_mult, monkeypatch):
+    """batched inverse with small decode windows; blocks much longer and much shorter than the walker spacing"""
+    import os
+    from conftest import ROOT
+    from msufsort_b200.api import Engine, Library
+    monkeypatch.setenv("B200SA_UNBWT_CAP_MULT", cap_mult)
+    eng = Engine(0, library=Library(os.path.join(ROOT, "tests", "emu", "libb200sa_emu.so")))
+    try:
+        blocks = [gen("markov3", 50003), gen("zeros", 9000), gen("rand", 63), gen("rand", 64), gen("rand", 65), gen("fib", 20000),
+                  np.empty(0, np.uint8), gen("abcabca", 127), gen("abcabca", 128), gen("rand", 1)]
+        bw, sent = [], []
+        for x in blocks:
+            if x.size:
+                b, s = oracle.bwt(x)
+            else:
+                b, s = x, 0
+            bw.append(b); sent.append(s)
+        back = eng.unbwt_batch(bw, sent)
+        for b, x in enumerate(blocks):
+            assert np.array_equal(back[b], x), (b, cap_mult)
+        before = eng.launch_count()
+        eng.unbwt_batch(bw * 8, sent * 8)
+        assert eng.launch_count() - before < 60  # one sort + one walk, whatever the number of blocks
+    finally:
+        eng.close()
+
+
 def test_emu_batch_errors(emu_engine):
     from msufsort_b200.api import B200SAError
     assert emu_engine.suffix_array_batch([]) == []
@@ -96,6 +124,7 @@ def test_gpu_batch_many_blocks_device_resident(gpu_engine, oracle):
         assert np.array_equal(sa[offsets[b] + b: offsets[b + 1] + b + 1], want), b
         wb, ws = oracle.bwt_from_sa(x, want)
         assert int(sent[b]) == ws and np.array_equal(bwt[offsets[b]:offsets[b + 1]], wb), b
-    back = gpu_engine.unbwt_batch([bwt[offsets[b]:offsets[b + 1]] for b in range(0, count, 64)], [int(sent[b]) for b in range(0, count, 64)])
-    for i, b in enumerate(range(0, count, 64)):
-        assert np.array_equal(back[i], text[offsets[b]:offsets[b + 1]]), b
+    d_back = torch.zeros(total, dtype=torch.uint8, device="cuda")
+    gpu_engine.unbwt_batch_dev(d_bwt, offsets, sent, d_back)
+    torch.cuda.synchronize()
+    assert torch.equal(d_back, d_blocks)

@@ -91,8 +91,13 @@ def main():
         ok = all(int(sent[b]) == sents[b] for b in range(sample))
         # last sampled block's bytes must agree too
         ok = ok and bool(torch.equal(d_one, d_bwt[(sample - 1) * bs: sample * bs]))
+        d_back = torch.empty(total, dtype=torch.uint8, device="cuda")
+        ms_unbwt = timed(lambda: eng.unbwt_batch_dev(d_bwt, offsets, sent, d_back), reps=2)
+        ok = ok and bool(torch.equal(d_back, d_text[:total]))
+        del d_back
         res[f"batch_{count}"] = {"blocks": count, "block_bytes": bs, "batch_ms": ms_batch, "batch_MBps": total / ms_batch / 1e3,
                                  "per_block_calls_ms_extrapolated": ms_loop, "speedup": ms_loop / ms_batch, "rounds": rounds,
+                                 "unbwt_batch_ms": ms_unbwt, "unbwt_batch_MBps": total / ms_unbwt / 1e3,
                                  "matches_per_block_calls": ok}
         print("BATCH", json.dumps(res[f"batch_{count}"]), flush=True)
     if a.out:

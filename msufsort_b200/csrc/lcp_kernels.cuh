@@ -84,7 +84,60 @@ k_plcp_level(const u8* __restrict__ text, u32 n, const u32* __restrict__ phi, u3
     }
 }
 
-// Overflow list of one level: one CTA per entry at a time, 256 threads x 4 units x 8 bytes per iteration.
+// A whole CTA extends ONE match: 256 threads x LC_UNITS x 8 bytes per iteration.  Must be called by all threads of
+// the CTA with identical arguments; returns lcp(p, q) given that the first l bytes are known to match.
+__device__ __forceinline__ u32 lc_cta_extend(const u8* __restrict__ text, const u32* __restrict__ words, u32 off, u32 n,
+                                             u32 p, u32 q, u32 l, u32* s_min /*[LC_THREADS/32]*/, u32* s_res)
+{
+    const u32 tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const u32 maxl = n - (p > q ? p : q);
+    const u32 chunk = LC_THREADS * LC_UNITS * 8u;
+    u32 result = LC_NONE;
+    while (result == LC_NONE) {
+        // first mismatching byte among this thread's units of [l, l + chunk), LC_NONE if all equal
+        u64 xa[LC_UNITS], xb[LC_UNITS];
+        u32 mine = LC_NONE;
+#pragma unroll
+        for (int k = 0; k < LC_UNITS; ++k) {
+            const u64 u = (u64)l + ((u32)k * LC_THREADS + tid) * 8u;
+            const bool ok = u + 8u <= (u64)maxl;
+            xa[k] = ok ? lc_load8(words, off, p + (u32)u) : 0ull;
+            xb[k] = ok ? lc_load8(words, off, q + (u32)u) : 0ull;
+        }
+#pragma unroll
+        for (int k = LC_UNITS - 1; k >= 0; --k) {
+            const u64 x = xa[k] ^ xb[k];
+            if (x) mine = l + ((u32)k * LC_THREADS + tid) * 8u + ((u32)(__ffsll((long long)x) - 1) >> 3);
+        }
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) {
+            const u32 o = __shfl_xor_sync(B200SA_FULL_MASK, mine, d);
+            mine = mine < o ? mine : o;
+        }
+        if (lane == 0) s_min[warp] = mine;
+        __syncthreads();
+        if (tid == 0) {
+            u32 m = LC_NONE;
+            for (int w = 0; w < LC_THREADS / 32; ++w) m = m < s_min[w] ? m : s_min[w];
+            if (m == LC_NONE) {
+                // whole chunk equal; the last (partial) chunk leaves fewer than 8 bytes to thread 0
+                const u64 next = (u64)l + chunk;
+                if (next + 8u > (u64)maxl) {
+                    u32 t = l + ((maxl - l) & ~7u);
+                    while (t < maxl && text[p + t] == text[q + t]) ++t;
+                    m = t;
+                }
+            }
+            *s_res = m;
+        }
+        __syncthreads();
+        result = *s_res;  // rewritten only after the next call's / iteration's first barrier
+        l += chunk;
+    }
+    return result;
+}
+
+// Overflow list of one level: one CTA per entry at a time.
 __global__ void __launch_bounds__(LC_THREADS)
 k_plcp_overflow(const u8* __restrict__ text, u32 n, const u32* __restrict__ phi, u32* __restrict__ plcp,
                 const u32* __restrict__ ovf_pos, const u32* __restrict__ ovf_len, const u32* __restrict__ ovf_count)
@@ -93,57 +146,91 @@ k_plcp_overflow(const u8* __restrict__ text, u32 n, const u32* __restrict__ phi,
     __shared__ u32 s_res;
     const u32 off = (u32)((uintptr_t)text & 3u);
     const u32* words = (const u32*)(text - off);
-    const u32 tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const u32 count = *ovf_count;
-    const u32 chunk = LC_THREADS * LC_UNITS * 8u;
     for (u32 e = blockIdx.x; e < count; e += gridDim.x) {
         const u32 p = ovf_pos[e];
-        const u32 q = phi[p];
-        const u32 maxl = n - (p > q ? p : q);
-        u32 l = ovf_len[e];
-        u32 result = LC_NONE;
-        while (result == LC_NONE) {
-            // first mismatching byte among this thread's units of [l, l + chunk), LC_NONE if all equal
-            u64 xa[LC_UNITS], xb[LC_UNITS];
-            u32 mine = LC_NONE;
-#pragma unroll
-            for (int k = 0; k < LC_UNITS; ++k) {
-                const u32 u = l + ((u32)k * LC_THREADS + tid) * 8u;
-                const bool ok = (u64)u + 8u <= (u64)maxl;
-                xa[k] = ok ? lc_load8(words, off, p + u) : 0ull;
-                xb[k] = ok ? lc_load8(words, off, q + u) : 0ull;
-            }
-#pragma unroll
-            for (int k = LC_UNITS - 1; k >= 0; --k) {
-                const u64 x = xa[k] ^ xb[k];
-                if (x) mine = l + ((u32)k * LC_THREADS + tid) * 8u + ((u32)(__ffsll((long long)x) - 1) >> 3);
-            }
-#pragma unroll
-            for (int d = 16; d >= 1; d >>= 1) {
-                const u32 o = __shfl_xor_sync(B200SA_FULL_MASK, mine, d);
-                mine = mine < o ? mine : o;
-            }
-            if (lane == 0) s_min[warp] = mine;
-            __syncthreads();
-            if (tid == 0) {
-                u32 m = LC_NONE;
-                for (int w = 0; w < LC_THREADS / 32; ++w) m = m < s_min[w] ? m : s_min[w];
-                if (m == LC_NONE) {
-                    // whole chunk equal; the last (partial) chunk leaves fewer than 8 bytes to thread 0
-                    const u64 next = (u64)l + chunk;
-                    if (next + 8u > (u64)maxl) {
-                        u32 t = l + ((maxl - l) & ~7u);
-                        while (t < maxl && text[p + t] == text[q + t]) ++t;
-                        m = t;
-                    }
-                }
-                s_res = m;
-            }
-            __syncthreads();
-            result = s_res;  // rewritten only after the next iteration's first barrier
-            l += chunk;
+        const u32 result = lc_cta_extend(text, words, off, n, p, phi[p], ovf_len[e], s_min, &s_res);
+        if (threadIdx.x == 0) plcp[p] = result;
+    }
+}
+
+// The five finest levels (S = 16, 8, 4, 2, 1) in one kernel.  Separate launches would read phi and read-modify-
+// write plcp once per level at a fraction of the sector width (positions 2S apart); here a CTA stages phi and
+// the already known plcp values (multiples of LF_SPAN) of LF_TILE consecutive positions in shared memory, runs
+// the levels on the tile — all dependencies of a position lie inside its LF_SPAN-aligned chunk — and writes plcp
+// back with one coalesced sweep.  Matches that outgrow a thread's budget are finished by the whole CTA between
+// two levels (lc_cta_extend), so the lower bounds the next level starts from are exact.
+static const int LF_SPAN = 32;
+static const int LF_TILE = 4096;
+static const int LF_LIST = 128;
+
+__global__ void __launch_bounds__(LC_THREADS)
+k_plcp_fine(const u8* __restrict__ text, u32 n, const u32* __restrict__ phi, u32* __restrict__ plcp)
+{
+    __shared__ u32 s_phi[LF_TILE], s_pl[LF_TILE];
+    __shared__ u32 s_lpos[LF_LIST], s_llen[LF_LIST];
+    __shared__ u32 s_nlist, s_res;
+    __shared__ u32 s_min[LC_THREADS / 32];
+    const u32 off = (u32)((uintptr_t)text & 3u);
+    const u32* words = (const u32*)(text - off);
+    const u32 tid = threadIdx.x;
+    const u32 ntiles = (u32)div_up_u64(n, LF_TILE);
+    for (u32 tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const u32 base = tile * (u32)LF_TILE;
+        for (u32 i = tid; i < (u32)LF_TILE; i += LC_THREADS) s_phi[i] = base + i < n ? ld_stream(phi + base + i) : 0u;
+        for (u32 c = tid; c < (u32)(LF_TILE / LF_SPAN); c += LC_THREADS) {
+            const u32 gp = base + c * (u32)LF_SPAN;
+            s_pl[c * LF_SPAN] = gp < n ? plcp[gp] : 0u;
         }
-        if (tid == 0) plcp[p] = result;
+        if (tid == 0) s_nlist = 0;
+        __syncthreads();
+        for (u32 S = LF_SPAN / 2; S >= 1u; S >>= 1) {
+            const u32 nsamp = (u32)LF_TILE / (2u * S);
+            for (u32 j = tid; j < nsamp; j += LC_THREADS) {
+                const u32 lp = S + j * 2u * S;
+                const u32 p = base + lp;
+                if (p >= n) continue;
+                const u32 q = s_phi[lp];
+                const u32 prev = s_pl[lp - S];
+                u32 l = prev > S ? prev - S : 0u;
+                if (q >= n) { s_pl[lp] = 0; continue; }
+                const u32 maxl = n - (p > q ? p : q);
+                u32 stop = (maxl - l) > LC_BUDGET ? l + LC_BUDGET : maxl;
+                bool open = true;
+                for (;;) {
+                    while (open && l + 8u <= stop) {
+                        const u64 x = lc_load8(words, off, p + l) ^ lc_load8(words, off, q + l);
+                        if (x) { l += (u32)(__ffsll((long long)x) - 1) >> 3; open = false; }
+                        else l += 8u;
+                    }
+                    while (open && l < stop) {
+                        if (text[p + l] != text[q + l]) open = false;
+                        else ++l;
+                    }
+                    if (!open || l >= maxl) break;
+                    // budget used up: hand the match to the CTA, or (list full) keep going alone
+                    const u32 slot = atomicAdd(&s_nlist, 1u);
+                    if (slot < (u32)LF_LIST) { s_lpos[slot] = lp; s_llen[slot] = l; break; }
+                    stop = maxl;
+                }
+                s_pl[lp] = l;  // exact, or a placeholder that the CTA pass below overwrites
+            }
+            __syncthreads();
+            const u32 nl = s_nlist < (u32)LF_LIST ? s_nlist : (u32)LF_LIST;
+            __syncthreads();  // everyone has read the count before the next level (or the reset below) touches it
+            if (nl) {
+                for (u32 e = 0; e < nl; ++e) {
+                    const u32 lp = s_lpos[e];
+                    const u32 r = lc_cta_extend(text, words, off, n, base + lp, s_phi[lp], s_llen[e], s_min, &s_res);
+                    if (tid == 0) s_pl[lp] = r;
+                }
+                if (tid == 0) s_nlist = 0;
+                __syncthreads();
+            }
+        }
+        for (u32 i = tid; i < (u32)LF_TILE; i += LC_THREADS)
+            if (base + i < n) st_stream(plcp + base + i, s_pl[i]);
+        __syncthreads();
     }
 }
 

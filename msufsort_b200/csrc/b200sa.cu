@@ -102,7 +102,6 @@ int Engine::init(int dev)
     if (const char* e3 = getenv("B200SA_GROUPSORT_AVG")) groupsort_max_avg = (u32)strtoul(e3, nullptr, 10);
     if (const char* e4 = getenv("B200SA_GROUPSORT_TINY")) groupsort_tiny = (u32)strtoul(e4, nullptr, 10);
     if (const char* e5 = getenv("B200SA_GROUPSORT_MEDIUM")) groupsort_medium = (u32)strtoul(e5, nullptr, 10);
-    if (const char* e7 = getenv("B200SA_LCP_FUSED")) lcp_fused_fine = atoi(e7) != 0;
     if (const char* e6 = getenv("B200SA_UNBWT_CAP_MULT")) unbwt_cap_mult = (u32)strtoul(e6, nullptr, 10);
     if (unbwt_cap_mult < 1) unbwt_cap_mult = 1;
     if (groupsort_tiny > (u32)GS_TINY) groupsort_tiny = GS_TINY;
@@ -880,17 +879,9 @@ int Engine::lcp_dev(const u8* d_text, i64 n64, const i32* d_sa, i32* d_lcp, cuda
         return 0;
     };
     B200SA_TRY(run_level(0, top, 0, (u32)div_up_u64(n, top)));
-    // coarse levels one launch pair each; the five finest levels (S < LF_SPAN) fused in one kernel
-    const bool fused = lcp_fused_fine && top >= (u64)LF_SPAN;
-    for (u64 S = top >> 1; S >= (fused ? (u64)LF_SPAN : 1); S >>= 1) {
+    for (u64 S = top >> 1; S >= 1; S >>= 1) {
         const u32 ns = (u64)n > S ? (u32)(((u64)n - S - 1) / (2 * S) + 1) : 0u;
         B200SA_TRY(run_level((u32)S, 2 * S, (u32)S, ns));
-    }
-    if (fused) {
-        const u32 tiles = (u32)div_up_u64(n, LF_TILE);
-        const u32 grid = tiles < (u32)(num_sms * 6) ? tiles : (u32)(num_sms * 6);
-        B200SA_LAUNCH(k_plcp_fine, grid, LC_THREADS, 0, st, d_text, n, (const u32*)phi, plcp);
-        count_launch(B200SA_PH_LCP);
     }
     // ---- lcp[r] = plcp[SA[r]]
     {

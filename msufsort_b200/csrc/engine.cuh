@@ -79,9 +79,6 @@ struct Engine {
     // inverse BWT: bytes of decode window per walker = unbwt_cap_mult * D (D = mean segment length)
     u32 unbwt_cap_mult = 4;
 
-    // LCP: run the five finest PLCP levels in one shared-memory kernel (0: one launch pair per level, for tests)
-    bool lcp_fused_fine = true;
-
     // instrumentation
     bool profiling = false;
     b200sa_profile prof;

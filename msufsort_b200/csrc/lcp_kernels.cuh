@@ -11,7 +11,8 @@
 //
 // The inequality is used hierarchically so that every position is an independent thread: level L handles the
 // positions that are odd multiples of S = 2^L, each starting from the lower bound given by the position S to
-// its left, which a coarser level has already finished.  The sum of all extensions of one level is < 3n
+// its left, which a coarser level has already finished (one launch pair per level: a fused shared-memory kernel
+// for the five finest levels measured 8.9 ms against 7.2 ms for the five launches, profiles/r01_negative_results.md).  The sum of all extensions of one level is < 3n
 // bytes whatever the text looks like, and the extension of one position beyond a small budget is handed to a
 // second kernel in which a whole CTA compares 8 KB per iteration, so periodic / Fibonacci inputs (lcp ~ n)
 // cost a bounded number of streaming passes instead of n * LCP byte compares.
@@ -151,86 +152,6 @@ k_plcp_overflow(const u8* __restrict__ text, u32 n, const u32* __restrict__ phi,
         const u32 p = ovf_pos[e];
         const u32 result = lc_cta_extend(text, words, off, n, p, phi[p], ovf_len[e], s_min, &s_res);
         if (threadIdx.x == 0) plcp[p] = result;
-    }
-}
-
-// The five finest levels (S = 16, 8, 4, 2, 1) in one kernel.  Separate launches would read phi and read-modify-
-// write plcp once per level at a fraction of the sector width (positions 2S apart); here a CTA stages phi and
-// the already known plcp values (multiples of LF_SPAN) of LF_TILE consecutive positions in shared memory, runs
-// the levels on the tile — all dependencies of a position lie inside its LF_SPAN-aligned chunk — and writes plcp
-// back with one coalesced sweep.  Matches that outgrow a thread's budget are finished by the whole CTA between
-// two levels (lc_cta_extend), so the lower bounds the next level starts from are exact.
-static const int LF_SPAN = 32;
-static const int LF_TILE = 4096;
-static const int LF_LIST = 128;
-
-__global__ void __launch_bounds__(LC_THREADS)
-k_plcp_fine(const u8* __restrict__ text, u32 n, const u32* __restrict__ phi, u32* __restrict__ plcp)
-{
-    __shared__ u32 s_phi[LF_TILE], s_pl[LF_TILE];
-    __shared__ u32 s_lpos[LF_LIST], s_llen[LF_LIST];
-    __shared__ u32 s_nlist, s_res;
-    __shared__ u32 s_min[LC_THREADS / 32];
-    const u32 off = (u32)((uintptr_t)text & 3u);
-    const u32* words = (const u32*)(text - off);
-    const u32 tid = threadIdx.x;
-    const u32 ntiles = (u32)div_up_u64(n, LF_TILE);
-    for (u32 tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const u32 base = tile * (u32)LF_TILE;
-        for (u32 i = tid; i < (u32)LF_TILE; i += LC_THREADS) s_phi[i] = base + i < n ? ld_stream(phi + base + i) : 0u;
-        for (u32 c = tid; c < (u32)(LF_TILE / LF_SPAN); c += LC_THREADS) {
-            const u32 gp = base + c * (u32)LF_SPAN;
-            s_pl[c * LF_SPAN] = gp < n ? plcp[gp] : 0u;
-        }
-        if (tid == 0) s_nlist = 0;
-        __syncthreads();
-        for (u32 S = LF_SPAN / 2; S >= 1u; S >>= 1) {
-            const u32 nsamp = (u32)LF_TILE / (2u * S);
-            for (u32 j = tid; j < nsamp; j += LC_THREADS) {
-                const u32 lp = S + j * 2u * S;
-                const u32 p = base + lp;
-                if (p >= n) continue;
-                const u32 q = s_phi[lp];
-                const u32 prev = s_pl[lp - S];
-                u32 l = prev > S ? prev - S : 0u;
-                if (q >= n) { s_pl[lp] = 0; continue; }
-                const u32 maxl = n - (p > q ? p : q);
-                u32 stop = (maxl - l) > LC_BUDGET ? l + LC_BUDGET : maxl;
-                bool open = true;
-                for (;;) {
-                    while (open && l + 8u <= stop) {
-                        const u64 x = lc_load8(words, off, p + l) ^ lc_load8(words, off, q + l);
-                        if (x) { l += (u32)(__ffsll((long long)x) - 1) >> 3; open = false; }
-                        else l += 8u;
-                    }
-                    while (open && l < stop) {
-                        if (text[p + l] != text[q + l]) open = false;
-                        else ++l;
-                    }
-                    if (!open || l >= maxl) break;
-                    // budget used up: hand the match to the CTA, or (list full) keep going alone
-                    const u32 slot = atomicAdd(&s_nlist, 1u);
-                    if (slot < (u32)LF_LIST) { s_lpos[slot] = lp; s_llen[slot] = l; break; }
-                    stop = maxl;
-                }
-                s_pl[lp] = l;  // exact, or a placeholder that the CTA pass below overwrites
-            }
-            __syncthreads();
-            const u32 nl = s_nlist < (u32)LF_LIST ? s_nlist : (u32)LF_LIST;
-            __syncthreads();  // everyone has read the count before the next level (or the reset below) touches it
-            if (nl) {
-                for (u32 e = 0; e < nl; ++e) {
-                    const u32 lp = s_lpos[e];
-                    const u32 r = lc_cta_extend(text, words, off, n, base + lp, s_phi[lp], s_llen[e], s_min, &s_res);
-                    if (tid == 0) s_pl[lp] = r;
-                }
-                if (tid == 0) s_nlist = 0;
-                __syncthreads();
-            }
-        }
-        for (u32 i = tid; i < (u32)LF_TILE; i += LC_THREADS)
-            if (base + i < n) st_stream(plcp + base + i, s_pl[i]);
-        __syncthreads();
     }
 }
 

@@ -64,14 +64,12 @@ def test_emu_lcp_long_matches_and_unaligned_text(emu_engine, oracle):
             assert np.array_equal(out, lcp), (family, shift)
 
 
-@pytest.mark.parametrize("fused", ["0", "1"])
-def test_emu_lcp_bucketed_phi(oracle, monkeypatch, fused):
-    """bucketed phi scatter; fine levels as one fused kernel and as one launch pair per level"""
+def test_emu_lcp_bucketed_phi(oracle, monkeypatch):
+    """phi scattered through the bucketed (radix sweep + L2-window) path"""
     from conftest import ROOT
     from msufsort_b200.api import Engine, Library
     monkeypatch.setenv("B200SA_ISA_DIRECT_BYTES", "0")
     monkeypatch.setenv("B200SA_ISA_MIN_UPDATES", "1")
-    monkeypatch.setenv("B200SA_LCP_FUSED", fused)
     eng = Engine(0, library=Library(os.path.join(ROOT, "tests", "emu", "libb200sa_emu.so")))
     try:
         for family, n in [("markov3", 70011), ("acgt_rep", 40000), ("zeros", 35000), ("fib", 46368), ("rand", 1)]:

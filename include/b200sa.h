@@ -164,6 +164,25 @@ B200SA_API int b200sa_batch_dev(b200sa_ctx* ctx, const uint8_t* d_blocks, const 
 B200SA_API int b200sa_unbwt_batch_dev(b200sa_ctx* ctx, const uint8_t* d_bwt, const int64_t* offsets, int64_t count,
                                       const int32_t* sentinel_index, uint8_t* d_text_out, void* stream);
 
+/* Streaming pipeline over batches ("pinned-buffer pipeline overlapping H2D, sort, D2H").
+ * `depth` contexts with their own streams, workspaces and worker threads serve one queue of submitted batches,
+ * so the upload of batch i+1 and the download of batch i-1 overlap the sort of batch i.  submit returns at once
+ * with a ticket; the host buffers must stay valid (and untouched) until b200sa_pipeline_wait(ticket) returns
+ * the job's status.  Pinned host memory makes the copies asynchronous.  Results are identical to the
+ * b200sa_*_batch calls.  The reference has no counterpart (its callers loop over blocks, main.cpp:466-487). */
+typedef struct b200sa_pipeline b200sa_pipeline;
+B200SA_API int b200sa_pipeline_create(b200sa_pipeline** out, int device, int depth);
+B200SA_API void b200sa_pipeline_destroy(b200sa_pipeline* p);
+B200SA_API int b200sa_pipeline_submit_bwt(b200sa_pipeline* p, uint8_t* blocks_inout, const int64_t* offsets, int64_t count,
+                                          int32_t* sentinel_index_out, int64_t* ticket_out);
+B200SA_API int b200sa_pipeline_submit_unbwt(b200sa_pipeline* p, uint8_t* blocks_inout, const int64_t* offsets, int64_t count,
+                                            const int32_t* sentinel_index, int64_t* ticket_out);
+B200SA_API int b200sa_pipeline_submit_suffix_array(b200sa_pipeline* p, const uint8_t* blocks, const int64_t* offsets,
+                                                   int64_t count, int32_t* sa_out, int64_t* ticket_out);
+B200SA_API int b200sa_pipeline_wait(b200sa_pipeline* p, int64_t ticket);
+/* Waits for everything submitted so far; returns the first failure among tickets nobody waited for. */
+B200SA_API int b200sa_pipeline_drain(b200sa_pipeline* p);
+
 /* ---- sharded (multi-GPU) building blocks --------------------------------------------------
  *
  * One text, G GPUs, one process and one context per GPU (msufsort_b200/sharded.py drives these over

@@ -10,6 +10,7 @@ from .api import (  # noqa: F401
     B200SAError,
     Library,
     Engine,
+    Pipeline,
     load_library,
     make_suffix_array,
     forward_burrows_wheeler_transform,
@@ -20,6 +21,6 @@ from .api import (  # noqa: F401
 from . import textgen  # noqa: F401
 
 __all__ = [
-    "B200SAError", "Library", "Engine", "load_library", "make_suffix_array",
+    "B200SAError", "Library", "Engine", "Pipeline", "load_library", "make_suffix_array",
     "forward_burrows_wheeler_transform", "reverse_burrows_wheeler_transform", "make_lcp_array", "textgen", "PHASES",
 ]

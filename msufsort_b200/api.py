@@ -71,6 +71,13 @@ ABI = [
     ("b200sa_unbwt_batch", C.c_int, [_P, _P, _P, C.c_int64, _P]),
     ("b200sa_batch_dev", C.c_int, [_P, _P, _P, C.c_int64, _P, _P, _P, _P]),
     ("b200sa_unbwt_batch_dev", C.c_int, [_P, _P, _P, C.c_int64, _P, _P, _P]),
+    ("b200sa_pipeline_create", C.c_int, [C.POINTER(_P), C.c_int, C.c_int]),
+    ("b200sa_pipeline_destroy", None, [_P]),
+    ("b200sa_pipeline_submit_bwt", C.c_int, [_P, _P, _P, C.c_int64, _P, C.POINTER(C.c_int64)]),
+    ("b200sa_pipeline_submit_unbwt", C.c_int, [_P, _P, _P, C.c_int64, _P, C.POINTER(C.c_int64)]),
+    ("b200sa_pipeline_submit_suffix_array", C.c_int, [_P, _P, _P, C.c_int64, _P, C.POINTER(C.c_int64)]),
+    ("b200sa_pipeline_wait", C.c_int, [_P, C.c_int64]),
+    ("b200sa_pipeline_drain", C.c_int, [_P]),
     ("b200sa_shard_begin", C.c_int, [_P, _P, C.c_int64, _P, C.c_int, C.c_int, C.POINTER(C.c_int64), _P]),
     ("b200sa_shard_round0", C.c_int, [_P, C.c_int64, C.POINTER(C.c_int64), _P]),
     ("b200sa_shard_round", C.c_int, [_P, C.POINTER(C.c_int64), _P]),
@@ -433,6 +440,71 @@ class Engine:
 
     def release_workspace(self) -> None:
         self.lib.check(self.lib.cdll.b200sa_release_workspace(self._ctx))
+
+
+class Pipeline:
+    """Streaming pipeline over batches: ``depth`` contexts behind one queue, so that the transfers of one batch
+    overlap the sort of another (b200sa_pipeline_*).  Buffers passed to submit must stay alive and untouched
+    until ``wait``; numpy arrays are kept referenced here until then."""
+
+    def __init__(self, device: int = 0, depth: int = 2, library: Optional[Library] = None):
+        self.lib = library if library is not None else load_library()
+        self._p = _P()
+        self.lib.check(self.lib.cdll.b200sa_pipeline_create(C.byref(self._p), device, depth))
+        self._keep = {}
+
+    def submit_bwt(self, packed: np.ndarray, offsets: np.ndarray, sentinels_out: np.ndarray) -> int:
+        """packed: writable uint8 array (transformed in place); offsets: int64[count+1]; sentinels_out: int32[count]"""
+        t = C.c_int64(0)
+        self.lib.check(self.lib.cdll.b200sa_pipeline_submit_bwt(self._p, _ptr(packed), _ptr(offsets), offsets.size - 1, _ptr(sentinels_out), C.byref(t)))
+        self._keep[t.value] = (packed, offsets, sentinels_out)
+        return int(t.value)
+
+    def submit_unbwt(self, packed: np.ndarray, offsets: np.ndarray, sentinels: np.ndarray) -> int:
+        t = C.c_int64(0)
+        self.lib.check(self.lib.cdll.b200sa_pipeline_submit_unbwt(self._p, _ptr(packed), _ptr(offsets), offsets.size - 1, _ptr(sentinels), C.byref(t)))
+        self._keep[t.value] = (packed, offsets, sentinels)
+        return int(t.value)
+
+    def submit_suffix_array(self, packed: np.ndarray, offsets: np.ndarray, sa_out: np.ndarray) -> int:
+        t = C.c_int64(0)
+        self.lib.check(self.lib.cdll.b200sa_pipeline_submit_suffix_array(self._p, _ptr(packed), _ptr(offsets), offsets.size - 1, _ptr(sa_out), C.byref(t)))
+        self._keep[t.value] = (packed, offsets, sa_out)
+        return int(t.value)
+
+    def submit_bwt_ptr(self, blocks_ptr: int, offsets: np.ndarray, sentinels_ptr: int) -> int:
+        t = C.c_int64(0)
+        self.lib.check(self.lib.cdll.b200sa_pipeline_submit_bwt(self._p, blocks_ptr, _ptr(offsets), offsets.size - 1, sentinels_ptr, C.byref(t)))
+        self._keep[t.value] = (offsets,)
+        return int(t.value)
+
+    def wait(self, ticket: int) -> None:
+        rc = self.lib.cdll.b200sa_pipeline_wait(self._p, ticket)
+        self._keep.pop(ticket, None)
+        self.lib.check(rc)
+
+    def drain(self) -> None:
+        rc = self.lib.cdll.b200sa_pipeline_drain(self._p)
+        self._keep.clear()
+        self.lib.check(rc)
+
+    def close(self) -> None:
+        if getattr(self, "_p", None) is not None and self._p:
+            self.lib.cdll.b200sa_pipeline_destroy(self._p)
+            self._p = _P()
+            self._keep.clear()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
 
 
 # ---- module-level functions with the reference's names ---------------------------------------

@@ -1374,6 +1374,167 @@ int b200sa_unbwt_batch(b200sa_ctx* ctx, uint8_t* blocks_inout, const int64_t* of
     return 0;
 }
 
+// ---- streaming pipeline over batches --------------------------------------------------------------
+//
+// `depth` contexts (each: own stream, own workspace, own worker thread) take submitted batches from one queue.
+// While one context sorts, another uploads its next batch and a third downloads its results, so the copy
+// engines and the SMs overlap across batches; inside a batch nothing changes.  Host buffers handed to submit
+// must stay valid until the ticket has been waited for; pinned memory makes the copies truly asynchronous.
+
+}  // extern "C"
+
+#include <condition_variable>
+#include <deque>
+#include <map>
+#include <thread>
+
+struct b200sa_pipeline {
+    struct Job {
+        int64_t ticket;
+        int kind;  // 0 forward BWT, 1 inverse BWT, 2 suffix arrays
+        uint8_t* blocks;
+        const int64_t* offsets;
+        int64_t count;
+        int32_t* sentinels;  // out (forward) / in (inverse)
+        int32_t* sa_out;
+    };
+    std::vector<b200sa_ctx*> ctxs;
+    std::vector<std::thread> workers;
+    std::mutex mu;
+    std::condition_variable cv_work, cv_done;
+    std::deque<Job> queue;
+    std::map<int64_t, std::pair<int, std::string>> done;  // ticket -> (status, message)
+    int64_t next_ticket = 1;
+    int64_t in_flight = 0;
+    bool stopping = false;
+
+    void run(size_t w)
+    {
+        for (;;) {
+            Job job;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv_work.wait(lk, [&] { return stopping || !queue.empty(); });
+                if (queue.empty()) return;
+                job = queue.front();
+                queue.pop_front();
+            }
+            int rc;
+            {
+#ifdef B200SA_EMU
+                static std::mutex emu_mu;  // the CPU emulator is single-threaded
+                std::lock_guard<std::mutex> g(emu_mu);
+#endif
+                if (job.kind == 0) rc = b200sa_bwt_batch(ctxs[w], job.blocks, job.offsets, job.count, job.sentinels);
+                else if (job.kind == 1) rc = b200sa_unbwt_batch(ctxs[w], job.blocks, job.offsets, job.count, job.sentinels);
+                else rc = b200sa_suffix_array_batch(ctxs[w], job.blocks, job.offsets, job.count, job.sa_out);
+            }
+            std::string msg = rc ? b200sa_last_error() : "";
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                done[job.ticket] = std::make_pair(rc, msg);
+                --in_flight;
+            }
+            cv_done.notify_all();
+        }
+    }
+};
+
+extern "C" {
+
+int b200sa_pipeline_create(b200sa_pipeline** out, int device, int depth)
+{
+    if (!out) return b200sa::set_error(B200SA_EINVAL, "null out pointer");
+    *out = nullptr;
+    if (depth < 1 || depth > 8) return b200sa::set_error(B200SA_EINVAL, "pipeline depth %d outside [1, 8]", depth);
+    b200sa_pipeline* p = new (std::nothrow) b200sa_pipeline();
+    if (!p) return b200sa::set_error(B200SA_ENOMEM, "out of host memory");
+    for (int i = 0; i < depth; ++i) {
+        b200sa_ctx* c = nullptr;
+        const int rc = b200sa_create(&c, device);
+        if (rc != 0) {
+            for (auto* q : p->ctxs) b200sa_destroy(q);
+            delete p;
+            return rc;
+        }
+        p->ctxs.push_back(c);
+    }
+    for (int i = 0; i < depth; ++i) p->workers.emplace_back([p, i] { p->run((size_t)i); });
+    *out = p;
+    return 0;
+}
+
+void b200sa_pipeline_destroy(b200sa_pipeline* p)
+{
+    if (!p) return;
+    {
+        std::lock_guard<std::mutex> lk(p->mu);
+        p->stopping = true;  // workers finish what is queued, then leave
+    }
+    p->cv_work.notify_all();
+    for (auto& t : p->workers) t.join();
+    for (auto* c : p->ctxs) b200sa_destroy(c);
+    delete p;
+}
+
+static int pipeline_submit(b200sa_pipeline* p, int kind, uint8_t* blocks, const int64_t* offsets, int64_t count, int32_t* sentinels,
+                           int32_t* sa_out, int64_t* ticket_out)
+{
+    if (!p || !ticket_out) return b200sa::set_error(B200SA_EINVAL, "null pipeline or ticket pointer");
+    {
+        std::lock_guard<std::mutex> lk(p->mu);
+        if (p->stopping) return b200sa::set_error(B200SA_EINVAL, "pipeline is shutting down");
+        *ticket_out = p->next_ticket++;
+        p->queue.push_back(b200sa_pipeline::Job{*ticket_out, kind, blocks, offsets, count, sentinels, sa_out});
+        ++p->in_flight;
+    }
+    p->cv_work.notify_one();
+    return 0;
+}
+
+int b200sa_pipeline_submit_bwt(b200sa_pipeline* p, uint8_t* blocks_inout, const int64_t* offsets, int64_t count,
+                               int32_t* sentinel_index_out, int64_t* ticket_out)
+{
+    return pipeline_submit(p, 0, blocks_inout, offsets, count, sentinel_index_out, nullptr, ticket_out);
+}
+
+int b200sa_pipeline_submit_unbwt(b200sa_pipeline* p, uint8_t* blocks_inout, const int64_t* offsets, int64_t count,
+                                 const int32_t* sentinel_index, int64_t* ticket_out)
+{
+    return pipeline_submit(p, 1, blocks_inout, offsets, count, const_cast<int32_t*>(sentinel_index), nullptr, ticket_out);
+}
+
+int b200sa_pipeline_submit_suffix_array(b200sa_pipeline* p, const uint8_t* blocks, const int64_t* offsets, int64_t count,
+                                        int32_t* sa_out, int64_t* ticket_out)
+{
+    return pipeline_submit(p, 2, const_cast<uint8_t*>(blocks), offsets, count, nullptr, sa_out, ticket_out);
+}
+
+int b200sa_pipeline_wait(b200sa_pipeline* p, int64_t ticket)
+{
+    if (!p) return b200sa::set_error(B200SA_EINVAL, "null pipeline");
+    std::unique_lock<std::mutex> lk(p->mu);
+    if (ticket < 1 || ticket >= p->next_ticket) return b200sa::set_error(B200SA_EINVAL, "unknown ticket %lld", (long long)ticket);
+    p->cv_done.wait(lk, [&] { return p->done.count(ticket) != 0; });
+    auto it = p->done.find(ticket);
+    const int rc = it->second.first;
+    if (rc) b200sa::set_error(rc, "%s", it->second.second.c_str());
+    p->done.erase(it);
+    return rc;
+}
+
+int b200sa_pipeline_drain(b200sa_pipeline* p)
+{
+    if (!p) return b200sa::set_error(B200SA_EINVAL, "null pipeline");
+    std::unique_lock<std::mutex> lk(p->mu);
+    p->cv_done.wait(lk, [&] { return p->in_flight == 0; });
+    int first = 0;
+    for (auto& kv : p->done)
+        if (kv.second.first && !first) { first = kv.second.first; b200sa::set_error(first, "%s", kv.second.second.c_str()); }
+    p->done.clear();
+    return first;
+}
+
 // ---- sharded (multi-GPU) building blocks ---------------------------------------------------------
 
 int b200sa_shard_begin(b200sa_ctx* ctx, const uint8_t* d_text, int64_t n, int32_t* d_sa, int part, int nparts,

@@ -128,3 +128,58 @@ def test_gpu_batch_many_blocks_device_resident(gpu_engine, oracle):
     gpu_engine.unbwt_batch_dev(d_bwt, offsets, sent, d_back)
     torch.cuda.synchronize()
     assert torch.equal(d_back, d_blocks)
+
+
+# ---- streaming pipeline ---------------------------------------------------------------------------
+def _pipeline_roundtrip(lib, oracle, nbatches, blocks_per_batch, block_len, depth):
+    from msufsort_b200.api import Pipeline
+    rng = np.random.default_rng(depth)
+    jobs = []
+    with Pipeline(0, depth, library=lib) as pipe:
+        for j in range(nbatches):
+            blocks = [gen(["markov3", "rand", "acgt_rep", "zeros"][(j + b) % 4], int(rng.integers(1, block_len))) for b in range(blocks_per_batch)]
+            packed = np.concatenate(blocks)
+            offsets = np.zeros(len(blocks) + 1, dtype=np.int64)
+            np.cumsum([x.size for x in blocks], out=offsets[1:])
+            sent = np.zeros(len(blocks), dtype=np.int32)
+            orig = packed.copy()
+            jobs.append((pipe.submit_bwt(packed, offsets, sent), packed, offsets, sent, orig, blocks))
+        for t, packed, offsets, sent, orig, blocks in jobs:
+            pipe.wait(t)
+            for b, x in enumerate(blocks):
+                wb, ws = oracle.bwt(x)
+                assert ws == sent[b] and np.array_equal(packed[offsets[b]:offsets[b + 1]], wb), b
+        # inverse through the same pipeline, all in flight at once, then drain
+        for t, packed, offsets, sent, orig, blocks in jobs:
+            pipe.submit_unbwt(packed, offsets, sent)
+        pipe.drain()
+        for t, packed, offsets, sent, orig, blocks in jobs:
+            assert np.array_equal(packed, orig)
+        # suffix arrays
+        packed, offsets = jobs[0][4], jobs[0][2]
+        sa = np.empty(packed.size + offsets.size - 1, dtype=np.int32)
+        pipe.wait(pipe.submit_suffix_array(packed, offsets, sa))
+        for b, x in enumerate(jobs[0][5]):
+            assert np.array_equal(sa[offsets[b] + b: offsets[b + 1] + b + 1], oracle.sa(x))
+
+
+def test_emu_pipeline(oracle):
+    import os
+    from conftest import ROOT
+    from msufsort_b200.api import B200SAError, Library, Pipeline
+    lib = Library(os.path.join(ROOT, "tests", "emu", "libb200sa_emu.so"))
+    _pipeline_roundtrip(lib, oracle, nbatches=5, blocks_per_batch=6, block_len=3000, depth=3)
+    with Pipeline(0, 2, library=lib) as pipe:
+        bad = np.zeros(4, dtype=np.uint8)
+        t = pipe.submit_unbwt(bad, np.array([0, 4], dtype=np.int64), np.array([9], dtype=np.int32))  # sentinel outside [1, n]
+        with pytest.raises(B200SAError):
+            pipe.wait(t)
+        with pytest.raises(B200SAError):
+            pipe.wait(12345)
+    with pytest.raises(B200SAError):
+        Pipeline(0, 0, library=lib)
+
+
+@pytest.mark.gpu
+def test_gpu_pipeline(gpu_engine, oracle):
+    _pipeline_roundtrip(gpu_engine.lib, oracle, nbatches=8, blocks_per_batch=24, block_len=200000, depth=3)

@@ -389,6 +389,8 @@ def run_sharded(args, wl):
                              for k, v in prof["phases"].items() if v["launches"]},
         }
         print(json.dumps(line))
+    dist.barrier()
+    eng.close()
     dist.destroy_process_group()
     return 0
 
@@ -402,7 +404,7 @@ def main():
     ap.add_argument("--workload", default="markov3_256MiB", choices=sorted(WORKLOADS))
     ap.add_argument("--n", type=int, default=0, help="override the text size (debugging)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--isa", default="owner", choices=["owner", "replicated"], help="sharded mode: how the ISA travels (see msufsort_b200/sharded.py)")
+    ap.add_argument("--isa", default="owner", choices=["owner", "replicated", "peer"], help="sharded mode: how the ISA travels (see msufsort_b200/sharded.py)")
     ap.add_argument("--mode", default="independent", choices=["independent", "sharded"],
                     help="N>1 only. independent (default): one text per GPU, no data-path collective, weak scaling. "
                          "sharded: ONE text partitioned by key range over the N GPUs, ISA updates all-gathered over NCCL "

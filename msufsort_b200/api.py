@@ -87,6 +87,10 @@ ABI = [
     ("b200sa_shard_partition", C.c_int, [_P, _P, _P, C.c_int64, C.c_int, _P, _P, C.POINTER(C.c_uint32), _P]),
     ("b200sa_shard_requests", C.c_int, [_P, _P, C.c_int64, C.POINTER(C.c_int64), _P]),
     ("b200sa_shard_gather_ranks", C.c_int, [_P, _P, C.c_int64, _P, _P]),
+    ("b200sa_shard_peer_export", C.c_int, [_P, C.c_int64, _P]),
+    ("b200sa_shard_peer_attach", C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int64, _P]),
+    ("b200sa_shard_peer_scatter", C.c_int, [_P, _P]),
+    ("b200sa_shard_peer_detach", C.c_int, [_P]),
     ("b200sa_shard_bwt", C.c_int, [_P, C.c_int64, C.c_int64, _P, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int32), _P]),
     ("b200sa_unbwt_shard_build", C.c_int, [_P, _P, C.c_int64, C.c_int32, C.POINTER(C.c_int64), _P]),
     ("b200sa_unbwt_shard_measure", C.c_int, [_P, C.c_int64, C.c_int64, _P]),
@@ -399,6 +403,22 @@ class Engine:
 
     def shard_gather_ranks(self, d_pos, count: int, d_out, stream: Optional[int] = None) -> None:
         self.lib.check(self.lib.cdll.b200sa_shard_gather_ranks(self._ctx, _ptr(d_pos), count, _ptr(d_out), self._st(stream)))
+
+    def shard_peer_export(self, n: int) -> bytes:
+        buf = (C.c_uint8 * 64)()
+        self.lib.check(self.lib.cdll.b200sa_shard_peer_export(self._ctx, n, buf))
+        return bytes(buf)
+
+    def shard_peer_attach(self, part: int, nparts: int, shift: int, n: int, handles: bytes) -> None:
+        assert len(handles) == 64 * nparts
+        buf = (C.c_uint8 * len(handles)).from_buffer_copy(handles)
+        self.lib.check(self.lib.cdll.b200sa_shard_peer_attach(self._ctx, part, nparts, shift, n, buf))
+
+    def shard_peer_scatter(self, stream: Optional[int] = None) -> None:
+        self.lib.check(self.lib.cdll.b200sa_shard_peer_scatter(self._ctx, self._st(stream)))
+
+    def shard_peer_detach(self) -> None:
+        self.lib.check(self.lib.cdll.b200sa_shard_peer_detach(self._ctx))
 
     def shard_bwt(self, row_begin: int, row_end: int, d_bwt, stream: Optional[int] = None):
         ob, oe, s = C.c_int64(0), C.c_int64(0), C.c_int32(0)

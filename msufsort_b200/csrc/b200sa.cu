@@ -130,6 +130,7 @@ int Engine::release_workspace()
 void Engine::shutdown()
 {
     cudaSetDevice(device);
+    peer_detach();
     release_workspace();
     for (auto& s : spans) { event_pool.push_back(s.a); event_pool.push_back(s.b); }
     spans.clear();
@@ -505,6 +506,11 @@ int Engine::sort_round(u32* m_local, cudaStream_t st)
     const int act = ss.act;
     const int gid_bits = ss.groups <= 1 ? 0 : bit_length_u64((u64)ss.groups - 1);
     int sorted_side = -1;
+    // where rank[suffix + h] is read from: this GPU's array, or the shards of all GPUs through peer memory
+    const bool use_peer = peer.active && ss.nparts > 1;
+    if (use_peer && (peer.view.n != n || peer.nparts != ss.nparts)) return set_error(B200SA_EINVAL, "peer ISA attached for another text size / GPU count");
+    LocalRank local_rank{rank.as<u32>(), n};
+    PeerRank peer_rank{peer.view};
 
     // ---- small groups: sort every group where it lies (no radix sweeps)
     if (groupsort_max_avg > 0 && (u64)m <= (u64)ss.groups * groupsort_max_avg) {
@@ -516,9 +522,15 @@ int Engine::sort_round(u32* m_local, cudaStream_t st)
         B200SA_CU(cudaMemsetAsync(d_cnt, 0, 16, st));
         prof.memsets++;
         B200SA_TRY(phase_begin(B200SA_PH_SEGSORT, st));
-        B200SA_LAUNCH(k_group_sort_tiny, (u32)div_up_u64(G, GS_THREADS), GS_THREADS, 0, st, (const u32*)gstart.as<u32>(), G, v2[act],
-                      (const u32*)rank.as<u32>(), n, (u32)ss.h, ss.rank_bits, k2[act], groupsort_tiny, groupsort_medium,
-                      medium_list, huge_list, d_cnt);
+        if (use_peer) {
+            auto kt = k_group_sort_tiny<PeerRank>;
+            B200SA_LAUNCH(kt, (u32)div_up_u64(G, GS_THREADS), GS_THREADS, 0, st, (const u32*)gstart.as<u32>(), G, v2[act],
+                          peer_rank, n, (u32)ss.h, ss.rank_bits, k2[act], groupsort_tiny, groupsort_medium, medium_list, huge_list, d_cnt);
+        } else {
+            auto kt = k_group_sort_tiny<LocalRank>;
+            B200SA_LAUNCH(kt, (u32)div_up_u64(G, GS_THREADS), GS_THREADS, 0, st, (const u32*)gstart.as<u32>(), G, v2[act],
+                          local_rank, n, (u32)ss.h, ss.rank_bits, k2[act], groupsort_tiny, groupsort_medium, medium_list, huge_list, d_cnt);
+        }
         count_launch(B200SA_PH_SEGSORT);
         B200SA_CU(cudaMemcpyAsync(h_pinned + 20, d_cnt, 16, cudaMemcpyDeviceToHost, st));
         B200SA_CU(cudaStreamSynchronize(st));
@@ -526,8 +538,15 @@ int Engine::sort_round(u32* m_local, cudaStream_t st)
         prof.alg_bytes[B200SA_PH_SEGSORT] += (u64)G * 4 + (u64)m * 20;
         if (nhuge <= 64) {
             if (nmedium) {
-                B200SA_LAUNCH(k_group_sort_medium, nmedium, GM_THREADS, 0, st, (const u32*)medium_list, (const u32*)gstart.as<u32>(),
-                              v2[act], (const u32*)rank.as<u32>(), n, (u32)ss.h, ss.rank_bits, k2[act]);
+                if (use_peer) {
+                    auto km = k_group_sort_medium<PeerRank>;
+                    B200SA_LAUNCH(km, nmedium, GM_THREADS, 0, st, (const u32*)medium_list, (const u32*)gstart.as<u32>(), v2[act], peer_rank, n,
+                                  (u32)ss.h, ss.rank_bits, k2[act]);
+                } else {
+                    auto km = k_group_sort_medium<LocalRank>;
+                    B200SA_LAUNCH(km, nmedium, GM_THREADS, 0, st, (const u32*)medium_list, (const u32*)gstart.as<u32>(), v2[act], local_rank, n,
+                                  (u32)ss.h, ss.rank_bits, k2[act]);
+                }
                 count_launch(B200SA_PH_SEGSORT);
             }
             B200SA_TRY(phase_end(st));
@@ -545,8 +564,15 @@ int Engine::sort_round(u32* m_local, cudaStream_t st)
                     B200SA_TRY(phase_begin(B200SA_PH_BUILD, st));
                     const u32 tiles = (u32)div_up_u64(sz, BK_THREADS * BK_IPT);
                     const u32 grid = tiles < (u32)(num_sms * 8) ? tiles : (u32)(num_sms * 8);
-                    B200SA_LAUNCH(k_build_keys, grid, BK_THREADS, 0, st, (const u32*)(v2[act] + s0), (const u32*)(gid.as<u32>() + s0),
-                                  (const u32*)rank.as<u32>(), sz, n, (u32)ss.h, ss.rank_bits, k2[act] + s0);
+                    if (use_peer) {
+                        auto kb = k_build_keys<PeerRank>;
+                        B200SA_LAUNCH(kb, grid, BK_THREADS, 0, st, (const u32*)(v2[act] + s0), (const u32*)(gid.as<u32>() + s0), peer_rank, sz, n,
+                                      (u32)ss.h, ss.rank_bits, k2[act] + s0);
+                    } else {
+                        auto kb = k_build_keys<LocalRank>;
+                        B200SA_LAUNCH(kb, grid, BK_THREADS, 0, st, (const u32*)(v2[act] + s0), (const u32*)(gid.as<u32>() + s0), local_rank, sz, n,
+                                      (u32)ss.h, ss.rank_bits, k2[act] + s0);
+                    }
                     count_launch(B200SA_PH_BUILD);
                     B200SA_TRY(phase_end(st));
                     u64* kk[2] = {k2[act] + s0, k2[act ^ 1] + s0};
@@ -572,8 +598,15 @@ int Engine::sort_round(u32* m_local, cudaStream_t st)
         {
             const u32 tiles = (u32)div_up_u64(m, BK_THREADS * BK_IPT);
             const u32 grid = tiles < (u32)(num_sms * 8) ? tiles : (u32)(num_sms * 8);
-            B200SA_LAUNCH(k_build_keys, grid, BK_THREADS, 0, st, (const u32*)v2[act], (const u32*)gid.as<u32>(),
-                          (const u32*)rank.as<u32>(), m, n, (u32)ss.h, ss.rank_bits, k2[act]);
+            if (use_peer) {
+                auto kb = k_build_keys<PeerRank>;
+                B200SA_LAUNCH(kb, grid, BK_THREADS, 0, st, (const u32*)v2[act], (const u32*)gid.as<u32>(), peer_rank, m, n, (u32)ss.h,
+                              ss.rank_bits, k2[act]);
+            } else {
+                auto kb = k_build_keys<LocalRank>;
+                B200SA_LAUNCH(kb, grid, BK_THREADS, 0, st, (const u32*)v2[act], (const u32*)gid.as<u32>(), local_rank, m, n, (u32)ss.h,
+                              ss.rank_bits, k2[act]);
+            }
             count_launch(B200SA_PH_BUILD);
         }
         B200SA_TRY(phase_end(st));
@@ -622,6 +655,88 @@ int Engine::suffix_array_dev(const u8* d_text, i64 n64, i32* d_sa, cudaStream_t 
 }
 
 // ---------------------------------------------------------------------------------------------
+// ISA sharded over the GPUs of one box, accessed through peer memory (CUDA IPC; msufsort_b200/sharded.py isa="peer")
+
+int Engine::peer_export(u64 n, unsigned char* handle_out)
+{
+    if (n == 0 || n > (u64)B200SA_MAX_N_INT32 || !handle_out) return set_error(B200SA_EINVAL, "bad argument");
+    B200SA_CU(cudaSetDevice(device));
+    B200SA_TRY(ensure_sa_workspace(n));  // the ISA array keeps its address as long as n does not grow
+    cudaIpcMemHandle_t h;
+    B200SA_CU(cudaIpcGetMemHandle(&h, rank.p));
+    static_assert(sizeof(h) == 64, "IPC handle size");
+    memcpy(handle_out, &h, 64);
+    return 0;
+}
+
+int Engine::peer_detach()
+{
+    for (auto& o : peer.opened) cudaIpcCloseMemHandle(o.second);
+    peer.opened.clear();
+    peer = PeerState();
+    return 0;
+}
+
+int Engine::peer_attach(int part, int nparts, int shift, u64 n, const unsigned char* handles)
+{
+    if (nparts < 2 || nparts > kMaxPeers || part < 0 || part >= nparts || shift < 0 || shift > 31 || !handles || n == 0 ||
+        n > (u64)B200SA_MAX_N_INT32)
+        return set_error(B200SA_EINVAL, "bad argument (at most %d GPUs)", kMaxPeers);
+    if (((n - 1) >> shift) >= (u64)nparts) return set_error(B200SA_EINVAL, "shift %d does not spread %llu positions over %d GPUs", shift, (unsigned long long)n, nparts);
+    B200SA_CU(cudaSetDevice(device));
+    B200SA_TRY(ensure_sa_workspace(n));
+    // mappings of an earlier attach are reused when the peer still exports the same allocation
+    std::vector<std::pair<std::string, void*>> keep;
+    PeerState next;
+    for (int g = 0; g < nparts; ++g) {
+        if (g == part) { next.view.base[g] = rank.as<u32>(); continue; }
+        const std::string key((const char*)handles + (size_t)g * 64, 64);
+        void* ptr = nullptr;
+        for (auto& o : peer.opened)
+            if (o.first == key) { ptr = o.second; o.second = nullptr; }
+        if (!ptr) {
+            cudaIpcMemHandle_t h;
+            memcpy(&h, key.data(), 64);
+            cudaError_t e = cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess);
+            if (e != cudaSuccess) {
+                cudaGetLastError();
+                for (auto& k : keep) cudaIpcCloseMemHandle(k.second);
+                return set_error(B200SA_ECOMM, "cudaIpcOpenMemHandle for GPU %d failed: %s", g, cudaGetErrorString(e));
+            }
+        }
+        keep.emplace_back(key, ptr);
+        next.view.base[g] = (u32*)ptr;
+    }
+    for (auto& o : peer.opened)
+        if (o.second) cudaIpcCloseMemHandle(o.second);
+    next.opened = keep;
+    next.active = true;
+    next.part = part;
+    next.nparts = nparts;
+    next.view.shift = shift;
+    next.view.n = (u32)n;
+    peer = next;
+    return 0;
+}
+
+// publishes the (suffix, rank) pairs of the last round0 / round step to the owners of the suffixes
+int Engine::peer_scatter(cudaStream_t st)
+{
+    if (!peer.active || ss.stage < 2) return set_error(B200SA_EINVAL, "no sharded sort with a peer ISA in progress");
+    const u32 count = ss.upd_count;
+    if (count) {
+        B200SA_TRY(phase_begin(B200SA_PH_ISA, st));
+        B200SA_LAUNCH(k_peer_scatter, (u32)div_up_u64(count, SP_THREADS * SP_IPT), SP_THREADS, 0, st, ss.upd_idx, ss.upd_rank, count, peer.view);
+        count_launch(B200SA_PH_ISA);
+        B200SA_TRY(phase_end(st));
+        prof.alg_bytes[B200SA_PH_ISA] += (u64)count * 12;
+        B200SA_CU(cudaGetLastError());
+    }
+    B200SA_CU(cudaStreamSynchronize(st));  // stores to peer memory have landed when the kernel has completed
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
 // forward BWT
 
 // output bytes [o_begin, o_end) from a finished SA (+ rank[0] = sentinel row); the sentinel row lands
@@ -634,7 +749,9 @@ int Engine::bwt_rows(const u8* d_text, u32 n, const i32* d_sa, u32 o_begin, u32 
         const u32 groups = (u32)div_up_u64(o_end - o_begin, 4);
         const u32 want = (u32)div_up_u64(groups, BW_THREADS * BW_STEPS);
         const u32 grid = want < (u32)(num_sms * 16) ? (want ? want : 1u) : (u32)(num_sms * 16);
-        B200SA_LAUNCH(k_bwt_gather, grid, BW_THREADS, 0, st, d_text, d_sa, (const u32*)rank.as<u32>(), o_begin, o_end, d_bwt, d_sent);
+        // rank[0] (the sentinel row) lives on GPU 0 when the ISA is sharded in peer memory
+        const u32* rank0 = (peer.active && ss.nparts > 1) ? (const u32*)peer.view.base[0] : (const u32*)rank.as<u32>();
+        B200SA_LAUNCH(k_bwt_gather, grid, BW_THREADS, 0, st, d_text, d_sa, rank0, o_begin, o_end, d_bwt, d_sent);
         count_launch(B200SA_PH_BWT);
     }
     B200SA_TRY(phase_end(st));
@@ -1610,6 +1727,32 @@ int b200sa_shard_apply_updates(b200sa_ctx* ctx, const uint32_t* d_idx, const uin
     return 0;
 }
 
+int b200sa_shard_peer_export(b200sa_ctx* ctx, int64_t n, uint8_t* handle_out)
+{
+    B200SA_NEED_CTX(ctx);
+    if (n <= 0) return b200sa::set_error(B200SA_EINVAL, "bad argument");
+    return ctx->eng.peer_export((u64)n, handle_out);
+}
+
+int b200sa_shard_peer_attach(b200sa_ctx* ctx, int part, int nparts, int shift, int64_t n, const uint8_t* handles)
+{
+    B200SA_NEED_CTX(ctx);
+    if (n <= 0) return b200sa::set_error(B200SA_EINVAL, "bad argument");
+    return ctx->eng.peer_attach(part, nparts, shift, (u64)n, handles);
+}
+
+int b200sa_shard_peer_scatter(b200sa_ctx* ctx, void* stream)
+{
+    B200SA_NEED_CTX(ctx);
+    return ctx->eng.peer_scatter(ctx->eng.pick(stream));
+}
+
+int b200sa_shard_peer_detach(b200sa_ctx* ctx)
+{
+    B200SA_NEED_CTX(ctx);
+    return ctx->eng.peer_detach();
+}
+
 int b200sa_shard_bwt(b200sa_ctx* ctx, int64_t row_begin, int64_t row_end, uint8_t* d_bwt, int64_t* out_begin, int64_t* out_end,
                      int32_t* sentinel_index_out, void* stream)
 {
@@ -1621,7 +1764,8 @@ int b200sa_shard_bwt(b200sa_ctx* ctx, int64_t row_begin, int64_t row_end, uint8_
         return b200sa::set_error(B200SA_EINVAL, "bad argument");
     cudaStream_t st = e.pick(stream);
     // sentinel row s = rank[0]; rows [row_begin,row_end) minus row s map to bytes [rb - (rb > s), re - (re > s))
-    B200SA_CU(cudaMemcpyAsync(e.h_pinned + 9, e.rank.as<u32>(), 4, cudaMemcpyDeviceToHost, st));
+    const u32* rank0 = (e.peer.active && e.ss.nparts > 1) ? (const u32*)e.peer.view.base[0] : (const u32*)e.rank.as<u32>();
+    B200SA_CU(cudaMemcpyAsync(e.h_pinned + 9, rank0, 4, cudaMemcpyDefault, st));
     B200SA_CU(cudaStreamSynchronize(st));
     const int64_t s = e.h_pinned[9];
     const int64_t ob = row_begin - (row_begin > s ? 1 : 0), oe = row_end - (row_end > s ? 1 : 0);

@@ -113,6 +113,26 @@ __device__ __forceinline__ u32 warp_peers_digit8(u32 d)
     return peers;
 }
 
+// Where a doubling round reads rank[p] (the inverse suffix array) from.  LocalRank: this GPU's array.  PeerRank:
+// the array is sharded over the GPUs of the box — text position p belongs to GPU p >> shift, every GPU maps the
+// arrays of all peers (CUDA IPC over NVLink / NVSwitch) and kernels load and store peer memory directly; no
+// collective moves ranks around (msufsort_b200/sharded.py, isa="peer").
+static const int kMaxPeers = 16;
+struct RankView {
+    u32* base[kMaxPeers];
+    int shift;
+    u32 n;
+};
+struct LocalRank {
+    const u32* r;
+    u32 n;
+    __device__ __forceinline__ u32 operator()(u64 p) const { return r[p < n ? p : n]; }  // r[n] = 0: the empty suffix
+};
+struct PeerRank {
+    RankView v;
+    __device__ __forceinline__ u32 operator()(u64 p) const { return p < v.n ? v.base[(u32)p >> v.shift][(u32)p] : 0u; }
+};
+
 // Inclusive warp scan (sum) over 32 lanes.
 __device__ __forceinline__ u32 warp_incl_scan_u32(u32 v)
 {

@@ -129,6 +129,17 @@ struct Engine {
         u32 batch_count = 0;
         int batch_bits = 0;
     } ss;
+    // ISA sharded over the GPUs of one box and read / written through peer memory (isa="peer")
+    struct PeerState {
+        bool active = false;
+        int part = 0, nparts = 1;
+        RankView view{};
+        std::vector<std::pair<std::string, void*>> opened;  // IPC handle bytes -> mapped pointer
+    } peer;
+    int peer_export(u64 n, unsigned char* handle_out);
+    int peer_attach(int part, int nparts, int shift, u64 n, const unsigned char* handles);
+    int peer_scatter(cudaStream_t st);
+    int peer_detach();
     struct BatchDesc { const u32* d_ends = nullptr; u32 count = 0; } next_batch;  // consumed by the next sort_begin
     int sort_begin(const u8* d_text, u32 n, i32* d_sa, int part, int nparts, u32* n_local, cudaStream_t st);
     int sort_round0(u32 slot_base, u32* m_local, cudaStream_t st);

@@ -230,8 +230,9 @@ __global__ void k_sa_init(u32* __restrict__ rank, i32* __restrict__ sa, u32 n)
 static const int BK_THREADS = 256;
 static const int BK_IPT = 4;
 
+template <typename RankT>
 __global__ void __launch_bounds__(BK_THREADS)
-k_build_keys(const u32* __restrict__ idx, const u32* __restrict__ gid, const u32* __restrict__ rank,
+k_build_keys(const u32* __restrict__ idx, const u32* __restrict__ gid, RankT rank,
              u32 m, u32 n, u32 h, int rank_bits, u64* __restrict__ keys)
 {
     const u32 tile = BK_THREADS * BK_IPT;
@@ -247,8 +248,7 @@ k_build_keys(const u32* __restrict__ idx, const u32* __restrict__ gid, const u32
         }
 #pragma unroll
         for (int q = 0; q < BK_IPT; ++q) {
-            const u64 p = (u64)i[q] + h;
-            r[q] = rank[p < n ? p : n];
+            r[q] = rank((u64)i[q] + h);
         }
 #pragma unroll
         for (int q = 0; q < BK_IPT; ++q) {
@@ -475,8 +475,9 @@ static const int GS_MEDIUM = 4096;
 static const int GS_THREADS = 128;
 
 // counters: [0] #medium groups, [1] #huge groups, [2] tuples in medium groups, [3] tuples in huge groups
+template <typename RankT>
 __global__ void __launch_bounds__(GS_THREADS)
-k_group_sort_tiny(const u32* __restrict__ gstart, u32 groups, u32* __restrict__ idx, const u32* __restrict__ rank,
+k_group_sort_tiny(const u32* __restrict__ gstart, u32 groups, u32* __restrict__ idx, RankT rank,
                   u32 n, u32 h, int rank_bits, u64* __restrict__ keys, u32 tiny_max, u32 medium_max,
                   u32* __restrict__ medium_list, u32* __restrict__ huge_list, u32* __restrict__ counters)
 {
@@ -495,10 +496,7 @@ k_group_sort_tiny(const u32* __restrict__ gstart, u32 groups, u32* __restrict__ 
     }
     u32 a[GS_TINY], k2[GS_TINY];
     for (u32 i = 0; i < sz; ++i) a[i] = idx[s + i];
-    for (u32 i = 0; i < sz; ++i) {
-        const u64 p = (u64)a[i] + h;
-        k2[i] = rank[p < n ? p : n];
-    }
+    for (u32 i = 0; i < sz; ++i) k2[i] = rank((u64)a[i] + h);
     for (u32 i = 1; i < sz; ++i) {
         const u32 x = k2[i], y = a[i];
         u32 j = i;
@@ -516,9 +514,10 @@ k_group_sort_tiny(const u32* __restrict__ gstart, u32 groups, u32* __restrict__ 
 // one CTA per listed group (GS_TINY < size <= GS_MEDIUM): bitonic sort of (rank[i+h] << 32 | suffix)
 static const int GM_THREADS = 256;
 
+template <typename RankT>
 __global__ void __launch_bounds__(GM_THREADS)
 k_group_sort_medium(const u32* __restrict__ list, const u32* __restrict__ gstart, u32* __restrict__ idx,
-                    const u32* __restrict__ rank, u32 n, u32 h, int rank_bits, u64* __restrict__ keys)
+                    RankT rank, u32 n, u32 h, int rank_bits, u64* __restrict__ keys)
 {
     __shared__ u64 buf[GS_MEDIUM];
     const u32 g = list[blockIdx.x];
@@ -529,8 +528,7 @@ k_group_sort_medium(const u32* __restrict__ list, const u32* __restrict__ gstart
         u64 v = ~0ull;
         if (i < sz) {
             const u32 sfx = idx[s + i];
-            const u64 p = (u64)sfx + h;
-            v = ((u64)rank[p < n ? p : n] << 32) | sfx;
+            v = ((u64)rank((u64)sfx + h) << 32) | sfx;
         }
         buf[i] = v;
     }
@@ -579,6 +577,26 @@ k_scatter_pairs(const u32* __restrict__ key, const u32* __restrict__ val, u32 m,
     for (int q = 0; q < SP_IPT; ++q) {
         const u32 j = base + (u32)q * SP_THREADS;
         if (j < m) rank[k[q]] = v[q];
+    }
+}
+
+// Sharded ISA in peer memory: rank[key[j]] = val[j] with the store going to the GPU that owns position key[j]
+// (4-byte stores over NVLink; the owner's shard is 1/G of the array, so the local part mostly stays in L2).
+__global__ void __launch_bounds__(SP_THREADS)
+k_peer_scatter(const u32* __restrict__ key, const u32* __restrict__ val, u32 m, RankView view)
+{
+    const u32 tile = SP_THREADS * SP_IPT;
+    const u32 base = blockIdx.x * tile + threadIdx.x;
+    u32 k[SP_IPT], v[SP_IPT];
+#pragma unroll
+    for (int q = 0; q < SP_IPT; ++q) {
+        const u32 j = base + (u32)q * SP_THREADS;
+        if (j < m) { k[q] = ld_stream(key + j); v[q] = ld_stream(val + j); }
+    }
+#pragma unroll
+    for (int q = 0; q < SP_IPT; ++q) {
+        const u32 j = base + (u32)q * SP_THREADS;
+        if (j < m && k[q] < view.n) view.base[k[q] >> view.shift][k[q]] = v[q];
     }
 }
 

@@ -14,6 +14,10 @@ Scheme (north_star item 4; include/b200sa.h "sharded building blocks"):
     ranks it is about to read (all-to-all of positions, all-to-all of values) and caches the replies in its
     own array — all three exchanges and all ISA work scale with 1/G.  ``isa="replicated"``: the pairs are
     all-gathered and every rank applies all of them (simpler, but the ISA update is replicated work);
+    ``isa="peer"`` (the NVLink-native variant): the ISA is sharded the same way, but every rank maps the arrays
+    of all peers (CUDA IPC) and the kernels load rank[suffix + h] from, and store new ranks into, the owner's HBM
+    directly; the only collectives left are two tiny all-reduces per round that separate its read phase from
+    its write phase (and carry the termination test);
   * a rank ends up owning a contiguous slice of the suffix array and of the BWT.
 The exchanges are the only collectives on the data path; counts and the termination test are tiny.
 """
@@ -43,13 +47,14 @@ class ShardedResult:
 
 class ShardedSorter:
     def __init__(self, engine, group: Optional[dist.ProcessGroup] = None, isa: str = "owner"):
-        assert isa in ("owner", "replicated")
+        assert isa in ("owner", "replicated", "peer")
         self.eng = engine
         self.group = group
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
         self.isa = isa
         assert self.world <= 256, "the owner routing sweep has 256 buckets"
+        assert isa != "peer" or self.world <= 16, "the peer table holds 16 GPUs (one NVSwitch domain)"
 
     # -- owner-sharded ISA ---------------------------------------------------------------------------
     def _owner_shift(self, n: int) -> int:
@@ -103,6 +108,18 @@ class ShardedSorter:
         if cnt:
             self.eng.shard_apply_updates(kout[:cnt], replies, cnt, stream)
 
+    # -- ISA in peer memory ----------------------------------------------------------------------------
+    def _attach_peers(self, n: int, shift: int, device) -> None:
+        mine = torch.frombuffer(bytearray(self.eng.shard_peer_export(n)), dtype=torch.uint8).to(device)
+        allh = torch.empty(64 * self.world, dtype=torch.uint8, device=device)
+        dist.all_gather_into_tensor(allh, mine, group=self.group)
+        self.eng.shard_peer_attach(self.rank, self.world, shift, n, bytes(allh.cpu().numpy().tobytes()))
+
+    def _sum_int(self, value: int, device) -> int:
+        t = torch.tensor([value], dtype=torch.int64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+        return int(t.item())
+
     # -- tiny collectives ------------------------------------------------------------------------
     def _gather_int(self, value: int, device) -> list:
         t = torch.tensor([value], dtype=torch.int64, device=device)
@@ -139,14 +156,27 @@ class ShardedSorter:
         stream = torch_stream_handle() if device.type == "cuda" else 0
         res = ShardedResult()
         res.sa = torch.empty(n + 1, dtype=torch.int32, device=device)
+        shift = self._owner_shift(n)
+        if self.isa == "peer" and self.world > 1:
+            self._attach_peers(n, shift, device)
         n_local = self.eng.shard_begin(d_text, n, res.sa, self.rank, self.world, stream)
         res.counts = self._gather_int(n_local, device)
         assert sum(res.counts) == n, "key-range parts do not cover the text"
         slot_base = sum(res.counts[: self.rank])
-        shift = self._owner_shift(n)
         m_local = self.eng.shard_round0(slot_base, stream)
         res.rounds = 1
-        while True:
+        while self.isa == "peer" and self.world > 1:
+            # every rank has finished READING ranks (its round is complete) ...
+            total = self._sum_int(m_local, device)
+            _, _, cnt = self.eng.shard_updates()
+            self.eng.shard_peer_scatter(stream)          # ... new ranks go straight into the owners' HBM ...
+            res.exchanged_bytes += 8 * cnt * (self.world - 1) // self.world
+            self._sum_int(0, device)                     # ... and have landed everywhere before anyone reads again
+            if total == 0:
+                break
+            m_local = self.eng.shard_round(stream)
+            res.rounds += 1
+        while self.isa != "peer" or self.world == 1:
             if self.isa == "owner":
                 self._route_updates(device, stream, res, shift)
             else:

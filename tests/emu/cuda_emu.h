@@ -358,6 +358,12 @@ static inline cudaError_t cudaGetDevice(int* d) { *d = 0; return 0; }
 static inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp* p, int) { memset(p, 0, sizeof(*p)); p->multiProcessorCount = 148; p->major = 10; p->minor = 0; p->totalGlobalMem = (size_t)8 << 30; p->sharedMemPerBlockOptin = 227 * 1024; strcpy(p->name, "cuda_emu"); return 0; }
 static inline cudaError_t cudaMalloc(void** p, size_t n) { size_t r = (n + 255) & ~(size_t)255; *p = aligned_alloc(256, r); if (*p) memset(*p, 0xA5, r); /* poison: device memory is never zero-initialised */ return *p ? 0 : cudaErrorMemoryAllocation; }
 static inline cudaError_t cudaFree(void* p) { free(p); return 0; }
+// "IPC" inside one process: the handle carries the pointer (tests drive several contexts of one process in lock step)
+struct cudaIpcMemHandle_t { char reserved[64]; };
+enum { cudaIpcMemLazyEnablePeerAccess = 1 };
+static inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t* h, void* p) { memset(h, 0, sizeof(*h)); memcpy(h->reserved, &p, sizeof(p)); return 0; }
+static inline cudaError_t cudaIpcOpenMemHandle(void** p, cudaIpcMemHandle_t h, unsigned) { memcpy(p, h.reserved, sizeof(*p)); return 0; }
+static inline cudaError_t cudaIpcCloseMemHandle(void*) { return 0; }
 static inline cudaError_t cudaMallocHost(void** p, size_t n) { return cudaMalloc(p, n); }
 static inline cudaError_t cudaHostAlloc(void** p, size_t n, unsigned) { return cudaMalloc(p, n); }
 static inline cudaError_t cudaFreeHost(void* p) { free(p); return 0; }

@@ -72,3 +72,66 @@ def test_sharded_matches_oracle(oracle, world, family, n, isa):
     assert np.array_equal(sa, want), (family, n, world)
     wb, ws = oracle.bwt_from_sa(x, want)
     assert sentinel == ws and np.array_equal(bwt, wb)
+
+
+# ---- ISA in peer memory (isa="peer"): G contexts of ONE process driven in lock step ------------------------------
+# CUDA IPC needs real GPUs; under the emulator the "handle" carries the pointer, so the contexts of one process can
+# map each other's ISA arrays.  This exercises the engine side of the protocol (export / attach / peer reads in the
+# doubling rounds / peer scatter / BWT through the shard of GPU 0); the torch.distributed side runs in the GPU tier.
+@pytest.mark.parametrize("world", [2, 3, 5])
+@pytest.mark.parametrize("family,n", [("markov3", 40000), ("acgt_rep", 30011), ("abcabca", 9000), ("zeros", 3000), ("fib", 10000),
+                                      ("periodic7", 5000), ("rand", 64)])
+def test_peer_isa_lockstep(oracle, world, family, n, monkeypatch):
+    from cases import gen
+    from msufsort_b200.api import Engine, Library
+    monkeypatch.setenv("B200SA_GROUPSORT_TINY", "4")      # reach the CTA and the radix paths at these sizes too
+    monkeypatch.setenv("B200SA_GROUPSORT_MEDIUM", "64")
+    lib = Library(os.path.join(ROOT, "tests", "emu", "libb200sa_emu.so"))
+    engs = [Engine(0, library=lib) for _ in range(world)]
+    try:
+        x = gen(family, n)
+        per = (n + world - 1) // world
+        shift = max(0, (per - 1).bit_length())
+        handles = b"".join(e.shard_peer_export(n) for e in engs)
+        for g, e in enumerate(engs):
+            e.shard_peer_attach(g, world, shift, n, handles)
+        sas = [np.zeros(n + 1, dtype=np.int32) for _ in range(world)]
+        counts = [e.shard_begin(x, n, sas[g], g, world) for g, e in enumerate(engs)]
+        assert sum(counts) == n
+        bases = [sum(counts[:g]) for g in range(world)]
+        m = [e.shard_round0(bases[g]) for g, e in enumerate(engs)]
+        rounds = 1
+        while True:
+            for e in engs:            # write phase: everyone has finished reading
+                e.shard_peer_scatter()
+            if sum(m) == 0:
+                break
+            m = [e.shard_round() for e in engs]   # read phase
+            rounds += 1
+            assert rounds < 64
+        want = oracle.sa(x)
+        sa = np.zeros(n + 1, dtype=np.int32)
+        bwt = np.zeros(n, dtype=np.uint8)
+        sentinel = None
+        for g, e in enumerate(engs):
+            rb = 0 if g == 0 else bases[g] + 1
+            re = bases[g] + counts[g] + 1
+            sa[rb:re] = sas[g][rb:re]
+            part = np.zeros(n, dtype=np.uint8)
+            ob, oe, s = e.shard_bwt(rb, re, part)
+            bwt[ob:oe] = part[ob:oe]
+            assert sentinel in (None, s)
+            sentinel = s
+        assert np.array_equal(sa, want), (family, n, world)
+        wb, ws = oracle.bwt_from_sa(x, want)
+        assert sentinel == ws and np.array_equal(bwt, wb)
+        # a second text of another size through the same contexts: mappings are re-established
+        x2 = gen("markov3", n // 2 + 7)
+        handles = b"".join(e.shard_peer_export(x2.size) for e in engs)
+        for g, e in enumerate(engs):
+            e.shard_peer_attach(g, world, max(0, ((x2.size + world - 1) // world - 1).bit_length()), x2.size, handles)
+        for e in engs:
+            e.shard_peer_detach()
+    finally:
+        for e in engs:
+            e.close()

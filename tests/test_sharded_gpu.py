@@ -49,7 +49,7 @@ def _worker(rank, world, port, family, n, q, isa="owner"):
 
 
 @pytest.mark.skipif(_ngpus() < 2, reason="needs at least 2 GPUs")
-@pytest.mark.parametrize("isa", ["owner", "replicated"])
+@pytest.mark.parametrize("isa", ["peer", "owner", "replicated"])
 @pytest.mark.parametrize("family,n", [("markov3", (1 << 22) + 5), ("acgt_rep", 1 << 22), ("rand", 1 << 20), ("abcabca", 1 << 20),
                                       ("fib", 1 << 19), ("zeros", 1 << 18)])
 def test_sharded_nccl_matches_oracle(oracle, family, n, isa):

@@ -246,7 +246,7 @@ int Engine::radix_sort_pairs(u64* keys2[2], u32* vals2[2], bool gen_vals, u32 m,
 // ISA update rank[idx[j]] = val[j] for `count` pairs.  Large arrays go through one radix sweep on the
 // top 8 bits of the suffix index so that the scatter proper works inside an L2-resident window.
 int Engine::isa_update(const u32* d_idx, const u32* d_val, u32 count, u32 n, u32* bk_key, u32* bk_val, bool all_suffixes, cudaStream_t st,
-                       u32* target)
+                       u32* target, const RankView* peer_view)
 {
     if (count == 0) return 0;
     if (!target) target = rank.as<u32>();
@@ -284,13 +284,19 @@ int Engine::isa_update(const u32* d_idx, const u32* d_val, u32 count, u32 n, u32
         B200SA_LAUNCH(kp, tiles, RS_THREADS, rs_pass_smem_bytes<u32>(), st, d_idx, bk_key, d_val, bk_val,
                       count, shift, 0xffffffffu, (const u32*)ghist, status, counters);
         count_launch(B200SA_PH_ISA);
-        B200SA_LAUNCH(k_scatter_pairs, (u32)div_up_u64(count, SP_THREADS * SP_IPT), SP_THREADS, 0, st, (const u32*)bk_key,
-                      (const u32*)bk_val, count, target);
+        if (peer_view)
+            B200SA_LAUNCH(k_peer_scatter, (u32)div_up_u64(count, SP_THREADS * SP_IPT), SP_THREADS, 0, st, (const u32*)bk_key,
+                          (const u32*)bk_val, count, *peer_view);
+        else
+            B200SA_LAUNCH(k_scatter_pairs, (u32)div_up_u64(count, SP_THREADS * SP_IPT), SP_THREADS, 0, st, (const u32*)bk_key,
+                          (const u32*)bk_val, count, target);
         count_launch(B200SA_PH_ISA);
         prof.alg_bytes[B200SA_PH_ISA] += (u64)count * (4 + 8 + 8 + 8 + 4);
     } else {
-        B200SA_LAUNCH(k_scatter_pairs, (u32)div_up_u64(count, SP_THREADS * SP_IPT), SP_THREADS, 0, st, d_idx, d_val, count,
-                      target);
+        if (peer_view)
+            B200SA_LAUNCH(k_peer_scatter, (u32)div_up_u64(count, SP_THREADS * SP_IPT), SP_THREADS, 0, st, d_idx, d_val, count, *peer_view);
+        else
+            B200SA_LAUNCH(k_scatter_pairs, (u32)div_up_u64(count, SP_THREADS * SP_IPT), SP_THREADS, 0, st, d_idx, d_val, count, target);
         count_launch(B200SA_PH_ISA);
         prof.alg_bytes[B200SA_PH_ISA] += (u64)count * 12;
     }
@@ -725,12 +731,10 @@ int Engine::peer_scatter(cudaStream_t st)
     if (!peer.active || ss.stage < 2) return set_error(B200SA_EINVAL, "no sharded sort with a peer ISA in progress");
     const u32 count = ss.upd_count;
     if (count) {
-        B200SA_TRY(phase_begin(B200SA_PH_ISA, st));
-        B200SA_LAUNCH(k_peer_scatter, (u32)div_up_u64(count, SP_THREADS * SP_IPT), SP_THREADS, 0, st, ss.upd_idx, ss.upd_rank, count, peer.view);
-        count_launch(B200SA_PH_ISA);
-        B200SA_TRY(phase_end(st));
-        prof.alg_bytes[B200SA_PH_ISA] += (u64)count * 12;
-        B200SA_CU(cudaGetLastError());
+        // same bucketing as the single-GPU ISA update (one radix sweep on the top bits of the suffix): consecutive stores
+        // then fall into one L2-sized window of ONE owner's shard, whichever side of the NVLink that L2 sits on
+        B200SA_TRY(agg_max.ensure((size_t)count * 4 + 64));
+        B200SA_TRY(isa_update(ss.upd_idx, ss.upd_rank, count, ss.n, agg_max.as<u32>(), (u32*)ss.upd_rank + count, false, st, nullptr, &peer.view));
     }
     B200SA_CU(cudaStreamSynchronize(st));  // stores to peer memory have landed when the kernel has completed
     return 0;

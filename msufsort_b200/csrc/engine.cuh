@@ -106,7 +106,7 @@ struct Engine {
                          int* result_side, cudaStream_t st);
     // target == nullptr: the engine's rank[] (ISA); the LCP path scatters phi[] with the same machinery
     int isa_update(const u32* d_idx, const u32* d_val, u32 count, u32 n, u32* bk_key, u32* bk_val, bool all_suffixes, cudaStream_t st,
-                   u32* target = nullptr);
+                   u32* target = nullptr, const RankView* peer_view = nullptr);
     int rerank(const u64* keys_sorted, const u32* idx_sorted, const u32* slot_in, u32 slot_base, u32 m, u32 n, i32* d_sa,
                u32* idx_out, u32* slot_out, u64* free_keys, int mode, u32* next_m, u32* next_groups, cudaStream_t st);
 

@@ -86,6 +86,9 @@ def test_peer_isa_lockstep(oracle, world, family, n, monkeypatch):
     from msufsort_b200.api import Engine, Library
     monkeypatch.setenv("B200SA_GROUPSORT_TINY", "4")      # reach the CTA and the radix paths at these sizes too
     monkeypatch.setenv("B200SA_GROUPSORT_MEDIUM", "64")
+    if world != 3:                                        # bucketed peer scatter (world 3 keeps the direct one)
+        monkeypatch.setenv("B200SA_ISA_DIRECT_BYTES", "0")
+        monkeypatch.setenv("B200SA_ISA_MIN_UPDATES", "1")
     lib = Library(os.path.join(ROOT, "tests", "emu", "libb200sa_emu.so"))
     engs = [Engine(0, library=lib) for _ in range(world)]
     try:

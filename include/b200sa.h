@@ -224,17 +224,23 @@ B200SA_API int b200sa_shard_partition(b200sa_ctx* ctx, const uint32_t* d_keys, c
 B200SA_API int b200sa_shard_requests(b200sa_ctx* ctx, uint32_t* d_pos_out, int64_t capacity, int64_t* count_out, void* stream);
 B200SA_API int b200sa_shard_gather_ranks(b200sa_ctx* ctx, const uint32_t* d_pos, int64_t count, uint32_t* d_out, void* stream);
 /* ISA in peer memory (the NVLink-native variant): GPU g owns rank[] of the positions [g << shift, (g+1) << shift) and
- * every GPU maps the ISA arrays of all its peers (CUDA IPC), so doubling rounds load rank[suffix + h] straight from
- * the owner's HBM and publish new ranks with 4-byte stores into it — no all-to-all, no routing sweep; the caller
- * only separates the read phase and the write phase of a round with two tiny collectives (barriers).
- *   export: allocates this context's ISA array for an n-byte text and returns its 64-byte IPC handle;
- *   attach: handles = nparts x 64 bytes (all-gathered by the caller; the own slot is ignored); mappings persist
- *           across sorts while the peers keep exporting the same allocation;
- *   scatter: after shard_round0 / shard_round, stores that step's (suffix, rank) pairs into the owners' arrays.
- * While a peer ISA is attached, shard_round and shard_bwt read ranks through it.                          */
-B200SA_API int b200sa_shard_peer_export(b200sa_ctx* ctx, int64_t n, uint8_t* handle_out /*64*/);
+ * every GPU maps two allocations of each peer (CUDA IPC): its ISA array and its inbox.  Doubling rounds LOAD
+ * rank[suffix + h] straight from the owner's HBM; new ranks are routed by owner with one radix sweep and STORED in
+ * bulk into the owners' inboxes (coalesced stores over NVLink), then every owner applies its inbox locally.  No NCCL
+ * all-to-all, no count exchange, no request/reply lookups: the caller only separates the phases of a round with
+ * tiny all-reduces (done reading | sends landed | shards updated).
+ *   export : allocates ISA array + inbox for an n-byte text, returns their two 64-byte IPC handles (128 bytes);
+ *   attach : handles = nparts x 128 bytes (all-gathered by the caller; the own slot is ignored); mappings persist
+ *            across sorts while the peers keep exporting the same allocations;
+ *   layout : counts[g] = suffixes owned by GPU g in this sort (the n_local values): fixes the inbox regions;
+ *   scatter: after shard_round0 / shard_round — route + send that step's (suffix, rank) pairs;
+ *   apply  : after a barrier — scatter what arrived in the own inbox into the own ISA shard.
+ * While a peer ISA is attached, shard_round and shard_bwt read ranks through it.                              */
+B200SA_API int b200sa_shard_peer_export(b200sa_ctx* ctx, int64_t n, uint8_t* handles_out /*128*/);
 B200SA_API int b200sa_shard_peer_attach(b200sa_ctx* ctx, int part, int nparts, int shift, int64_t n, const uint8_t* handles);
+B200SA_API int b200sa_shard_peer_layout(b200sa_ctx* ctx, const int64_t* counts, int nparts);
 B200SA_API int b200sa_shard_peer_scatter(b200sa_ctx* ctx, void* stream);
+B200SA_API int b200sa_shard_peer_apply(b200sa_ctx* ctx, void* stream);
 B200SA_API int b200sa_shard_peer_detach(b200sa_ctx* ctx);
 /* BWT bytes of SA rows [row_begin,row_end) into d_bwt (an n-byte buffer; bytes
  * [*out_begin,*out_end) are written). */

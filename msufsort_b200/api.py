@@ -89,7 +89,9 @@ ABI = [
     ("b200sa_shard_gather_ranks", C.c_int, [_P, _P, C.c_int64, _P, _P]),
     ("b200sa_shard_peer_export", C.c_int, [_P, C.c_int64, _P]),
     ("b200sa_shard_peer_attach", C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int64, _P]),
+    ("b200sa_shard_peer_layout", C.c_int, [_P, _P, C.c_int]),
     ("b200sa_shard_peer_scatter", C.c_int, [_P, _P]),
+    ("b200sa_shard_peer_apply", C.c_int, [_P, _P]),
     ("b200sa_shard_peer_detach", C.c_int, [_P]),
     ("b200sa_shard_bwt", C.c_int, [_P, C.c_int64, C.c_int64, _P, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int32), _P]),
     ("b200sa_unbwt_shard_build", C.c_int, [_P, _P, C.c_int64, C.c_int32, C.POINTER(C.c_int64), _P]),
@@ -405,14 +407,21 @@ class Engine:
         self.lib.check(self.lib.cdll.b200sa_shard_gather_ranks(self._ctx, _ptr(d_pos), count, _ptr(d_out), self._st(stream)))
 
     def shard_peer_export(self, n: int) -> bytes:
-        buf = (C.c_uint8 * 64)()
+        buf = (C.c_uint8 * 128)()
         self.lib.check(self.lib.cdll.b200sa_shard_peer_export(self._ctx, n, buf))
         return bytes(buf)
 
     def shard_peer_attach(self, part: int, nparts: int, shift: int, n: int, handles: bytes) -> None:
-        assert len(handles) == 64 * nparts
+        assert len(handles) == 128 * nparts
         buf = (C.c_uint8 * len(handles)).from_buffer_copy(handles)
         self.lib.check(self.lib.cdll.b200sa_shard_peer_attach(self._ctx, part, nparts, shift, n, buf))
+
+    def shard_peer_layout(self, counts) -> None:
+        arr = (C.c_int64 * len(counts))(*[int(c) for c in counts])
+        self.lib.check(self.lib.cdll.b200sa_shard_peer_layout(self._ctx, arr, len(counts)))
+
+    def shard_peer_apply(self, stream: Optional[int] = None) -> None:
+        self.lib.check(self.lib.cdll.b200sa_shard_peer_apply(self._ctx, self._st(stream)))
 
     def shard_peer_scatter(self, stream: Optional[int] = None) -> None:
         self.lib.check(self.lib.cdll.b200sa_shard_peer_scatter(self._ctx, self._st(stream)))

@@ -124,6 +124,7 @@ int Engine::release_workspace()
     gid.release(); gstart.release(); glist.release(); rank.release(); sa_ws.release(); sortmeta.release(); agg_cnt.release(); agg_max.release();
     misc.release(); text_ws.release(); bwt_ws.release(); walk.release();
     batch_text.release(); batch_meta.release(); batch_out.release();
+    if (!peer.active) peer_inbox.release();  // mapped by the peers while a peer ISA is attached
     return 0;
 }
 
@@ -246,7 +247,7 @@ int Engine::radix_sort_pairs(u64* keys2[2], u32* vals2[2], bool gen_vals, u32 m,
 // ISA update rank[idx[j]] = val[j] for `count` pairs.  Large arrays go through one radix sweep on the
 // top 8 bits of the suffix index so that the scatter proper works inside an L2-resident window.
 int Engine::isa_update(const u32* d_idx, const u32* d_val, u32 count, u32 n, u32* bk_key, u32* bk_val, bool all_suffixes, cudaStream_t st,
-                       u32* target, const RankView* peer_view)
+                       u32* target)
 {
     if (count == 0) return 0;
     if (!target) target = rank.as<u32>();
@@ -284,19 +285,12 @@ int Engine::isa_update(const u32* d_idx, const u32* d_val, u32 count, u32 n, u32
         B200SA_LAUNCH(kp, tiles, RS_THREADS, rs_pass_smem_bytes<u32>(), st, d_idx, bk_key, d_val, bk_val,
                       count, shift, 0xffffffffu, (const u32*)ghist, status, counters);
         count_launch(B200SA_PH_ISA);
-        if (peer_view)
-            B200SA_LAUNCH(k_peer_scatter, (u32)div_up_u64(count, SP_THREADS * SP_IPT), SP_THREADS, 0, st, (const u32*)bk_key,
-                          (const u32*)bk_val, count, *peer_view);
-        else
-            B200SA_LAUNCH(k_scatter_pairs, (u32)div_up_u64(count, SP_THREADS * SP_IPT), SP_THREADS, 0, st, (const u32*)bk_key,
-                          (const u32*)bk_val, count, target);
+        B200SA_LAUNCH(k_scatter_pairs, (u32)div_up_u64(count, SP_THREADS * SP_IPT), SP_THREADS, 0, st, (const u32*)bk_key,
+                      (const u32*)bk_val, count, target);
         count_launch(B200SA_PH_ISA);
         prof.alg_bytes[B200SA_PH_ISA] += (u64)count * (4 + 8 + 8 + 8 + 4);
     } else {
-        if (peer_view)
-            B200SA_LAUNCH(k_peer_scatter, (u32)div_up_u64(count, SP_THREADS * SP_IPT), SP_THREADS, 0, st, d_idx, d_val, count, *peer_view);
-        else
-            B200SA_LAUNCH(k_scatter_pairs, (u32)div_up_u64(count, SP_THREADS * SP_IPT), SP_THREADS, 0, st, d_idx, d_val, count, target);
+        B200SA_LAUNCH(k_scatter_pairs, (u32)div_up_u64(count, SP_THREADS * SP_IPT), SP_THREADS, 0, st, d_idx, d_val, count, target);
         count_launch(B200SA_PH_ISA);
         prof.alg_bytes[B200SA_PH_ISA] += (u64)count * 12;
     }
@@ -661,17 +655,23 @@ int Engine::suffix_array_dev(const u8* d_text, i64 n64, i32* d_sa, cudaStream_t 
 }
 
 // ---------------------------------------------------------------------------------------------
-// ISA sharded over the GPUs of one box, accessed through peer memory (CUDA IPC; msufsort_b200/sharded.py isa="peer")
+// ISA sharded over the GPUs of one box, accessed through peer memory (CUDA IPC; msufsort_b200/sharded.py isa="peer").
+// Two allocations per GPU are mapped by all peers: the ISA array (peers LOAD rank[suffix + h] from it) and an inbox
+// (peers STORE the new ranks of the suffixes this GPU owns into it, in bulk; the owner then applies them locally).
 
-int Engine::peer_export(u64 n, unsigned char* handle_out)
+static const size_t kInboxHeader = 256;  // u32 count[kMaxPeers] written by the sources, padded
+
+int Engine::peer_export(u64 n, unsigned char* handles_out)
 {
-    if (n == 0 || n > (u64)B200SA_MAX_N_INT32 || !handle_out) return set_error(B200SA_EINVAL, "bad argument");
+    if (n == 0 || n > (u64)B200SA_MAX_N_INT32 || !handles_out) return set_error(B200SA_EINVAL, "bad argument");
     B200SA_CU(cudaSetDevice(device));
     B200SA_TRY(ensure_sa_workspace(n));  // the ISA array keeps its address as long as n does not grow
-    cudaIpcMemHandle_t h;
-    B200SA_CU(cudaIpcGetMemHandle(&h, rank.p));
-    static_assert(sizeof(h) == 64, "IPC handle size");
-    memcpy(handle_out, &h, 64);
+    B200SA_TRY(peer_inbox.ensure(kInboxHeader + (size_t)n * 8 + 64));
+    cudaIpcMemHandle_t h[2];
+    static_assert(sizeof(h[0]) == 64, "IPC handle size");
+    B200SA_CU(cudaIpcGetMemHandle(&h[0], rank.p));
+    B200SA_CU(cudaIpcGetMemHandle(&h[1], peer_inbox.p));
+    memcpy(handles_out, h, 128);
     return 0;
 }
 
@@ -691,30 +691,45 @@ int Engine::peer_attach(int part, int nparts, int shift, u64 n, const unsigned c
     if (((n - 1) >> shift) >= (u64)nparts) return set_error(B200SA_EINVAL, "shift %d does not spread %llu positions over %d GPUs", shift, (unsigned long long)n, nparts);
     B200SA_CU(cudaSetDevice(device));
     B200SA_TRY(ensure_sa_workspace(n));
+    B200SA_TRY(peer_inbox.ensure(kInboxHeader + (size_t)n * 8 + 64));
     // mappings of an earlier attach are reused when the peer still exports the same allocation
     std::vector<std::pair<std::string, void*>> keep;
     PeerState next;
-    for (int g = 0; g < nparts; ++g) {
-        if (g == part) { next.view.base[g] = rank.as<u32>(); continue; }
-        const std::string key((const char*)handles + (size_t)g * 64, 64);
+    auto open_one = [&](const unsigned char* hb, void** out) -> int {
+        const std::string key((const char*)hb, 64);
         void* ptr = nullptr;
         for (auto& o : peer.opened)
-            if (o.first == key) { ptr = o.second; o.second = nullptr; }
+            if (o.second && o.first == key) { ptr = o.second; o.second = nullptr; break; }
         if (!ptr) {
             cudaIpcMemHandle_t h;
-            memcpy(&h, key.data(), 64);
+            memcpy(&h, hb, 64);
             cudaError_t e = cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess);
             if (e != cudaSuccess) {
                 cudaGetLastError();
-                for (auto& k : keep) cudaIpcCloseMemHandle(k.second);
-                return set_error(B200SA_ECOMM, "cudaIpcOpenMemHandle for GPU %d failed: %s", g, cudaGetErrorString(e));
+                return set_error(B200SA_ECOMM, "cudaIpcOpenMemHandle failed: %s", cudaGetErrorString(e));
             }
         }
         keep.emplace_back(key, ptr);
-        next.view.base[g] = (u32*)ptr;
+        *out = ptr;
+        return 0;
+    };
+    int rc = 0;
+    for (int g = 0; g < nparts && rc == 0; ++g) {
+        if (g == part) { next.view.base[g] = rank.as<u32>(); next.inbox[g] = peer_inbox.as<u8>(); continue; }
+        void *pr = nullptr, *pi = nullptr;
+        rc = open_one(handles + (size_t)g * 128, &pr);
+        if (rc == 0) rc = open_one(handles + (size_t)g * 128 + 64, &pi);
+        next.view.base[g] = (u32*)pr;
+        next.inbox[g] = (u8*)pi;
     }
     for (auto& o : peer.opened)
         if (o.second) cudaIpcCloseMemHandle(o.second);
+    peer.opened.clear();
+    if (rc != 0) {
+        for (auto& k : keep) cudaIpcCloseMemHandle(k.second);
+        peer = PeerState();
+        return rc;
+    }
     next.opened = keep;
     next.active = true;
     next.part = part;
@@ -725,18 +740,99 @@ int Engine::peer_attach(int part, int nparts, int shift, u64 n, const unsigned c
     return 0;
 }
 
-// publishes the (suffix, rank) pairs of the last round0 / round step to the owners of the suffixes
+// inbox regions: source s stores its pairs at kInboxHeader + 8 * (suffixes owned by lower-numbered sources) of EVERY
+// destination's inbox (keys first, then values); a source never sends more pairs than it owns suffixes
+int Engine::peer_layout(const i64* counts, int nparts)
+{
+    if (!peer.active || nparts != peer.nparts || !counts) return set_error(B200SA_EINVAL, "no peer ISA attached for %d GPUs", nparts);
+    u64 acc = 0;
+    for (int g = 0; g < nparts; ++g) {
+        if (counts[g] < 0) return set_error(B200SA_EINVAL, "negative count");
+        peer.region_off[g] = kInboxHeader + 8 * acc;
+        peer.region_cap[g] = (u32)counts[g];
+        acc += (u64)counts[g];
+    }
+    if (acc != peer.view.n) return set_error(B200SA_EINVAL, "suffix counts of the parts add up to %llu, not n = %u", (unsigned long long)acc, peer.view.n);
+    peer.laid_out = true;
+    return 0;
+}
+
+// Write phase, part 1: route the (suffix, rank) pairs of the last round0 / round step by owner (one radix sweep) and
+// store every owner's run into this GPU's region of that owner's inbox — coalesced 128-byte stores over NVLink.
 int Engine::peer_scatter(cudaStream_t st)
 {
-    if (!peer.active || ss.stage < 2) return set_error(B200SA_EINVAL, "no sharded sort with a peer ISA in progress");
+    if (!peer.active || !peer.laid_out || ss.stage < 2) return set_error(B200SA_EINVAL, "no sharded sort with a peer ISA in progress");
     const u32 count = ss.upd_count;
-    if (count) {
-        // same bucketing as the single-GPU ISA update (one radix sweep on the top bits of the suffix): consecutive stores
-        // then fall into one L2-sized window of ONE owner's shard, whichever side of the NVLink that L2 sits on
-        B200SA_TRY(agg_max.ensure((size_t)count * 4 + 64));
-        B200SA_TRY(isa_update(ss.upd_idx, ss.upd_rank, count, ss.n, agg_max.as<u32>(), (u32*)ss.upd_rank + count, false, st, nullptr, &peer.view));
+    const int G = peer.nparts, me = peer.part;
+    if (count > peer.region_cap[me]) return set_error(B200SA_EINTERNAL, "%u updates exceed this GPU's inbox region (%u)", count, peer.region_cap[me]);
+    u32* d_tab = misc.as<u32>() + 896;  // [0..15] counts per owner, [16..32] exclusive offsets
+    PeerSend ps;
+    for (int g = 0; g < kMaxPeers; ++g) {
+        ps.keys[g] = g < G ? (u32*)(peer.inbox[g] + peer.region_off[me]) : nullptr;
+        ps.vals[g] = g < G ? ps.keys[g] + peer.region_cap[me] : nullptr;
+        ps.count_slot[g] = g < G ? (u32*)peer.inbox[g] + me : nullptr;
     }
+    ps.nparts = G;
+    B200SA_TRY(phase_begin(B200SA_PH_ISA, st));
+    if (count) {
+        const u32 tiles = (u32)div_up_u64(count, RS_TILE);
+        const size_t status_bytes = (size_t)tiles * RS_RADIX * sizeof(u64);
+        B200SA_TRY(sortmeta.ensure(kSortMetaHeader + status_bytes));
+        B200SA_TRY(agg_max.ensure((size_t)count * 4 + 64));
+        u32* ghist = sortmeta.as<u32>();
+        u32* counters = ghist + RS_MAX_PASSES * RS_RADIX;
+        u64* status = (u64*)((u8*)sortmeta.p + kSortMetaHeader);
+        u32* bk_key = agg_max.as<u32>();
+        u32* bk_val = (u32*)ss.upd_rank + count;  // second half of the key buffer the new ranks sit in
+        B200SA_CU(cudaMemsetAsync(sortmeta.p, 0, kSortMetaHeader + status_bytes, st));
+        prof.memsets++;
+        const u32 htiles = (u32)div_up_u64(count, RH_THREADS * RH_IPT);
+        const u32 hgrid = htiles < (u32)(num_sms * 6) ? htiles : (u32)(num_sms * 6);
+        auto kh = k_radix_hist<u32>;
+        B200SA_LAUNCH(kh, hgrid, RH_THREADS, rh_smem_bytes(1), st, ss.upd_idx, count, peer.view.shift, 1, ghist);
+        count_launch(B200SA_PH_ISA);
+        B200SA_CU(cudaMemcpyAsync(d_tab, ghist, kMaxPeers * 4, cudaMemcpyDeviceToDevice, st));
+        B200SA_LAUNCH(k_radix_scan_bins, 1, RS_RADIX, 0, st, ghist);
+        count_launch(B200SA_PH_ISA);
+        B200SA_CU(cudaMemcpyAsync(d_tab + 16, ghist, (kMaxPeers + 1) * 4, cudaMemcpyDeviceToDevice, st));
+        auto kp = k_onesweep_pass<u32, true>;
+        B200SA_LAUNCH(kp, tiles, RS_THREADS, rs_pass_smem_bytes<u32>(), st, ss.upd_idx, bk_key, ss.upd_rank, bk_val, count, peer.view.shift,
+                      0xffffffffu, (const u32*)ghist, status, counters);
+        count_launch(B200SA_PH_ISA);
+        const u32 want = (u32)div_up_u64(count, 256 * 4);
+        const u32 grid = want < (u32)(num_sms * 16) ? want : (u32)(num_sms * 16);
+        B200SA_LAUNCH(k_peer_send, grid, 256, 0, st, (const u32*)bk_key, (const u32*)bk_val, count, (const u32*)d_tab, ps);
+        count_launch(B200SA_PH_ISA);
+        prof.alg_bytes[B200SA_PH_ISA] += (u64)count * (4 + 16 + 16);
+    } else {
+        B200SA_CU(cudaMemsetAsync(d_tab, 0, 33 * 4, st));
+        B200SA_LAUNCH(k_peer_send, 1, 256, 0, st, (const u32*)nullptr, (const u32*)nullptr, 0u, (const u32*)d_tab, ps);
+        count_launch(B200SA_PH_ISA);
+    }
+    B200SA_TRY(phase_end(st));
+    B200SA_CU(cudaGetLastError());
     B200SA_CU(cudaStreamSynchronize(st));  // stores to peer memory have landed when the kernel has completed
+    return 0;
+}
+
+// Write phase, part 2 (after a barrier): apply what the peers left in this GPU's inbox to its ISA shard.
+int Engine::peer_apply(cudaStream_t st)
+{
+    if (!peer.active || !peer.laid_out) return set_error(B200SA_EINVAL, "no peer ISA attached");
+    const int G = peer.nparts;
+    B200SA_CU(cudaMemcpyAsync(h_pinned + 400, peer_inbox.p, kMaxPeers * 4, cudaMemcpyDeviceToHost, st));
+    B200SA_CU(cudaStreamSynchronize(st));
+    for (int s = 0; s < G; ++s) {
+        const u32 cnt = h_pinned[400 + s];
+        if (cnt == 0) continue;
+        if (cnt > peer.region_cap[s]) return set_error(B200SA_EINTERNAL, "GPU %d announced %u pairs for a region of %u", s, cnt, peer.region_cap[s]);
+        const u32* keys_s = (const u32*)(peer_inbox.as<u8>() + peer.region_off[s]);
+        const u32* vals_s = keys_s + peer.region_cap[s];
+        B200SA_TRY(agg_max.ensure((size_t)cnt * 4 + 64));
+        B200SA_TRY(walk.ensure((size_t)cnt * 4 + 64));
+        B200SA_TRY(isa_update(keys_s, vals_s, cnt, peer.view.n, agg_max.as<u32>(), walk.as<u32>(), false, st));
+    }
+    B200SA_CU(cudaStreamSynchronize(st));
     return 0;
 }
 
@@ -1749,6 +1845,18 @@ int b200sa_shard_peer_scatter(b200sa_ctx* ctx, void* stream)
 {
     B200SA_NEED_CTX(ctx);
     return ctx->eng.peer_scatter(ctx->eng.pick(stream));
+}
+
+int b200sa_shard_peer_layout(b200sa_ctx* ctx, const int64_t* counts, int nparts)
+{
+    B200SA_NEED_CTX(ctx);
+    return ctx->eng.peer_layout(counts, nparts);
+}
+
+int b200sa_shard_peer_apply(b200sa_ctx* ctx, void* stream)
+{
+    B200SA_NEED_CTX(ctx);
+    return ctx->eng.peer_apply(ctx->eng.pick(stream));
 }
 
 int b200sa_shard_peer_detach(b200sa_ctx* ctx)

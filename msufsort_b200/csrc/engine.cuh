@@ -106,7 +106,7 @@ struct Engine {
                          int* result_side, cudaStream_t st);
     // target == nullptr: the engine's rank[] (ISA); the LCP path scatters phi[] with the same machinery
     int isa_update(const u32* d_idx, const u32* d_val, u32 count, u32 n, u32* bk_key, u32* bk_val, bool all_suffixes, cudaStream_t st,
-                   u32* target = nullptr, const RankView* peer_view = nullptr);
+                   u32* target = nullptr);
     int rerank(const u64* keys_sorted, const u32* idx_sorted, const u32* slot_in, u32 slot_base, u32 m, u32 n, i32* d_sa,
                u32* idx_out, u32* slot_out, u64* free_keys, int mode, u32* next_m, u32* next_groups, cudaStream_t st);
 
@@ -134,9 +134,16 @@ struct Engine {
         bool active = false;
         int part = 0, nparts = 1;
         RankView view{};
+        u8* inbox[kMaxPeers] = {};          // every GPU's inbox (own one included)
+        u64 region_off[kMaxPeers] = {};     // region of source s inside any inbox
+        u32 region_cap[kMaxPeers] = {};
+        bool laid_out = false;
         std::vector<std::pair<std::string, void*>> opened;  // IPC handle bytes -> mapped pointer
     } peer;
-    int peer_export(u64 n, unsigned char* handle_out);
+    DevBuf peer_inbox;
+    int peer_export(u64 n, unsigned char* handles_out /*128*/);
+    int peer_layout(const i64* counts, int nparts);
+    int peer_apply(cudaStream_t st);
     int peer_attach(int part, int nparts, int shift, u64 n, const unsigned char* handles);
     int peer_scatter(cudaStream_t st);
     int peer_detach();

@@ -580,23 +580,32 @@ k_scatter_pairs(const u32* __restrict__ key, const u32* __restrict__ val, u32 m,
     }
 }
 
-// Sharded ISA in peer memory: rank[key[j]] = val[j] with the store going to the GPU that owns position key[j]
-// (4-byte stores over NVLink; the owner's shard is 1/G of the array, so the local part mostly stays in L2).
-__global__ void __launch_bounds__(SP_THREADS)
-k_peer_scatter(const u32* __restrict__ key, const u32* __restrict__ val, u32 m, RankView view)
+// Sharded ISA in peer memory, write phase: the pairs arrive here routed by owner (runs [off[d], off[d+1]) of the
+// input); run d is copied into this GPU's region of owner d's inbox with consecutive threads on consecutive
+// addresses, i.e. full 128-byte stores over NVLink (direct 4-byte stores of the ranks into the owners' ISA arrays
+// measured 9.5 ms for 1.3e8 pairs on two GPUs — NVLink moves small scattered stores at a few G/s).
+struct PeerSend {
+    u32* keys[kMaxPeers];        // destination of run d: keys, values
+    u32* vals[kMaxPeers];
+    u32* count_slot[kMaxPeers];  // where owner d reads how many pairs this GPU sent
+    int nparts;
+};
+
+__global__ void __launch_bounds__(256)
+k_peer_send(const u32* __restrict__ key, const u32* __restrict__ val, u32 m, const u32* __restrict__ tab /*[0..15] counts, [16..32] offsets*/,
+            PeerSend ps)
 {
-    const u32 tile = SP_THREADS * SP_IPT;
-    const u32 base = blockIdx.x * tile + threadIdx.x;
-    u32 k[SP_IPT], v[SP_IPT];
+    __shared__ u32 s_off[kMaxPeers + 1];
+    if (threadIdx.x <= (u32)kMaxPeers) s_off[threadIdx.x] = threadIdx.x < (u32)ps.nparts ? tab[16 + threadIdx.x] : m;
+    if (blockIdx.x == 0 && threadIdx.x < (u32)ps.nparts) *ps.count_slot[threadIdx.x] = tab[threadIdx.x];
+    __syncthreads();
+    for (u32 j = blockIdx.x * blockDim.x + threadIdx.x; j < m; j += gridDim.x * blockDim.x) {
+        int d = 0;
 #pragma unroll
-    for (int q = 0; q < SP_IPT; ++q) {
-        const u32 j = base + (u32)q * SP_THREADS;
-        if (j < m) { k[q] = ld_stream(key + j); v[q] = ld_stream(val + j); }
-    }
-#pragma unroll
-    for (int q = 0; q < SP_IPT; ++q) {
-        const u32 j = base + (u32)q * SP_THREADS;
-        if (j < m && k[q] < view.n) view.base[k[q] >> view.shift][k[q]] = v[q];
+        for (int g = 1; g < kMaxPeers; ++g) d += (g < ps.nparts && s_off[g] <= j) ? 1 : 0;
+        const u32 dst = j - s_off[d];
+        ps.keys[d][dst] = ld_stream(key + j);
+        ps.vals[d][dst] = ld_stream(val + j);
     }
 }
 

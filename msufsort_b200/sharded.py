@@ -16,8 +16,8 @@ Scheme (north_star item 4; include/b200sa.h "sharded building blocks"):
     all-gathered and every rank applies all of them (simpler, but the ISA update is replicated work);
     ``isa="peer"`` (the NVLink-native variant): the ISA is sharded the same way, but every rank maps the arrays
     of all peers (CUDA IPC) and the kernels load rank[suffix + h] from, and store new ranks into, the owner's HBM
-    directly; the only collectives left are two tiny all-reduces per round that separate its read phase from
-    its write phase (and carry the termination test);
+    directly in bulk (an inbox per GPU, applied locally); the only collectives left are three tiny all-reduces
+    per round that separate its phases (and carry the termination test);
   * a rank ends up owning a contiguous slice of the suffix array and of the BWT.
 The exchanges are the only collectives on the data path; counts and the termination test are tiny.
 """
@@ -111,7 +111,7 @@ class ShardedSorter:
     # -- ISA in peer memory ----------------------------------------------------------------------------
     def _attach_peers(self, n: int, shift: int, device) -> None:
         mine = torch.frombuffer(bytearray(self.eng.shard_peer_export(n)), dtype=torch.uint8).to(device)
-        allh = torch.empty(64 * self.world, dtype=torch.uint8, device=device)
+        allh = torch.empty(128 * self.world, dtype=torch.uint8, device=device)
         dist.all_gather_into_tensor(allh, mine, group=self.group)
         self.eng.shard_peer_attach(self.rank, self.world, shift, n, bytes(allh.cpu().numpy().tobytes()))
 
@@ -163,15 +163,19 @@ class ShardedSorter:
         res.counts = self._gather_int(n_local, device)
         assert sum(res.counts) == n, "key-range parts do not cover the text"
         slot_base = sum(res.counts[: self.rank])
+        if self.isa == "peer" and self.world > 1:
+            self.eng.shard_peer_layout(res.counts)
         m_local = self.eng.shard_round0(slot_base, stream)
         res.rounds = 1
         while self.isa == "peer" and self.world > 1:
             # every rank has finished READING ranks (its round is complete) ...
             total = self._sum_int(m_local, device)
             _, _, cnt = self.eng.shard_updates()
-            self.eng.shard_peer_scatter(stream)          # ... new ranks go straight into the owners' HBM ...
+            self.eng.shard_peer_scatter(stream)          # ... new ranks are stored into the owners' inboxes ...
             res.exchanged_bytes += 8 * cnt * (self.world - 1) // self.world
-            self._sum_int(0, device)                     # ... and have landed everywhere before anyone reads again
+            self._sum_int(0, device)                     # ... all of them have landed ...
+            self.eng.shard_peer_apply(stream)            # ... every owner updates its ISA shard ...
+            self._sum_int(0, device)                     # ... and all shards are current before anyone reads again
             if total == 0:
                 break
             m_local = self.eng.shard_round(stream)

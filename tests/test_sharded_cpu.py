@@ -102,11 +102,15 @@ def test_peer_isa_lockstep(oracle, world, family, n, monkeypatch):
         counts = [e.shard_begin(x, n, sas[g], g, world) for g, e in enumerate(engs)]
         assert sum(counts) == n
         bases = [sum(counts[:g]) for g in range(world)]
+        for e in engs:
+            e.shard_peer_layout(counts)
         m = [e.shard_round0(bases[g]) for g, e in enumerate(engs)]
         rounds = 1
         while True:
             for e in engs:            # write phase: everyone has finished reading
                 e.shard_peer_scatter()
+            for e in engs:            # all sends have landed
+                e.shard_peer_apply()
             if sum(m) == 0:
                 break
             m = [e.shard_round() for e in engs]   # read phase

@@ -765,7 +765,12 @@ int Engine::peer_scatter(cudaStream_t st)
     const u32 count = ss.upd_count;
     const int G = peer.nparts, me = peer.part;
     if (count > peer.region_cap[me]) return set_error(B200SA_EINTERNAL, "%u updates exceed this GPU's inbox region (%u)", count, peer.region_cap[me]);
-    u32* d_tab = misc.as<u32>() + 896;  // [0..15] counts per owner, [16..32] exclusive offsets
+    // ONE sweep on the top 8 bits of the suffix index both routes by owner (a bucket never straddles two owners:
+    // bucket width 2^bshift divides the shard width 2^shift) and pre-buckets every run for the owner's scatter
+    const int nbits = bit_length_u64((u64)ss.n - 1);
+    int bshift = nbits > RS_RADIX_BITS ? nbits - RS_RADIX_BITS : 0;
+    if (bshift > peer.view.shift) bshift = peer.view.shift;
+    const int per_owner_log = peer.view.shift - bshift;  // buckets per owner = 2^per_owner_log
     PeerSend ps;
     for (int g = 0; g < kMaxPeers; ++g) {
         ps.keys[g] = g < G ? (u32*)(peer.inbox[g] + peer.region_off[me]) : nullptr;
@@ -773,40 +778,39 @@ int Engine::peer_scatter(cudaStream_t st)
         ps.count_slot[g] = g < G ? (u32*)peer.inbox[g] + me : nullptr;
     }
     ps.nparts = G;
+    ps.per_owner_log = per_owner_log;
+    const u32 tiles = (u32)div_up_u64(count ? count : 1, RS_TILE);
+    const size_t status_bytes = (size_t)tiles * RS_RADIX * sizeof(u64);
+    B200SA_TRY(sortmeta.ensure(kSortMetaHeader + status_bytes));
+    u32* ghist = sortmeta.as<u32>();
+    B200SA_CU(cudaMemsetAsync(sortmeta.p, 0, kSortMetaHeader + status_bytes, st));
+    prof.memsets++;
     B200SA_TRY(phase_begin(B200SA_PH_ISA, st));
     if (count) {
-        const u32 tiles = (u32)div_up_u64(count, RS_TILE);
-        const size_t status_bytes = (size_t)tiles * RS_RADIX * sizeof(u64);
-        B200SA_TRY(sortmeta.ensure(kSortMetaHeader + status_bytes));
         B200SA_TRY(agg_max.ensure((size_t)count * 4 + 64));
-        u32* ghist = sortmeta.as<u32>();
         u32* counters = ghist + RS_MAX_PASSES * RS_RADIX;
         u64* status = (u64*)((u8*)sortmeta.p + kSortMetaHeader);
         u32* bk_key = agg_max.as<u32>();
         u32* bk_val = (u32*)ss.upd_rank + count;  // second half of the key buffer the new ranks sit in
-        B200SA_CU(cudaMemsetAsync(sortmeta.p, 0, kSortMetaHeader + status_bytes, st));
-        prof.memsets++;
         const u32 htiles = (u32)div_up_u64(count, RH_THREADS * RH_IPT);
         const u32 hgrid = htiles < (u32)(num_sms * 6) ? htiles : (u32)(num_sms * 6);
         auto kh = k_radix_hist<u32>;
-        B200SA_LAUNCH(kh, hgrid, RH_THREADS, rh_smem_bytes(1), st, ss.upd_idx, count, peer.view.shift, 1, ghist);
+        B200SA_LAUNCH(kh, hgrid, RH_THREADS, rh_smem_bytes(1), st, ss.upd_idx, count, bshift, 1, ghist);
         count_launch(B200SA_PH_ISA);
-        B200SA_CU(cudaMemcpyAsync(d_tab, ghist, kMaxPeers * 4, cudaMemcpyDeviceToDevice, st));
         B200SA_LAUNCH(k_radix_scan_bins, 1, RS_RADIX, 0, st, ghist);
         count_launch(B200SA_PH_ISA);
-        B200SA_CU(cudaMemcpyAsync(d_tab + 16, ghist, (kMaxPeers + 1) * 4, cudaMemcpyDeviceToDevice, st));
         auto kp = k_onesweep_pass<u32, true>;
-        B200SA_LAUNCH(kp, tiles, RS_THREADS, rs_pass_smem_bytes<u32>(), st, ss.upd_idx, bk_key, ss.upd_rank, bk_val, count, peer.view.shift,
+        B200SA_LAUNCH(kp, tiles, RS_THREADS, rs_pass_smem_bytes<u32>(), st, ss.upd_idx, bk_key, ss.upd_rank, bk_val, count, bshift,
                       0xffffffffu, (const u32*)ghist, status, counters);
         count_launch(B200SA_PH_ISA);
         const u32 want = (u32)div_up_u64(count, 256 * 4);
         const u32 grid = want < (u32)(num_sms * 16) ? want : (u32)(num_sms * 16);
-        B200SA_LAUNCH(k_peer_send, grid, 256, 0, st, (const u32*)bk_key, (const u32*)bk_val, count, (const u32*)d_tab, ps);
+        B200SA_LAUNCH(k_peer_send, grid, 256, 0, st, (const u32*)bk_key, (const u32*)bk_val, count, (const u32*)ghist, ps);
         count_launch(B200SA_PH_ISA);
         prof.alg_bytes[B200SA_PH_ISA] += (u64)count * (4 + 16 + 16);
     } else {
-        B200SA_CU(cudaMemsetAsync(d_tab, 0, 33 * 4, st));
-        B200SA_LAUNCH(k_peer_send, 1, 256, 0, st, (const u32*)nullptr, (const u32*)nullptr, 0u, (const u32*)d_tab, ps);
+        // nothing to send this round: the counts the owners read must still be reset (ghist is all zero)
+        B200SA_LAUNCH(k_peer_send, 1, 256, 0, st, (const u32*)nullptr, (const u32*)nullptr, 0u, (const u32*)ghist, ps);
         count_launch(B200SA_PH_ISA);
     }
     B200SA_TRY(phase_end(st));
@@ -828,10 +832,14 @@ int Engine::peer_apply(cudaStream_t st)
         if (cnt > peer.region_cap[s]) return set_error(B200SA_EINTERNAL, "GPU %d announced %u pairs for a region of %u", s, cnt, peer.region_cap[s]);
         const u32* keys_s = (const u32*)(peer_inbox.as<u8>() + peer.region_off[s]);
         const u32* vals_s = keys_s + peer.region_cap[s];
-        B200SA_TRY(agg_max.ensure((size_t)cnt * 4 + 64));
-        B200SA_TRY(walk.ensure((size_t)cnt * 4 + 64));
-        B200SA_TRY(isa_update(keys_s, vals_s, cnt, peer.view.n, agg_max.as<u32>(), walk.as<u32>(), false, st));
+        // the run arrives bucketed by the top bits of the suffix index: the stores walk through L2-sized windows
+        B200SA_TRY(phase_begin(B200SA_PH_ISA, st));
+        B200SA_LAUNCH(k_scatter_pairs, (u32)div_up_u64(cnt, SP_THREADS * SP_IPT), SP_THREADS, 0, st, keys_s, vals_s, cnt, rank.as<u32>());
+        count_launch(B200SA_PH_ISA);
+        B200SA_TRY(phase_end(st));
+        prof.alg_bytes[B200SA_PH_ISA] += (u64)cnt * 12;
     }
+    B200SA_CU(cudaGetLastError());
     B200SA_CU(cudaStreamSynchronize(st));
     return 0;
 }

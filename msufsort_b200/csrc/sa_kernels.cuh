@@ -580,8 +580,8 @@ k_scatter_pairs(const u32* __restrict__ key, const u32* __restrict__ val, u32 m,
     }
 }
 
-// Sharded ISA in peer memory, write phase: the pairs arrive here routed by owner (runs [off[d], off[d+1]) of the
-// input); run d is copied into this GPU's region of owner d's inbox with consecutive threads on consecutive
+// Sharded ISA in peer memory, write phase: the pairs arrive here sorted by the top 8 bits of the suffix index, hence
+// routed by owner (a run of consecutive digits per owner); run d is copied into this GPU's region of owner d's inbox with consecutive threads on consecutive
 // addresses, i.e. full 128-byte stores over NVLink (direct 4-byte stores of the ranks into the owners' ISA arrays
 // measured 9.5 ms for 1.3e8 pairs on two GPUs — NVLink moves small scattered stores at a few G/s).
 struct PeerSend {
@@ -589,16 +589,20 @@ struct PeerSend {
     u32* vals[kMaxPeers];
     u32* count_slot[kMaxPeers];  // where owner d reads how many pairs this GPU sent
     int nparts;
+    int per_owner_log;           // the input is sorted by a 256-way digit; owner d holds digits [d << per_owner_log, (d+1) << per_owner_log)
 };
 
 __global__ void __launch_bounds__(256)
-k_peer_send(const u32* __restrict__ key, const u32* __restrict__ val, u32 m, const u32* __restrict__ tab /*[0..15] counts, [16..32] offsets*/,
+k_peer_send(const u32* __restrict__ key, const u32* __restrict__ val, u32 m, const u32* __restrict__ bins /*256 exclusive digit offsets*/,
             PeerSend ps)
 {
     __shared__ u32 s_off[kMaxPeers + 1];
-    if (threadIdx.x <= (u32)kMaxPeers) s_off[threadIdx.x] = threadIdx.x < (u32)ps.nparts ? tab[16 + threadIdx.x] : m;
-    if (blockIdx.x == 0 && threadIdx.x < (u32)ps.nparts) *ps.count_slot[threadIdx.x] = tab[threadIdx.x];
+    if (threadIdx.x <= (u32)kMaxPeers) {
+        const u32 first_digit = threadIdx.x << ps.per_owner_log;
+        s_off[threadIdx.x] = (threadIdx.x < (u32)ps.nparts && first_digit < 256u) ? bins[first_digit] : m;
+    }
     __syncthreads();
+    if (blockIdx.x == 0 && threadIdx.x < (u32)ps.nparts) *ps.count_slot[threadIdx.x] = s_off[threadIdx.x + 1] - s_off[threadIdx.x];
     for (u32 j = blockIdx.x * blockDim.x + threadIdx.x; j < m; j += gridDim.x * blockDim.x) {
         int d = 0;
 #pragma unroll

@@ -778,6 +778,7 @@ int Engine::peer_scatter(cudaStream_t st)
         ps.count_slot[g] = g < G ? (u32*)peer.inbox[g] + me : nullptr;
     }
     ps.nparts = G;
+    ps.me = me;
     ps.per_owner_log = per_owner_log;
     const u32 tiles = (u32)div_up_u64(count ? count : 1, RS_TILE);
     const size_t status_bytes = (size_t)tiles * RS_RADIX * sizeof(u64);

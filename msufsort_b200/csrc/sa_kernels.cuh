@@ -589,6 +589,7 @@ struct PeerSend {
     u32* vals[kMaxPeers];
     u32* count_slot[kMaxPeers];  // where owner d reads how many pairs this GPU sent
     int nparts;
+    int me;                      // sending GPU: its copy loop starts with the run of owner me + 1 (see k_peer_send)
     int per_owner_log;           // the input is sorted by a 256-way digit; owner d holds digits [d << per_owner_log, (d+1) << per_owner_log)
 };
 
@@ -603,7 +604,11 @@ k_peer_send(const u32* __restrict__ key, const u32* __restrict__ val, u32 m, con
     }
     __syncthreads();
     if (blockIdx.x == 0 && threadIdx.x < (u32)ps.nparts) *ps.count_slot[threadIdx.x] = s_off[threadIdx.x + 1] - s_off[threadIdx.x];
-    for (u32 j = blockIdx.x * blockDim.x + threadIdx.x; j < m; j += gridDim.x * blockDim.x) {
+    // every GPU walks its runs starting with its right-hand neighbour's, so at any moment the G senders store into
+    // G different inboxes (all starting with owner 0 measured G-fold ingress contention on that GPU's links)
+    const u32 rot = s_off[(ps.me + 1) % ps.nparts];
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) {
+        const u32 j = i + rot < m ? i + rot : i + rot - m;
         int d = 0;
 #pragma unroll
         for (int g = 1; g < kMaxPeers; ++g) d += (g < ps.nparts && s_off[g] <= j) ? 1 : 0;

@@ -56,6 +56,10 @@ enum {
  * The reference itself is only correct up to 2^30-2 (flag bits, msufsort.h:84-93). */
 #define B200SA_MAX_N_INT32 ((int64_t)2147483646)
 
+/* Largest n of the wide (uint32) entry points: tile arithmetic keeps 8 KiB of headroom below 2^32.  One GPU holds
+ * about 53 n bytes of workspace, i.e. n up to ~3.3e9 on a 180 GB B200. */
+#define B200SA_MAX_N_UINT32 ((int64_t)4294959102)
+
 typedef struct b200sa_ctx b200sa_ctx;
 
 /* ---- lifetime -------------------------------------------------------------------------- */
@@ -121,6 +125,21 @@ B200SA_API int b200sa_unbwt_dev(b200sa_ctx* ctx, const uint8_t* d_bwt, int64_t n
  * being unique — bit-identical to the reference's). */
 B200SA_API int b200sa_check_suffix_array_dev(b200sa_ctx* ctx, const uint8_t* d_text, int64_t n,
                                              const int32_t* d_sa, int64_t* bad_rows_out, void* stream);
+
+/* ---- wide-index superset -----------------------------------------------------------
+ * The reference's suffix_index is int32 (msufsort.h:47) and its flag bits corrupt results above 2^30-2 bytes
+ * (msufsort.h:84-93).  These entry points return the same suffix array with uint32 entries and the sentinel row as
+ * int64, for texts up to B200SA_MAX_N_UINT32 bytes (e.g. the 2 GiB = 2^31-byte configuration); results for
+ * n <= 2^31-2 are bit-identical to the int32 calls.  The inverse transform, the LCP array and the batch / sharded
+ * paths stay at the int32 limit (the psi table keeps its seed mark in bit 31). */
+B200SA_API int b200sa_suffix_array_u32_dev(b200sa_ctx* ctx, const uint8_t* d_text, int64_t n, uint32_t* d_sa_out, void* stream);
+B200SA_API int b200sa_bwt_u32_dev(b200sa_ctx* ctx, const uint8_t* d_text, int64_t n, uint8_t* d_bwt_out, uint32_t* d_sa_out,
+                                  int64_t* sentinel_index_out, void* stream);
+B200SA_API int b200sa_check_suffix_array_u32_dev(b200sa_ctx* ctx, const uint8_t* d_text, int64_t n, const uint32_t* d_sa,
+                                                 int64_t* bad_rows_out, void* stream);
+/* Host buffers; sa_out (n+1 uint32) and / or bwt_out (n bytes, may alias text) and sentinel_index_out may be NULL. */
+B200SA_API int b200sa_suffix_array_bwt_u32(b200sa_ctx* ctx, const uint8_t* text, int64_t n, uint32_t* sa_out, uint8_t* bwt_out,
+                                           int64_t* sentinel_index_out);
 
 /* LCP array.  Replaces the demo's LCP construction (src/executable/msufsort/main.cpp:16-105:
  * match_length, lcp, lcp_multithreaded), which is the only LCP code the reference ships.  Convention:
@@ -306,6 +325,10 @@ B200SA_API uint64_t b200sa_launch_count(b200sa_ctx* ctx);
 B200SA_API int b200sa_radix_sort_pairs_dev(b200sa_ctx* ctx, uint64_t* d_keys, uint64_t* d_keys_alt,
                                            uint32_t* d_vals, uint32_t* d_vals_alt, int64_t m,
                                            int begin_bit, int end_bit, int* result_in_alt, void* stream);
+
+/* Test hook: packs and unpacks the rerank look-back descriptors for one triple; out5 = {kept, kept heads,
+ * 1 + last head slot, flag bits of A, flag bits of B}. */
+B200SA_API int b200sa_debug_rerank_descriptor(uint32_t kept, uint32_t kheads, uint32_t last_head1, uint64_t* out5);
 
 #ifdef __cplusplus
 }

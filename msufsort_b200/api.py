@@ -64,6 +64,10 @@ ABI = [
     ("b200sa_bwt_dev", C.c_int, [_P, _P, C.c_int64, _P, _P, C.POINTER(C.c_int32), _P]),
     ("b200sa_unbwt_dev", C.c_int, [_P, _P, C.c_int64, C.c_int32, _P, _P]),
     ("b200sa_check_suffix_array_dev", C.c_int, [_P, _P, C.c_int64, _P, C.POINTER(C.c_int64), _P]),
+    ("b200sa_suffix_array_u32_dev", C.c_int, [_P, _P, C.c_int64, _P, _P]),
+    ("b200sa_bwt_u32_dev", C.c_int, [_P, _P, C.c_int64, _P, _P, C.POINTER(C.c_int64), _P]),
+    ("b200sa_check_suffix_array_u32_dev", C.c_int, [_P, _P, C.c_int64, _P, C.POINTER(C.c_int64), _P]),
+    ("b200sa_suffix_array_bwt_u32", C.c_int, [_P, _P, C.c_int64, _P, _P, C.POINTER(C.c_int64)]),
     ("b200sa_lcp_dev", C.c_int, [_P, _P, C.c_int64, _P, _P, _P]),
     ("b200sa_lcp", C.c_int, [_P, _P, C.c_int64, _P, _P, _P]),
     ("b200sa_suffix_array_batch", C.c_int, [_P, _P, _P, C.c_int64, _P]),
@@ -102,6 +106,7 @@ ABI = [
     ("b200sa_profile_reset", C.c_int, [_P]),
     ("b200sa_profile_get", C.c_int, [_P, C.POINTER(_Profile)]),
     ("b200sa_launch_count", C.c_uint64, [_P]),
+    ("b200sa_debug_rerank_descriptor", C.c_int, [C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint64)]),
     ("b200sa_radix_sort_pairs_dev", C.c_int, [_P, _P, _P, _P, _P, C.c_int64, C.c_int, C.c_int, C.POINTER(C.c_int), _P]),
 ]
 
@@ -349,6 +354,30 @@ class Engine:
 
     def unbwt_dev(self, d_bwt, n: int, sentinel_index: int, d_out, stream: Optional[int] = None) -> None:
         self.lib.check(self.lib.cdll.b200sa_unbwt_dev(self._ctx, _ptr(d_bwt), n, int(sentinel_index), _ptr(d_out), self._st(stream)))
+
+    # ---- wide-index superset (uint32 suffix arrays, n up to 2^32 - 8194) -----------------------------
+    def suffix_array_u32_dev(self, d_text, n: int, d_sa, stream: Optional[int] = None) -> None:
+        self.lib.check(self.lib.cdll.b200sa_suffix_array_u32_dev(self._ctx, _ptr(d_text), n, _ptr(d_sa), self._st(stream)))
+
+    def bwt_u32_dev(self, d_text, n: int, d_bwt, d_sa=None, stream: Optional[int] = None) -> int:
+        s = C.c_int64(0)
+        self.lib.check(self.lib.cdll.b200sa_bwt_u32_dev(self._ctx, _ptr(d_text), n, _ptr(d_bwt), _ptr(d_sa), C.byref(s), self._st(stream)))
+        return int(s.value)
+
+    def check_suffix_array_u32_dev(self, d_text, n: int, d_sa, stream: Optional[int] = None) -> int:
+        bad = C.c_int64(-1)
+        self.lib.check(self.lib.cdll.b200sa_check_suffix_array_u32_dev(self._ctx, _ptr(d_text), n, _ptr(d_sa), C.byref(bad), self._st(stream)))
+        return int(bad.value)
+
+    def suffix_array_and_bwt_u32(self, data):
+        """(uint32 SA, BWT bytes, sentinel index) through the wide host entry point."""
+        buf = np.ascontiguousarray(np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else data)
+        n = buf.size
+        sa = np.empty(n + 1, dtype=np.uint32)
+        bwt = np.empty(n, dtype=np.uint8)
+        s = C.c_int64(0)
+        self.lib.check(self.lib.cdll.b200sa_suffix_array_bwt_u32(self._ctx, _ptr(buf) if n else None, n, _ptr(sa), _ptr(bwt) if n else None, C.byref(s)))
+        return sa, bwt, int(s.value)
 
     def lcp_dev(self, d_text, n: int, d_sa, d_lcp, stream: Optional[int] = None) -> None:
         self.lib.check(self.lib.cdll.b200sa_lcp_dev(self._ctx, _ptr(d_text), n, _ptr(d_sa), _ptr(d_lcp), self._st(stream)))

@@ -634,9 +634,9 @@ int Engine::sort_round(u32* m_local, cudaStream_t st)
     return 0;
 }
 
-int Engine::suffix_array_dev(const u8* d_text, i64 n64, i32* d_sa, cudaStream_t st)
+int Engine::suffix_array_dev(const u8* d_text, i64 n64, i32* d_sa, cudaStream_t st, i64 max_n)
 {
-    if (n64 < 0 || n64 > B200SA_MAX_N_INT32) return set_error(B200SA_EINVAL, "n = %lld outside [0, 2^31-2]", (long long)n64);
+    if (n64 < 0 || n64 > max_n) return set_error(B200SA_EINVAL, "n = %lld outside [0, %lld]", (long long)n64, (long long)max_n);
     if (!d_sa || (n64 > 0 && !d_text)) return set_error(B200SA_EINVAL, "null pointer");
     B200SA_CU(cudaSetDevice(device));
     const u32 n = (u32)n64;
@@ -872,9 +872,9 @@ int Engine::bwt_rows(const u8* d_text, u32 n, const i32* d_sa, u32 o_begin, u32 
     return 0;
 }
 
-int Engine::bwt_dev(const u8* d_text, i64 n64, u8* d_bwt, i32* d_sa_or_null, i32* sentinel_host, cudaStream_t st)
+int Engine::bwt_dev(const u8* d_text, i64 n64, u8* d_bwt, i32* d_sa_or_null, i64* sentinel_host, cudaStream_t st, i64 max_n)
 {
-    if (n64 < 0 || n64 > B200SA_MAX_N_INT32) return set_error(B200SA_EINVAL, "n = %lld outside [0, 2^31-2]", (long long)n64);
+    if (n64 < 0 || n64 > max_n) return set_error(B200SA_EINVAL, "n = %lld outside [0, %lld]", (long long)n64, (long long)max_n);
     if (n64 > 0 && (!d_text || !d_bwt)) return set_error(B200SA_EINVAL, "null pointer");
     if (n64 == 0) {
         if (sentinel_host) *sentinel_host = 0;
@@ -887,9 +887,9 @@ int Engine::bwt_dev(const u8* d_text, i64 n64, u8* d_bwt, i32* d_sa_or_null, i32
         B200SA_TRY(sa_ws.ensure(((size_t)n + 1) * 4));
         d_sa = sa_ws.as<i32>();
     }
-    B200SA_TRY(suffix_array_dev(d_text, n64, d_sa, st));
+    B200SA_TRY(suffix_array_dev(d_text, n64, d_sa, st, max_n));
     B200SA_TRY(bwt_rows(d_text, n, d_sa, 0, n, d_bwt, st));
-    if (sentinel_host) *sentinel_host = (i32)h_pinned[8];
+    if (sentinel_host) *sentinel_host = (i64)h_pinned[8];
     if (profiling) B200SA_TRY(collect_profile());
     return 0;
 }
@@ -1023,9 +1023,9 @@ int Engine::unbwt_dev(const u8* d_bwt, i64 n64, i32 sentinel, u8* d_out, cudaStr
 // ---------------------------------------------------------------------------------------------
 // validator
 
-int Engine::check_sa_dev(const u8* d_text, i64 n64, const i32* d_sa, i64* bad_rows, cudaStream_t st)
+int Engine::check_sa_dev(const u8* d_text, i64 n64, const i32* d_sa, i64* bad_rows, cudaStream_t st, i64 max_n)
 {
-    if (n64 < 0 || n64 > B200SA_MAX_N_INT32 || !d_sa || !bad_rows) return set_error(B200SA_EINVAL, "bad argument");
+    if (n64 < 0 || n64 > max_n || !d_sa || !bad_rows) return set_error(B200SA_EINVAL, "bad argument");
     B200SA_CU(cudaSetDevice(device));
     const u32 n = (u32)n64;
     B200SA_TRY(rank.ensure(((size_t)n + 1) * 4 + 64));
@@ -1405,7 +1405,33 @@ int b200sa_bwt_dev(b200sa_ctx* ctx, const uint8_t* d_text, int64_t n, uint8_t* d
 {
     B200SA_NEED_CTX(ctx);
     if (n > 0 && d_text == d_bwt_out) return b200sa::set_error(B200SA_EINVAL, "d_bwt_out must not alias d_text");
-    return ctx->eng.bwt_dev(d_text, n, d_bwt_out, d_sa_out, sentinel_index_out, ctx->eng.pick(stream));
+    i64 s64 = 0;
+    B200SA_TRY(ctx->eng.bwt_dev(d_text, n, d_bwt_out, d_sa_out, &s64, ctx->eng.pick(stream)));
+    if (sentinel_index_out) *sentinel_index_out = (int32_t)s64;
+    return 0;
+}
+
+// ---- wide-index superset: uint32 suffix arrays, n up to B200SA_MAX_N_UINT32 ---------------------------
+
+int b200sa_suffix_array_u32_dev(b200sa_ctx* ctx, const uint8_t* d_text, int64_t n, uint32_t* d_sa_out, void* stream)
+{
+    B200SA_NEED_CTX(ctx);
+    return ctx->eng.suffix_array_dev(d_text, n, (i32*)d_sa_out, ctx->eng.pick(stream), B200SA_MAX_N_UINT32);
+}
+
+int b200sa_bwt_u32_dev(b200sa_ctx* ctx, const uint8_t* d_text, int64_t n, uint8_t* d_bwt_out, uint32_t* d_sa_out,
+                       int64_t* sentinel_index_out, void* stream)
+{
+    B200SA_NEED_CTX(ctx);
+    if (n > 0 && d_text == d_bwt_out) return b200sa::set_error(B200SA_EINVAL, "d_bwt_out must not alias d_text");
+    return ctx->eng.bwt_dev(d_text, n, d_bwt_out, (i32*)d_sa_out, sentinel_index_out, ctx->eng.pick(stream), B200SA_MAX_N_UINT32);
+}
+
+int b200sa_check_suffix_array_u32_dev(b200sa_ctx* ctx, const uint8_t* d_text, int64_t n, const uint32_t* d_sa, int64_t* bad_rows_out,
+                                      void* stream)
+{
+    B200SA_NEED_CTX(ctx);
+    return ctx->eng.check_sa_dev(d_text, n, (const i32*)d_sa, bad_rows_out, ctx->eng.pick(stream), B200SA_MAX_N_UINT32);
 }
 
 int b200sa_unbwt_dev(b200sa_ctx* ctx, const uint8_t* d_bwt, int64_t n, int32_t sentinel_index, uint8_t* d_text_out, void* stream)
@@ -1451,12 +1477,43 @@ int b200sa_suffix_array_bwt(b200sa_ctx* ctx, const uint8_t* text, int64_t n, int
     const bool want_bwt = bwt_out != nullptr || sentinel_index_out != nullptr;
     if (want_bwt) {
         B200SA_TRY(e.bwt_ws.ensure((size_t)n));
-        int32_t sentinel = 0;
+        i64 sentinel = 0;
         B200SA_TRY(e.bwt_dev(e.text_ws.as<u8>(), n, e.bwt_ws.as<u8>(), e.sa_ws.as<i32>(), &sentinel, st));
-        if (sentinel_index_out) *sentinel_index_out = sentinel;
+        if (sentinel_index_out) *sentinel_index_out = (int32_t)sentinel;
         if (bwt_out) B200SA_CU(cudaMemcpyAsync(bwt_out, e.bwt_ws.p, (size_t)n, cudaMemcpyDeviceToHost, st));
     } else {
         B200SA_TRY(e.suffix_array_dev(e.text_ws.as<u8>(), n, e.sa_ws.as<i32>(), st));
+    }
+    if (sa_out) B200SA_CU(cudaMemcpyAsync(sa_out, e.sa_ws.p, ((size_t)n + 1) * 4, cudaMemcpyDeviceToHost, st));
+    B200SA_CU(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int b200sa_suffix_array_bwt_u32(b200sa_ctx* ctx, const uint8_t* text, int64_t n, uint32_t* sa_out, uint8_t* bwt_out,
+                                int64_t* sentinel_index_out)
+{
+    B200SA_NEED_CTX(ctx);
+    Engine& e = ctx->eng;
+    if (n < 0 || n > B200SA_MAX_N_UINT32) return b200sa::set_error(B200SA_EINVAL, "n = %lld outside [0, 2^32-8194]", (long long)n);
+    if (n > 0 && !text) return b200sa::set_error(B200SA_EINVAL, "null text");
+    if (n == 0) {
+        if (sa_out) sa_out[0] = 0;
+        if (sentinel_index_out) *sentinel_index_out = 0;
+        return 0;
+    }
+    B200SA_CU(cudaSetDevice(e.device));
+    cudaStream_t st = e.own_stream;
+    B200SA_TRY(e.text_ws.ensure((size_t)n));
+    B200SA_TRY(e.sa_ws.ensure(((size_t)n + 1) * 4));
+    B200SA_CU(cudaMemcpyAsync(e.text_ws.p, text, (size_t)n, cudaMemcpyHostToDevice, st));
+    if (bwt_out || sentinel_index_out) {
+        B200SA_TRY(e.bwt_ws.ensure((size_t)n));
+        i64 sentinel = 0;
+        B200SA_TRY(e.bwt_dev(e.text_ws.as<u8>(), n, e.bwt_ws.as<u8>(), e.sa_ws.as<i32>(), &sentinel, st, B200SA_MAX_N_UINT32));
+        if (sentinel_index_out) *sentinel_index_out = sentinel;
+        if (bwt_out) B200SA_CU(cudaMemcpyAsync(bwt_out, e.bwt_ws.p, (size_t)n, cudaMemcpyDeviceToHost, st));
+    } else {
+        B200SA_TRY(e.suffix_array_dev(e.text_ws.as<u8>(), n, e.sa_ws.as<i32>(), st, B200SA_MAX_N_UINT32));
     }
     if (sa_out) B200SA_CU(cudaMemcpyAsync(sa_out, e.sa_ws.p, ((size_t)n + 1) * 4, cudaMemcpyDeviceToHost, st));
     B200SA_CU(cudaStreamSynchronize(st));
@@ -2071,6 +2128,21 @@ extern "C" __attribute__((visibility("default"))) int b200sa_debug_phase_cycles(
 #endif
 
 // ---- building blocks ---------------------------------------------------------------------------
+
+// round trip of the two rerank look-back descriptors (sa_kernels.cuh) for one (kept, kept heads, last head) triple:
+// out = {kept, kept heads, 1 + last head slot, flags of A, flags of B}; lets the CPU tier check counts >= 2^31
+int b200sa_debug_rerank_descriptor(uint32_t kept, uint32_t kheads, uint32_t last_head1, uint64_t* out5)
+{
+    if (!out5 || kheads > 0x7fffffffu) return b200sa::set_error(B200SA_EINVAL, "bad argument");
+    const u64 a = b200sa::rr_pack_a(b200sa::RR_FLAG_INCLUSIVE, kept, kheads);
+    const u64 b = b200sa::rr_pack_b(b200sa::RR_FLAG_INCLUSIVE, kept, last_head1);
+    out5[0] = b200sa::rr_ab_kept(a, b);
+    out5[1] = b200sa::rr_a_kheads(a);
+    out5[2] = b200sa::rr_b_last_head1(b);
+    out5[3] = a >> 62;
+    out5[4] = b >> 62;
+    return 0;
+}
 
 int b200sa_radix_sort_pairs_dev(b200sa_ctx* ctx, uint64_t* d_keys, uint64_t* d_keys_alt, uint32_t* d_vals, uint32_t* d_vals_alt,
                                 int64_t m, int begin_bit, int end_bit, int* result_in_alt, void* stream)

@@ -154,15 +154,16 @@ struct Engine {
 
     // entry points
     int ensure_sa_workspace(u64 n);
-    int suffix_array_dev(const u8* d_text, i64 n, i32* d_sa, cudaStream_t st);
+    // max_n: B200SA_MAX_N_INT32 for the reference-shaped int32 entry points, B200SA_MAX_N_UINT32 for the wide ones
+    int suffix_array_dev(const u8* d_text, i64 n, i32* d_sa, cudaStream_t st, i64 max_n = B200SA_MAX_N_INT32);
     int bwt_rows(const u8* d_text, u32 n, const i32* d_sa, u32 o_begin, u32 o_end, u8* d_bwt, cudaStream_t st);
-    int bwt_dev(const u8* d_text, i64 n, u8* d_bwt, i32* d_sa_or_null, i32* sentinel_host, cudaStream_t st);
+    int bwt_dev(const u8* d_text, i64 n, u8* d_bwt, i32* d_sa_or_null, i64* sentinel_host, cudaStream_t st, i64 max_n = B200SA_MAX_N_INT32);
     struct UnbwtState { int stage = 0; u32 n = 0, s = 0, D = 0, nreg = 0, nwalkers = 0, cap = 0; } us;
     int unbwt_build(const u8* d_bwt, u32 n, u32 s, u32* nwalkers_out, cudaStream_t st);
     int unbwt_measure(u32 w_begin, u32 w_end, cudaStream_t st);
     int unbwt_finish(u32 w_begin, u32 w_end, u8* d_out, cudaStream_t st);
     int unbwt_dev(const u8* d_bwt, i64 n, i32 sentinel, u8* d_out, cudaStream_t st);
-    int check_sa_dev(const u8* d_text, i64 n, const i32* d_sa, i64* bad_rows, cudaStream_t st);
+    int check_sa_dev(const u8* d_text, i64 n, const i32* d_sa, i64* bad_rows, cudaStream_t st, i64 max_n = B200SA_MAX_N_INT32);
     int lcp_dev(const u8* d_text, i64 n, const i32* d_sa, i32* d_lcp, cudaStream_t st);
     // batch of independent blocks, packed back to back at offsets[0..count]; any of the outputs may be null
     int batch_dev(const u8* d_packed, const i64* offsets, i64 count, u8* d_bwt_out, i32* d_sa_out, i32* sentinels_host, cudaStream_t st);

@@ -277,12 +277,16 @@ static const int RR_CHUNKS = RR_IPT * RR_WARPS;  // 128 warp-rows of 32 items pe
 #endif
 static const int RR_MIN_BLOCKS = B200SA_RR_MIN_BLOCKS;
 
-// descriptor A: flag(2) | kept heads (31) | kept (31);  descriptor B: flag(2) | 1 + last head slot (32)
+// descriptor A: flag(2) | kept heads (31) | kept, low 31 bits;  descriptor B: flag(2) | kept, bit 31 | 1 + last head slot (32).
+// Counts of up to 2^32-1 tuples fit (the uint32 entry points): a kept group has at least two members, so the number
+// of kept heads stays below 2^31, and the 32nd bit of the kept count travels in the spare bits of B.
 static const u64 RR_FLAG_PARTIAL = 1ull << 62;
 static const u64 RR_FLAG_INCLUSIVE = 2ull << 62;
-__device__ __forceinline__ u64 rr_pack_a(u64 flag, u32 kept, u32 kheads) { return flag | ((u64)kheads << 31) | (u64)kept; }
-__device__ __forceinline__ u32 rr_a_kept(u64 a) { return (u32)(a & 0x7fffffffull); }
-__device__ __forceinline__ u32 rr_a_kheads(u64 a) { return (u32)((a >> 31) & 0x7fffffffull); }
+__host__ __device__ __forceinline__ u64 rr_pack_a(u64 flag, u32 kept, u32 kheads) { return flag | ((u64)kheads << 31) | (u64)(kept & 0x7fffffffu); }
+__host__ __device__ __forceinline__ u64 rr_pack_b(u64 flag, u32 kept, u32 last_head1) { return flag | ((u64)(kept >> 31) << 32) | (u64)last_head1; }
+__host__ __device__ __forceinline__ u32 rr_ab_kept(u64 a, u64 b) { return (u32)(a & 0x7fffffffull) | ((u32)((b >> 32) & 1ull) << 31); }
+__host__ __device__ __forceinline__ u32 rr_a_kheads(u64 a) { return (u32)((a >> 31) & 0x7fffffffull); }
+__host__ __device__ __forceinline__ u32 rr_b_last_head1(u64 b) { return (u32)(b & 0xffffffffull); }
 
 //   slot_in == nullptr  -> round 0: active slot j is global position slot_base + j (slot_base = number
 //       of suffixes owned by lower-numbered parts in a sharded run, else 0)
@@ -374,12 +378,12 @@ k_rerank(const u64* __restrict__ keys, const u32* __restrict__ idx_in, const u32
         if (tile == 0) {
             if (lane == 0) {
                 st_relaxed_u64(da + tile, rr_pack_a(RR_FLAG_INCLUSIVE, tot_k, tot_kh));
-                st_relaxed_u64(db + tile, RR_FLAG_INCLUSIVE | (u64)tot_lh);
+                st_relaxed_u64(db + tile, rr_pack_b(RR_FLAG_INCLUSIVE, tot_k, tot_lh));
             }
         } else {
             if (lane == 0) {
                 st_relaxed_u64(da + tile, rr_pack_a(RR_FLAG_PARTIAL, tot_k, tot_kh));
-                st_relaxed_u64(db + tile, RR_FLAG_PARTIAL | (u64)tot_lh);
+                st_relaxed_u64(db + tile, rr_pack_b(RR_FLAG_PARTIAL, tot_k, tot_lh));
             }
             // window look-back: lane l inspects tile (t - l)
             i64 t = (i64)tile - 1;
@@ -396,8 +400,8 @@ k_rerank(const u64* __restrict__ keys, const u32* __restrict__ idx_in, const u32
                 const u32 incl = __ballot_sync(B200SA_FULL_MASK, have && (a >> 62) == 2);
                 const u32 cutoff = incl ? (u32)__ffs((int)incl) - 1u : 31u;
                 const bool use = have && lane <= cutoff;
-                u32 ck = use ? rr_a_kept(a) : 0u, ch = use ? rr_a_kheads(a) : 0u;
-                u32 cl = use ? (u32)(b & 0xffffffffull) : 0u;
+                u32 ck = use ? rr_ab_kept(a, b) : 0u, ch = use ? rr_a_kheads(a) : 0u;
+                u32 cl = use ? rr_b_last_head1(b) : 0u;
 #pragma unroll
                 for (int d = 16; d >= 1; d >>= 1) {
                     ck += __shfl_xor_sync(B200SA_FULL_MASK, ck, d);
@@ -412,7 +416,7 @@ k_rerank(const u64* __restrict__ keys, const u32* __restrict__ idx_in, const u32
             if (lane == 0) {
                 const u32 inc_lh = tot_lh > pre_lh ? tot_lh : pre_lh;
                 st_relaxed_u64(da + tile, rr_pack_a(RR_FLAG_INCLUSIVE, pre_k + tot_k, pre_kh + tot_kh));
-                st_relaxed_u64(db + tile, RR_FLAG_INCLUSIVE | (u64)inc_lh);
+                st_relaxed_u64(db + tile, rr_pack_b(RR_FLAG_INCLUSIVE, pre_k + tot_k, inc_lh));
             }
         }
         if (lane == 0) {
@@ -625,9 +629,9 @@ k_check_scatter(const i32* __restrict__ sa, u32 n, u32* __restrict__ isa, unsign
 {
     const u64 total = (u64)n + 1;
     for (u64 r = (u64)blockIdx.x * blockDim.x + threadIdx.x; r < total; r += (u64)gridDim.x * blockDim.x) {
-        const i64 v = sa[r];
-        bool ok = v >= 0 && v <= (i64)n;
-        if (r == 0 && v != (i64)n) ok = false;
+        const u32 v = (u32)sa[r];  // int32 and uint32 suffix arrays alike: a negative int32 entry is > n
+        bool ok = v <= n;
+        if (r == 0 && v != n) ok = false;
         if (ok) {
             const u32 old = atomicExch(&isa[v], (u32)r);
             if (old != 0xffffffffu) ok = false;

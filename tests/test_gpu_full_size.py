@@ -45,3 +45,25 @@ def test_config3_and_4_acgt_repeats_1gib(gpu_engine):
 @pytest.mark.skipif(os.environ.get("B200SA_TEST_HUGE") != "1", reason="2 GiB deep-doubling run (≈130 GB of HBM, ≈10 s): set B200SA_TEST_HUGE=1")
 def test_config5_periodic_2gib(gpu_engine):
     _run(gpu_engine, "periodic7", (1 << 31) - 2)
+
+
+@pytest.mark.skipif(os.environ.get("B200SA_TEST_HUGE") != "1", reason="2 GiB wide-index run (≈140 GB of HBM): set B200SA_TEST_HUGE=1")
+def test_config5_periodic_exactly_2gib_wide_index(gpu_engine):
+    """n = 2^31 + 4099: beyond every int32 suffix index — the uint32 entry points (SA + BWT), judged by the O(n) validator"""
+    import torch
+    n = (1 << 31) + 4099
+    x = gen("periodic1009", n)
+    d_text = torch.from_numpy(x).cuda()
+    d_sa = torch.empty(n + 1, dtype=torch.int32, device="cuda")      # uint32 payload in an int32 tensor
+    d_bwt = torch.empty(n, dtype=torch.uint8, device="cuda")
+    s = gpu_engine.bwt_u32_dev(d_text, n, d_bwt, d_sa)
+    assert gpu_engine.check_suffix_array_u32_dev(d_text, n, d_sa) == 0
+    as_u32 = lambda t: t.long() & 0xffffffff
+    assert int(as_u32(d_sa[s])) == 0 and int(as_u32(d_sa[0])) == n
+    rows = torch.randint(1, n + 1, (4096,), device="cuda")
+    rows = torch.cat([rows[rows != s], torch.tensor([n, n - 1, 1], device="cuda")])
+    rows = rows[rows != s]
+    out_idx = rows - (rows > s).long()
+    assert bool((d_bwt[out_idx] == d_text[as_u32(d_sa[rows]) - 1]).all())
+    assert int((as_u32(d_sa) >= (1 << 31)).sum()) == n - (1 << 31) + 1   # every suffix start >= 2^31 appears exactly once
+    gpu_engine.release_workspace()

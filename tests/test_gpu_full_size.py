@@ -58,6 +58,7 @@ def test_config5_periodic_exactly_2gib_wide_index(gpu_engine):
     d_bwt = torch.empty(n, dtype=torch.uint8, device="cuda")
     s = gpu_engine.bwt_u32_dev(d_text, n, d_bwt, d_sa)
     assert gpu_engine.check_suffix_array_u32_dev(d_text, n, d_sa) == 0
+    gpu_engine.release_workspace()
     as_u32 = lambda t: t.long() & 0xffffffff
     assert int(as_u32(d_sa[s])) == 0 and int(as_u32(d_sa[0])) == n
     rows = torch.randint(1, n + 1, (4096,), device="cuda")
@@ -66,4 +67,3 @@ def test_config5_periodic_exactly_2gib_wide_index(gpu_engine):
     out_idx = rows - (rows > s).long()
     assert bool((d_bwt[out_idx] == d_text[as_u32(d_sa[rows]) - 1]).all())
     assert int((as_u32(d_sa) >= (1 << 31)).sum()) == n - (1 << 31) + 1   # every suffix start >= 2^31 appears exactly once
-    gpu_engine.release_workspace()

@@ -20,6 +20,7 @@ s = eng.bwt_u32_dev(d_text, n, d_bwt, d_sa)
 e1.record(); torch.cuda.synchronize()
 p = eng.profile()
 bad = eng.check_suffix_array_u32_dev(d_text, n, d_sa)
+eng.release_workspace()  # the index arithmetic below needs 8 bytes per row of scratch
 u = lambda t: t.long() & 0xffffffff
 rows = torch.randint(1, n + 1, (65536,), device="cuda"); rows = rows[rows != s]
 ok_bwt = bool((d_bwt[rows - (rows > s).long()] == d_text[u(d_sa[rows]) - 1]).all())

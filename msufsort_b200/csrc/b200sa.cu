@@ -53,8 +53,9 @@ void DevBuf::release()
 // ---------------------------------------------------------------------------------------------
 // alphabet plan: dense symbol codes; as many symbols as fit next to the clamped-length field
 
-AlphabetPlan plan_alphabet(const u32* hist, int reserved_bits)
+AlphabetPlan plan_alphabet(const u32* hist, int reserved_bits, int max_key_bits)
 {
+    if (max_key_bits < 16 || max_key_bits > 64) max_key_bits = 64;
     AlphabetPlan a;
     int sigma = 0;
     for (int c = 0; c < 256; ++c) {
@@ -69,7 +70,7 @@ AlphabetPlan plan_alphabet(const u32* hist, int reserved_bits)
     a.bits = bits;
     int k = 1;
     for (int cand = 1; cand <= 58; ++cand)
-        if (cand * bits + bit_length_u64((u64)cand) <= 64 - reserved_bits) k = cand;
+        if (cand * bits + bit_length_u64((u64)cand) <= max_key_bits - reserved_bits) k = cand;
     a.k = k;
     a.len_bits = bit_length_u64((u64)k);
     return a;
@@ -102,6 +103,7 @@ int Engine::init(int dev)
     if (const char* e3 = getenv("B200SA_GROUPSORT_AVG")) groupsort_max_avg = (u32)strtoul(e3, nullptr, 10);
     if (const char* e4 = getenv("B200SA_GROUPSORT_TINY")) groupsort_tiny = (u32)strtoul(e4, nullptr, 10);
     if (const char* e5 = getenv("B200SA_GROUPSORT_MEDIUM")) groupsort_medium = (u32)strtoul(e5, nullptr, 10);
+    if (const char* e8 = getenv("B200SA_MAX_KEY_BITS")) max_key_bits = atoi(e8);
     if (const char* e6 = getenv("B200SA_UNBWT_CAP_MULT")) unbwt_cap_mult = (u32)strtoul(e6, nullptr, 10);
     if (unbwt_cap_mult < 1) unbwt_cap_mult = 1;
     if (groupsort_tiny > (u32)GS_TINY) groupsort_tiny = GS_TINY;
@@ -392,7 +394,7 @@ int Engine::sort_begin(const u8* d_text, u32 n, i32* d_sa, int part, int nparts,
     B200SA_CU(cudaMemcpyAsync(h_hist, d_hist, sizeof(h_hist), cudaMemcpyDeviceToHost, st));
     B200SA_CU(cudaStreamSynchronize(st));
     if (ss.batch_count) h_hist[0] -= ss.batch_count;  // the separator slots of a batch are not symbols
-    ss.plan = plan_alphabet(h_hist, ss.batch_bits);
+    ss.plan = plan_alphabet(h_hist, ss.batch_bits, max_key_bits);
     const AlphabetPlan& plan = ss.plan;
     B200SA_CU(cudaMemcpyAsync(d_code, plan.code, 256, cudaMemcpyHostToDevice, st));
 

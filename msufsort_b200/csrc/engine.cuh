@@ -52,7 +52,7 @@ struct AlphabetPlan {
 };
 
 // reserved_bits: key bits kept free above the symbols (the block number of a batched sort)
-AlphabetPlan plan_alphabet(const u32* hist256, int reserved_bits = 0);
+AlphabetPlan plan_alphabet(const u32* hist256, int reserved_bits = 0, int max_key_bits = 64);
 static inline int bit_length_u64(u64 x) { int b = 0; while (x) { ++b; x >>= 1; } return b; }
 
 struct Engine {
@@ -78,6 +78,10 @@ struct Engine {
 
     // inverse BWT: bytes of decode window per walker = unbwt_cap_mult * D (D = mean segment length)
     u32 unbwt_cap_mult = 4;
+
+    // width of the round-0 key (symbols + length field + block bits): fewer bits = fewer radix sweeps in round 0 but
+    // more suffixes left for the doubling rounds (B200SA_MAX_KEY_BITS; measured in profiles/)
+    int max_key_bits = 64;
 
     // instrumentation
     bool profiling = false;

@@ -296,6 +296,15 @@ def run_ours(args, wl):
             cpu = {"value": ns / t / 1e6, "unit": "MB/s", "cores": threads, "kind": "reference",
                    "sample": f"first {ns} bytes of the workload text, SA + BWT via the reference's two public calls, 1 repetition, {threads} threads"}
 
+    # ---- the rows around the hot path, measured after and outside the timed regions above: LCP array of
+    # the same text from the finished SA, and the text cut into 1024 blocks transformed as ONE batch (forward + inverse)
+    extras = None
+    if world == 1 and not args.no_extras:
+        try:
+            extras = measure_extras(eng, torch, d_text, d_sa, d_bwt, n, stream)
+        except Exception as exc:  # the headline line must not depend on the extras
+            extras = {"error": str(exc)[:200]}
+
     line = {
         "metric": "sa_bwt_input_throughput", "value": value, "unit": "MB/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -318,11 +327,49 @@ def run_ours(args, wl):
         "clocks": clocks,
         "rounds_per_step": prof["rounds"] / args.steps, "sort_passes_per_step": prof["sort_passes"] / args.steps,
         "phases": phases,
+        "extras": extras,
     }
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def measure_extras(eng, torch, d_text, d_sa, d_bwt, n, stream):
+    """LCP array and batched-blocks timings (device resident, CUDA events, best of 2 after one warm-up call)."""
+    def timed(fn):
+        fn()
+        best = 1e30
+        for _ in range(2):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        return best
+
+    out = {}
+    d_lcp = torch.empty(n + 1, dtype=torch.int32, device="cuda")
+    ms = timed(lambda: eng.lcp_dev(d_text, n, d_sa, d_lcp, stream))
+    out["lcp"] = {"ms": ms, "MBps": n / ms / 1e3, "max_lcp": int(d_lcp.max().item())}
+    del d_lcp
+    count = 1024
+    bs = n // count
+    if bs >= 1:
+        offsets = np.arange(count + 1, dtype=np.int64) * bs
+        total = int(offsets[-1])
+        sent = [None]
+
+        def fwd():
+            sent[0] = eng.batch_dev(d_text, offsets, d_bwt, None, stream)
+        ms_f = timed(fwd)
+        d_back = torch.empty(total, dtype=torch.uint8, device="cuda")
+        ms_i = timed(lambda: eng.unbwt_batch_dev(d_bwt, offsets, sent[0], d_back, stream))
+        out["batch_1024_blocks"] = {"block_bytes": bs, "bwt_ms": ms_f, "bwt_MBps": total / ms_f / 1e3, "unbwt_ms": ms_i,
+                                    "unbwt_MBps": total / ms_i / 1e3, "roundtrip_ok": bool(torch.equal(d_back, d_text[:total]))}
+    return out
 
 
 def run_sharded(args, wl):
@@ -404,6 +451,7 @@ def main():
     ap.add_argument("--workload", default="markov3_256MiB", choices=sorted(WORKLOADS))
     ap.add_argument("--n", type=int, default=0, help="override the text size (debugging)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the LCP / batched-blocks timings appended as 'extras'")
     ap.add_argument("--isa", default="owner", choices=["owner", "replicated", "peer"], help="sharded mode: how the ISA travels (see msufsort_b200/sharded.py)")
     ap.add_argument("--mode", default="independent", choices=["independent", "sharded"],
                     help="N>1 only. independent (default): one text per GPU, no data-path collective, weak scaling. "

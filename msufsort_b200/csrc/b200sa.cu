@@ -122,11 +122,12 @@ int Engine::init(int dev)
 
 int Engine::release_workspace()
 {
+    if (peer.active) peer_detach();  // the ISA array and the inbox go away: peers must re-attach before the next sharded sort
     for (int i = 0; i < 2; ++i) { keys[i].release(); idx[i].release(); slot[i].release(); }
     gid.release(); gstart.release(); glist.release(); rank.release(); sa_ws.release(); sortmeta.release(); agg_cnt.release(); agg_max.release();
     misc.release(); text_ws.release(); bwt_ws.release(); walk.release();
     batch_text.release(); batch_meta.release(); batch_out.release();
-    if (!peer.active) peer_inbox.release();  // mapped by the peers while a peer ISA is attached
+    peer_inbox.release();
     return 0;
 }
 
@@ -1671,6 +1672,7 @@ int b200sa_unbwt_batch(b200sa_ctx* ctx, uint8_t* blocks_inout, const int64_t* of
 #include <condition_variable>
 #include <deque>
 #include <map>
+#include <set>
 #include <thread>
 
 struct b200sa_pipeline {
@@ -1688,7 +1690,8 @@ struct b200sa_pipeline {
     std::mutex mu;
     std::condition_variable cv_work, cv_done;
     std::deque<Job> queue;
-    std::map<int64_t, std::pair<int, std::string>> done;  // ticket -> (status, message)
+    std::map<int64_t, std::pair<int, std::string>> done;  // ticket -> (status, message), until somebody waits for it
+    std::set<int64_t> open_tickets;                       // submitted and not yet collected by wait / drain
     int64_t next_ticket = 1;
     int64_t in_flight = 0;
     bool stopping = false;
@@ -1770,6 +1773,7 @@ static int pipeline_submit(b200sa_pipeline* p, int kind, uint8_t* blocks, const 
         std::lock_guard<std::mutex> lk(p->mu);
         if (p->stopping) return b200sa::set_error(B200SA_EINVAL, "pipeline is shutting down");
         *ticket_out = p->next_ticket++;
+        p->open_tickets.insert(*ticket_out);
         p->queue.push_back(b200sa_pipeline::Job{*ticket_out, kind, blocks, offsets, count, sentinels, sa_out});
         ++p->in_flight;
     }
@@ -1799,12 +1803,14 @@ int b200sa_pipeline_wait(b200sa_pipeline* p, int64_t ticket)
 {
     if (!p) return b200sa::set_error(B200SA_EINVAL, "null pipeline");
     std::unique_lock<std::mutex> lk(p->mu);
-    if (ticket < 1 || ticket >= p->next_ticket) return b200sa::set_error(B200SA_EINVAL, "unknown ticket %lld", (long long)ticket);
+    if (p->open_tickets.count(ticket) == 0)
+        return b200sa::set_error(B200SA_EINVAL, "ticket %lld is unknown or has already been collected", (long long)ticket);
     p->cv_done.wait(lk, [&] { return p->done.count(ticket) != 0; });
     auto it = p->done.find(ticket);
     const int rc = it->second.first;
     if (rc) b200sa::set_error(rc, "%s", it->second.second.c_str());
     p->done.erase(it);
+    p->open_tickets.erase(ticket);
     return rc;
 }
 
@@ -1817,6 +1823,7 @@ int b200sa_pipeline_drain(b200sa_pipeline* p)
     for (auto& kv : p->done)
         if (kv.second.first && !first) { first = kv.second.first; b200sa::set_error(first, "%s", kv.second.second.c_str()); }
     p->done.clear();
+    p->open_tickets.clear();
     return first;
 }
 

@@ -36,6 +36,7 @@ def _cases(scale):
     yield "tiny", [rng.integers(0, 3, size=int(rng.integers(0, 12)), dtype=np.uint8) for _ in range(700)]
     yield "families", [gen(f, int(rng.integers(1, 9000 * scale))) for f in FAMILIES for _ in range(3)]
     yield "two-random", [gen("rand", 30000 * scale), gen("rand", 20000 * scale)]
+    yield "all-empty", [np.empty(0, np.uint8)] * 3
     yield "zero-bytes", [np.zeros(5, np.uint8), np.array([0, 0, 1, 0], np.uint8), np.array([1, 0, 0], np.uint8)]
 
 
@@ -176,6 +177,8 @@ def test_emu_pipeline(oracle):
             pipe.wait(t)
         with pytest.raises(B200SAError):
             pipe.wait(12345)
+        with pytest.raises(B200SAError):
+            pipe.wait(t)                     # a ticket can be collected once
     with pytest.raises(B200SAError):
         Pipeline(0, 0, library=lib)
 

@@ -53,7 +53,7 @@ void DevBuf::release()
 // ---------------------------------------------------------------------------------------------
 // alphabet plan: dense symbol codes; as many symbols as fit next to the clamped-length field
 
-AlphabetPlan plan_alphabet(const u32* hist, int reserved_bits, int max_key_bits)
+AlphabetPlan plan_alphabet(const u32* hist, int reserved_bits, int max_key_bits, bool allow_radix)
 {
     if (max_key_bits < 16 || max_key_bits > 64) max_key_bits = 64;
     AlphabetPlan a;
@@ -73,6 +73,27 @@ AlphabetPlan plan_alphabet(const u32* hist, int reserved_bits, int max_key_bits)
         if (cand * bits + bit_length_u64((u64)cand) <= max_key_bits - reserved_bits) k = cand;
     a.k = k;
     a.len_bits = bit_length_u64((u64)k);
+    a.radix = 0;
+    a.key_bits = a.k * a.bits + a.len_bits;
+    memset(a.pow, 0, sizeof(a.pow));
+    if (allow_radix && sigma <= 255) {
+        // the most digits of base sigma + 1 whose number fits the same bit budget
+        const int budget = max_key_bits - reserved_bits;
+        const unsigned __int128 limit = (unsigned __int128)1 << budget;
+        const u64 B = (u64)sigma + 1;
+        unsigned __int128 p = 1;
+        int kr = 0;
+        u64 pw[66] = {1};
+        while (kr < 64 && p * B <= limit) { p *= B; ++kr; pw[kr] = (u64)p; }  // p == 2^64 cannot occur: B is not a power of two when it matters
+        if (kr > a.k && kr <= 58 && p - 1 <= (unsigned __int128)~0ull) {
+            a.radix = B;
+            a.k = kr;
+            a.len_bits = 0;
+            a.bits = 0;
+            a.key_bits = bit_length_u64((u64)(p - 1));
+            memcpy(a.pow, pw, sizeof(pw));
+        }
+    }
     return a;
 }
 
@@ -104,6 +125,7 @@ int Engine::init(int dev)
     if (const char* e4 = getenv("B200SA_GROUPSORT_TINY")) groupsort_tiny = (u32)strtoul(e4, nullptr, 10);
     if (const char* e5 = getenv("B200SA_GROUPSORT_MEDIUM")) groupsort_medium = (u32)strtoul(e5, nullptr, 10);
     if (const char* e8 = getenv("B200SA_MAX_KEY_BITS")) max_key_bits = atoi(e8);
+    if (const char* e9 = getenv("B200SA_PACK_RADIX")) pack_radix = atoi(e9) != 0;
     if (const char* e6 = getenv("B200SA_UNBWT_CAP_MULT")) unbwt_cap_mult = (u32)strtoul(e6, nullptr, 10);
     if (unbwt_cap_mult < 1) unbwt_cap_mult = 1;
     if (groupsort_tiny > (u32)GS_TINY) groupsort_tiny = GS_TINY;
@@ -395,7 +417,7 @@ int Engine::sort_begin(const u8* d_text, u32 n, i32* d_sa, int part, int nparts,
     B200SA_CU(cudaMemcpyAsync(h_hist, d_hist, sizeof(h_hist), cudaMemcpyDeviceToHost, st));
     B200SA_CU(cudaStreamSynchronize(st));
     if (ss.batch_count) h_hist[0] -= ss.batch_count;  // the separator slots of a batch are not symbols
-    ss.plan = plan_alphabet(h_hist, ss.batch_bits, max_key_bits);
+    ss.plan = plan_alphabet(h_hist, ss.batch_bits, max_key_bits, pack_radix);
     const AlphabetPlan& plan = ss.plan;
     B200SA_CU(cudaMemcpyAsync(d_code, plan.code, 256, cudaMemcpyHostToDevice, st));
 
@@ -406,12 +428,25 @@ int Engine::sort_begin(const u8* d_text, u32 n, i32* d_sa, int part, int nparts,
     {
         const u32 tiles = (u32)div_up_u64(n, PK_TILE);
         const u32 grid = tiles < (u32)(num_sms * 4) ? tiles : (u32)(num_sms * 4);
-        if (ss.batch_count)
-            B200SA_LAUNCH(k_pack_keys_batch, grid, PK_THREADS, 0, st, d_text, n, (const u8*)d_code, plan.bits, plan.k, plan.len_bits,
+        if (plan.radix) {
+            u64* d_pow = (u64*)(misc.as<u32>() + 320);  // 66 words of u64 behind the symbol codes
+            B200SA_CU(cudaMemcpyAsync(d_pow, plan.pow, sizeof(plan.pow), cudaMemcpyHostToDevice, st));
+            if (ss.batch_count) {
+                auto kp = k_pack_keys_batch<true>;
+                B200SA_LAUNCH(kp, grid, PK_THREADS, 0, st, d_text, n, (const u8*)d_code, plan.key_bits, plan.k, 0, plan.radix, (const u64*)d_pow,
+                              ss.batch_ends, ss.batch_count, keys[0].as<u64>());
+            } else {
+                auto kp = k_pack_keys<true>;
+                B200SA_LAUNCH(kp, grid, PK_THREADS, 0, st, d_text, n, (const u8*)d_code, 0, plan.k, 0, plan.radix, plan.pow[plan.k - 1], keys[0].as<u64>());
+            }
+        } else if (ss.batch_count) {
+            auto kp = k_pack_keys_batch<false>;
+            B200SA_LAUNCH(kp, grid, PK_THREADS, 0, st, d_text, n, (const u8*)d_code, plan.bits, plan.k, plan.len_bits, (u64)0, (const u64*)nullptr,
                           ss.batch_ends, ss.batch_count, keys[0].as<u64>());
-        else
-            B200SA_LAUNCH(k_pack_keys, grid, PK_THREADS, 0, st, d_text, n, (const u8*)d_code, plan.bits, plan.k, plan.len_bits,
-                          keys[0].as<u64>());
+        } else {
+            auto kp = k_pack_keys<false>;
+            B200SA_LAUNCH(kp, grid, PK_THREADS, 0, st, d_text, n, (const u8*)d_code, plan.bits, plan.k, plan.len_bits, (u64)0, (u64)0, keys[0].as<u64>());
+        }
         count_launch(B200SA_PH_PACK);
     }
     B200SA_TRY(phase_end(st));
@@ -420,7 +455,7 @@ int Engine::sort_begin(const u8* d_text, u32 n, i32* d_sa, int part, int nparts,
 
     u64* k2[2] = {keys[0].as<u64>(), keys[1].as<u64>()};
     u32* v2[2] = {idx[0].as<u32>(), idx[1].as<u32>()};
-    const int key_bits = plan.bits * plan.k + plan.len_bits + ss.batch_bits;
+    const int key_bits = plan.key_bits + ss.batch_bits;
     int side = 0;
     u32 count = n;
     if (nparts > 1) {

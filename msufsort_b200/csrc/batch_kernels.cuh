@@ -57,19 +57,24 @@ k_batch_expand(const u8* __restrict__ packed, const u32* __restrict__ ends, u32 
 }
 
 // Initial keys of the expanded text (see k_pack_keys for the staging / write-out scheme).
+// RADIX: mixed-radix symbol part (see k_pack_keys); `bits` then holds the width of the symbol part, pw[j] = B^j.
+template <bool RADIX>
 __global__ void __launch_bounds__(PK_THREADS)
-k_pack_keys_batch(const u8* __restrict__ text, u32 n, const u8* __restrict__ code, int bits, int k, int len_bits,
-                  const u32* __restrict__ ends, u32 count, u64* __restrict__ keys)
+k_pack_keys_batch(const u8* __restrict__ text, u32 n, const u8* __restrict__ code, int bits, int k, int len_bits, u64 B,
+                  const u64* __restrict__ pw, const u32* __restrict__ ends, u32 count, u64* __restrict__ keys)
 {
     __shared__ u8 s_code[256];
     __shared__ __align__(16) u8 s_sym[PK_TILE + PK_HALO];
     __shared__ u64 s_out[PK_THREADS / 32][PK_IPT * 33];
     const u32 tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    s_code[tid] = code[tid];
+    __shared__ u64 s_pw[66];
+    s_code[tid] = RADIX ? (u8)(code[tid] + 1u) : code[tid];
+    if (RADIX && tid < 66u) s_pw[tid] = pw[tid];
     __syncthreads();
     const u32 ntiles = (u32)div_up_u64(n, PK_TILE);
-    const u64 sym_mask = (k * bits >= 64) ? ~0ull : ((1ull << (k * bits)) - 1ull);
-    const int bshift = k * bits + len_bits;  // < 64 whenever count > 1 (plan_alphabet reserves the block bits)
+    const u64 sym_mask = (RADIX || k * bits >= 64) ? ~0ull : ((1ull << (k * bits)) - 1ull);
+    const int bshift = RADIX ? bits : k * bits + len_bits;  // < 64 whenever count > 1 (plan_alphabet reserves the block bits)
+    const u64 top_pow = RADIX ? s_pw[k - 1] : 0ull;
     for (u32 t = blockIdx.x; t < ntiles; t += gridDim.x) {
         const u32 base = t * (u32)PK_TILE;
         const bool aligned = (((uintptr_t)(text + base)) & 15u) == 0;
@@ -88,7 +93,7 @@ k_pack_keys_batch(const u8* __restrict__ text, u32 n, const u8* __restrict__ cod
         __syncthreads();
         const u32 p0 = tid * PK_IPT;
         u64 win = 0;
-        for (int j = 0; j < k; ++j) win = (win << bits) | (u64)s_sym[p0 + j];
+        for (int j = 0; j < k; ++j) win = RADIX ? win * B + (u64)s_sym[p0 + j] : ((win << bits) | (u64)s_sym[p0 + j]);
         u32 b = 0, e = 0;
         if (base + p0 < n) { b = bt_block_of(ends, count, base + p0); e = ends[b]; }
 #pragma unroll
@@ -100,11 +105,17 @@ k_pack_keys_batch(const u8* __restrict__ text, u32 n, const u8* __restrict__ cod
                 const u32 rem = e - gp;
                 const u32 r = rem < (u32)k ? rem : (u32)k;
                 // symbols beyond the block's end belong to the separator / the next block: drop them
-                const u64 w = r == (u32)k ? win : (r ? (win & (~0ull << (((u32)k - r) * (u32)bits))) : 0ull);
-                key = (bshift < 64 ? ((u64)b << bshift) : 0ull) | (w << len_bits) | (u64)r;
+                if (RADIX) {
+                    const u64 w = r == (u32)k ? win : (r ? win - win % s_pw[(u32)k - r] : 0ull);
+                    key = (bshift < 64 ? ((u64)b << bshift) : 0ull) | w;
+                } else {
+                    const u64 w = r == (u32)k ? win : (r ? (win & (~0ull << (((u32)k - r) * (u32)bits))) : 0ull);
+                    key = (bshift < 64 ? ((u64)b << bshift) : 0ull) | (w << len_bits) | (u64)r;
+                }
             }
             s_out[warp][i * 33 + lane] = key;
-            win = ((win << bits) | (u64)s_sym[p0 + i + k]) & sym_mask;
+            win = RADIX ? (win - (u64)s_sym[p0 + i] * top_pow) * B + (u64)s_sym[p0 + i + k]
+                        : (((win << bits) | (u64)s_sym[p0 + i + k]) & sym_mask);
         }
         __syncwarp();
         const u32 wb = base + warp * (32u * PK_IPT);

@@ -49,10 +49,16 @@ struct AlphabetPlan {
     int bits;      // bits per dense symbol
     int k;         // symbols packed into the initial key
     int len_bits;  // bits of the clamped-length field
+    // mixed-radix packing (experimental, B200SA_PACK_RADIX=1): key = sum digit_j * radix^(k-1-j), digit = symbol + 1, 0 past
+    // the end of the text — no length field, and no bits wasted on alphabets that are not a power of two (27 letters:
+    // 13 symbols per key instead of 12).  radix == 0: the bit-packed layout above.
+    u64 radix;
+    u64 pow[66];   // radix^j
+    int key_bits;  // significant bits of the symbol part of the key (both layouts)
 };
 
 // reserved_bits: key bits kept free above the symbols (the block number of a batched sort)
-AlphabetPlan plan_alphabet(const u32* hist256, int reserved_bits = 0, int max_key_bits = 64);
+AlphabetPlan plan_alphabet(const u32* hist256, int reserved_bits = 0, int max_key_bits = 64, bool allow_radix = false);
 static inline int bit_length_u64(u64 x) { int b = 0; while (x) { ++b; x >>= 1; } return b; }
 
 struct Engine {
@@ -82,6 +88,7 @@ struct Engine {
     // width of the round-0 key (symbols + length field + block bits): fewer bits = fewer radix sweeps in round 0 but
     // more suffixes left for the doubling rounds (B200SA_MAX_KEY_BITS; measured in profiles/)
     int max_key_bits = 64;
+    bool pack_radix = false;  // B200SA_PACK_RADIX=1: mixed-radix round-0 keys where they hold more symbols (unmeasured: off)
 
     // instrumentation
     bool profiling = false;

@@ -80,15 +80,18 @@ static const int PK_IPT = 16;
 static const int PK_TILE = PK_THREADS * PK_IPT;  // 4096 positions
 static const int PK_HALO = 64;                   // k <= 58
 
+// RADIX = true (experimental): key = sum_{j<k} digit_j * B^(k-1-j) with digit = code + 1 inside the text and 0 past its end
+// (B = sigma + 1, top_pow = B^(k-1)) — the same order, no length field, no bits wasted on odd alphabet sizes.
+template <bool RADIX>
 __global__ void __launch_bounds__(PK_THREADS)
-k_pack_keys(const u8* __restrict__ text, u32 n, const u8* __restrict__ code, int bits, int k, int len_bits,
+k_pack_keys(const u8* __restrict__ text, u32 n, const u8* __restrict__ code, int bits, int k, int len_bits, u64 B, u64 top_pow,
             u64* __restrict__ keys)
 {
     __shared__ u8 s_code[256];
     __shared__ __align__(16) u8 s_sym[PK_TILE + PK_HALO];
     __shared__ u64 s_out[PK_THREADS / 32][PK_IPT * 33];
     const u32 tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    s_code[tid] = code[tid];
+    s_code[tid] = RADIX ? (u8)(code[tid] + 1u) : code[tid];  // sigma <= 255 in the mixed-radix layout: digits fit a byte
     __syncthreads();
     const u32 ntiles = (u32)div_up_u64(n, PK_TILE);
     const u64 sym_mask = (k * bits >= 64) ? ~0ull : ((1ull << (k * bits)) - 1ull);
@@ -113,14 +116,19 @@ k_pack_keys(const u8* __restrict__ text, u32 n, const u8* __restrict__ code, int
         // thread handles 16 consecutive positions with a sliding window
         const u32 p0 = tid * PK_IPT;
         u64 win = 0;
-        for (int j = 0; j < k; ++j) win = (win << bits) | (u64)s_sym[p0 + j];
+        for (int j = 0; j < k; ++j) win = RADIX ? win * B + (u64)s_sym[p0 + j] : ((win << bits) | (u64)s_sym[p0 + j]);
 #pragma unroll
         for (int i = 0; i < PK_IPT; ++i) {
             const u32 gp = base + p0 + i;
-            const u32 rem = gp < n ? n - gp : 0u;
-            const u64 key = (win << len_bits) | (u64)(rem < (u32)k ? rem : (u32)k);
-            s_out[warp][i * 33 + lane] = key;
-            win = ((win << bits) | (u64)s_sym[p0 + i + k]) & sym_mask;
+            if (RADIX) {
+                s_out[warp][i * 33 + lane] = win;
+                win = (win - (u64)s_sym[p0 + i] * top_pow) * B + (u64)s_sym[p0 + i + k];
+            } else {
+                const u32 rem = gp < n ? n - gp : 0u;
+                const u64 key = (win << len_bits) | (u64)(rem < (u32)k ? rem : (u32)k);
+                s_out[warp][i * 33 + lane] = key;
+                win = ((win << bits) | (u64)s_sym[p0 + i + k]) & sym_mask;
+            }
         }
         __syncwarp();
         // the warp's 512 keys are positions base + warp*512 + lane*16 + i; write them coalesced

@@ -85,7 +85,9 @@ def test_emu_profile_accounting(emu_engine):
     {"B200SA_GROUPSORT_TINY": "3", "B200SA_GROUPSORT_MEDIUM": "4096", "B200SA_GROUPSORT_AVG": "1000000"},  # CTA bitonic path
     {"B200SA_GROUPSORT_AVG": "0"},                                                                        # radix rounds only
     {"B200SA_ISA_DIRECT_BYTES": "0", "B200SA_ISA_MIN_UPDATES": "1"},                                      # bucketed ISA update
-], ids=["groups-small-thresholds", "groups-cta", "radix-only", "bucketed-isa"])
+    {"B200SA_PACK_RADIX": "1"},                                                                           # mixed-radix round-0 keys
+    {"B200SA_MAX_KEY_BITS": "24"},                                                                        # narrow round-0 keys
+], ids=["groups-small-thresholds", "groups-cta", "radix-only", "bucketed-isa", "mixed-radix-keys", "narrow-keys"])
 def test_emu_round_variants(oracle, env, monkeypatch):
     """every way a doubling round can run (in-place group sort: thread / CTA / per-group radix / fallback; radix
     rounds; direct and bucketed ISA update) gives the oracle's suffix array"""
@@ -97,9 +99,13 @@ def test_emu_round_variants(oracle, env, monkeypatch):
     eng = Engine(0, library=Library(os.path.join(ROOT, "tests", "emu", "libb200sa_emu.so")))
     try:
         for family, n in [("markov3", 30011), ("acgt_rep", 20000), ("zeros", 3000), ("abcabca", 5000), ("fib", 6000),
-                          ("sigma2", 4097), ("periodic1009", 9000), ("zero_tail", 777)]:
+                          ("sigma2", 4097), ("sigma3", 5000), ("periodic1009", 9000), ("zero_tail", 777), ("rand", 2000)]:
             x = gen(family, n)
             assert np.array_equal(eng.make_suffix_array(x), oracle.sa(x)), (family, n, env)
+        # the same variants through the batched sort (block number above the symbol part of the key)
+        blocks = [gen("markov3", 5000), gen("sigma3", 700), gen("zeros", 300), np.empty(0, np.uint8), gen("rand", 40)]
+        for got, x in zip(eng.suffix_array_batch(blocks), blocks):
+            assert np.array_equal(got, oracle.sa(x)) if x.size else got.tolist() == [0], env
     finally:
         eng.close()
 

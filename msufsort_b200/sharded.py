@@ -46,13 +46,17 @@ class ShardedResult:
 
 
 class ShardedSorter:
-    def __init__(self, engine, group: Optional[dist.ProcessGroup] = None, isa: str = "owner"):
+    def __init__(self, engine, group: Optional[dist.ProcessGroup] = None, isa: str = "owner", merged_barrier: bool = False):
         assert isa in ("owner", "replicated", "peer")
         self.eng = engine
         self.group = group
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
         self.isa = isa
+        # isa="peer": fold the "everybody has finished reading" all-reduce into the "all sends have landed" one (sends go to
+        # the inboxes, which no reader touches; a rank reaches the second barrier only after its own round).  Two instead of
+        # three collectives per round; not yet measured on hardware, hence off by default.
+        self.merged_barrier = merged_barrier
         assert self.world <= 256, "the owner routing sweep has 256 buckets"
         assert isa != "peer" or self.world <= 16, "the peer table holds 16 GPUs (one NVSwitch domain)"
 
@@ -169,11 +173,13 @@ class ShardedSorter:
         res.rounds = 1
         while self.isa == "peer" and self.world > 1:
             # every rank has finished READING ranks (its round is complete) ...
-            total = self._sum_int(m_local, device)
+            total = None if self.merged_barrier else self._sum_int(m_local, device)
             _, _, cnt = self.eng.shard_updates()
             self.eng.shard_peer_scatter(stream)          # ... new ranks are stored into the owners' inboxes ...
             res.exchanged_bytes += 8 * cnt * (self.world - 1) // self.world
-            self._sum_int(0, device)                     # ... all of them have landed ...
+            t2 = self._sum_int(m_local if self.merged_barrier else 0, device)   # ... all of them have landed ...
+            if self.merged_barrier:
+                total = t2
             self.eng.shard_peer_apply(stream)            # ... every owner updates its ISA shard ...
             self._sum_int(0, device)                     # ... and all shards are current before anyone reads again
             if total == 0:

@@ -39,6 +39,27 @@ def test_oracle_lcp_bruteforce_small(oracle):
             assert lcp[r] == l
 
 
+def _golden():
+    import json
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "kat_lcp.json")) as f:
+        return json.load(f)["cases"]
+
+
+def test_oracle_lcp_matches_golden_vectors(oracle):
+    """digests produced by the reference (library SA + demo LCP) with tests/golden/make_golden_lcp.py; they travel to the
+    GPU box, where /root/reference does not exist"""
+    for c in _golden():
+        x = gen(c["family"], c["n"])
+        assert f"{oracle.fnv(x):016x}" == c["text_fnv"]
+        sa = oracle.sa(x)
+        for kasai in (False, True):
+            if not kasai and c["lcp_max"] > 1000 and c["n"] > 20000:
+                continue
+            lcp = oracle.lcp(x, sa, kasai=kasai)
+            assert f"{oracle.fnv(lcp):016x}" == c["lcp_fnv"], (c["family"], c["n"], kasai)
+            assert int(lcp.max()) == c["lcp_max"] and int(lcp.astype(np.int64).sum()) == c["lcp_sum"]
+
+
 # ---- emulator ---------------------------------------------------------------------------------
 @pytest.mark.parametrize("family", LCP_FAMILIES)
 def test_emu_lcp(emu_engine, oracle, family):
@@ -99,6 +120,14 @@ def test_gpu_lcp_parity(gpu_engine, oracle, family):
         want_sa = oracle.sa(x)
         assert np.array_equal(sa, want_sa), (family, n)
         assert np.array_equal(lcp, oracle.lcp(x, want_sa, kasai=True)), (family, n)
+
+
+@pytest.mark.gpu
+def test_gpu_lcp_matches_golden_vectors(gpu_engine, oracle):
+    for c in _golden():
+        x = gen(c["family"], c["n"])
+        lcp = gpu_engine.make_lcp_array(x)
+        assert f"{oracle.fnv(lcp):016x}" == c["lcp_fnv"], (c["family"], c["n"])
 
 
 @pytest.mark.gpu

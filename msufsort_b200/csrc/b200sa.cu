@@ -126,6 +126,8 @@ int Engine::init(int dev)
     if (const char* e5 = getenv("B200SA_GROUPSORT_MEDIUM")) groupsort_medium = (u32)strtoul(e5, nullptr, 10);
     if (const char* e8 = getenv("B200SA_MAX_KEY_BITS")) max_key_bits = atoi(e8);
     if (const char* e9 = getenv("B200SA_PACK_RADIX")) pack_radix = atoi(e9) != 0;
+    if (const char* e10 = getenv("B200SA_RS_PERSISTENT")) rs_persistent = atoi(e10) != 0;
+    if (const char* e11 = getenv("B200SA_NUM_SMS")) { const int v = atoi(e11); if (v >= 1 && v <= 1024) num_sms = v; }  // tests: small persistent grids
     if (const char* e6 = getenv("B200SA_UNBWT_CAP_MULT")) unbwt_cap_mult = (u32)strtoul(e6, nullptr, 10);
     if (unbwt_cap_mult < 1) unbwt_cap_mult = 1;
     if (groupsort_tiny > (u32)GS_TINY) groupsort_tiny = GS_TINY;
@@ -133,6 +135,8 @@ int Engine::init(int dev)
     // the scatter kernels use more than the default 48 KB of dynamic shared memory
     {
         auto k64 = k_onesweep_pass<u64, true>;
+        auto k64p = k_onesweep_pass_persistent<u64, true>;
+        B200SA_CU(cudaFuncSetAttribute(k64p, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_pass_smem_bytes<u64>()));
         auto k8 = k_onesweep_pass<u8, false>;
         auto k32 = k_onesweep_pass<u32, true>;
         B200SA_CU(cudaFuncSetAttribute(k32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_pass_smem_bytes<u32>()));
@@ -249,11 +253,19 @@ int Engine::radix_sort_pairs(u64* keys2[2], u32* vals2[2], bool gen_vals, u32 m,
     int side = 0;
     for (int p = 0; p < passes; ++p) {
         B200SA_TRY(phase_begin(B200SA_PH_SORT_PASS, st));
-        auto kp = k_onesweep_pass<u64, true>;
         const u32* vin = (p == 0 && gen_vals) ? nullptr : vals2[side];
-        B200SA_LAUNCH(kp, tiles, RS_THREADS, rs_pass_smem_bytes<u64>(), st,
-                      keys2[side], keys2[side ^ 1], vin, vals2[side ^ 1], m, begin_bit + p * RS_RADIX_BITS, 0xffffffffu,
-                      ghist + p * RS_RADIX, status + (size_t)p * tiles * RS_RADIX, counters + p);
+        if (rs_persistent) {
+            auto kp = k_onesweep_pass_persistent<u64, true>;
+            const u32 grid = tiles < (u32)(num_sms * RS_MIN_BLOCKS) ? tiles : (u32)(num_sms * RS_MIN_BLOCKS);
+            B200SA_LAUNCH(kp, grid, RS_THREADS, rs_pass_smem_bytes<u64>(), st,
+                          keys2[side], keys2[side ^ 1], vin, vals2[side ^ 1], m, begin_bit + p * RS_RADIX_BITS, 0xffffffffu,
+                          ghist + p * RS_RADIX, status + (size_t)p * tiles * RS_RADIX, counters + p, tiles);
+        } else {
+            auto kp = k_onesweep_pass<u64, true>;
+            B200SA_LAUNCH(kp, tiles, RS_THREADS, rs_pass_smem_bytes<u64>(), st,
+                          keys2[side], keys2[side ^ 1], vin, vals2[side ^ 1], m, begin_bit + p * RS_RADIX_BITS, 0xffffffffu,
+                          ghist + p * RS_RADIX, status + (size_t)p * tiles * RS_RADIX, counters + p);
+        }
         count_launch(B200SA_PH_SORT_PASS);
         B200SA_TRY(phase_end(st));
         prof.alg_bytes[B200SA_PH_SORT_PASS] += (u64)m * (vin ? 24 : 20);

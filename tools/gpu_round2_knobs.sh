@@ -1,0 +1,18 @@
+#!/bin/bash
+# First GPU call of the next round: the experiments that are correct under the emulator but still unmeasured.
+#   B200SA_PACK_RADIX=1     mixed-radix round-0 keys (more symbols per key)
+#   B200SA_RS_PERSISTENT=1  persistent sweep with next-tile key prefetch
+cd "${GRAFT_REPO_ROOT:-/root/repo}"
+mkdir -p gpurun_out
+run() {  # name, env...
+  local name=$1; shift
+  echo "== $name"
+  env "$@" timeout 200 python bench.py --steps 3 --warmup 2 --no-cpu-baseline --no-extras > gpurun_out/knob_$name.json 2> gpurun_out/knob_$name.err || tail -3 gpurun_out/knob_$name.err
+  python tools/bench_summary.py gpurun_out/knob_$name.json | head -12
+}
+run baseline B200SA_DUMMY=0
+run pack_radix B200SA_PACK_RADIX=1
+run persistent B200SA_RS_PERSISTENT=1
+run both B200SA_PACK_RADIX=1 B200SA_RS_PERSISTENT=1
+echo "== parity with the knobs on"
+B200SA_PACK_RADIX=1 B200SA_RS_PERSISTENT=1 timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_batch.py -m gpu -x -q 2>&1 | tail -3

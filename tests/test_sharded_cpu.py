@@ -78,21 +78,12 @@ def test_sharded_matches_oracle(oracle, world, family, n, isa):
 # CUDA IPC needs real GPUs; under the emulator the "handle" carries the pointer, so the contexts of one process can
 # map each other's ISA arrays.  This exercises the engine side of the protocol (export / attach / peer reads in the
 # doubling rounds / peer scatter / BWT through the shard of GPU 0); the torch.distributed side runs in the GPU tier.
-@pytest.mark.parametrize("world", [2, 3, 5])
-@pytest.mark.parametrize("family,n", [("markov3", 40000), ("acgt_rep", 30011), ("abcabca", 9000), ("zeros", 3000), ("fib", 10000),
-                                      ("periodic7", 5000), ("rand", 64)])
-def test_peer_isa_lockstep(oracle, world, family, n, monkeypatch):
-    from cases import gen
-    from msufsort_b200.api import Engine, Library
-    monkeypatch.setenv("B200SA_GROUPSORT_TINY", "4")      # reach the CTA and the radix paths at these sizes too
-    monkeypatch.setenv("B200SA_GROUPSORT_MEDIUM", "64")
-    if world != 3:                                        # bucketed peer scatter (world 3 keeps the direct one)
-        monkeypatch.setenv("B200SA_ISA_DIRECT_BYTES", "0")
-        monkeypatch.setenv("B200SA_ISA_MIN_UPDATES", "1")
-    lib = Library(os.path.join(ROOT, "tests", "emu", "libb200sa_emu.so"))
+def _peer_lockstep(lib, oracle, x, world):
+    """G contexts of one process run the peer-ISA protocol in lock step; returns nothing, asserts SA / BWT / sentinel."""
+    from msufsort_b200.api import Engine
+    n = x.size
     engs = [Engine(0, library=lib) for _ in range(world)]
     try:
-        x = gen(family, n)
         per = (n + world - 1) // world
         shift = max(0, (per - 1).bit_length())
         handles = b"".join(e.shard_peer_export(n) for e in engs)
@@ -129,9 +120,30 @@ def test_peer_isa_lockstep(oracle, world, family, n, monkeypatch):
             bwt[ob:oe] = part[ob:oe]
             assert sentinel in (None, s)
             sentinel = s
-        assert np.array_equal(sa, want), (family, n, world)
+        assert np.array_equal(sa, want), (n, world)
         wb, ws = oracle.bwt_from_sa(x, want)
         assert sentinel == ws and np.array_equal(bwt, wb)
+        return engs
+    except Exception:
+        for e in engs:
+            e.close()
+        raise
+
+
+@pytest.mark.parametrize("world", [2, 3, 5])
+@pytest.mark.parametrize("family,n", [("markov3", 40000), ("acgt_rep", 30011), ("abcabca", 9000), ("zeros", 3000), ("fib", 10000),
+                                      ("periodic7", 5000), ("rand", 64)])
+def test_peer_isa_lockstep(oracle, world, family, n, monkeypatch):
+    from cases import gen
+    from msufsort_b200.api import Library
+    monkeypatch.setenv("B200SA_GROUPSORT_TINY", "4")      # reach the CTA and the radix paths at these sizes too
+    monkeypatch.setenv("B200SA_GROUPSORT_MEDIUM", "64")
+    if world != 3:                                        # bucketed ISA apply (world 3 keeps the direct one)
+        monkeypatch.setenv("B200SA_ISA_DIRECT_BYTES", "0")
+        monkeypatch.setenv("B200SA_ISA_MIN_UPDATES", "1")
+    lib = Library(os.path.join(ROOT, "tests", "emu", "libb200sa_emu.so"))
+    engs = _peer_lockstep(lib, oracle, gen(family, n), world)
+    try:
         # a second text of another size through the same contexts: mappings are re-established
         x2 = gen("markov3", n // 2 + 7)
         handles = b"".join(e.shard_peer_export(x2.size) for e in engs)
@@ -142,3 +154,19 @@ def test_peer_isa_lockstep(oracle, world, family, n, monkeypatch):
     finally:
         for e in engs:
             e.close()
+
+
+def test_peer_isa_lockstep_fuzz(oracle):
+    """random small texts over tiny alphabets (deep rounds, huge groups, empty key ranges) on 2..6 GPUs-in-one-process"""
+    from hypothesis import HealthCheck, given, settings, strategies as st
+    from msufsort_b200.api import Library
+    lib = Library(os.path.join(ROOT, "tests", "emu", "libb200sa_emu.so"))
+
+    @settings(max_examples=40, deadline=None, suppress_health_check=[HealthCheck.too_slow])
+    @given(text=st.lists(st.integers(0, 2), min_size=2, max_size=400), world=st.integers(2, 6))
+    def run(text, world):
+        engs = _peer_lockstep(lib, oracle, np.array(text, dtype=np.uint8), world)
+        for e in engs:
+            e.close()
+
+    run()

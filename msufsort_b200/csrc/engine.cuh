@@ -69,7 +69,7 @@ struct Engine {
     // workspace (sized for the largest n seen; see DESIGN.md "data layout in HBM")
     DevBuf keys[2], idx[2], slot[2], gid, gstart, glist, rank, sa_ws, sortmeta, agg_cnt, agg_max, misc, text_ws, bwt_ws, walk;
     DevBuf batch_text, batch_meta, batch_out;  // batched sort: expanded text, block tables, staging of packed results
-    u32* h_pinned = nullptr;  // 64 words of pinned host memory for small read-backs
+    u32* h_pinned = nullptr;  // 512 words of pinned host memory for small read-backs (offsets: see the uses in b200sa.cu)
 
     // rank[] arrays up to this size are updated by direct scatter (they stay resident in the 126 MB
     // L2); larger ones by the bucketed update when a round has at least isa_min_updates tuples

@@ -1350,7 +1350,12 @@ int Engine::unbwt_batch_dev(const u8* d_bwt, const i64* offsets, i64 count64, co
     if (D < 64) D = 64;
     const u32 nreg = (u32)div_up_u64(N, D);
     const u32 W = nreg + 2 * count;
-    const u32 cap = (unbwt_cap_mult * D + 7u) & ~7u;
+    // the longest chain is the largest block's: (rows / D) regular walkers + start + terminal; no segment is longer than
+    // the largest block either, which bounds the decode windows when a batch consists of very many tiny blocks
+    u64 max_rows = 0;
+    for (u32 b = 0; b < count; ++b) { const u64 r = (u64)(offsets[b + 1] - offsets[b]) + 1; max_rows = r > max_rows ? r : max_rows; }
+    u32 cap = (unbwt_cap_mult * D + 7u) & ~7u;
+    if ((u64)cap > ((max_rows + 7) & ~(u64)7)) cap = (u32)((max_rows + 7) & ~(u64)7);
     B200SA_TRY(walk.ensure((size_t)W * 5 * 4 + 64));
     B200SA_LAUNCH(k_ubb_mark, (u32)div_up_u64(nreg + count, 256), 256, 0, st, table, (const u32*)d_ends, (const i32*)d_sent, count, nreg, D, N);
     count_launch(B200SA_PH_UNBWT_BUILD);
@@ -1371,9 +1376,6 @@ int Engine::unbwt_batch_dev(const u8* d_bwt, const i64* offsets, i64 count64, co
     B200SA_CU(cudaMemcpyAsync(idx[0].p, ds[0], (size_t)W * 4, cudaMemcpyDeviceToDevice, st));
     const u32 g256 = (u32)div_up_u64(W, 256);
     int cur = 0;
-    // the longest chain is the largest block's: (rows / D) regular walkers + start + terminal
-    u64 max_rows = 0;
-    for (u32 b = 0; b < count; ++b) { const u64 r = (u64)(offsets[b + 1] - offsets[b]) + 1; max_rows = r > max_rows ? r : max_rows; }
     const int jumps = bit_length_u64(max_rows / D + 3);
     for (int it = 0; it < jumps; ++it) {
         B200SA_LAUNCH(k_unbwt_jump, g256, 256, 0, st, (const u32*)nx[cur], (const u32*)ds[cur], nx[cur ^ 1], ds[cur ^ 1], W);

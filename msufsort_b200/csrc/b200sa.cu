@@ -127,6 +127,7 @@ int Engine::init(int dev)
     if (const char* e8 = getenv("B200SA_MAX_KEY_BITS")) max_key_bits = atoi(e8);
     if (const char* e9 = getenv("B200SA_PACK_RADIX")) pack_radix = atoi(e9) != 0;
     if (const char* e10 = getenv("B200SA_RS_PERSISTENT")) rs_persistent = atoi(e10) != 0;
+    if (const char* e12 = getenv("B200SA_LCP_DIRECT")) lcp_direct = atoi(e12) != 0;
     if (const char* e11 = getenv("B200SA_NUM_SMS")) { const int v = atoi(e11); if (v >= 1 && v <= 1024) num_sms = v; }  // tests: small persistent grids
     if (const char* e6 = getenv("B200SA_UNBWT_CAP_MULT")) unbwt_cap_mult = (u32)strtoul(e6, nullptr, 10);
     if (unbwt_cap_mult < 1) unbwt_cap_mult = 1;
@@ -1116,6 +1117,38 @@ int Engine::lcp_dev(const u8* d_text, i64 n64, const i32* d_sa, i32* d_lcp, cuda
         B200SA_CU(cudaMemsetAsync(d_lcp, 0, sizeof(i32), st));
         B200SA_CU(cudaStreamSynchronize(st));
         return 0;
+    }
+    if (lcp_direct && n >= 2) {
+        // ---- direct route first (see k_lcp_direct); falls through to the PLCP route when too many rows outgrow the budget
+        const u32 ovf_cap = n / 64 + 1024;
+        B200SA_TRY(slot[1].ensure((size_t)ovf_cap * 4 + 64));
+        B200SA_TRY(misc.ensure(4096));
+        u32* d_ovf = misc.as<u32>() + 1000;
+        B200SA_CU(cudaMemsetAsync(d_ovf, 0, 4, st));
+        prof.memsets++;
+        B200SA_TRY(phase_begin(B200SA_PH_LCP, st));
+        const u32 want = (u32)div_up_u64((u64)n + 1, 256);
+        const u32 grid = want < (u32)(num_sms * 16) ? want : (u32)(num_sms * 16);
+        B200SA_LAUNCH(k_lcp_direct, grid, 256, 0, st, d_text, n, d_sa, d_lcp, slot[1].as<u32>(), ovf_cap, d_ovf);
+        count_launch(B200SA_PH_LCP);
+        B200SA_TRY(phase_end(st));
+        B200SA_CU(cudaMemcpyAsync(h_pinned + 440, d_ovf, 4, cudaMemcpyDeviceToHost, st));
+        B200SA_CU(cudaStreamSynchronize(st));
+        const u32 novf = h_pinned[440];
+        if (novf <= ovf_cap) {
+            if (novf) {
+                B200SA_TRY(phase_begin(B200SA_PH_LCP, st));
+                const u32 g2 = novf < (u32)(num_sms * 4) ? novf : (u32)(num_sms * 4);
+                B200SA_LAUNCH(k_lcp_direct_finish, g2, LC_THREADS, 0, st, d_text, n, d_sa, d_lcp, (const u32*)slot[1].as<u32>(), novf);
+                count_launch(B200SA_PH_LCP);
+                B200SA_TRY(phase_end(st));
+            }
+            prof.alg_bytes[B200SA_PH_LCP] += (u64)n * (4 + 8 + 4);
+            B200SA_CU(cudaGetLastError());
+            B200SA_CU(cudaStreamSynchronize(st));
+            if (profiling) B200SA_TRY(collect_profile());
+            return 0;
+        }
     }
     // workspace: phi -> gid, plcp -> slot[0], overflow list -> slot[1], bucketed scatter scratch -> agg_max / keys[0]
     B200SA_TRY(gid.ensure((size_t)n * 4 + 64));

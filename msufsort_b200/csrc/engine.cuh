@@ -88,6 +88,7 @@ struct Engine {
     // width of the round-0 key (symbols + length field + block bits): fewer bits = fewer radix sweeps in round 0 but
     // more suffixes left for the doubling rounds (B200SA_MAX_KEY_BITS; measured in profiles/)
     int max_key_bits = 64;
+    bool lcp_direct = false;     // B200SA_LCP_DIRECT=1: budgeted row-wise comparison before the PLCP route (unmeasured: off)
     bool rs_persistent = false;  // B200SA_RS_PERSISTENT=1: persistent sweep with next-tile key prefetch (unmeasured: off)
     bool pack_radix = false;  // B200SA_PACK_RADIX=1: mixed-radix round-0 keys where they hold more symbols (unmeasured: off)
 

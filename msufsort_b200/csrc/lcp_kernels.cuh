@@ -155,6 +155,61 @@ k_plcp_overflow(const u8* __restrict__ text, u32 n, const u32* __restrict__ phi,
     }
 }
 
+// Direct route for texts whose LCP values are small (experimental, B200SA_LCP_DIRECT=1; not yet measured): row r compares
+// suffixes SA[r-1] and SA[r] byte-wise up to LD_BUDGET bytes.  Thread r's right-hand suffix is thread r+1's left-hand
+// one, so a row costs ONE random text access (the other hits L1/L2) instead of the three random accesses per position of
+// the PLCP route (phi scatter, probe, gather).  Rows that exhaust the budget are counted and listed; the host then
+// either finishes the few of them with the CTA-wide compare or, when they are many (repetitive text), discards this
+// pass and runs the PLCP route, whose cost is bounded whatever the text looks like.
+static const u32 LD_BUDGET = 64;
+
+__global__ void __launch_bounds__(256)
+k_lcp_direct(const u8* __restrict__ text, u32 n, const i32* __restrict__ sa, i32* __restrict__ lcp,
+             u32* __restrict__ ovf_rows, u32 ovf_cap, u32* __restrict__ ovf_count)
+{
+    const u32 off = (u32)((uintptr_t)text & 3u);
+    const u32* words = (const u32*)(text - off);
+    const u64 total = (u64)n + 1;
+    for (u64 r = (u64)blockIdx.x * blockDim.x + threadIdx.x; r < total; r += (u64)gridDim.x * blockDim.x) {
+        if (r < 2) { lcp[r] = 0; continue; }  // row 0 is the empty suffix
+        const u32 p = (u32)sa[r - 1], q = (u32)sa[r];
+        const u32 maxl = n - (p > q ? p : q);
+        const u32 stop = maxl > LD_BUDGET ? LD_BUDGET : maxl;
+        u32 l = 0;
+        bool open = true;
+        while (open && l + 8u <= stop) {
+            const u64 x = lc_load8(words, off, p + l) ^ lc_load8(words, off, q + l);
+            if (x) { l += (u32)(__ffsll((long long)x) - 1) >> 3; open = false; }
+            else l += 8u;
+        }
+        while (open && l < stop) {
+            if (text[p + l] != text[q + l]) open = false;
+            else ++l;
+        }
+        lcp[r] = (i32)l;
+        if (open && l < maxl) {  // budget exhausted, the match is still running
+            const u32 e = atomicAdd(ovf_count, 1u);
+            if (e < ovf_cap) ovf_rows[e] = (u32)r;
+        }
+    }
+}
+
+// the listed rows, one CTA at a time: lcp[r] = lcp(SA[r-1], SA[r]) continued from the budget
+__global__ void __launch_bounds__(LC_THREADS)
+k_lcp_direct_finish(const u8* __restrict__ text, u32 n, const i32* __restrict__ sa, i32* __restrict__ lcp,
+                    const u32* __restrict__ ovf_rows, u32 count)
+{
+    __shared__ u32 s_min[LC_THREADS / 32];
+    __shared__ u32 s_res;
+    const u32 off = (u32)((uintptr_t)text & 3u);
+    const u32* words = (const u32*)(text - off);
+    for (u32 e = blockIdx.x; e < count; e += gridDim.x) {
+        const u32 r = ovf_rows[e];
+        const u32 result = lc_cta_extend(text, words, off, n, (u32)sa[r - 1], (u32)sa[r], LD_BUDGET, s_min, &s_res);
+        if (threadIdx.x == 0) lcp[r] = (i32)result;
+    }
+}
+
 // lcp[r] = lcp(SA[r-1], SA[r]) = plcp[SA[r]] for r = 1..n; lcp[0] = 0 (row 0 is the empty suffix).
 __global__ void __launch_bounds__(256)
 k_lcp_gather(const i32* __restrict__ sa, u32 n, const u32* __restrict__ plcp, i32* __restrict__ lcp)

@@ -101,6 +101,37 @@ def test_emu_lcp_bucketed_phi(oracle, monkeypatch):
         eng.close()
 
 
+def test_emu_lcp_direct_route(oracle, monkeypatch):
+    """B200SA_LCP_DIRECT=1: budgeted row-wise comparison; few long rows are finished by the CTA-wide compare, many of them
+    send the call down the PLCP route"""
+    from conftest import ROOT
+    from msufsort_b200.api import Engine, Library
+    monkeypatch.setenv("B200SA_LCP_DIRECT", "1")
+    eng = Engine(0, library=Library(os.path.join(ROOT, "tests", "emu", "libb200sa_emu.so")))
+    try:
+        for family, n in [("markov3", 50011), ("acgt_rep", 60000), ("rand", 3000), ("zeros", 9000), ("fib", 17711), ("rand", 1), ("rand", 2)]:
+            buf = gen(family, n + 1)
+            x = buf[1:]
+            sa = oracle.sa(x)
+            before = eng.launch_count()
+            assert np.array_equal(eng.make_lcp_array(x, sa), oracle.lcp(x, sa, kasai=True)), (family, n)
+            launches = eng.launch_count() - before
+            if family in ("markov3", "rand") and n > 2:
+                assert launches <= 2, launches          # direct pass (+ finish), no PLCP levels
+            if family in ("zeros", "fib"):
+                assert launches > 10, launches          # fell through to the PLCP route
+        # long matches in a few rows only: one repeated 5000-byte segment inside random text
+        rng = np.random.default_rng(9)
+        x = rng.integers(0, 256, size=80000, dtype=np.uint8)
+        x[60000:61000] = x[1000:2000]
+        sa = oracle.sa(x)
+        before = eng.launch_count()
+        assert np.array_equal(eng.make_lcp_array(x, sa), oracle.lcp(x, sa, kasai=True))
+        assert eng.launch_count() - before == 2
+    finally:
+        eng.close()
+
+
 def test_emu_lcp_empty_and_errors(emu_engine):
     from msufsort_b200.api import B200SAError
     assert emu_engine.make_lcp_array(np.empty(0, dtype=np.uint8)).tolist() == [0]

@@ -2,6 +2,7 @@
 # First GPU call of the next round: the experiments that are correct under the emulator but still unmeasured.
 #   B200SA_PACK_RADIX=1     mixed-radix round-0 keys (more symbols per key)
 #   B200SA_RS_PERSISTENT=1  persistent sweep with next-tile key prefetch
+#   B200SA_LCP_DIRECT=1     budgeted row-wise LCP comparison before the PLCP route
 cd "${GRAFT_REPO_ROOT:-/root/repo}"
 mkdir -p gpurun_out
 run() {  # name, env...
@@ -14,5 +15,10 @@ run baseline B200SA_DUMMY=0
 run pack_radix B200SA_PACK_RADIX=1
 run persistent B200SA_RS_PERSISTENT=1
 run both B200SA_PACK_RADIX=1 B200SA_RS_PERSISTENT=1
+echo "== LCP: PLCP route vs budgeted direct route (extras.lcp of the bench line)"
+for D in 0 1; do
+  B200SA_LCP_DIRECT=$D timeout 200 python bench.py --steps 2 --warmup 2 --no-cpu-baseline > gpurun_out/knob_lcp_direct$D.json 2> gpurun_out/knob_lcp_direct$D.err
+  python -c "import json; d=json.load(open('gpurun_out/knob_lcp_direct$D.json')); print('LCP_DIRECT=$D', d['extras']['lcp'])"
+done
 echo "== parity with the knobs on"
-B200SA_PACK_RADIX=1 B200SA_RS_PERSISTENT=1 timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_batch.py -m gpu -x -q 2>&1 | tail -3
+B200SA_PACK_RADIX=1 B200SA_RS_PERSISTENT=1 B200SA_LCP_DIRECT=1 timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_batch.py tests/test_lcp.py -m gpu -x -q 2>&1 | tail -3

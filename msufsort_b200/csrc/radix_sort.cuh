@@ -41,6 +41,21 @@ static const int RS_RADIX = 256;
 #ifndef B200SA_RS_THREADS
 #define B200SA_RS_THREADS 256
 #endif
+// 1: keep the sixteen within-warp ranks of a thread (each < 32 * IPT <= 65535) two to a register.  The sweep compiles to 80
+// registers with 80 bytes of spills; this frees eight registers.  Compile-time experiment (make NVCC_DEFS=-DB200SA_RS_PACK_POS=1),
+// not yet measured.
+#ifndef B200SA_RS_PACK_POS
+#define B200SA_RS_PACK_POS 0
+#endif
+#if B200SA_RS_PACK_POS
+#define RS_POS_DECL(IPT) u32 pos2[((IPT) + 1) / 2]; for (int i_ = 0; i_ < ((IPT) + 1) / 2; ++i_) pos2[i_] = 0
+#define RS_POS_SET(k, v) pos2[(k) >> 1] |= (u32)(v) << (((k) & 1) * 16)
+#define RS_POS_GET(k) ((pos2[(k) >> 1] >> (((k) & 1) * 16)) & 0xffffu)
+#else
+#define RS_POS_DECL(IPT) u32 pos[IPT]
+#define RS_POS_SET(k, v) pos[k] = (v)
+#define RS_POS_GET(k) pos[k]
+#endif
 static const int RS_THREADS = B200SA_RS_THREADS;
 static const int RS_IPT = B200SA_RS_IPT;
 static const int RS_TILE = RS_THREADS * RS_IPT;  // 4096 pairs per tile
@@ -192,7 +207,7 @@ k_onesweep_pass(const KeyT* __restrict__ kin, KeyT* __restrict__ kout,
     // ---- load (warp-striped): element order inside the tile is (warp, item, lane)
     KeyT key[IPT];
     u32 val[IPT];
-    u32 pos[IPT];
+    RS_POS_DECL(IPT);
     const u32 wbase = warp * (32u * IPT) + lane;
     const bool full = valid == (u32)TILE;  // block-uniform: no bounds checks on the common path
     if (full) {
@@ -245,7 +260,7 @@ k_onesweep_pass(const KeyT* __restrict__ kin, KeyT* __restrict__ kout,
             mywh[d] = prev + (u32)__popc(peers);
         }
         __syncwarp();
-        pos[k] = prev + below;
+        RS_POS_SET(k, prev + below);
     }
     PT_MARK(1);  // ranking
     // values are fetched only now: during ranking they would cost 16 more live registers (spills at
@@ -306,7 +321,7 @@ k_onesweep_pass(const KeyT* __restrict__ kin, KeyT* __restrict__ kout,
 #pragma unroll
     for (int k = 0; k < IPT; ++k) {
         const u32 d = rs_digit<KeyT>(key[k], shift);
-        const u32 p = pos[k] + mywh[d];
+        const u32 p = RS_POS_GET(k) + mywh[d];
         skeys[p] = key[k];
         svals[p] = val[k];
     }
@@ -434,7 +449,7 @@ k_onesweep_pass_persistent(const KeyT* __restrict__ kin, KeyT* __restrict__ kout
 
     // keys of this tile were loaded while the previous tile was in its look-back / write-out (or by the prologue)
     u32 val[IPT];
-    u32 pos[IPT];
+    RS_POS_DECL(IPT);
     const bool full = valid == (u32)TILE;  // block-uniform
     PT_MARK(0);  // keys arrived
     // ---- 1. rank inside the warp.  Peers = lanes holding my digit.  Two interchangeable ways to find
@@ -472,7 +487,7 @@ k_onesweep_pass_persistent(const KeyT* __restrict__ kin, KeyT* __restrict__ kout
             mywh[d] = prev + (u32)__popc(peers);
         }
         __syncwarp();
-        pos[k] = prev + below;
+        RS_POS_SET(k, prev + below);
     }
     PT_MARK(1);  // ranking
     // values are fetched only now: during ranking they would cost 16 more live registers (spills at
@@ -534,7 +549,7 @@ k_onesweep_pass_persistent(const KeyT* __restrict__ kin, KeyT* __restrict__ kout
 #pragma unroll
     for (int k = 0; k < IPT; ++k) {
         const u32 d = rs_digit<KeyT>(key[k], shift);
-        const u32 p = pos[k] + mywh[d];
+        const u32 p = RS_POS_GET(k) + mywh[d];
         skeys[p] = key[k];
         svals[p] = val[k];
     }

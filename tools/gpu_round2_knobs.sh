@@ -15,6 +15,13 @@ run baseline B200SA_DUMMY=0
 run pack_radix B200SA_PACK_RADIX=1
 run persistent B200SA_RS_PERSISTENT=1
 run both B200SA_PACK_RADIX=1 B200SA_RS_PERSISTENT=1
+echo "== compile-time variant: within-warp ranks packed two per register (sweep: 80 B of spills -> 0)"
+cp msufsort_b200/lib/libb200sa.so /tmp/libb200sa_default.so
+if nvcc -gencode arch=compute_100a,code=sm_100a -DB200SA_RS_PACK_POS=1 -lineinfo -O3 -std=c++17 -Xcompiler -fPIC,-fvisibility=hidden --expt-relaxed-constexpr -shared -o msufsort_b200/lib/libb200sa.so msufsort_b200/csrc/b200sa.cu 2> gpurun_out/knob_packpos_build.err; then
+  run packpos B200SA_DUMMY=0
+  run packpos_persistent B200SA_RS_PERSISTENT=1
+fi
+cp /tmp/libb200sa_default.so msufsort_b200/lib/libb200sa.so
 echo "== LCP: PLCP route vs budgeted direct route (extras.lcp of the bench line)"
 for D in 0 1; do
   B200SA_LCP_DIRECT=$D timeout 200 python bench.py --steps 2 --warmup 2 --no-cpu-baseline > gpurun_out/knob_lcp_direct$D.json 2> gpurun_out/knob_lcp_direct$D.err

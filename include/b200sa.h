@@ -202,6 +202,10 @@ B200SA_API int b200sa_pipeline_wait(b200sa_pipeline* p, int64_t ticket);
 /* Waits for everything submitted so far; returns the first failure among tickets nobody waited for. */
 B200SA_API int b200sa_pipeline_drain(b200sa_pipeline* p);
 
+/* Host-buffer form of the O(n) validator (the role of validate_suffix_array, main.cpp:236-270, whose byte compares
+ * are O(n * LCP)): *bad_rows_out = 0 iff sa is the suffix array of text. */
+B200SA_API int b200sa_check_suffix_array(b200sa_ctx* ctx, const uint8_t* text, int64_t n, const int32_t* sa, int64_t* bad_rows_out);
+
 /* ---- sharded (multi-GPU) building blocks --------------------------------------------------
  *
  * One text, G GPUs, one process and one context per GPU (msufsort_b200/sharded.py drives these over

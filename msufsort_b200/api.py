@@ -82,6 +82,7 @@ ABI = [
     ("b200sa_pipeline_submit_suffix_array", C.c_int, [_P, _P, _P, C.c_int64, _P, C.POINTER(C.c_int64)]),
     ("b200sa_pipeline_wait", C.c_int, [_P, C.c_int64]),
     ("b200sa_pipeline_drain", C.c_int, [_P]),
+    ("b200sa_check_suffix_array", C.c_int, [_P, _P, C.c_int64, _P, C.POINTER(C.c_int64)]),
     ("b200sa_shard_begin", C.c_int, [_P, _P, C.c_int64, _P, C.c_int, C.c_int, C.POINTER(C.c_int64), _P]),
     ("b200sa_shard_round0", C.c_int, [_P, C.c_int64, C.POINTER(C.c_int64), _P]),
     ("b200sa_shard_round", C.c_int, [_P, C.POINTER(C.c_int64), _P]),
@@ -245,6 +246,16 @@ class Engine:
         if not buf.flags.writeable or not buf.flags.c_contiguous or buf.dtype.itemsize != 1:
             raise TypeError("reverse_burrows_wheeler_transform needs a writable contiguous byte buffer")
         self.lib.check(self.lib.cdll.b200sa_unbwt(self._ctx, _ptr(buf) if buf.size else None, buf.size, int(sentinel_index)))
+
+    def check_suffix_array(self, data, sa) -> int:
+        """Number of offending rows of ``sa`` as the suffix array of ``data`` (0 = correct): the O(n) validator."""
+        buf = np.ascontiguousarray(np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else data)
+        sa = np.ascontiguousarray(sa, dtype=np.int32)
+        if sa.size != buf.size + 1:
+            raise ValueError("suffix array must have len(data)+1 entries")
+        bad = C.c_int64(-1)
+        self.lib.check(self.lib.cdll.b200sa_check_suffix_array(self._ctx, _ptr(buf) if buf.size else None, buf.size, _ptr(sa), C.byref(bad)))
+        return int(bad.value)
 
     def suffix_array_and_bwt(self, data):
         """Superset call: one sort, returns (sa, bwt, sentinel_index)."""

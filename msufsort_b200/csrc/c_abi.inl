@@ -177,6 +177,20 @@ int b200sa_suffix_array_bwt_u32(b200sa_ctx* ctx, const uint8_t* text, int64_t n,
     return 0;
 }
 
+int b200sa_check_suffix_array(b200sa_ctx* ctx, const uint8_t* text, int64_t n, const int32_t* sa, int64_t* bad_rows_out)
+{
+    B200SA_NEED_CTX(ctx);
+    Engine& e = ctx->eng;
+    if (n < 0 || n > B200SA_MAX_N_INT32 || !sa || !bad_rows_out || (n > 0 && !text)) return b200sa::set_error(B200SA_EINVAL, "bad argument");
+    B200SA_CU(cudaSetDevice(e.device));
+    cudaStream_t st = e.own_stream;
+    B200SA_TRY(e.text_ws.ensure((size_t)n + 64));
+    B200SA_TRY(e.sa_ws.ensure(((size_t)n + 1) * 4));
+    if (n) B200SA_CU(cudaMemcpyAsync(e.text_ws.p, text, (size_t)n, cudaMemcpyHostToDevice, st));
+    B200SA_CU(cudaMemcpyAsync(e.sa_ws.p, sa, ((size_t)n + 1) * 4, cudaMemcpyHostToDevice, st));
+    return e.check_sa_dev(e.text_ws.as<u8>(), n, e.sa_ws.as<i32>(), bad_rows_out, st);
+}
+
 int b200sa_suffix_array(b200sa_ctx* ctx, const uint8_t* text, int64_t n, int32_t* sa_out)
 {
     if (!sa_out) return b200sa::set_error(B200SA_EINVAL, "null sa_out");

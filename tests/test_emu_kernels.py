@@ -69,6 +69,17 @@ def test_emu_checker_detects_corruption(emu_engine, oracle):
     assert emu_engine.check_suffix_array_dev(x, x.size, bad) > 0
 
 
+def test_emu_host_validator(emu_engine, oracle):
+    x = gen("acgt_rep", 30000)
+    sa = oracle.sa(x)
+    assert emu_engine.check_suffix_array(x, sa) == 0
+    bad = sa.copy(); bad[[7, 9]] = bad[[9, 7]]
+    assert emu_engine.check_suffix_array(x, bad) > 0
+    assert emu_engine.check_suffix_array(np.empty(0, np.uint8), np.zeros(1, np.int32)) == 0
+    with pytest.raises(ValueError):
+        emu_engine.check_suffix_array(x, sa[:-1])
+
+
 def test_emu_profile_accounting(emu_engine):
     emu_engine.profile_reset()
     x = gen("markov3", 30000)

@@ -92,11 +92,19 @@ B200SA_API int b200sa_suffix_array(b200sa_ctx* ctx, const uint8_t* text, int64_t
 B200SA_API int b200sa_bwt(b200sa_ctx* ctx, uint8_t* text_inout, int64_t n, int32_t* sentinel_index_out);
 
 /* Replaces: msufsort::reverse_burrows_wheeler_transform(uint8_t*, uint8_t*, int32 sentinelIndex,
- * int32 numThreads) (msufsort.cpp:1821-2096; template msufsort.h:466-476).  In place. */
+ * int32 numThreads) (msufsort.cpp:1821-2096; template msufsort.h:466-476).  In place.
+ * Untrusted input: bytes + sentinel index that are not the BWT of any text (a corrupted block) make the call fail
+ * with B200SA_EINVAL and leave the caller's buffer unchanged; no access leaves the buffers (the reference returns
+ * garbage of the right length in that case).  The same holds for the _dev, _u32 and batch forms; the device
+ * output buffer of a failed call holds no valid text. */
 B200SA_API int b200sa_unbwt(b200sa_ctx* ctx, uint8_t* bwt_inout, int64_t n, int32_t sentinel_index);
 
 /* Superset of the reference API: one suffix sort, both results (the reference needs its two
- * public calls, i.e. two sorts, for this).  sa_out and/or bwt_out may be NULL. */
+ * public calls, i.e. two sorts, for this).  sa_out and/or bwt_out may be NULL.
+ * The host-buffer calls keep the last text and its suffix array resident in the context: when b200sa_bwt (or this
+ * call) is handed, right after b200sa_suffix_array, the same bytes — compared on the device after the upload — it
+ * reuses that sort.  Pageable host buffers are moved by several threads through pinned staging buffers
+ * (B200SA_COPY_THREADS, default 4); pinned / registered buffers are copied directly. */
 B200SA_API int b200sa_suffix_array_bwt(b200sa_ctx* ctx, const uint8_t* text, int64_t n,
                                        int32_t* sa_out, uint8_t* bwt_out, int32_t* sentinel_index_out);
 
@@ -130,13 +138,22 @@ B200SA_API int b200sa_check_suffix_array_dev(b200sa_ctx* ctx, const uint8_t* d_t
  * The reference's suffix_index is int32 (msufsort.h:47) and its flag bits corrupt results above 2^30-2 bytes
  * (msufsort.h:84-93).  These entry points return the same suffix array with uint32 entries and the sentinel row as
  * int64, for texts up to B200SA_MAX_N_UINT32 bytes (e.g. the 2 GiB = 2^31-byte configuration); results for
- * n <= 2^31-2 are bit-identical to the int32 calls.  The inverse transform, the LCP array and the batch / sharded
- * paths stay at the int32 limit (the psi table keeps its seed mark in bit 31). */
+ * n <= 2^31-2 are bit-identical to the int32 calls.  So do the inverse transform (its walkers are seeded at rows that are
+ * multiples of a power of two, so the psi table needs no mark bit and all 32 bits of an entry are row number) and the LCP
+ * array (uint32 values).  Batches keep block-local int32 indices and a combined size below 2^31-2; sharded runs stay at the
+ * int32 limit. */
 B200SA_API int b200sa_suffix_array_u32_dev(b200sa_ctx* ctx, const uint8_t* d_text, int64_t n, uint32_t* d_sa_out, void* stream);
 B200SA_API int b200sa_bwt_u32_dev(b200sa_ctx* ctx, const uint8_t* d_text, int64_t n, uint8_t* d_bwt_out, uint32_t* d_sa_out,
                                   int64_t* sentinel_index_out, void* stream);
 B200SA_API int b200sa_check_suffix_array_u32_dev(b200sa_ctx* ctx, const uint8_t* d_text, int64_t n, const uint32_t* d_sa,
                                                  int64_t* bad_rows_out, void* stream);
+/* Replaces reverse_burrows_wheeler_transform (msufsort.cpp:1821-2096) beyond its int32 sentinelIndex. */
+B200SA_API int b200sa_unbwt_u32_dev(b200sa_ctx* ctx, const uint8_t* d_bwt, int64_t n, int64_t sentinel_index, uint8_t* d_text_out,
+                                    void* stream);
+B200SA_API int b200sa_unbwt_u32(b200sa_ctx* ctx, uint8_t* bwt_inout, int64_t n, int64_t sentinel_index);
+/* LCP array with uint32 entries (the demo's lcp_multithreaded, main.cpp:16-105, beyond int32). */
+B200SA_API int b200sa_lcp_u32_dev(b200sa_ctx* ctx, const uint8_t* d_text, int64_t n, const uint32_t* d_sa, uint32_t* d_lcp_out,
+                                  void* stream);
 /* Host buffers; sa_out (n+1 uint32) and / or bwt_out (n bytes, may alias text) and sentinel_index_out may be NULL. */
 B200SA_API int b200sa_suffix_array_bwt_u32(b200sa_ctx* ctx, const uint8_t* text, int64_t n, uint32_t* sa_out, uint8_t* bwt_out,
                                            int64_t* sentinel_index_out);

@@ -68,6 +68,9 @@ ABI = [
     ("b200sa_bwt_u32_dev", C.c_int, [_P, _P, C.c_int64, _P, _P, C.POINTER(C.c_int64), _P]),
     ("b200sa_check_suffix_array_u32_dev", C.c_int, [_P, _P, C.c_int64, _P, C.POINTER(C.c_int64), _P]),
     ("b200sa_suffix_array_bwt_u32", C.c_int, [_P, _P, C.c_int64, _P, _P, C.POINTER(C.c_int64)]),
+    ("b200sa_unbwt_u32_dev", C.c_int, [_P, _P, C.c_int64, C.c_int64, _P, _P]),
+    ("b200sa_unbwt_u32", C.c_int, [_P, _P, C.c_int64, C.c_int64]),
+    ("b200sa_lcp_u32_dev", C.c_int, [_P, _P, C.c_int64, _P, _P, _P]),
     ("b200sa_lcp_dev", C.c_int, [_P, _P, C.c_int64, _P, _P, _P]),
     ("b200sa_lcp", C.c_int, [_P, _P, C.c_int64, _P, _P, _P]),
     ("b200sa_suffix_array_batch", C.c_int, [_P, _P, _P, C.c_int64, _P]),
@@ -389,6 +392,17 @@ class Engine:
         s = C.c_int64(0)
         self.lib.check(self.lib.cdll.b200sa_suffix_array_bwt_u32(self._ctx, _ptr(buf) if n else None, n, _ptr(sa), _ptr(bwt) if n else None, C.byref(s)))
         return sa, bwt, int(s.value)
+
+    def unbwt_u32_dev(self, d_bwt, n: int, sentinel_index: int, d_out, stream: Optional[int] = None) -> None:
+        self.lib.check(self.lib.cdll.b200sa_unbwt_u32_dev(self._ctx, _ptr(d_bwt), n, int(sentinel_index), _ptr(d_out), self._st(stream)))
+
+    def reverse_burrows_wheeler_transform_u32(self, data, sentinel_index: int) -> None:
+        """In-place inverse BWT through the wide host entry point (int64 sentinel index)."""
+        buf = data if isinstance(data, np.ndarray) else np.frombuffer(data, dtype=np.uint8)
+        self.lib.check(self.lib.cdll.b200sa_unbwt_u32(self._ctx, _ptr(buf) if buf.size else None, buf.size, int(sentinel_index)))
+
+    def lcp_u32_dev(self, d_text, n: int, d_sa, d_lcp, stream: Optional[int] = None) -> None:
+        self.lib.check(self.lib.cdll.b200sa_lcp_u32_dev(self._ctx, _ptr(d_text), n, _ptr(d_sa), _ptr(d_lcp), self._st(stream)))
 
     def lcp_dev(self, d_text, n: int, d_sa, d_lcp, stream: Optional[int] = None) -> None:
         self.lib.check(self.lib.cdll.b200sa_lcp_dev(self._ctx, _ptr(d_text), n, _ptr(d_sa), _ptr(d_lcp), self._st(stream)))

@@ -7,6 +7,8 @@
 
 #include <mutex>
 #include <new>
+#include <thread>
+#include <atomic>
 
 namespace b200sa {
 
@@ -116,6 +118,7 @@ int Engine::init(int dev)
     B200SA_CU(cudaGetDeviceProperties(&prop, dev));
     num_sms = prop.multiProcessorCount > 0 ? prop.multiProcessorCount : kNumSMs;
     B200SA_CU(cudaStreamCreateWithFlags(&own_stream, cudaStreamNonBlocking));
+    B200SA_CU(cudaStreamCreateWithFlags(&copy_stream, cudaStreamNonBlocking));
     B200SA_CU(cudaHostAlloc((void**)&h_pinned, 512 * sizeof(u32), cudaHostAllocDefault));
     memset(&prof, 0, sizeof(prof));
     // tuning knobs (tests lower them to drive the bucketed ISA update at small n)
@@ -126,9 +129,9 @@ int Engine::init(int dev)
     if (const char* e5 = getenv("B200SA_GROUPSORT_MEDIUM")) groupsort_medium = (u32)strtoul(e5, nullptr, 10);
     if (const char* e8 = getenv("B200SA_MAX_KEY_BITS")) max_key_bits = atoi(e8);
     if (const char* e9 = getenv("B200SA_PACK_RADIX")) pack_radix = atoi(e9) != 0;
-    if (const char* e10 = getenv("B200SA_RS_PERSISTENT")) rs_persistent = atoi(e10) != 0;
     if (const char* e12 = getenv("B200SA_LCP_DIRECT")) lcp_direct = atoi(e12) != 0;
     if (const char* e11 = getenv("B200SA_NUM_SMS")) { const int v = atoi(e11); if (v >= 1 && v <= 1024) num_sms = v; }  // tests: small persistent grids
+    if (const char* e13 = getenv("B200SA_COPY_THREADS")) copy_threads = atoi(e13);
     if (const char* e6 = getenv("B200SA_UNBWT_CAP_MULT")) unbwt_cap_mult = (u32)strtoul(e6, nullptr, 10);
     if (unbwt_cap_mult < 1) unbwt_cap_mult = 1;
     if (groupsort_tiny > (u32)GS_TINY) groupsort_tiny = GS_TINY;
@@ -136,8 +139,6 @@ int Engine::init(int dev)
     // the scatter kernels use more than the default 48 KB of dynamic shared memory
     {
         auto k64 = k_onesweep_pass<u64, true>;
-        auto k64p = k_onesweep_pass_persistent<u64, true>;
-        B200SA_CU(cudaFuncSetAttribute(k64p, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_pass_smem_bytes<u64>()));
         auto k8 = k_onesweep_pass<u8, false>;
         auto k32 = k_onesweep_pass<u32, true>;
         B200SA_CU(cudaFuncSetAttribute(k32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_pass_smem_bytes<u32>()));
@@ -169,8 +170,135 @@ void Engine::shutdown()
     event_pool.clear();
     if (h_pinned) cudaFreeHost(h_pinned);
     h_pinned = nullptr;
+#ifndef B200SA_EMU
+    for (int t = 0; t < stage.threads; ++t) {
+        for (int b = 0; b < 2; ++b) { cudaFreeHost(stage.buf[t][b]); cudaEventDestroy(stage.done[t][b]); }
+        cudaStreamDestroy(stage.stream[t]);
+    }
+    if (stage.fence) cudaEventDestroy(stage.fence);
+    stage = HostStage();
+#endif
     if (own_stream) cudaStreamDestroy(own_stream);
     own_stream = nullptr;
+    if (copy_stream) cudaStreamDestroy(copy_stream);
+    copy_stream = nullptr;
+}
+
+// ---------------------------------------------------------------------------------------------
+// host <-> device transfers (see engine.cuh)
+
+#ifndef B200SA_EMU
+static bool host_pointer_is_pinned(const void* p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+}
+#endif
+
+int Engine::stage_ensure()
+{
+#ifndef B200SA_EMU
+    if (stage.threads) return 0;
+    int T = copy_threads < 1 ? 1 : (copy_threads > HostStage::kMaxThreads ? HostStage::kMaxThreads : copy_threads);
+    B200SA_CU(cudaEventCreateWithFlags(&stage.fence, cudaEventDisableTiming));
+    for (int t = 0; t < T; ++t) {
+        B200SA_CU(cudaStreamCreateWithFlags(&stage.stream[t], cudaStreamNonBlocking));
+        for (int b = 0; b < 2; ++b) {
+            B200SA_CU(cudaHostAlloc(&stage.buf[t][b], stage.chunk, cudaHostAllocDefault));
+            B200SA_CU(cudaEventCreateWithFlags(&stage.done[t][b], cudaEventDisableTiming));
+        }
+    }
+    stage.threads = T;
+#endif
+    return 0;
+}
+
+// direction 0: host -> device, 1: device -> host.  Thread t takes chunks t, t + T, ...; per chunk the PCIe copy and the host
+// memcpy run on alternating staging buffers.
+#ifndef B200SA_EMU
+static cudaError_t staged_worker(Engine::HostStage& hs, int device, int t, int T, int direction, char* dev, char* host, size_t bytes)
+{
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) return e;
+    const size_t chunk = hs.chunk;
+    const size_t nchunks = (bytes + chunk - 1) / chunk;
+    cudaStream_t s = hs.stream[t];
+    if (direction == 0) {
+        int b = 0;
+        for (size_t c = (size_t)t; c < nchunks; c += (size_t)T, b ^= 1) {
+            const size_t off = c * chunk, len = bytes - off < chunk ? bytes - off : chunk;
+            if ((e = cudaEventSynchronize(hs.done[t][b])) != cudaSuccess) return e;  // the copy that last used this buffer
+            memcpy(hs.buf[t][b], host + off, len);
+            if ((e = cudaMemcpyAsync(dev + off, hs.buf[t][b], len, cudaMemcpyHostToDevice, s)) != cudaSuccess) return e;
+            if ((e = cudaEventRecord(hs.done[t][b], s)) != cudaSuccess) return e;
+        }
+        return cudaStreamSynchronize(s);
+    }
+    // device -> host: keep one copy in flight while the previous chunk is moved out of its staging buffer
+    size_t c = (size_t)t;
+    int b = 0;
+    if (c < nchunks) {
+        const size_t off = c * chunk, len = bytes - off < chunk ? bytes - off : chunk;
+        if ((e = cudaMemcpyAsync(hs.buf[t][b], dev + off, len, cudaMemcpyDeviceToHost, s)) != cudaSuccess) return e;
+        if ((e = cudaEventRecord(hs.done[t][b], s)) != cudaSuccess) return e;
+    }
+    for (; c < nchunks; c += (size_t)T, b ^= 1) {
+        const size_t nc = c + (size_t)T;
+        if (nc < nchunks) {
+            const size_t off = nc * chunk, len = bytes - off < chunk ? bytes - off : chunk;
+            if ((e = cudaMemcpyAsync(hs.buf[t][b ^ 1], dev + off, len, cudaMemcpyDeviceToHost, s)) != cudaSuccess) return e;
+            if ((e = cudaEventRecord(hs.done[t][b ^ 1], s)) != cudaSuccess) return e;
+        }
+        if ((e = cudaEventSynchronize(hs.done[t][b])) != cudaSuccess) return e;
+        const size_t off = c * chunk, len = bytes - off < chunk ? bytes - off : chunk;
+        memcpy(host + off, hs.buf[t][b], len);
+    }
+    return cudaSuccess;
+}
+
+static int staged_copy(Engine& e, int direction, void* dev, void* host, size_t bytes, cudaStream_t st, bool independent)
+{
+    B200SA_TRY(e.stage_ensure());
+    Engine::HostStage& hs = e.stage;
+    const int T = hs.threads;
+    // the workers' streams start after everything already enqueued on st (the producer of a download, the last reader of an
+    // upload target)
+    if (!independent) {
+        B200SA_CU(cudaEventRecord(hs.fence, st));
+        for (int t = 0; t < T; ++t) B200SA_CU(cudaStreamWaitEvent(hs.stream[t], hs.fence, 0));
+    }
+    cudaError_t err[Engine::HostStage::kMaxThreads];
+    std::thread th[Engine::HostStage::kMaxThreads];
+    for (int t = 1; t < T; ++t)
+        th[t] = std::thread([&, t] { err[t] = staged_worker(hs, e.device, t, T, direction, (char*)dev, (char*)host, bytes); });
+    err[0] = staged_worker(hs, e.device, 0, T, direction, (char*)dev, (char*)host, bytes);
+    for (int t = 1; t < T; ++t) th[t].join();
+    for (int t = 0; t < T; ++t)
+        if (err[t] != cudaSuccess) return set_error(B200SA_ECUDA, "staged host copy failed: %s", cudaGetErrorString(err[t]));
+    // every worker synchronised its stream (uploads) or its last event (downloads): the data is in place; st needs no wait
+    return 0;
+}
+#endif
+
+int Engine::copy_in(void* d_dst, const void* h_src, size_t bytes, cudaStream_t st)
+{
+    if (bytes == 0) return 0;
+#ifndef B200SA_EMU
+    if (copy_threads > 0 && bytes >= copy_staged_min && !host_pointer_is_pinned(h_src)) return staged_copy(*this, 0, d_dst, (void*)h_src, bytes, st, false);
+#endif
+    B200SA_CU(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, st));
+    return 0;
+}
+
+int Engine::copy_out(void* h_dst, const void* d_src, size_t bytes, cudaStream_t st, bool independent)
+{
+    if (bytes == 0) return 0;
+#ifndef B200SA_EMU
+    if (copy_threads > 0 && bytes >= copy_staged_min && !host_pointer_is_pinned(h_dst)) return staged_copy(*this, 1, (void*)d_src, h_dst, bytes, st, independent);
+#endif
+    B200SA_CU(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, independent ? copy_stream : st));
+    return 0;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -255,18 +383,10 @@ int Engine::radix_sort_pairs(u64* keys2[2], u32* vals2[2], bool gen_vals, u32 m,
     for (int p = 0; p < passes; ++p) {
         B200SA_TRY(phase_begin(B200SA_PH_SORT_PASS, st));
         const u32* vin = (p == 0 && gen_vals) ? nullptr : vals2[side];
-        if (rs_persistent) {
-            auto kp = k_onesweep_pass_persistent<u64, true>;
-            const u32 grid = tiles < (u32)(num_sms * RS_MIN_BLOCKS) ? tiles : (u32)(num_sms * RS_MIN_BLOCKS);
-            B200SA_LAUNCH(kp, grid, RS_THREADS, rs_pass_smem_bytes<u64>(), st,
-                          keys2[side], keys2[side ^ 1], vin, vals2[side ^ 1], m, begin_bit + p * RS_RADIX_BITS, 0xffffffffu,
-                          ghist + p * RS_RADIX, status + (size_t)p * tiles * RS_RADIX, counters + p, tiles);
-        } else {
-            auto kp = k_onesweep_pass<u64, true>;
-            B200SA_LAUNCH(kp, tiles, RS_THREADS, rs_pass_smem_bytes<u64>(), st,
-                          keys2[side], keys2[side ^ 1], vin, vals2[side ^ 1], m, begin_bit + p * RS_RADIX_BITS, 0xffffffffu,
-                          ghist + p * RS_RADIX, status + (size_t)p * tiles * RS_RADIX, counters + p);
-        }
+        auto kp = k_onesweep_pass<u64, true>;
+        B200SA_LAUNCH(kp, tiles, RS_THREADS, rs_pass_smem_bytes<u64>(), st,
+                      keys2[side], keys2[side ^ 1], vin, vals2[side ^ 1], m, begin_bit + p * RS_RADIX_BITS, 0xffffffffu,
+                      ghist + p * RS_RADIX, status + (size_t)p * tiles * RS_RADIX, counters + p);
         count_launch(B200SA_PH_SORT_PASS);
         B200SA_TRY(phase_end(st));
         prof.alg_bytes[B200SA_PH_SORT_PASS] += (u64)m * (vin ? 24 : 20);
@@ -712,7 +832,7 @@ int Engine::suffix_array_dev(const u8* d_text, i64 n64, i32* d_sa, cudaStream_t 
 
 // output bytes [o_begin, o_end) from a finished SA (+ rank[0] = sentinel row); the sentinel row lands
 // in h_pinned[8]
-int Engine::bwt_rows(const u8* d_text, u32 n, const i32* d_sa, u32 o_begin, u32 o_end, u8* d_bwt, cudaStream_t st)
+int Engine::bwt_rows(const u8* d_text, u32 n, const i32* d_sa, u32 o_begin, u32 o_end, u8* d_bwt, cudaStream_t st, bool defer_sync)
 {
     i32* d_sent = (i32*)(misc.as<u32>() + 528);
     B200SA_TRY(phase_begin(B200SA_PH_BWT, st));
@@ -728,9 +848,10 @@ int Engine::bwt_rows(const u8* d_text, u32 n, const i32* d_sa, u32 o_begin, u32 
     B200SA_TRY(phase_end(st));
     prof.alg_bytes[B200SA_PH_BWT] += (u64)(o_end - o_begin) * 6;
     B200SA_CU(cudaGetLastError());
+    (void)n;
+    if (defer_sync) return 0;
     B200SA_CU(cudaMemcpyAsync(h_pinned + 8, d_sent, sizeof(i32), cudaMemcpyDeviceToHost, st));
     B200SA_CU(cudaStreamSynchronize(st));
-    (void)n;
     return 0;
 }
 
@@ -759,9 +880,11 @@ int Engine::bwt_dev(const u8* d_text, i64 n64, u8* d_bwt, i32* d_sa_or_null, i64
 // ---------------------------------------------------------------------------------------------
 // inverse BWT
 
-// Three steps so that a sharded run can split the walkers over GPUs: build (psi table, F-column table,
-// seed marks: replicated), measure (a slice of the walkers), finish (list ranking over all walkers, then
+// Three steps so that a sharded run can split the walkers over GPUs: build (psi table, F-column table:
+// replicated), measure (a slice of the walkers), finish (list ranking over all walkers, validity check, then
 // emit the slice's bytes).
+static const int kUnbwtBadWord = 544;  // misc word raised by k_unbwt_place when the input is not a BWT
+
 int Engine::unbwt_build(const u8* d_bwt, u32 n, u32 s, u32* nwalkers_out, cudaStream_t st)
 {
     B200SA_TRY(keys[0].ensure(((size_t)n + 1) * 4 + 64));
@@ -789,24 +912,23 @@ int Engine::unbwt_build(const u8* d_bwt, u32 n, u32 s, u32* nwalkers_out, cudaSt
         count_launch(B200SA_PH_UNBWT_BUILD);
         B200SA_LAUNCH(k_radix_scan_bins, 1, RS_RADIX, 0, st, ghist);
         count_launch(B200SA_PH_UNBWT_BUILD);
-        B200SA_LAUNCH(k_unbwt_fstart, 1, 256, 0, st, (const u32*)ghist, n, fstart);
+        B200SA_LAUNCH(k_unbwt_fstart, 1, 256, 0, st, (const u32*)ghist, n, fstart, psi, s, misc.as<u32>() + kUnbwtBadWord);
         count_launch(B200SA_PH_UNBWT_BUILD);
         auto kp = k_onesweep_pass<u8, false>;
         B200SA_LAUNCH(kp, tiles, RS_THREADS, rs_pass_smem_bytes<u8>(), st, d_bwt, (u8*)nullptr, (const u32*)nullptr, psi + 1,
                       n, 0, s, (const u32*)ghist, status, counters);
         count_launch(B200SA_PH_UNBWT_BUILD);
     }
-    // ---- walkers: every D-th row plus row s
-    u32 D = (u32)div_up_u64((u64)n + 1, (u64)1 << 21);
-    if (D < 64) D = 64;
-    us.D = D;
-    us.nreg = (u32)div_up_u64((u64)n + 1, D);
-    us.nwalkers = us.nreg + ((s % D) != 0 ? 1u : 0u);
-    B200SA_TRY(walk.ensure((size_t)us.nwalkers * 5 * 4 + 64));
-    us.cap = (unbwt_cap_mult * D + 7u) & ~7u;  // window bytes per walker, 8-byte granular (64-bit stores)
-    B200SA_LAUNCH(k_unbwt_mark, (u32)div_up_u64(us.nwalkers, 256), 256, 0, st, psi, us.nwalkers, us.nreg, D, s);
-    count_launch(B200SA_PH_UNBWT_BUILD);
     B200SA_TRY(phase_end(st));
+    // ---- walkers: every D-th row (D a power of two: seed test = mask, no mark bit in psi) plus row s
+    int dshift = 6;
+    while (((u64)n + 1) >> dshift > ((u64)1 << 21)) ++dshift;
+    us.dshift = dshift;
+    us.D = 1u << dshift;
+    us.nreg = (u32)div_up_u64((u64)n + 1, us.D);
+    us.nwalkers = us.nreg + ((s & (us.D - 1u)) != 0 ? 1u : 0u);
+    B200SA_TRY(walk.ensure((size_t)us.nwalkers * 5 * 4 + 64));
+    us.cap = (unbwt_cap_mult * us.D + 7u) & ~7u;  // window bytes per walker, 8-byte granular (64-bit stores)
     prof.alg_bytes[B200SA_PH_UNBWT_BUILD] += (u64)n * 6;
     B200SA_CU(cudaGetLastError());
     us.stage = 1;
@@ -827,7 +949,7 @@ int Engine::unbwt_measure(u32 w_begin, u32 w_end, cudaStream_t st)
     B200SA_TRY(idx[0].ensure((size_t)W * 4 + 64));
     B200SA_TRY(phase_begin(B200SA_PH_UNBWT_WALK, st));
     B200SA_LAUNCH(k_unbwt_walk, (u32)div_up_u64(w_end - w_begin, UW_THREADS), UW_THREADS, 0, st, (const u32*)keys[0].as<u32>(),
-                  (const u32*)(misc.as<u32>() + 600), w_begin, w_end, us.nreg, us.D, us.s, us.cap, keys[1].as<u8>(), ds0, nx0, ovf);
+                  (const u32*)(misc.as<u32>() + 600), w_begin, w_end, us.nreg, us.dshift, us.s, us.cap, keys[1].as<u8>(), ds0, nx0, ovf);
     count_launch(B200SA_PH_UNBWT_WALK);
     // the list ranking below overwrites the lengths: keep a copy for the placement pass
     B200SA_CU(cudaMemcpyAsync(idx[0].as<u32>() + w_begin, ds0 + w_begin, (size_t)(w_end - w_begin) * 4, cudaMemcpyDeviceToDevice, st));
@@ -843,6 +965,7 @@ int Engine::unbwt_finish(u32 w_begin, u32 w_end, u8* d_out, cudaStream_t st)
     u32* nx[2] = {walk.as<u32>(), walk.as<u32>() + W};
     u32* ds[2] = {walk.as<u32>() + 2 * W, walk.as<u32>() + 3 * W};
     u32* ovf = walk.as<u32>() + 4 * W;
+    u32* d_bad = misc.as<u32>() + kUnbwtBadWord;
     B200SA_TRY(phase_begin(B200SA_PH_UNBWT_WALK, st));
     const u32 g256 = (u32)div_up_u64(W, 256);
     int cur = 0;
@@ -853,33 +976,38 @@ int Engine::unbwt_finish(u32 w_begin, u32 w_end, u8* d_out, cudaStream_t st)
         cur ^= 1;
     }
     if (w_end > w_begin) {
+        const u32 start_walker = (us.s & (us.D - 1u)) ? us.nreg : (us.s >> us.dshift);
         B200SA_LAUNCH(k_unbwt_place, (u32)div_up_u64(w_end - w_begin, UP_THREADS / 32), UP_THREADS, 0, st, (const u32*)keys[0].as<u32>(),
-                      (const u32*)(misc.as<u32>() + 600), (const u32*)ds[cur], (const u32*)idx[0].as<u32>(), (const u32*)ovf,
-                      (const u8*)keys[1].as<u8>(), us.cap, w_begin, w_end, us.n, d_out);
+                      (const u32*)(misc.as<u32>() + 600), (const u32*)ds[cur], (const u32*)nx[cur], (const u32*)idx[0].as<u32>(), (const u32*)ovf,
+                      (const u8*)keys[1].as<u8>(), us.cap, w_begin, w_end, us.n, start_walker, d_out, d_bad);
         count_launch(B200SA_PH_UNBWT_WALK);
     }
     B200SA_TRY(phase_end(st));
     prof.alg_bytes[B200SA_PH_UNBWT_WALK] += (u64)us.n * 7;
     B200SA_CU(cudaGetLastError());
+    B200SA_CU(cudaMemcpyAsync(h_pinned + 24, d_bad, 4, cudaMemcpyDeviceToHost, st));
     B200SA_CU(cudaStreamSynchronize(st));
     // the jumps consumed the measured segments: a second finish needs a new measure pass
     us.stage = 0;
+    if (h_pinned[24] != 0)
+        return set_error(B200SA_EINVAL, "the input is not a Burrows-Wheeler transform (its LF mapping does not form one cycle through the sentinel row); "
+                                        "the output buffer holds no valid text");
     return 0;
 }
 
-int Engine::unbwt_dev(const u8* d_bwt, i64 n64, i32 sentinel, u8* d_out, cudaStream_t st)
+int Engine::unbwt_dev(const u8* d_bwt, i64 n64, i64 sentinel, u8* d_out, cudaStream_t st, i64 max_n)
 {
-    if (n64 < 0 || n64 > B200SA_MAX_N_INT32) return set_error(B200SA_EINVAL, "n = %lld outside [0, 2^31-2]", (long long)n64);
+    if (n64 < 0 || n64 > max_n) return set_error(B200SA_EINVAL, "n = %lld outside [0, %lld]", (long long)n64, (long long)max_n);
     if (n64 == 0) return 0;
     if (!d_bwt || !d_out) return set_error(B200SA_EINVAL, "null pointer");
-    if (sentinel < 1 || (i64)sentinel > n64) return set_error(B200SA_EINVAL, "sentinel index %d outside [1, n]", sentinel);
+    if (sentinel < 1 || sentinel > n64) return set_error(B200SA_EINVAL, "sentinel index %lld outside [1, n]", (long long)sentinel);
     B200SA_CU(cudaSetDevice(device));
     u32 W = 0;
     B200SA_TRY(unbwt_build(d_bwt, (u32)n64, (u32)sentinel, &W, st));
     B200SA_TRY(unbwt_measure(0, W, st));
-    B200SA_TRY(unbwt_finish(0, W, d_out, st));
+    const int rc = unbwt_finish(0, W, d_out, st);
     if (profiling) B200SA_TRY(collect_profile());
-    return 0;
+    return rc;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -211,15 +211,16 @@ k_bwt_gather_batch(const u8* __restrict__ text, const i32* __restrict__ sa, cons
 // Inverse BWT of a batch.  Rows live in the same expanded coordinates as the forward transform: block b owns
 // rows [start_b, end_b], local row 0 (= start_b) is the row of the block's empty suffix, the block's text
 // starts at local row s_b (its sentinel index).  One table entry per row, 8 bytes:
-//     bits 0..30  psi''[row]  (the row of the suffix one text position to the right; same block)
-//     bit  31     the row is a walker seed / a terminal
+//     bits 0..31  psi''[row]  (the row of the suffix one text position to the right; same block)
 //     bits 32..39 first byte of the row's suffix (what the walker emits when it stands on the row)
+//     bit  40     the row is a walker seed / a terminal
 // psi and the symbols of all blocks come from ONE stable sort of the BWT bytes by (block << 8 | byte) with the
 // rows as values — the batched form of the reference's phase C (msufsort.cpp:1898-1915) — so no per-block
 // F-column table is needed.  Walkers: every D-th row, every block's start row and every block's row 0
 // (terminal); walker ids are [0, nreg) regular, [nreg, nreg + count) block starts, [nreg + count, nreg + 2 count)
 // terminals.  A regular walker whose row is also a start or a terminal row is dead (the special walker owns it).
 static const u64 UBB_SYM_SHIFT = 32;
+static const u64 UBB_MARK = 1ull << 40;
 
 __device__ __forceinline__ u32 ubb_block_start(const u32* __restrict__ ends, u32 b) { return b ? ends[b - 1u] + 1u : 0u; }
 
@@ -299,7 +300,7 @@ k_ubb_rows0(const u32* __restrict__ ends, const i32* __restrict__ sent, u32 coun
     const u32 b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= count) return;
     const u32 start = ubb_block_start(ends, b);
-    table[start] = (u64)(start + (u32)sent[b]) | UB_MARK;
+    table[start] = (u64)(start + (u32)sent[b]) | UBB_MARK;
 }
 
 __global__ void __launch_bounds__(256)
@@ -308,7 +309,7 @@ k_ubb_mark(u64* __restrict__ table, const u32* __restrict__ ends, const i32* __r
     const u32 w = blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= nreg + count) return;  // terminals are marked by k_ubb_rows0
     u32 row = 0, b = 0;
-    if (ubb_walker_seed(w, ends, sent, count, nreg, D, N, &row, &b)) atomicOr((u32*)(table + row), UB_MARK);  // low word = psi | mark
+    if (ubb_walker_seed(w, ends, sent, count, nreg, D, N, &row, &b)) atomicOr((u32*)(table + row) + 1, (u32)(UBB_MARK >> 32));  // high word = symbol | mark
 }
 
 __global__ void __launch_bounds__(UW_THREADS)
@@ -327,7 +328,7 @@ k_ubb_walk(const u64* __restrict__ table, const u32* __restrict__ ends, const i3
     u32 len = 0, ovf = UB_NO_OVERFLOW;
     u64 acc = 0;
     do {
-        const u32 nxt = (u32)e & UB_IDX;
+        const u32 nxt = (u32)e;
         const u64 e2 = table[nxt];
         if (len < cap) {
             acc |= ((e >> UBB_SYM_SHIFT) & 255ull) << (8 * (len & 7u));
@@ -338,18 +339,20 @@ k_ubb_walk(const u64* __restrict__ table, const u32* __restrict__ ends, const i3
         ++len;
         cur = nxt;
         e = e2;
-    } while (!((u32)e & UB_MARK));
+    } while (!(e & UBB_MARK));
     if (len < cap && (len & 7u)) win[len >> 3] = acc;
     seg_len[w] = len;
     seg_next[w] = ubb_row_walker(cur, ends, sent, count, nreg, D);
     ovf_row[w] = ovf;
 }
 
-// one warp per walker: window -> offs[block + 1] - dist[w] in the packed output
+// one warp per walker: window -> offs[block + 1] - dist[w] in the packed output.  Untrusted input (see bwt_kernels.cuh): a
+// walker writes only if its chain ended in its own block's terminal and its segment lies inside the block; the block's
+// start walker must be exactly the block's size away from the end.  Anything else raises `bad`.
 __global__ void __launch_bounds__(UP_THREADS)
 k_ubb_place(const u64* __restrict__ table, const u32* __restrict__ ends, const u32* __restrict__ offs, const i32* __restrict__ sent, u32 count,
-            u32 nreg, u32 D, u32 N, u32 nwalkers, const u32* __restrict__ dist, const u32* __restrict__ seg_len,
-            const u32* __restrict__ ovf_row, const u8* __restrict__ scratch, u32 cap, u8* __restrict__ out)
+            u32 nreg, u32 D, u32 N, u32 nwalkers, const u32* __restrict__ dist, const u32* __restrict__ final_next, const u32* __restrict__ seg_len,
+            const u32* __restrict__ ovf_row, const u8* __restrict__ scratch, u32 cap, u8* __restrict__ out, u32* __restrict__ bad)
 {
     const u32 lane = threadIdx.x & 31u;
     const u32 w = blockIdx.x * (UP_THREADS / 32) + (threadIdx.x >> 5);
@@ -357,7 +360,12 @@ k_ubb_place(const u64* __restrict__ table, const u32* __restrict__ ends, const u
     u32 row = 0, blk = 0;
     if (!ubb_walker_seed(w, ends, sent, count, nreg, D, N, &row, &blk)) return;
     const u32 len = seg_len[w];
-    const u32 pos = offs[blk + 1u] - dist[w];
+    const u32 d = dist[w], nb = offs[blk + 1u] - offs[blk];
+    if (final_next[w] != nreg + count + blk || d > nb || len > d || (w == nreg + blk && d != nb)) {
+        if (lane == 0) atomicOr(bad, 1u);
+        return;
+    }
+    const u32 pos = offs[blk + 1u] - d;
     const u32 stored = len < cap ? len : cap;
     const u8* src = scratch + (u64)w * cap;
     for (u32 i = lane; i < stored; i += 32u) out[pos + i] = src[i];
@@ -366,7 +374,7 @@ k_ubb_place(const u64* __restrict__ table, const u32* __restrict__ ends, const u
         u64 e = table[cur];
         u32 o = pos + cap;
         for (u32 k = cap; k < len; ++k) {
-            const u32 nxt = (u32)e & UB_IDX;
+            const u32 nxt = (u32)e;
             const u64 e2 = table[nxt];
             out[o++] = (u8)(e >> UBB_SYM_SHIFT);
             cur = nxt;

@@ -59,6 +59,24 @@ k_bwt_gather(const u8* __restrict__ text, const i32* __restrict__ sa, const u32*
 }
 
 // ---------------------------------------------------------------------------------------------
+// *differ |= (a[0..n) != b[0..n)).  Both buffers are workspace allocations (16-byte aligned).  Used by the host entry points
+// to recognise that the text they are handed is byte for byte the one whose suffix array is still resident (the
+// reference's users call make_suffix_array and forward_burrows_wheeler_transform on the same bytes: one sort serves both).
+__global__ void __launch_bounds__(256)
+k_bytes_differ(const u8* __restrict__ a, const u8* __restrict__ b, u64 n, u32* __restrict__ differ)
+{
+    const u64 nvec = n / 16;
+    bool d = false;
+    for (u64 v = (u64)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += (u64)gridDim.x * blockDim.x) {
+        const uint4 x = ((const uint4*)a)[v], y = ((const uint4*)b)[v];
+        d |= (x.x != y.x) | (x.y != y.y) | (x.z != y.z) | (x.w != y.w);
+    }
+    if (blockIdx.x == 0)
+        for (u64 i = nvec * 16 + threadIdx.x; i < n; i += blockDim.x) d |= a[i] != b[i];
+    if (d) atomicOr(differ, 1u);
+}
+
+// ---------------------------------------------------------------------------------------------
 // Inverse BWT.
 //
 // Rows of the conceptual (n+1)-row matrix: row 0 is the sentinel's row ("" / suffix n), L[row] for
@@ -71,36 +89,34 @@ k_bwt_gather(const u8* __restrict__ text, const i32* __restrict__ sa, const u32*
 //
 // Decoding follows psi from row s (suffix 0) and emits F[row] at every step.  It is split over
 // walkers seeded at every D-th row plus row s (the reference seeds 256 x threads walkers,
-// :1922-1944): bit 31 of psi[row] marks seed rows.  Pass A measures each walker's segment (length,
-// successor walker); a pointer-jumping list ranking turns the segment chain into text offsets; pass
-// B copies the decoded windows to their final positions (and finishes the few overlong segments).
-static const u32 UB_MARK = 0x80000000u;
-static const u32 UB_IDX = 0x7fffffffu;
+// :1922-1944).  D is a power of two, so "is this row a seed" is (row & (D-1)) == 0 || row == s: psi
+// carries no mark bit and all 32 bits of an entry are row number (texts up to 2^32 - 8194 bytes).
+// Pass A measures each walker's segment (length, successor walker) and decodes it into a private
+// window; a pointer-jumping list ranking turns the segment chain into text offsets; pass B copies
+// the windows to their final positions (and finishes the few overlong segments).
+//
+// Untrusted input: psi is a permutation of the rows whatever the bytes are, but only a real BWT
+// makes it ONE cycle 0 -> s -> ... -> 0.  On anything else some walkers sit on cycles that never
+// reach the terminal (row 0) and the list ranking adds lengths around them, so pass B first checks,
+// per walker, that its chain ended in the terminal and that its segment lies inside the text
+// (len <= dist <= n), and that the walker of row s is n bytes from the end.  A violation raises the
+// `bad` flag (the host entry point then fails with B200SA_EINVAL) and the walker writes nothing.
 
 // fstart[c] = first F-row of symbol c (rows 1..n), fstart[256] = n+1.  bins = exclusive byte counts.
-__global__ void k_unbwt_fstart(const u32* __restrict__ bins, u32 n, u32* __restrict__ fstart)
+__global__ void k_unbwt_fstart(const u32* __restrict__ bins, u32 n, u32* __restrict__ fstart, u32* __restrict__ psi, u32 s, u32* __restrict__ bad)
 {
     const u32 t = threadIdx.x;
     if (t < 256) fstart[t] = bins[t] + 1u;
-    if (t == 0) fstart[256] = n + 1u;
+    if (t == 0) { fstart[256] = n + 1u; psi[0] = s; *bad = 0; }
 }
 
 // walker w < nreg starts at row w*D (walker 0 = row 0 is the terminal, it never walks);
-// walker nreg (only if s % D != 0) starts at row s.
-__device__ __forceinline__ u32 ub_walker_row(u32 w, u32 nreg, u32 D, u32 s) { return w < nreg ? w * D : s; }
-__device__ __forceinline__ u32 ub_row_walker(u32 row, u32 nreg, u32 D, u32 s)
+// walker nreg (only if s % D != 0) starts at row s.  D = 1 << dshift.
+__device__ __forceinline__ u32 ub_walker_row(u32 w, u32 nreg, int dshift, u32 s) { return w < nreg ? w << dshift : s; }
+__device__ __forceinline__ bool ub_is_seed(u32 row, u32 dmask, u32 s) { return (row & dmask) == 0u || row == s; }
+__device__ __forceinline__ u32 ub_row_walker(u32 row, u32 nreg, int dshift, u32 dmask)
 {
-    return (row % D == 0) ? row / D : nreg;  // only called on marked rows
-}
-
-__global__ void __launch_bounds__(256)
-k_unbwt_mark(u32* __restrict__ psi, u32 nwalkers, u32 nreg, u32 D, u32 s)
-{
-    const u32 w = blockIdx.x * blockDim.x + threadIdx.x;
-    if (w >= nwalkers) return;
-    const u32 row = ub_walker_row(w, nreg, D, s);
-    if (w == 0) psi[0] = s | UB_MARK;
-    else psi[row] |= UB_MARK;
+    return (row & dmask) == 0u ? row >> dshift : nreg;  // only called on seed rows
 }
 
 // symbol of F-row `row` (row >= 1): the largest c with f[c] <= row; f = 257-entry table in shared memory
@@ -127,7 +143,7 @@ static const int UW_THREADS = 128;
 static const u32 UB_NO_OVERFLOW = 0xffffffffu;
 
 __global__ void __launch_bounds__(UW_THREADS)
-k_unbwt_walk(const u32* __restrict__ psi, const u32* __restrict__ fstart, u32 w_begin, u32 w_end, u32 nreg, u32 D, u32 s,
+k_unbwt_walk(const u32* __restrict__ psi, const u32* __restrict__ fstart, u32 w_begin, u32 w_end, u32 nreg, int dshift, u32 s,
              u32 cap, u8* __restrict__ scratch, u32* __restrict__ seg_len, u32* __restrict__ seg_next, u32* __restrict__ ovf_row)
 {
     __shared__ u32 s_f[257];
@@ -136,14 +152,14 @@ k_unbwt_walk(const u32* __restrict__ psi, const u32* __restrict__ fstart, u32 w_
     const u32 w = w_begin + blockIdx.x * UW_THREADS + threadIdx.x;
     if (w >= w_end) return;
     if (w == 0) { seg_len[0] = 0; seg_next[0] = 0; ovf_row[0] = UB_NO_OVERFLOW; return; }  // terminal node points to itself
+    const u32 dmask = (1u << dshift) - 1u;
     u64* win = (u64*)(scratch + (u64)w * cap);  // cap is a multiple of 8 and scratch is 256-byte aligned
-    u32 cur = ub_walker_row(w, nreg, D, s);
-    u32 e = psi[cur];
+    u32 cur = ub_walker_row(w, nreg, dshift, s);
+    u32 nxt = psi[cur];
     u32 len = 0, ovf = UB_NO_OVERFLOW;
     u64 acc = 0;
     do {
-        const u32 nxt = e & UB_IDX;
-        const u32 e2 = psi[nxt];                      // dependent load first ...
+        const u32 nxt2 = psi[nxt];                    // dependent load first ...
         if (len < cap) {
             const u64 c = ub_row_symbol(s_f, cur);    // ... symbol search while it is in flight
             acc |= c << (8 * (len & 7u));
@@ -153,11 +169,11 @@ k_unbwt_walk(const u32* __restrict__ psi, const u32* __restrict__ fstart, u32 w_
         }
         ++len;
         cur = nxt;
-        e = e2;
-    } while (!(e & UB_MARK));
+        nxt = nxt2;
+    } while (!ub_is_seed(cur, dmask, s));
     if (len < cap && (len & 7u)) win[len >> 3] = acc;  // partial last word (inside the window: cap % 8 == 0)
     seg_len[w] = len;
-    seg_next[w] = ub_row_walker(cur, nreg, D, s);
+    seg_next[w] = ub_row_walker(cur, nreg, dshift, dmask);
     ovf_row[w] = ovf;
 }
 
@@ -176,12 +192,13 @@ k_unbwt_jump(const u32* __restrict__ next_in, const u32* __restrict__ dist_in,
 
 // Pass B: one warp per walker copies the decoded window to its final place (text offset n - dist[w]);
 // the few walkers that outgrew their window continue decoding from ovf_row straight into the text.
+// start_walker = the walker seeded at row s (text offset 0): it must be exactly n bytes from the end.
 static const int UP_THREADS = 256;
 
 __global__ void __launch_bounds__(UP_THREADS)
-k_unbwt_place(const u32* __restrict__ psi, const u32* __restrict__ fstart, const u32* __restrict__ dist,
+k_unbwt_place(const u32* __restrict__ psi, const u32* __restrict__ fstart, const u32* __restrict__ dist, const u32* __restrict__ final_next,
               const u32* __restrict__ seg_len, const u32* __restrict__ ovf_row, const u8* __restrict__ scratch, u32 cap,
-              u32 w_begin, u32 w_end, u32 n, u8* __restrict__ out)
+              u32 w_begin, u32 w_end, u32 n, u32 start_walker, u8* __restrict__ out, u32* __restrict__ bad)
 {
     __shared__ u32 s_f[257];
     for (u32 i = threadIdx.x; i < 257; i += UP_THREADS) s_f[i] = fstart[i];
@@ -190,20 +207,24 @@ k_unbwt_place(const u32* __restrict__ psi, const u32* __restrict__ fstart, const
     const u32 w = w_begin + blockIdx.x * (UP_THREADS / 32) + (threadIdx.x >> 5);
     if (w >= w_end || w == 0) return;
     const u32 len = seg_len[w];
-    const u32 pos = n - dist[w];
+    const u32 d = dist[w];
+    if (final_next[w] != 0u || d > n || len > d || (w == start_walker && d != n)) {  // not a BWT: see the note on untrusted input
+        if (lane == 0) atomicOr(bad, 1u);
+        return;
+    }
+    const u32 pos = n - d;
     const u32 stored = len < cap ? len : cap;
     const u8* src = scratch + (u64)w * cap;
     for (u32 i = lane; i < stored; i += 32u) out[pos + i] = src[i];
     if (len > cap && lane == 0) {
         u32 cur = ovf_row[w];
-        u32 e = psi[cur];
+        u32 nxt = psi[cur];
         u32 o = pos + cap;
         for (u32 k = cap; k < len; ++k) {
-            const u32 nxt = e & UB_IDX;
-            const u32 e2 = psi[nxt];
+            const u32 nxt2 = psi[nxt];
             out[o++] = (u8)ub_row_symbol(s_f, cur);
             cur = nxt;
-            e = e2;
+            nxt = nxt2;
         }
     }
 }

@@ -48,8 +48,10 @@ int b200sa_release_workspace(b200sa_ctx* ctx)
     return ctx->eng.release_workspace();
 }
 
+// every entry point drops the resident-suffix-array cache (Engine::sa_cache); b200sa_suffix_array_bwt re-establishes it
 #define B200SA_NEED_CTX(ctx) \
-    if (!(ctx)) return b200sa::set_error(B200SA_EINVAL, "null context (call b200sa_create first)")
+    if (!(ctx)) return b200sa::set_error(B200SA_EINVAL, "null context (call b200sa_create first)"); \
+    (ctx)->eng.sa_cache.valid = false
 
 int b200sa_suffix_array_dev(b200sa_ctx* ctx, const uint8_t* d_text, int64_t n, int32_t* d_sa_out, void* stream)
 {
@@ -98,6 +100,19 @@ int b200sa_unbwt_dev(b200sa_ctx* ctx, const uint8_t* d_bwt, int64_t n, int32_t s
     return ctx->eng.unbwt_dev(d_bwt, n, sentinel_index, d_text_out, ctx->eng.pick(stream));
 }
 
+int b200sa_unbwt_u32_dev(b200sa_ctx* ctx, const uint8_t* d_bwt, int64_t n, int64_t sentinel_index, uint8_t* d_text_out, void* stream)
+{
+    B200SA_NEED_CTX(ctx);
+    if (n > 0 && d_bwt == d_text_out) return b200sa::set_error(B200SA_EINVAL, "d_text_out must not alias d_bwt");
+    return ctx->eng.unbwt_dev(d_bwt, n, sentinel_index, d_text_out, ctx->eng.pick(stream), B200SA_MAX_N_UINT32);
+}
+
+int b200sa_lcp_u32_dev(b200sa_ctx* ctx, const uint8_t* d_text, int64_t n, const uint32_t* d_sa, uint32_t* d_lcp_out, void* stream)
+{
+    B200SA_NEED_CTX(ctx);
+    return ctx->eng.lcp_dev(d_text, n, (const i32*)d_sa, (i32*)d_lcp_out, ctx->eng.pick(stream), B200SA_MAX_N_UINT32);
+}
+
 int b200sa_check_suffix_array_dev(b200sa_ctx* ctx, const uint8_t* d_text, int64_t n, const int32_t* d_sa,
                                   int64_t* bad_rows_out, void* stream)
 {
@@ -113,67 +128,82 @@ int b200sa_lcp_dev(b200sa_ctx* ctx, const uint8_t* d_text, int64_t n, const int3
 
 // ---- host-buffer entry points ----------------------------------------------------------------
 
-int b200sa_suffix_array_bwt(b200sa_ctx* ctx, const uint8_t* text, int64_t n, int32_t* sa_out, uint8_t* bwt_out,
-                            int32_t* sentinel_index_out)
+// SA and / or BWT of a host text, int32 or uint32 indices.  The text and its suffix array stay resident afterwards
+// (Engine::sa_cache); when the next call brings the same bytes only the missing result is computed.
+static int sa_bwt_host(b200sa_ctx* ctx, const uint8_t* text, int64_t n, void* sa_out, uint8_t* bwt_out, int64_t* sentinel_out, int64_t max_n)
 {
+    const bool had_cache = ctx && ctx->eng.sa_cache.valid && ctx->eng.sa_cache.n == (u64)n;
     B200SA_NEED_CTX(ctx);
     Engine& e = ctx->eng;
-    if (n < 0 || n > B200SA_MAX_N_INT32) return b200sa::set_error(B200SA_EINVAL, "n = %lld outside [0, 2^31-2]", (long long)n);
+    if (n < 0 || n > max_n) return b200sa::set_error(B200SA_EINVAL, "n = %lld outside [0, %lld]", (long long)n, (long long)max_n);
     if (n > 0 && !text) return b200sa::set_error(B200SA_EINVAL, "null text");
     if (n == 0) {
-        if (sa_out) sa_out[0] = 0;
-        if (sentinel_index_out) *sentinel_index_out = 0;
-        // still require a device: this library never computes on the CPU
+        if (b200sa_device_count() <= 0) return b200sa::set_error(B200SA_ENODEVICE, "no CUDA device available; this library has no CPU fallback");
+        if (sa_out) ((int32_t*)sa_out)[0] = 0;
+        if (sentinel_out) *sentinel_out = 0;
         return 0;
     }
     B200SA_CU(cudaSetDevice(e.device));
     cudaStream_t st = e.own_stream;
-    B200SA_TRY(e.text_ws.ensure((size_t)n));
+    B200SA_TRY(e.text_ws.ensure((size_t)n + 64));
     B200SA_TRY(e.sa_ws.ensure(((size_t)n + 1) * 4));
-    B200SA_CU(cudaMemcpyAsync(e.text_ws.p, text, (size_t)n, cudaMemcpyHostToDevice, st));
-    const bool want_bwt = bwt_out != nullptr || sentinel_index_out != nullptr;
-    if (want_bwt) {
-        B200SA_TRY(e.bwt_ws.ensure((size_t)n));
-        i64 sentinel = 0;
-        B200SA_TRY(e.bwt_dev(e.text_ws.as<u8>(), n, e.bwt_ws.as<u8>(), e.sa_ws.as<i32>(), &sentinel, st));
-        if (sentinel_index_out) *sentinel_index_out = (int32_t)sentinel;
-        if (bwt_out) B200SA_CU(cudaMemcpyAsync(bwt_out, e.bwt_ws.p, (size_t)n, cudaMemcpyDeviceToHost, st));
+    const bool want_bwt = bwt_out != nullptr || sentinel_out != nullptr;
+    if (want_bwt) B200SA_TRY(e.bwt_ws.ensure((size_t)n + 64));
+    bool reuse = false;
+    if (had_cache && want_bwt) {
+        // upload next to the resident text and compare on the device
+        B200SA_TRY(e.misc.ensure(8192));
+        u32* d_diff = e.misc.as<u32>() + 548;
+        B200SA_CU(cudaMemsetAsync(d_diff, 0, 4, st));
+        B200SA_TRY(e.copy_in(e.bwt_ws.p, text, (size_t)n, st));
+        B200SA_LAUNCH(b200sa::k_bytes_differ, (u32)(e.num_sms * 8), 256, 0, st, (const u8*)e.text_ws.as<u8>(), (const u8*)e.bwt_ws.as<u8>(), (u64)n, d_diff);
+        e.count_launch(B200SA_PH_ALPHABET);
+        B200SA_CU(cudaMemcpyAsync(e.h_pinned + 25, d_diff, 4, cudaMemcpyDeviceToHost, st));
+        B200SA_CU(cudaStreamSynchronize(st));
+        reuse = e.h_pinned[25] == 0;
+        if (!reuse) B200SA_CU(cudaMemcpyAsync(e.text_ws.p, e.bwt_ws.p, (size_t)n, cudaMemcpyDeviceToDevice, st));
     } else {
-        B200SA_TRY(e.suffix_array_dev(e.text_ws.as<u8>(), n, e.sa_ws.as<i32>(), st));
+        B200SA_TRY(e.copy_in(e.text_ws.p, text, (size_t)n, st));
     }
-    if (sa_out) B200SA_CU(cudaMemcpyAsync(sa_out, e.sa_ws.p, ((size_t)n + 1) * 4, cudaMemcpyDeviceToHost, st));
+    i64 sentinel = e.sa_cache.sentinel;
+    if (!reuse) {
+        B200SA_TRY(e.suffix_array_dev(e.text_ws.as<u8>(), n, e.sa_ws.as<i32>(), st, max_n));
+        B200SA_CU(cudaMemcpyAsync(e.h_pinned + 26, e.rank.p, 4, cudaMemcpyDeviceToHost, st));  // rank[0]: the row of suffix 0
+        B200SA_CU(cudaStreamSynchronize(st));
+        sentinel = (i64)e.h_pinned[26];
+    }
+    if (want_bwt) {
+        // the gather runs while the suffix array travels to the host (pageable destination: the staging threads' streams;
+        // pinned: enqueued behind it on the same stream)
+        B200SA_TRY(e.bwt_rows(e.text_ws.as<u8>(), (u32)n, e.sa_ws.as<i32>(), 0, (u32)n, e.bwt_ws.as<u8>(), st, /*defer_sync=*/true));
+    }
+    if (sa_out) B200SA_TRY(e.copy_out(sa_out, e.sa_ws.p, ((size_t)n + 1) * 4, st, /*independent=*/true));
+    if (bwt_out) B200SA_TRY(e.copy_out(bwt_out, e.bwt_ws.p, (size_t)n, st));
     B200SA_CU(cudaStreamSynchronize(st));
+    B200SA_CU(cudaStreamSynchronize(e.copy_stream));
+    if (sentinel_out) *sentinel_out = sentinel;
+    if (e.profiling) B200SA_TRY(e.collect_profile());
+    e.sa_cache.valid = true;
+    e.sa_cache.n = (u64)n;
+    e.sa_cache.sentinel = sentinel;
+    return 0;
+}
+
+int b200sa_suffix_array_bwt(b200sa_ctx* ctx, const uint8_t* text, int64_t n, int32_t* sa_out, uint8_t* bwt_out,
+                            int32_t* sentinel_index_out)
+{
+    int64_t s64 = 0;
+    B200SA_TRY(sa_bwt_host(ctx, text, n, sa_out, bwt_out, sentinel_index_out || bwt_out ? &s64 : nullptr, B200SA_MAX_N_INT32));
+    if (sentinel_index_out) *sentinel_index_out = (int32_t)s64;
     return 0;
 }
 
 int b200sa_suffix_array_bwt_u32(b200sa_ctx* ctx, const uint8_t* text, int64_t n, uint32_t* sa_out, uint8_t* bwt_out,
                                 int64_t* sentinel_index_out)
 {
-    B200SA_NEED_CTX(ctx);
-    Engine& e = ctx->eng;
-    if (n < 0 || n > B200SA_MAX_N_UINT32) return b200sa::set_error(B200SA_EINVAL, "n = %lld outside [0, 2^32-8194]", (long long)n);
-    if (n > 0 && !text) return b200sa::set_error(B200SA_EINVAL, "null text");
-    if (n == 0) {
-        if (sa_out) sa_out[0] = 0;
-        if (sentinel_index_out) *sentinel_index_out = 0;
-        return 0;
-    }
-    B200SA_CU(cudaSetDevice(e.device));
-    cudaStream_t st = e.own_stream;
-    B200SA_TRY(e.text_ws.ensure((size_t)n));
-    B200SA_TRY(e.sa_ws.ensure(((size_t)n + 1) * 4));
-    B200SA_CU(cudaMemcpyAsync(e.text_ws.p, text, (size_t)n, cudaMemcpyHostToDevice, st));
-    if (bwt_out || sentinel_index_out) {
-        B200SA_TRY(e.bwt_ws.ensure((size_t)n));
-        i64 sentinel = 0;
-        B200SA_TRY(e.bwt_dev(e.text_ws.as<u8>(), n, e.bwt_ws.as<u8>(), e.sa_ws.as<i32>(), &sentinel, st, B200SA_MAX_N_UINT32));
-        if (sentinel_index_out) *sentinel_index_out = sentinel;
-        if (bwt_out) B200SA_CU(cudaMemcpyAsync(bwt_out, e.bwt_ws.p, (size_t)n, cudaMemcpyDeviceToHost, st));
-    } else {
-        B200SA_TRY(e.suffix_array_dev(e.text_ws.as<u8>(), n, e.sa_ws.as<i32>(), st, B200SA_MAX_N_UINT32));
-    }
-    if (sa_out) B200SA_CU(cudaMemcpyAsync(sa_out, e.sa_ws.p, ((size_t)n + 1) * 4, cudaMemcpyDeviceToHost, st));
-    B200SA_CU(cudaStreamSynchronize(st));
+    int64_t s64 = 0;
+    B200SA_TRY(sa_bwt_host(ctx, text, n, sa_out, bwt_out, sentinel_index_out || bwt_out ? &s64 : nullptr, B200SA_MAX_N_UINT32));
+    if (sentinel_index_out) *sentinel_index_out = s64;
     return 0;
 }
 
@@ -186,8 +216,8 @@ int b200sa_check_suffix_array(b200sa_ctx* ctx, const uint8_t* text, int64_t n, c
     cudaStream_t st = e.own_stream;
     B200SA_TRY(e.text_ws.ensure((size_t)n + 64));
     B200SA_TRY(e.sa_ws.ensure(((size_t)n + 1) * 4));
-    if (n) B200SA_CU(cudaMemcpyAsync(e.text_ws.p, text, (size_t)n, cudaMemcpyHostToDevice, st));
-    B200SA_CU(cudaMemcpyAsync(e.sa_ws.p, sa, ((size_t)n + 1) * 4, cudaMemcpyHostToDevice, st));
+    if (n) B200SA_TRY(e.copy_in(e.text_ws.p, text, (size_t)n, st));
+    B200SA_TRY(e.copy_in(e.sa_ws.p, sa, ((size_t)n + 1) * 4, st));
     return e.check_sa_dev(e.text_ws.as<u8>(), n, e.sa_ws.as<i32>(), bad_rows_out, st);
 }
 
@@ -203,22 +233,33 @@ int b200sa_bwt(b200sa_ctx* ctx, uint8_t* text_inout, int64_t n, int32_t* sentine
     return b200sa_suffix_array_bwt(ctx, text_inout, n, nullptr, text_inout, sentinel_index_out);
 }
 
-int b200sa_unbwt(b200sa_ctx* ctx, uint8_t* bwt_inout, int64_t n, int32_t sentinel_index)
+static int unbwt_host(b200sa_ctx* ctx, uint8_t* bwt_inout, int64_t n, int64_t sentinel_index, int64_t max_n)
 {
     B200SA_NEED_CTX(ctx);
     Engine& e = ctx->eng;
-    if (n < 0 || n > B200SA_MAX_N_INT32) return b200sa::set_error(B200SA_EINVAL, "n = %lld outside [0, 2^31-2]", (long long)n);
+    if (n < 0 || n > max_n) return b200sa::set_error(B200SA_EINVAL, "n = %lld outside [0, %lld]", (long long)n, (long long)max_n);
     if (n == 0) return 0;
     if (!bwt_inout) return b200sa::set_error(B200SA_EINVAL, "null buffer");
     B200SA_CU(cudaSetDevice(e.device));
     cudaStream_t st = e.own_stream;
     B200SA_TRY(e.text_ws.ensure((size_t)n));
     B200SA_TRY(e.bwt_ws.ensure((size_t)n));
-    B200SA_CU(cudaMemcpyAsync(e.bwt_ws.p, bwt_inout, (size_t)n, cudaMemcpyHostToDevice, st));
-    B200SA_TRY(e.unbwt_dev(e.bwt_ws.as<u8>(), n, sentinel_index, e.text_ws.as<u8>(), st));
-    B200SA_CU(cudaMemcpyAsync(bwt_inout, e.text_ws.p, (size_t)n, cudaMemcpyDeviceToHost, st));
+    B200SA_TRY(e.copy_in(e.bwt_ws.p, bwt_inout, (size_t)n, st));
+    // an input that is not a BWT fails here with B200SA_EINVAL; the caller's buffer is then left as it was
+    B200SA_TRY(e.unbwt_dev(e.bwt_ws.as<u8>(), n, sentinel_index, e.text_ws.as<u8>(), st, max_n));
+    B200SA_TRY(e.copy_out(bwt_inout, e.text_ws.p, (size_t)n, st));
     B200SA_CU(cudaStreamSynchronize(st));
     return 0;
+}
+
+int b200sa_unbwt(b200sa_ctx* ctx, uint8_t* bwt_inout, int64_t n, int32_t sentinel_index)
+{
+    return unbwt_host(ctx, bwt_inout, n, sentinel_index, B200SA_MAX_N_INT32);
+}
+
+int b200sa_unbwt_u32(b200sa_ctx* ctx, uint8_t* bwt_inout, int64_t n, int64_t sentinel_index)
+{
+    return unbwt_host(ctx, bwt_inout, n, sentinel_index, B200SA_MAX_N_UINT32);
 }
 
 int b200sa_lcp(b200sa_ctx* ctx, const uint8_t* text, int64_t n, const int32_t* sa, int32_t* sa_out, int32_t* lcp_out)
@@ -237,13 +278,22 @@ int b200sa_lcp(b200sa_ctx* ctx, const uint8_t* text, int64_t n, const int32_t* s
     B200SA_TRY(e.text_ws.ensure((size_t)n));
     B200SA_TRY(e.sa_ws.ensure(((size_t)n + 1) * 4));
     B200SA_TRY(e.keys[1].ensure(((size_t)n + 1) * 4 + 64));  // LCP staging: keys[1] is not used by lcp_dev
-    B200SA_CU(cudaMemcpyAsync(e.text_ws.p, text, (size_t)n, cudaMemcpyHostToDevice, st));
-    if (sa) B200SA_CU(cudaMemcpyAsync(e.sa_ws.p, sa, ((size_t)n + 1) * 4, cudaMemcpyHostToDevice, st));
-    else B200SA_TRY(e.suffix_array_dev(e.text_ws.as<u8>(), n, e.sa_ws.as<i32>(), st));
-    if (sa_out) B200SA_CU(cudaMemcpyAsync(sa_out, e.sa_ws.p, ((size_t)n + 1) * 4, cudaMemcpyDeviceToHost, st));
+    B200SA_TRY(e.copy_in(e.text_ws.p, text, (size_t)n, st));
+    if (sa) {
+        // a suffix array from outside (another tool, a file): the phi scatter and the text probes index with its entries, so it
+        // is validated first (O(n), the validator of b200sa_check_suffix_array)
+        B200SA_TRY(e.copy_in(e.sa_ws.p, sa, ((size_t)n + 1) * 4, st));
+        i64 bad = 0;
+        B200SA_TRY(e.check_sa_dev(e.text_ws.as<u8>(), n, e.sa_ws.as<i32>(), &bad, st));
+        if (bad != 0) return b200sa::set_error(B200SA_EINVAL, "sa is not the suffix array of text (%lld offending rows)", (long long)bad);
+    } else {
+        B200SA_TRY(e.suffix_array_dev(e.text_ws.as<u8>(), n, e.sa_ws.as<i32>(), st));
+    }
+    if (sa_out) B200SA_TRY(e.copy_out(sa_out, e.sa_ws.p, ((size_t)n + 1) * 4, st, /*independent=*/true));
     B200SA_TRY(e.lcp_dev(e.text_ws.as<u8>(), n, e.sa_ws.as<i32>(), e.keys[1].as<i32>(), st));
-    B200SA_CU(cudaMemcpyAsync(lcp_out, e.keys[1].p, ((size_t)n + 1) * 4, cudaMemcpyDeviceToHost, st));
+    B200SA_TRY(e.copy_out(lcp_out, e.keys[1].p, ((size_t)n + 1) * 4, st));
     B200SA_CU(cudaStreamSynchronize(st));
+    B200SA_CU(cudaStreamSynchronize(e.copy_stream));
     return 0;
 }
 
@@ -278,16 +328,17 @@ static int batch_host(b200sa_ctx* ctx, const uint8_t* blocks, const int64_t* off
     B200SA_CU(cudaSetDevice(e.device));
     cudaStream_t st = e.own_stream;
     B200SA_TRY(e.text_ws.ensure((size_t)total + 64));
-    if (total) B200SA_CU(cudaMemcpyAsync(e.text_ws.p, blocks, (size_t)total, cudaMemcpyHostToDevice, st));
+    if (total) B200SA_TRY(e.copy_in(e.text_ws.p, blocks, (size_t)total, st));
     u8* d_bwt = nullptr;
     i32* d_sa = nullptr;
     if (bwt_out) { B200SA_TRY(e.bwt_ws.ensure((size_t)total + 64)); d_bwt = e.bwt_ws.as<u8>(); }
     if (sa_out) { B200SA_TRY(e.batch_out.ensure(((size_t)total + (size_t)count) * 4 + 64)); d_sa = e.batch_out.as<i32>(); }
-    B200SA_TRY(e.batch_dev(e.text_ws.as<u8>(), offsets, count, d_bwt, d_sa, sentinel_index_out, st));
-    if (bwt_out && total) B200SA_CU(cudaMemcpyAsync(bwt_out, d_bwt, (size_t)total, cudaMemcpyDeviceToHost, st));
-    if (sa_out) B200SA_CU(cudaMemcpyAsync(sa_out, d_sa, ((size_t)total + (size_t)count) * 4, cudaMemcpyDeviceToHost, st));
-    B200SA_CU(cudaStreamSynchronize(st));
-    return 0;
+    // on failure the stream is drained before returning: no copy into the caller's buffers is still in flight
+    int rc = e.batch_dev(e.text_ws.as<u8>(), offsets, count, d_bwt, d_sa, sentinel_index_out, st);
+    if (rc == 0 && bwt_out && total) rc = e.copy_out(bwt_out, d_bwt, (size_t)total, st);
+    if (rc == 0 && sa_out) rc = e.copy_out(sa_out, d_sa, ((size_t)total + (size_t)count) * 4, st);
+    if (cudaStreamSynchronize(st) != cudaSuccess && rc == 0) rc = b200sa::set_error(B200SA_ECUDA, "stream synchronisation failed");
+    return rc;
 }
 
 int b200sa_suffix_array_batch(b200sa_ctx* ctx, const uint8_t* blocks, const int64_t* offsets, int64_t count, int32_t* sa_out)
@@ -321,11 +372,11 @@ int b200sa_unbwt_batch(b200sa_ctx* ctx, uint8_t* blocks_inout, const int64_t* of
     cudaStream_t st = e.own_stream;
     B200SA_TRY(e.bwt_ws.ensure((size_t)total + 64));
     B200SA_TRY(e.text_ws.ensure((size_t)total + 64));
-    if (total) B200SA_CU(cudaMemcpyAsync(e.bwt_ws.p, blocks_inout, (size_t)total, cudaMemcpyHostToDevice, st));
-    B200SA_TRY(e.unbwt_batch_dev(e.bwt_ws.as<u8>(), offsets, count, sentinel_index, e.text_ws.as<u8>(), st));
-    if (total) B200SA_CU(cudaMemcpyAsync(blocks_inout, e.text_ws.p, (size_t)total, cudaMemcpyDeviceToHost, st));
-    B200SA_CU(cudaStreamSynchronize(st));
-    return 0;
+    int rc = total ? e.copy_in(e.bwt_ws.p, blocks_inout, (size_t)total, st) : 0;
+    if (rc == 0) rc = e.unbwt_batch_dev(e.bwt_ws.as<u8>(), offsets, count, sentinel_index, e.text_ws.as<u8>(), st);
+    if (rc == 0 && total) rc = e.copy_out(blocks_inout, e.text_ws.p, (size_t)total, st);
+    if (cudaStreamSynchronize(st) != cudaSuccess && rc == 0) rc = b200sa::set_error(B200SA_ECUDA, "stream synchronisation failed");
+    return rc;
 }
 
 // ---- streaming pipeline over batches --------------------------------------------------------------
@@ -473,12 +524,17 @@ int b200sa_pipeline_wait(b200sa_pipeline* p, int64_t ticket)
     std::unique_lock<std::mutex> lk(p->mu);
     if (p->open_tickets.count(ticket) == 0)
         return b200sa::set_error(B200SA_EINVAL, "ticket %lld is unknown or has already been collected", (long long)ticket);
-    p->cv_done.wait(lk, [&] { return p->done.count(ticket) != 0; });
+    // also wakes when somebody else collected the ticket meanwhile (a second waiter, or b200sa_pipeline_drain)
+    p->cv_done.wait(lk, [&] { return p->done.count(ticket) != 0 || p->open_tickets.count(ticket) == 0; });
     auto it = p->done.find(ticket);
+    if (it == p->done.end())
+        return b200sa::set_error(B200SA_EINVAL, "ticket %lld was collected by another waiter or by b200sa_pipeline_drain", (long long)ticket);
     const int rc = it->second.first;
     if (rc) b200sa::set_error(rc, "%s", it->second.second.c_str());
     p->done.erase(it);
     p->open_tickets.erase(ticket);
+    lk.unlock();
+    p->cv_done.notify_all();
     return rc;
 }
 
@@ -492,6 +548,8 @@ int b200sa_pipeline_drain(b200sa_pipeline* p)
         if (kv.second.first && !first) { first = kv.second.first; b200sa::set_error(first, "%s", kv.second.second.c_str()); }
     p->done.clear();
     p->open_tickets.clear();
+    lk.unlock();
+    p->cv_done.notify_all();  // waiters of tickets collected here wake up and report EINVAL
     return first;
 }
 

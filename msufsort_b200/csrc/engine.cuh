@@ -88,9 +88,10 @@ struct Engine {
     // width of the round-0 key (symbols + length field + block bits): fewer bits = fewer radix sweeps in round 0 but
     // more suffixes left for the doubling rounds (B200SA_MAX_KEY_BITS; measured in profiles/)
     int max_key_bits = 64;
-    bool lcp_direct = false;     // B200SA_LCP_DIRECT=1: budgeted row-wise comparison before the PLCP route (unmeasured: off)
-    bool rs_persistent = false;  // B200SA_RS_PERSISTENT=1: persistent sweep with next-tile key prefetch (unmeasured: off)
-    bool pack_radix = false;  // B200SA_PACK_RADIX=1: mixed-radix round-0 keys where they hold more symbols (unmeasured: off)
+    // measured on B200, 256 MiB Markov text (profiles/r02_knobs.txt): budgeted row-wise LCP comparison before the PLCP route
+    // 5.7 ms against 17.6 ms; mixed-radix round-0 keys (13 instead of 12 symbols) 31.4 ms per SA+BWT step against 33.9 ms
+    bool lcp_direct = true;   // B200SA_LCP_DIRECT=0: always take the PLCP route
+    bool pack_radix = true;   // B200SA_PACK_RADIX=0: bit-packed round-0 keys (symbols << len_bits | clamped length) only
 
     // instrumentation
     bool profiling = false;
@@ -105,6 +106,33 @@ struct Engine {
     int init(int dev);
     void shutdown();
     int release_workspace();
+
+    // Host <-> device transfers of the host-buffer entry points.  Pinned (or registered) host memory: one asynchronous copy on
+    // `st`.  Pageable memory (what a std::vector handed to the reference-shaped facade is): `copy_threads` host threads move
+    // chunks through their own pinned staging buffers and streams, so the PCIe copy of one chunk overlaps the host memcpy of
+    // the next (the driver's own pageable path is a single-threaded staging loop).  copy_in: work enqueued on `st` afterwards
+    // sees the data.  copy_out: ordered after the work already enqueued on `st`; complete on return for pageable memory.
+    struct HostStage {
+        static const int kMaxThreads = 8;
+        void* buf[kMaxThreads][2] = {};
+        cudaStream_t stream[kMaxThreads] = {};
+        cudaEvent_t done[kMaxThreads][2] = {};
+        cudaEvent_t fence = nullptr;
+        size_t chunk = (size_t)8 << 20;
+        int threads = 0;  // > 0 once allocated
+    } stage;
+    int copy_threads = 4;                       // B200SA_COPY_THREADS (0 = always the driver's own path)
+    size_t copy_staged_min = (size_t)4 << 20;   // smaller pageable transfers are left to the driver
+    // The host entry points keep the last text and its suffix array resident (text_ws, sa_ws).  A following call that is
+    // handed the same bytes (compared on the device after the upload) reuses the sort: make_suffix_array followed by
+    // forward_burrows_wheeler_transform on one msufsort object costs one sort, not two.  Every other entry point drops it.
+    struct SaCache { bool valid = false; u64 n = 0; i64 sentinel = 0; } sa_cache;
+    int stage_ensure();
+    int copy_in(void* d_dst, const void* h_src, size_t bytes, cudaStream_t st);
+    // independent: the source is complete already (the stream was synchronised after its producer) — the copy need not
+    // queue behind later work on `st`; pinned destinations then use copy_stream, which the caller synchronises
+    int copy_out(void* h_dst, const void* d_src, size_t bytes, cudaStream_t st, bool independent = false);
+    cudaStream_t copy_stream = nullptr;
 
     cudaStream_t pick(void* s) const { return s ? (cudaStream_t)s : own_stream; }
 
@@ -169,15 +197,16 @@ struct Engine {
     int ensure_sa_workspace(u64 n);
     // max_n: B200SA_MAX_N_INT32 for the reference-shaped int32 entry points, B200SA_MAX_N_UINT32 for the wide ones
     int suffix_array_dev(const u8* d_text, i64 n, i32* d_sa, cudaStream_t st, i64 max_n = B200SA_MAX_N_INT32);
-    int bwt_rows(const u8* d_text, u32 n, const i32* d_sa, u32 o_begin, u32 o_end, u8* d_bwt, cudaStream_t st);
+    // defer_sync: only enqueue the kernel (the caller knows the sentinel row already and synchronises later)
+    int bwt_rows(const u8* d_text, u32 n, const i32* d_sa, u32 o_begin, u32 o_end, u8* d_bwt, cudaStream_t st, bool defer_sync = false);
     int bwt_dev(const u8* d_text, i64 n, u8* d_bwt, i32* d_sa_or_null, i64* sentinel_host, cudaStream_t st, i64 max_n = B200SA_MAX_N_INT32);
-    struct UnbwtState { int stage = 0; u32 n = 0, s = 0, D = 0, nreg = 0, nwalkers = 0, cap = 0; } us;
+    struct UnbwtState { int stage = 0, dshift = 6; u32 n = 0, s = 0, D = 0, nreg = 0, nwalkers = 0, cap = 0; } us;
     int unbwt_build(const u8* d_bwt, u32 n, u32 s, u32* nwalkers_out, cudaStream_t st);
     int unbwt_measure(u32 w_begin, u32 w_end, cudaStream_t st);
     int unbwt_finish(u32 w_begin, u32 w_end, u8* d_out, cudaStream_t st);
-    int unbwt_dev(const u8* d_bwt, i64 n, i32 sentinel, u8* d_out, cudaStream_t st);
+    int unbwt_dev(const u8* d_bwt, i64 n, i64 sentinel, u8* d_out, cudaStream_t st, i64 max_n = B200SA_MAX_N_INT32);
     int check_sa_dev(const u8* d_text, i64 n, const i32* d_sa, i64* bad_rows, cudaStream_t st, i64 max_n = B200SA_MAX_N_INT32);
-    int lcp_dev(const u8* d_text, i64 n, const i32* d_sa, i32* d_lcp, cudaStream_t st);
+    int lcp_dev(const u8* d_text, i64 n, const i32* d_sa, i32* d_lcp, cudaStream_t st, i64 max_n = B200SA_MAX_N_INT32);
     // batch of independent blocks, packed back to back at offsets[0..count]; any of the outputs may be null
     int batch_dev(const u8* d_packed, const i64* offsets, i64 count, u8* d_bwt_out, i32* d_sa_out, i32* sentinels_host, cudaStream_t st);
     int batch_tables(const i64* offsets, u32 count, const i32* sentinels_or_null, u32** d_ends, u32** d_offs, i32** d_sent, cudaStream_t st);

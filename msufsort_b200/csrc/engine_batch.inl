@@ -194,6 +194,10 @@ int Engine::unbwt_batch_dev(const u8* d_bwt, const i64* offsets, i64 count64, co
     u32* nx[2] = {walk.as<u32>(), walk.as<u32>() + W};
     u32* ds[2] = {walk.as<u32>() + 2 * (size_t)W, walk.as<u32>() + 3 * (size_t)W};
     u32* ovf = walk.as<u32>() + 4 * (size_t)W;
+    B200SA_TRY(misc.ensure(8192));
+    u32* d_bad = misc.as<u32>() + kUnbwtBadWord;
+    B200SA_CU(cudaMemsetAsync(d_bad, 0, 4, st));
+    prof.memsets++;
     B200SA_TRY(phase_begin(B200SA_PH_UNBWT_WALK, st));
     B200SA_LAUNCH(k_ubb_walk, (u32)div_up_u64(W, UW_THREADS), UW_THREADS, 0, st, (const u64*)table, (const u32*)d_ends, (const i32*)d_sent, count,
                   nreg, D, N, W, cap, keys[0].as<u8>(), ds[0], nx[0], ovf);
@@ -208,14 +212,18 @@ int Engine::unbwt_batch_dev(const u8* d_bwt, const i64* offsets, i64 count64, co
         cur ^= 1;
     }
     B200SA_LAUNCH(k_ubb_place, (u32)div_up_u64(W, UP_THREADS / 32), UP_THREADS, 0, st, (const u64*)table, (const u32*)d_ends, (const u32*)d_offs,
-                  (const i32*)d_sent, count, nreg, D, N, W, (const u32*)ds[cur], (const u32*)idx[0].as<u32>(), (const u32*)ovf,
-                  (const u8*)keys[0].as<u8>(), cap, d_out);
+                  (const i32*)d_sent, count, nreg, D, N, W, (const u32*)ds[cur], (const u32*)nx[cur], (const u32*)idx[0].as<u32>(), (const u32*)ovf,
+                  (const u8*)keys[0].as<u8>(), cap, d_out, d_bad);
     count_launch(B200SA_PH_UNBWT_WALK);
     B200SA_TRY(phase_end(st));
     prof.alg_bytes[B200SA_PH_UNBWT_WALK] += (u64)total * 9;
     B200SA_CU(cudaGetLastError());
+    B200SA_CU(cudaMemcpyAsync(h_pinned + 24, d_bad, 4, cudaMemcpyDeviceToHost, st));
     B200SA_CU(cudaStreamSynchronize(st));
     if (profiling) B200SA_TRY(collect_profile());
+    if (h_pinned[24] != 0)
+        return set_error(B200SA_EINVAL, "a block of the batch is not a Burrows-Wheeler transform (its LF mapping does not form one cycle through "
+                                        "the sentinel row); the output buffer holds no valid text for that block");
     return 0;
 }
 

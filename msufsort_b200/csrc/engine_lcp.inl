@@ -4,9 +4,9 @@
 // ---------------------------------------------------------------------------------------------
 // LCP array (lcp_kernels.cuh): phi scatter, hierarchical PLCP levels, gather through the SA
 
-int Engine::lcp_dev(const u8* d_text, i64 n64, const i32* d_sa, i32* d_lcp, cudaStream_t st)
+int Engine::lcp_dev(const u8* d_text, i64 n64, const i32* d_sa, i32* d_lcp, cudaStream_t st, i64 max_n)
 {
-    if (n64 < 0 || n64 > B200SA_MAX_N_INT32) return set_error(B200SA_EINVAL, "n = %lld outside [0, 2^31-2]", (long long)n64);
+    if (n64 < 0 || n64 > max_n) return set_error(B200SA_EINVAL, "n = %lld outside [0, %lld]", (long long)n64, (long long)max_n);
     if (!d_sa || !d_lcp || (n64 > 0 && !d_text)) return set_error(B200SA_EINVAL, "null pointer");
     B200SA_CU(cudaSetDevice(device));
     const u32 n = (u32)n64;

@@ -41,11 +41,12 @@ static const int RS_RADIX = 256;
 #ifndef B200SA_RS_THREADS
 #define B200SA_RS_THREADS 256
 #endif
-// 1: keep the sixteen within-warp ranks of a thread (each < 32 * IPT <= 65535) two to a register.  The sweep compiles to 80
-// registers with 80 bytes of spills; this frees eight registers.  Compile-time experiment (make NVCC_DEFS=-DB200SA_RS_PACK_POS=1),
-// not yet measured.
+// 1: keep the sixteen within-warp ranks of a thread (each < 32 * IPT <= 65535) two to a register: the sweep then fits its
+// 80-register budget without spills (80 bytes of spills otherwise).  Measured on B200 (profiles/r02_knobs.txt, 2^28 pairs
+// per sweep): 1.76 ms against 1.89 ms; the persistent variant with next-tile key prefetch measured 1.81 ms (1.82 ms with
+// packed ranks) and was removed.
 #ifndef B200SA_RS_PACK_POS
-#define B200SA_RS_PACK_POS 0
+#define B200SA_RS_PACK_POS 1
 #endif
 #if B200SA_RS_PACK_POS
 #define RS_POS_DECL(IPT) u32 pos2[((IPT) + 1) / 2]; for (int i_ = 0; i_ < ((IPT) + 1) / 2; ++i_) pos2[i_] = 0
@@ -163,10 +164,11 @@ __device__ unsigned long long g_phase_cycles[8];
 #define PT_MARK(i) do { } while (0)
 #endif
 
-template <typename KeyT, bool WRITE_KEYS>
+//   ValT            -> u32 everywhere except the forward BWT, which carries the byte T[i-1] next to rank[i] (bwt_kernels.cuh)
+template <typename KeyT, bool WRITE_KEYS, typename ValT = u32>
 __global__ void __launch_bounds__(RS_THREADS, RS_MIN_BLOCKS)
 k_onesweep_pass(const KeyT* __restrict__ kin, KeyT* __restrict__ kout,
-                const u32* __restrict__ vin, u32* __restrict__ vout,
+                const ValT* __restrict__ vin, ValT* __restrict__ vout,
                 u32 m, int shift, u32 gen_skip,
                 const u32* __restrict__ bins, u64* __restrict__ status, u32* __restrict__ tile_counter)
 {
@@ -183,7 +185,7 @@ k_onesweep_pass(const KeyT* __restrict__ kin, KeyT* __restrict__ kout,
 #else
     KeyT* skeys = (KeyT*)(s_wtot + 16);  // [TILE]
 #endif
-    u32* svals = (u32*)(skeys + TILE);   // [TILE]
+    ValT* svals = (ValT*)(skeys + TILE);   // [TILE]
     __shared__ u32 s_tile;
 
     const u32 tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
@@ -206,7 +208,7 @@ k_onesweep_pass(const KeyT* __restrict__ kin, KeyT* __restrict__ kout,
 
     // ---- load (warp-striped): element order inside the tile is (warp, item, lane)
     KeyT key[IPT];
-    u32 val[IPT];
+    ValT val[IPT];
     RS_POS_DECL(IPT);
     const u32 wbase = warp * (32u * IPT) + lane;
     const bool full = valid == (u32)TILE;  // block-uniform: no bounds checks on the common path
@@ -267,21 +269,21 @@ k_onesweep_pass(const KeyT* __restrict__ kin, KeyT* __restrict__ kout,
     // the 80-register budget of 3 CTAs/SM); their latency overlaps the tile-level scan below
     if (vin) {
         if (full) {
-            const u32* vp = vin + base + wbase;
+            const ValT* vp = vin + base + wbase;
 #pragma unroll
             for (int k = 0; k < IPT; ++k) val[k] = ld_stream(vp + k * 32);
         } else {
 #pragma unroll
             for (int k = 0; k < IPT; ++k) {
                 const u32 li = wbase + (u32)k * 32u;
-                val[k] = li < valid ? ld_stream(vin + base + li) : 0u;
+                val[k] = li < valid ? ld_stream(vin + base + li) : (ValT)0;
             }
         }
     } else {
 #pragma unroll
         for (int k = 0; k < IPT; ++k) {
             const u32 gi = base + wbase + (u32)k * 32u;
-            val[k] = gi + (gi >= gen_skip ? 1u : 0u);
+            val[k] = (ValT)(gi + (gi >= gen_skip ? 1u : 0u));
         }
     }
     __syncthreads();
@@ -385,250 +387,5 @@ k_onesweep_pass(const KeyT* __restrict__ kin, KeyT* __restrict__ kout,
     }
     PT_MARK(6);  // write-out (issue only; stores retire asynchronously)
 }
-
-// Persistent, software-pipelined form of the sweep (experimental: B200SA_RS_PERSISTENT=1, not yet measured).  A CTA keeps
-// taking tile tickets; once a tile is staged in shared memory its key registers are dead, so the keys of the CTA's next
-// tile are fetched into them before the look-back, and arrive while this tile waits for its predecessors and writes out
-// (the ncu capture of the one-tile-per-CTA kernel shows 10 % of the stall samples on the first use of freshly loaded
-// keys and 12 % in the look-back wait).  Tickets are still handed out in ranking order: a CTA publishes the descriptor of
-// ticket b only after finishing its lower ticket a, so the lowest unfinished ticket can always make progress.
-template <typename KeyT, bool WRITE_KEYS>
-__global__ void __launch_bounds__(RS_THREADS, RS_MIN_BLOCKS)
-k_onesweep_pass_persistent(const KeyT* __restrict__ kin, KeyT* __restrict__ kout,
-                           const u32* __restrict__ vin, u32* __restrict__ vout,
-                           u32 m, int shift, u32 gen_skip,
-                           const u32* __restrict__ bins, u64* __restrict__ status, u32* __restrict__ tile_counter, u32 ntiles)
-{
-    constexpr int THREADS = RS_THREADS, IPT = RS_IPT, WARPS = THREADS / 32, TILE = THREADS * IPT;
-    B200SA_DYN_SMEM(smem);
-    u32* whist = (u32*)smem;             // [WARPS][256] per-warp digit counters, later warp-exclusive prefixes
-    u32* s_cnt = whist + WARPS * RS_RADIX;  // [256] tile digit counts
-    u32* s_coff = s_cnt + RS_RADIX;      // [256] exclusive scan of s_cnt (slot of the digit run in smem)
-    u32* s_gdelta = s_coff + RS_RADIX;   // [256] global offset of the digit run minus s_coff
-    u32* s_wtot = s_gdelta + RS_RADIX;   // [16]
-#if B200SA_RS_PEERS_ATOMIC_OR
-    u32* wmask = s_wtot + 16;            // [WARPS][256] per-warp peer masks (all zero between uses)
-    KeyT* skeys = (KeyT*)(wmask + WARPS * RS_RADIX);  // [TILE]
-#else
-    KeyT* skeys = (KeyT*)(s_wtot + 16);  // [TILE]
-#endif
-    u32* svals = (u32*)(skeys + TILE);   // [TILE]
-    __shared__ u32 s_tile, s_tile_next;
-
-    const u32 tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    if (tid == 0) s_tile = atomicAdd(tile_counter, 1u);
-    __syncthreads();
-    u32 tile = s_tile;
-    if (tile >= ntiles) return;
-    KeyT key[IPT];
-    const u32 wbase = warp * (32u * IPT) + lane;
-    {
-        const u32 base0 = tile * (u32)TILE;
-        const u32 valid0 = min((u32)TILE, m - base0);
-#pragma unroll
-        for (int k = 0; k < IPT; ++k) {
-            const u32 li = wbase + (u32)k * 32u;
-            key[k] = li < valid0 ? ld_stream(kin + base0 + li) : (KeyT)~(KeyT)0;
-        }
-    }
-  for (;;) {
-    for (u32 i = tid; i < (u32)(WARPS * RS_RADIX); i += THREADS) {
-        whist[i] = 0;
-#if B200SA_RS_PEERS_ATOMIC_OR
-        wmask[i] = 0;
-#endif
-    }
-    __syncthreads();
-    const u32 base = tile * (u32)TILE;
-    const u32 valid = min((u32)TILE, m - base);
-#ifdef B200SA_PHASE_TIMING
-    const bool pt_on = (tid == 0) && ((tile & 15u) == 0) && sizeof(KeyT) == 8;
-    long long pt_t = clock64();
-    if (pt_on) atomicAdd(&g_phase_cycles[7], 1ull);
-#endif
-
-    // keys of this tile were loaded while the previous tile was in its look-back / write-out (or by the prologue)
-    u32 val[IPT];
-    RS_POS_DECL(IPT);
-    const bool full = valid == (u32)TILE;  // block-uniform
-    PT_MARK(0);  // keys arrived
-    // ---- 1. rank inside the warp.  Peers = lanes holding my digit.  Two interchangeable ways to find
-    // them (tools/ubench on B200, SM-cycles per 32 keys at full occupancy): eight ballots 20.7,
-    // atomicOr into a shared mask word + read back 7.4, MATCH.ANY 60.  Inside this kernel the shared
-    // memory pipe is the scarcer resource (staging + counters already need ~25 wavefronts per 32
-    // keys), so the ballot form is faster in situ (R0 sweep 2.0 ms vs 2.4 ms) and is the default.
-    // All peers then read the warp's running count for the digit (one broadcast word) and the lowest
-    // peer bumps it by the group size.
-    u32* mywh = whist + warp * RS_RADIX;
-    const u32 lt = lanemask_lt();
-#if B200SA_RS_PEERS_ATOMIC_OR
-    u32* mymask = wmask + warp * RS_RADIX;
-    const u32 mybit = 1u << lane;
-#endif
-#pragma unroll
-    for (int k = 0; k < IPT; ++k) {
-        const u32 d = rs_digit<KeyT>(key[k], shift);
-#if B200SA_RS_PEERS_ATOMIC_OR
-        atomicOr(&mymask[d], mybit);
-        __syncwarp();
-        const u32 peers = mymask[d];
-#elif defined(B200SA_ABLATE_BALLOTS)
-        const u32 peers = 1u << lane;  // timing experiment only: wrong ranks
-#else
-        const u32 peers = warp_peers_digit8(d);
-#endif
-        const u32 prev = mywh[d];
-        __syncwarp();
-        const u32 below = (u32)__popc(peers & lt);
-        if (below == 0) {
-#if B200SA_RS_PEERS_ATOMIC_OR
-            mymask[d] = 0;
-#endif
-            mywh[d] = prev + (u32)__popc(peers);
-        }
-        __syncwarp();
-        RS_POS_SET(k, prev + below);
-    }
-    PT_MARK(1);  // ranking
-    // values are fetched only now: during ranking they would cost 16 more live registers (spills at
-    // the 80-register budget of 3 CTAs/SM); their latency overlaps the tile-level scan below
-    if (vin) {
-        if (full) {
-            const u32* vp = vin + base + wbase;
-#pragma unroll
-            for (int k = 0; k < IPT; ++k) val[k] = ld_stream(vp + k * 32);
-        } else {
-#pragma unroll
-            for (int k = 0; k < IPT; ++k) {
-                const u32 li = wbase + (u32)k * 32u;
-                val[k] = li < valid ? ld_stream(vin + base + li) : 0u;
-            }
-        }
-    } else {
-#pragma unroll
-        for (int k = 0; k < IPT; ++k) {
-            const u32 gi = base + wbase + (u32)k * 32u;
-            val[k] = gi + (gi >= gen_skip ? 1u : 0u);
-        }
-    }
-    __syncthreads();
-
-    // ---- 2. per-digit: warp-exclusive prefixes, tile count; publish the PARTIAL descriptor early
-    if (tid == 0) s_tile_next = atomicAdd(tile_counter, 1u);  // ticket of the tile this CTA ranks next (read after the next barrier)
-    u32 my_cnt = 0;
-    if (tid < (u32)RS_RADIX) {
-        u32 acc = 0;
-#pragma unroll
-        for (int w = 0; w < WARPS; ++w) {
-            const u32 c = whist[w * RS_RADIX + tid];
-            whist[w * RS_RADIX + tid] = acc;
-            acc += c;
-        }
-        my_cnt = acc;
-        st_relaxed_u64(status + (u64)tile * RS_RADIX + tid, (tile == 0 ? RS_FLAG_INCLUSIVE : RS_FLAG_PARTIAL) | (u64)acc);
-        // ---- 3a. exclusive scan of the 256 tile counts (8 full warps)
-        const u32 incl = warp_incl_scan_u32(acc);
-        if (lane == 31) s_wtot[warp] = incl;
-        s_cnt[tid] = incl - acc;  // warp-local exclusive, fixed up below
-    }
-    __syncthreads();
-    if (tid < (u32)RS_RADIX) {
-        u32 prefix = 0;
-        for (u32 w = 0; w < warp; ++w) prefix += s_wtot[w];
-        const u32 off = s_cnt[tid] + prefix;
-        s_coff[tid] = off;
-        // fold the digit's slot into every warp's exclusive prefix: staging then needs one lookup per key
-#pragma unroll
-        for (int w = 0; w < WARPS; ++w) whist[w * RS_RADIX + tid] += off;
-    }
-    __syncthreads();
-
-    PT_MARK(2);  // tile-level combine + scan (incl. barrier waits)
-    // ---- stage keys and values in digit order (needs only tile-local offsets; predecessors keep
-    // publishing their descriptors meanwhile)
-#pragma unroll
-    for (int k = 0; k < IPT; ++k) {
-        const u32 d = rs_digit<KeyT>(key[k], shift);
-        const u32 p = RS_POS_GET(k) + mywh[d];
-        skeys[p] = key[k];
-        svals[p] = val[k];
-    }
-
-    // keys, values and ranks of this tile are dead (staged in shared memory): fetch the next tile's keys now, their
-    // latency hides behind this tile's look-back and write-out
-    const u32 next_tile = s_tile_next;
-    if (next_tile < ntiles) {
-        const u32 nbase = next_tile * (u32)TILE;
-        const u32 nvalid = min((u32)TILE, m - nbase);
-#pragma unroll
-        for (int k = 0; k < IPT; ++k) {
-            const u32 li = wbase + (u32)k * 32u;
-            key[k] = li < nvalid ? ld_stream(kin + nbase + li) : (KeyT)~(KeyT)0;
-        }
-    }
-    PT_MARK(3);  // staging
-    // ---- 4. look-back for digit tid: B200SA_RS_LOOKBACK_DEPTH predecessor descriptors in flight per step
-    if (tid < (u32)RS_RADIX) {
-        u64 excl = 0;
-#ifdef B200SA_ABLATE_LOOKBACK
-        if (false) {
-#else
-        if (tile != 0) {
-#endif
-            const u64* col = status + tid;
-            i64 t = (i64)tile - 1;
-            bool done = false;
-            while (!done) {
-                // LB descriptors in flight per step: the inclusive frontier trails a running tile by some
-                // tens of tiles (clock64 phase timing: with 4 in flight the walk back cost 6.3 k of the 25 k
-                // cycles of a tile's life); keys/values/ranks are dead by now, so registers are free
-                constexpr int LB = B200SA_RS_LOOKBACK_DEPTH;
-                u64 v[LB];
-#pragma unroll
-                for (int i = 0; i < LB; ++i) v[i] = (t - i >= 0) ? ld_relaxed_u64(col + (u64)(t - i) * RS_RADIX) : 0ull;
-#pragma unroll
-                for (int i = 0; i < LB; ++i) {
-                    if (!done) {
-                        u64 x = v[i];
-                        while ((x >> 62) == 0) x = ld_relaxed_u64(col + (u64)(t - i) * RS_RADIX);
-                        excl += x & RS_VALUE_MASK;
-                        if (x & RS_FLAG_INCLUSIVE) done = true;
-                    }
-                }
-                t -= LB;
-            }
-            st_relaxed_u64(status + (u64)tile * RS_RADIX + tid, RS_FLAG_INCLUSIVE | (excl + (u64)my_cnt));
-        }
-        // global start of this tile's run of digit tid, minus its slot in shared memory
-        s_gdelta[tid] = bins[tid] + (u32)excl - s_coff[tid];
-    }
-    PT_MARK(4);  // look-back
-    __syncthreads();
-    PT_MARK(5);  // barrier after look-back
-    // ---- write out: consecutive threads take consecutive slots, i.e. consecutive addresses inside a digit run
-    if (full) {
-#pragma unroll
-        for (int i = 0; i < IPT; ++i) {
-            const u32 j = tid + (u32)i * THREADS;
-            const KeyT kk = skeys[j];
-            const u32 g = s_gdelta[rs_digit<KeyT>(kk, shift)] + j;
-            if (WRITE_KEYS) st_stream(kout + g, kk);
-            st_stream(vout + g, svals[j]);
-        }
-    } else {
-        for (u32 j = tid; j < valid; j += THREADS) {
-            const KeyT kk = skeys[j];
-            const u32 g = s_gdelta[rs_digit<KeyT>(kk, shift)] + j;
-            if (WRITE_KEYS) st_stream(kout + g, kk);
-            st_stream(vout + g, svals[j]);
-        }
-    }
-    PT_MARK(6);  // write-out (issue only; stores retire asynchronously)
-    if (next_tile >= ntiles) break;
-    tile = next_tile;
-    __syncthreads();  // shared memory of this tile is reused by the next one
-  }
-}
-
 
 }  // namespace b200sa

@@ -96,10 +96,9 @@ def test_emu_profile_accounting(emu_engine):
     {"B200SA_GROUPSORT_TINY": "3", "B200SA_GROUPSORT_MEDIUM": "4096", "B200SA_GROUPSORT_AVG": "1000000"},  # CTA bitonic path
     {"B200SA_GROUPSORT_AVG": "0"},                                                                        # radix rounds only
     {"B200SA_ISA_DIRECT_BYTES": "0", "B200SA_ISA_MIN_UPDATES": "1"},                                      # bucketed ISA update
-    {"B200SA_PACK_RADIX": "1"},                                                                           # mixed-radix round-0 keys
+    {"B200SA_PACK_RADIX": "0"},                                                                           # bit-packed round-0 keys (mixed radix is the default)
     {"B200SA_MAX_KEY_BITS": "24"},                                                                        # narrow round-0 keys
-    {"B200SA_RS_PERSISTENT": "1", "B200SA_NUM_SMS": "1", "B200SA_GROUPSORT_AVG": "0"},                    # persistent sweep, 3 CTAs walk all tiles
-], ids=["groups-small-thresholds", "groups-cta", "radix-only", "bucketed-isa", "mixed-radix-keys", "narrow-keys", "persistent-sweep"])
+], ids=["groups-small-thresholds", "groups-cta", "radix-only", "bucketed-isa", "bit-packed-keys", "narrow-keys"])
 def test_emu_round_variants(oracle, env, monkeypatch):
     """every way a doubling round can run (in-place group sort: thread / CTA / per-group radix / fallback; radix
     rounds; direct and bucketed ISA update) gives the oracle's suffix array"""

@@ -4,6 +4,7 @@
 #   textgen  msufsort_b200/lib/libb200sa_textgen.so  synthetic input generators (host C)
 #   facade   msufsort_b200/lib/libmsufsort.so        the reference-shaped C++ facade (src/library)
 #   cli      msufsort_b200/lib/msufsort              command line tool with the reference demo's modes (src/executable)
+#   facade_bench msufsort_b200/lib/facade_bench      end-to-end timing of the drop-in C++ path (tools/facade_bench.cpp; bench.py runs it)
 #   oracle   oracle/liboracle.so (+ oracle/_ref/ when /root/reference exists)   TEST INFRASTRUCTURE
 #   emu      tests/emu/libb200sa_emu.so              kernel logic under a CPU SIMT emulator (tests only)
 NVCC      ?= nvcc
@@ -14,9 +15,9 @@ NVCC_DEFS ?=
 NVCCFLAGS := $(ARCH) $(NVCC_DEFS) -lineinfo -O3 -std=c++17 -Xcompiler -fPIC,-fvisibility=hidden -Xptxas -v --expt-relaxed-constexpr
 CSRC      := msufsort_b200/csrc
 LIBDIR    := msufsort_b200/lib
-KSRC      := $(CSRC)/b200sa.cu $(CSRC)/engine_peer.inl $(CSRC)/engine_lcp.inl $(CSRC)/engine_batch.inl $(CSRC)/c_abi.inl $(CSRC)/engine.cuh $(CSRC)/common.cuh $(CSRC)/radix_sort.cuh $(CSRC)/sa_kernels.cuh $(CSRC)/bwt_kernels.cuh $(CSRC)/lcp_kernels.cuh $(CSRC)/batch_kernels.cuh include/b200sa.h
+KSRC      := $(CSRC)/b200sa.cu $(CSRC)/comm.cuh $(CSRC)/engine_shard.inl $(CSRC)/engine_peer.inl $(CSRC)/engine_lcp.inl $(CSRC)/engine_batch.inl $(CSRC)/c_abi.inl $(CSRC)/engine.cuh $(CSRC)/common.cuh $(CSRC)/radix_sort.cuh $(CSRC)/sa_kernels.cuh $(CSRC)/bwt_kernels.cuh $(CSRC)/lcp_kernels.cuh $(CSRC)/batch_kernels.cuh include/b200sa.h
 
-all: lib textgen facade cli oracle emu
+all: lib textgen facade cli facade_bench oracle emu
 
 lib: $(LIBDIR)/libb200sa.so
 $(LIBDIR)/libb200sa.so: $(KSRC)
@@ -37,6 +38,10 @@ cli: $(LIBDIR)/msufsort
 $(LIBDIR)/msufsort: src/executable/msufsort/main.cpp $(LIBDIR)/libmsufsort.so
 	$(CXX) -O2 -std=c++17 -Isrc -Iinclude -o $@ $< -L$(LIBDIR) -lmsufsort -lb200sa -Wl,-rpath,'$$ORIGIN'
 
+facade_bench: $(LIBDIR)/facade_bench
+$(LIBDIR)/facade_bench: tools/facade_bench.cpp $(LIBDIR)/libmsufsort.so
+	$(CXX) -O2 -std=c++17 -Isrc -Iinclude -o $@ $< -L$(LIBDIR) -lmsufsort -lb200sa -Wl,-rpath,'$$ORIGIN'
+
 oracle:
 	$(MAKE) -C oracle
 
@@ -45,7 +50,7 @@ tests/emu/libb200sa_emu.so: $(KSRC) tests/emu/cuda_emu.h
 	$(CXX) -O2 -g -std=c++17 -fPIC -shared -DB200SA_EMU -x c++ -Itests/emu -I$(CSRC) -Wno-unused-function -o $@ $(CSRC)/b200sa.cu
 
 clean:
-	rm -f $(LIBDIR)/*.so $(LIBDIR)/msufsort $(LIBDIR)/ptxas.log tests/emu/*.so
+	rm -f $(LIBDIR)/*.so $(LIBDIR)/msufsort $(LIBDIR)/facade_bench $(LIBDIR)/ptxas.log tests/emu/*.so
 	$(MAKE) -C oracle clean
 
-.PHONY: all lib textgen facade cli oracle emu clean
+.PHONY: all lib textgen facade cli facade_bench oracle emu clean

@@ -1,23 +1,28 @@
 #!/usr/bin/env python
-"""bench.py — headline benchmark of the SA + BWT hot path (BASELINE.json metric).
+"""bench.py — headline benchmark of the SA + BWT (and inverse BWT) hot path (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME] [--mode sharded|independent]
 
 One "step" = one pass of the hot path over one synthetic text: suffix array (n+1 int32) AND forward
 BWT (n bytes + sentinel index) of the text.
-  * value  : input MB/s, text already resident in HBM, results left in HBM (one sort + one gather per
+  * value  : input MB/s, text already resident in HBM, results left in HBM (one sort + one BWT pass per
              step through b200sa_bwt_dev), CUDA events on the launching stream, max over ranks.
   * e2e    : the same metric through the reference-facing host entry points with HOST buffers — the
              two drop-in calls a user of the reference makes (make_suffix_array then
-             forward_burrows_wheeler_transform => b200sa_suffix_array + b200sa_bwt), pinned host
-             memory, H2D and D2H copies inside the timed region.
+             forward_burrows_wheeler_transform => b200sa_suffix_array + b200sa_bwt; the second call recognises the
+             resident text and reuses the sort), pinned host memory, H2D and D2H copies inside the timed region.
+  * e2e_facade: the same two calls through the C++ facade with pageable std::vector storage (tools/facade_bench.cpp).
+  * unbwt  : the inverse transform of the 2^30-2 byte Markov text (BASELINE.json configs[3]): device-resident value,
+             e2e through b200sa_unbwt, roofline of the walk, the reference's inverse beside it.
   * roofline: the dominant kernel (k_onesweep_pass, radix scatter sweeps): algorithmic bytes (24 B per
              tuple per sweep, 20 B for the first sweep of round 0 whose values are generated) / summed
              CUDA-event time of those launches inside the timed region / measured HBM copy peak.
   * cpu_baseline: the UNMODIFIED reference (oracle/_ref, built from /root/reference) timed on this
-             box's host cores on a bounded prefix of the same text.
-N > 1: every rank sorts its own independent text of the same size (weak scaling, no collective on the
-data path — "batches of independent blocks" in north_star); value = total bytes / max-over-ranks time.
+             box's host cores on the same text.
+N > 1 (default --mode sharded): ONE text of the same configuration sharded over the N ranks — key-range partition of
+the suffixes, the inverse suffix array in NVLink peer memory, round loop in C++ (b200sa_shard_sort); strong scaling,
+value = n / max-over-ranks time.  The line also carries the 2^30-2 ACGT text (configs[2]) and the inverse BWT of the
+2^30-2 Markov text (configs[3]) on the same N GPUs.  --mode independent: one text per GPU, no exchange (weak scaling).
 """
 from __future__ import annotations
 
@@ -40,9 +45,12 @@ WORKLOADS = {
     "markov3_256MiB": ("markov3", 1 << 28, "256 MiB synthetic order-3 Markov English-like text: SA + BWT (BASELINE.json configs[1])"),
     "rand_16MiB": ("rand", 1 << 24, "16 MiB synthetic random bytes: SA + BWT (BASELINE.json configs[0])"),
     "markov3_64MiB": ("markov3", 1 << 26, "64 MiB Markov text (reduced; debugging only)"),
-    "acgt_1GiB": ("acgt_rep", (1 << 30) - 2, "2^30-2 ACGT bases with injected repeats: SA + BWT (BASELINE.json configs[2], single GPU)"),
+    "acgt_1GiB": ("acgt_rep", (1 << 30) - 2, "2^30-2 ACGT bases with injected repeats: SA + BWT (BASELINE.json configs[2])"),
+    "markov3_1GiB": ("markov3", (1 << 30) - 2, "2^30-2 bytes of the Markov text (BASELINE.json configs[3]: its BWT is the inverse transform's input)"),
 }
-CPU_SAMPLE_BYTES = 1 << 26  # reference arm / cpu_baseline: 64 MiB prefix of the workload text
+UNBWT_WORKLOAD = "markov3_1GiB"
+CPU_MAX_BYTES = 1 << 28     # reference arm / cpu_baseline: the whole text up to 256 MiB (the reference needs ~8 s per step there)
+REF_BUILD_NOTE = "oracle/_ref: unmodified reference, g++ -O3 -march=x86-64-v3 (portable across build and GPU box; the reference's own flags use -march=native)"
 
 
 def load_peaks():
@@ -124,17 +132,29 @@ def load_reference():
     lib.ref_make_suffix_array.argtypes = [P, I64, P, I32]
     lib.ref_forward_bwt.argtypes = [P, I64, I32]
     lib.ref_forward_bwt.restype = I32
+    lib.ref_reverse_bwt.argtypes = [P, I64, I32, I32]
     lib.ref_hardware_concurrency.restype = C.c_int
     return lib
 
 
-def reference_step(lib, text: np.ndarray, sa_out: np.ndarray, work: np.ndarray, threads: int) -> float:
-    """one step on the CPU: make_suffix_array + forward_burrows_wheeler_transform (its two public calls)"""
+def reference_step(lib, text: np.ndarray, sa_out: np.ndarray, work: np.ndarray, threads: int):
+    """one step on the CPU: make_suffix_array + forward_burrows_wheeler_transform (its two public calls);
+    returns (seconds, sentinel index); `work` holds the BWT afterwards"""
     np.copyto(work, text)
     t0 = time.perf_counter()
     lib.ref_make_suffix_array(text.ctypes.data, text.size, sa_out.ctypes.data, threads)
-    lib.ref_forward_bwt(work.ctypes.data, work.size, threads)
-    return time.perf_counter() - t0
+    s = lib.ref_forward_bwt(work.ctypes.data, work.size, threads)
+    return time.perf_counter() - t0, int(s)
+
+
+def reference_unbwt(lib, bwt: np.ndarray, sentinel: int, threads: int, want: np.ndarray):
+    """the reference's inverse transform of `bwt` in place; returns seconds (and checks the round trip)"""
+    t0 = time.perf_counter()
+    lib.ref_reverse_bwt(bwt.ctypes.data, bwt.size, sentinel, threads)
+    dt = time.perf_counter() - t0
+    if not np.array_equal(bwt, want):
+        raise SystemExit("bench.py: the reference's inverse BWT did not restore the text")
+    return dt
 
 
 def run_reference(args, wl):
@@ -147,23 +167,31 @@ def run_reference(args, wl):
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libmsufsort_ref.so not built (reference tree absent at build time)"}))
         return 0
     threads = lib.ref_hardware_concurrency()
-    ns = min(n, CPU_SAMPLE_BYTES)
-    text = gen_text(kind, n)[:ns].copy() if n <= (1 << 28) else gen_text(kind, ns)
+    ns = min(n, CPU_MAX_BYTES)
+    text = gen_text(kind, ns)
     sa = np.empty(ns + 1, dtype=np.int32)
     work = np.empty(ns, dtype=np.uint8)
     for _ in range(args.warmup):
         reference_step(lib, text, sa, work, threads)
-    times = [reference_step(lib, text, sa, work, threads) for _ in range(args.steps)]
+    times, sentinel = [], 0
+    for _ in range(args.steps):
+        dt, sentinel = reference_step(lib, text, sa, work, threads)
+        times.append(dt)
     total = sum(times)
     value = ns * args.steps / total / 1e6
-    sample = f"first {ns} bytes of the workload text, SA + BWT via the reference's two public calls, {threads} threads"
+    # the inverse transform of the BWT the last step left in `work` (one repetition; the reference needs ~4 s at 256 MiB)
+    un_s = reference_unbwt(lib, work, sentinel, threads, text)
+    whole = "the whole workload text" if ns == n else f"the first {ns} bytes of the workload text"
+    sample = f"{whole}, SA + BWT via the reference's two public calls, {threads} threads; {REF_BUILD_NOTE}"
     line = {
         "impl": "reference", "metric": "sa_bwt_input_throughput", "value": value, "unit": "MB/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "u8/int32", "data": "synthetic",
+        "scaling": "strong" if args.gpus > 1 and args.mode == "sharded" else "weak", "vs_baseline": None, "dtype": "u8/int32", "data": "synthetic",
         "config": {"workload": wl, "description": desc, "n_bytes": n, "sample_bytes": ns},
         "cpu_baseline": {"value": value, "unit": "MB/s", "cores": threads, "kind": "reference", "sample": sample},
         "e2e": {"value": value, "unit": "MB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "unbwt": {"value": ns / un_s / 1e6, "unit": "MB/s", "ms": 1e3 * un_s, "cores": threads,
+                  "sample": f"reverse_burrows_wheeler_transform of the BWT of {whole} ({ns} bytes), 1 repetition"},
     }
     print(json.dumps(line))
     return 0
@@ -242,9 +270,11 @@ def run_ours(args, wl):
     h_sa = torch.empty(n + 1, dtype=torch.int32, pin_memory=True)
     h_work = torch.empty(n, dtype=torch.uint8, pin_memory=True)
     e2e_times = []
+    e2e_launches = 0
     for it in range(min(args.warmup, 2) + args.steps):
         h_work.copy_(host_text)  # in-place API: restore the caller's buffer outside the timed region
         barrier()
+        l0 = eng.launch_count()
         t0 = time.perf_counter()
         eng.suffix_array_ptr(host_text.data_ptr(), n, h_sa.data_ptr())
         s2 = eng.bwt_ptr(h_work.data_ptr(), n)
@@ -252,13 +282,15 @@ def run_ours(args, wl):
         dt = time.perf_counter() - t0
         if it >= min(args.warmup, 2):
             e2e_times.append(dt)
+            e2e_launches = eng.launch_count() - l0
     e2e_s = sum(e2e_times) / len(e2e_times)
     if world > 1:
         tt = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e_s = float(tt.item())
     assert s2 == sentinel
-    assert int(h_sa[0]) == n
+    assert int(h_sa[0]) == n and int(h_sa[sentinel]) == 0
+    assert bool(torch.equal(h_work.cuda(), d_bwt)), "the end-to-end BWT differs from the device-resident one"
 
     if rank != 0:
         if world > 1:
@@ -268,33 +300,23 @@ def run_ours(args, wl):
     peak, peak_src = load_peaks()
     sp = prof["phases"]["sort_pass"]
     achieved = sp["alg_bytes"] / (sp["ms"] * 1e-3) / 1e9 if sp["ms"] > 0 else 0.0
-    # DRAM traffic per launch from the committed ncu --set full capture (profiles/r01_traffic.json), scaled to
-    # this run's average launch: traffic / algorithmic bytes was measured on the round-0 sweep (m = 2^28)
-    traffic = None
-    try:
-        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
-            tr = json.load(f)
-        traffic = tr["dram_bytes_per_launch"] / tr["algorithmic_bytes_per_launch"] * sp["alg_bytes"] / sp["launches"]
-    except Exception:
-        pass
+    # DRAM traffic per launch: NOT measured in this run (that needs a profiler).  It is the DRAM / algorithmic byte ratio of the
+    # committed ncu --set full capture of this kernel (profiles/*_traffic.json) applied to this run's algorithmic bytes per launch.
+    traffic, traffic_src = None, None
+    for name in ("r02_traffic.json", "r01_traffic.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                tr = json.load(f)
+            traffic = tr["dram_bytes_per_launch"] / tr["algorithmic_bytes_per_launch"] * sp["alg_bytes"] / sp["launches"]
+            traffic_src = f"from profiles/{name} (ncu --set full of the m=2^28 sweep: dram__bytes_read.sum + dram__bytes_write.sum = {tr['dram_bytes_per_launch']:.4g} B " \
+                          f"for {tr['algorithmic_bytes_per_launch']:.4g} algorithmic bytes), scaled to this run's algorithmic bytes per launch; not measured in this run"
+            break
+        except Exception:
+            continue
     ms_per_step = dev_ms / args.steps
     value = world * n / (ms_per_step * 1e-3) / 1e6
     phases = {k: {"ms_per_step": v["ms"] / args.steps, "launches_per_step": v["launches"] / args.steps,
                   "alg_GB_per_step": v["alg_bytes"] / args.steps / 1e9} for k, v in prof["phases"].items() if v["launches"]}
-
-    # ---- CPU baseline: the reference itself on a bounded sample (rank 0, N=1 only)
-    cpu = None
-    if world == 1 and not args.no_cpu_baseline:
-        lib = load_reference()
-        if lib is not None:
-            threads = lib.ref_hardware_concurrency()
-            ns = min(n, CPU_SAMPLE_BYTES)
-            text = host_text.numpy()[:ns].copy()
-            sa = np.empty(ns + 1, dtype=np.int32)
-            work = np.empty(ns, dtype=np.uint8)
-            t = reference_step(lib, text, sa, work, threads)
-            cpu = {"value": ns / t / 1e6, "unit": "MB/s", "cores": threads, "kind": "reference",
-                   "sample": f"first {ns} bytes of the workload text, SA + BWT via the reference's two public calls, 1 repetition, {threads} threads"}
 
     # ---- the rows around the hot path, measured after and outside the timed regions above: LCP array of
     # the same text from the finished SA, and the text cut into 1024 blocks transformed as ONE batch (forward + inverse)
@@ -305,25 +327,67 @@ def run_ours(args, wl):
         except Exception as exc:  # the headline line must not depend on the extras
             extras = {"error": str(exc)[:200]}
 
+    # ---- CPU baseline: the reference itself on the same text (rank 0, N=1 only): SA + BWT, then its inverse
+    cpu, cpu_unbwt = None, None
+    if world == 1 and not args.no_cpu_baseline:
+        lib = load_reference()
+        if lib is not None:
+            threads = lib.ref_hardware_concurrency()
+            ns = min(n, CPU_MAX_BYTES)
+            text = host_text.numpy()[:ns].copy()
+            sa = np.empty(ns + 1, dtype=np.int32)
+            work = np.empty(ns, dtype=np.uint8)
+            t, s_ref = reference_step(lib, text, sa, work, threads)
+            whole = "the whole workload text" if ns == n else f"the first {ns} bytes of the workload text"
+            cpu = {"value": ns / t / 1e6, "unit": "MB/s", "cores": threads, "kind": "reference",
+                   "sample": f"{whole}, SA + BWT via the reference's two public calls, 1 repetition, {threads} threads; {REF_BUILD_NOTE}"}
+            if ns == n and (s_ref != sentinel or not np.array_equal(work, h_work.numpy())):
+                raise SystemExit("bench.py: the reference's BWT of the workload text differs from ours")
+            tu = reference_unbwt(lib, work, s_ref, threads, text)
+            cpu_unbwt = {"value": ns / tu / 1e6, "unit": "MB/s", "cores": threads, "kind": "reference",
+                         "sample": f"reverse_burrows_wheeler_transform of the BWT of {whole} ({ns} bytes), 1 repetition, {threads} threads"}
+            del text, sa, work
+
+    # ---- the drop-in C++ path with pageable vectors (its own process; the text travels through /dev/shm)
+    e2e_facade = None
+    if world == 1 and not args.no_facade:
+        e2e_facade = measure_facade(host_text.numpy(), args)
+
+    # ---- inverse BWT (BASELINE.json configs[3]); frees the SA + BWT buffers first
+    del d_sa, d_bwt, h_sa, h_work, d_text, host_text
+    eng.release_workspace()
+    torch.cuda.empty_cache()
+    unbwt = None
+    if world == 1 and not args.no_unbwt:
+        try:
+            unbwt = measure_unbwt(eng, torch, args, stream, peak)
+            if unbwt is not None:
+                unbwt["cpu_baseline"] = cpu_unbwt
+        except Exception as exc:
+            unbwt = {"error": str(exc)[:300]}
+
     line = {
         "metric": "sa_bwt_input_throughput", "value": value, "unit": "MB/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8/int32 (u64 sort keys)", "data": "synthetic",
         "config": {"workload": wl, "description": desc, "n_bytes": n, "per_gpu_bytes": n,
-                   "parallelism": "1 independent text per GPU" if world > 1 else "single GPU",
+                   "parallelism": "1 independent text per GPU (--mode independent)" if world > 1 else "single GPU",
                    "l2": "working set (>= 44 n bytes) far larger than the 126 MB L2; no flush needed",
                    "step": "suffix array (n+1 int32) + forward BWT (n bytes + sentinel index) of the text"},
         "e2e": {"value": world * n / e2e_s / 1e6, "unit": "MB/s", "h2d_bytes_per_step": 2 * n, "d2h_bytes_per_step": 4 * (n + 1) + n + 4,
-                "ms_per_step": e2e_s * 1e3,
-                "path": "b200sa_suffix_array + b200sa_bwt (the reference's two public calls), pinned host buffers"},
+                "ms_per_step": e2e_s * 1e3, "gpu_launches_per_step": int(e2e_launches),
+                "path": "b200sa_suffix_array + b200sa_bwt (the reference's two public calls; the second recognises the resident text and reuses "
+                        "the sort), pinned host buffers"},
+        "e2e_facade": e2e_facade,
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": "k_onesweep_pass<u64> (radix scatter sweeps)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak if peak else None, "traffic": traffic, "peak_source": peak_src,
-                     "traffic_note": "bytes per average launch; ncu-measured DRAM/algorithmic ratio of the m=2^28 sweep (profiles/r01_traffic.json) x this run's algorithmic bytes per launch",
+                     "traffic_source": traffic_src,
                      "algorithmic_bytes_per_launch": sp["alg_bytes"] / sp["launches"] if sp["launches"] else None,
                      "launches": int(sp["launches"]), "avg_launch_ms": sp["ms"] / sp["launches"] if sp["launches"] else None,
                      "share_of_step": sp["ms"] / dev_ms if dev_ms else None},
         "cpu_baseline": cpu,
+        "unbwt": unbwt,
         "clocks": clocks,
         "rounds_per_step": prof["rounds"] / args.steps, "sort_passes_per_step": prof["sort_passes"] / args.steps,
         "phases": phases,
@@ -333,6 +397,100 @@ def run_ours(args, wl):
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def measure_facade(text: np.ndarray, args):
+    """tools/facade_bench.cpp: the reference-shaped C++ templates on pageable std::vector storage, in their own process"""
+    exe = os.path.join(ROOT, "msufsort_b200", "lib", "facade_bench")
+    if not os.path.exists(exe):
+        return {"error": "msufsort_b200/lib/facade_bench not built (make facade_bench)"}
+    tmpdir = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else "/tmp"
+    path = os.path.join(tmpdir, "b200sa_facade_bench_%d.bin" % os.getpid())
+    try:
+        text.tofile(path)
+        out = subprocess.run([exe, path, str(max(1, min(args.steps, 5))), "2"], capture_output=True, text=True, timeout=600)
+        for ln in out.stdout.splitlines():
+            if ln.startswith("{"):
+                return json.loads(ln)
+        return {"error": (out.stdout + out.stderr)[-300:]}
+    except Exception as exc:
+        return {"error": str(exc)[:300]}
+    finally:
+        try:
+            os.remove(path)
+        except OSError:
+            pass
+
+
+def measure_unbwt(eng, torch, args, stream, peak):
+    """inverse BWT of the 2^30-2 byte Markov text on one GPU: device-resident (CUDA events), end to end through
+    b200sa_unbwt (pinned host buffer, in place), phases from the engine's own event spans"""
+    kind, n, desc = WORKLOADS[UNBWT_WORKLOAD]
+    if args.unbwt_n:
+        n = args.unbwt_n
+    host_text = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+    np.copyto(host_text.numpy(), gen_text(kind, n))
+    d_text = host_text.cuda()
+    d_bwt = torch.empty(n, dtype=torch.uint8, device="cuda")
+    s = eng.bwt_dev(d_text, n, d_bwt, None, stream)          # the verified forward path produces the input
+    eng.release_workspace()
+    d_out = torch.empty(n, dtype=torch.uint8, device="cuda")
+    for _ in range(max(1, min(args.warmup, 2))):
+        eng.unbwt_dev(d_bwt, n, s, d_out, stream)
+    torch.cuda.synchronize()
+    eng.profile_reset()
+    eng.set_profiling(True)
+    l0 = eng.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        eng.unbwt_dev(d_bwt, n, s, d_out, stream)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    launches = (eng.launch_count() - l0) // args.steps
+    prof = eng.profile()
+    eng.set_profiling(False)
+    if not bool(torch.equal(d_out, d_text)):
+        raise SystemExit("bench.py: the inverse BWT did not restore the text")
+    del d_out, d_text
+    # end to end, in place on a pinned host buffer
+    h_bwt = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+    h_bwt.copy_(d_bwt)
+    h_work = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+    times = []
+    for it in range(1 + args.steps):
+        h_work.copy_(h_bwt)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        eng.unbwt_ptr(h_work.data_ptr(), n, s)
+        dt = time.perf_counter() - t0
+        if it >= 1:
+            times.append(dt)
+    if not bool(torch.equal(h_work, host_text)):
+        raise SystemExit("bench.py: the end-to-end inverse BWT did not restore the text")
+    e2e_s = sum(times) / len(times)
+    walk = prof["phases"]["unbwt_walk"]
+    build = prof["phases"]["unbwt_build"]
+    walk_ms = walk["ms"] / args.steps
+    out = {
+        "metric": "unbwt_input_throughput", "value": n / ms / 1e3, "unit": "MB/s", "ms_per_step": ms, "n_bytes": n, "gpu_launches": int(launches),
+        "config": {"workload": UNBWT_WORKLOAD + "_unbwt", "description": "inverse BWT of the " + desc.split(" (")[0] + " (BASELINE.json configs[3]), one GPU"},
+        "e2e": {"value": n / e2e_s / 1e6, "unit": "MB/s", "ms_per_step": e2e_s * 1e3, "h2d_bytes_per_step": n, "d2h_bytes_per_step": n,
+                "path": "b200sa_unbwt (reverse_burrows_wheeler_transform), pinned host buffer, in place"},
+        "phases": {"build_ms": build["ms"] / args.steps, "walk_ms": walk_ms},
+        "roofline": {"bound": "hbm", "kernel": "k_unbwt_walk + list ranking + k_unbwt_place (latency-bound: n dependent 4-byte reads)",
+                     "achieved": 7 * n / (walk_ms * 1e-3) / 1e9 if walk_ms else None, "peak": peak, "unit": "GB/s",
+                     "frac": 7 * n / (walk_ms * 1e-3) / 1e9 / peak if walk_ms and peak else None,
+                     "algorithmic_bytes": "7 n (4 B psi read + 1 B decoded + window store / reload + 1 B final store)",
+                     "sector_level_GBps": 32 * n / (walk_ms * 1e-3) / 1e9 if walk_ms else None,
+                     "sector_level_frac": 32 * n / (walk_ms * 1e-3) / 1e9 / peak if walk_ms and peak else None,
+                     "note": "every step of a walker is one dependent random 32-byte DRAM sector: the sector-level figure is the HBM traffic the walk causes"},
+    }
+    del h_bwt, h_work, d_bwt, host_text
+    eng.release_workspace()
+    torch.cuda.empty_cache()
+    return out
 
 
 def measure_extras(eng, torch, d_text, d_sa, d_bwt, n, stream):
@@ -373,7 +531,8 @@ def measure_extras(eng, torch, d_text, d_sa, d_bwt, n, stream):
 
 
 def run_sharded(args, wl):
-    """ONE text sharded over all ranks (strong scaling): value = n / max-over-ranks time."""
+    """ONE text sharded over all ranks (strong scaling): value = n / max-over-ranks time.  The line also carries configs[2]
+    (2^30-2 ACGT + repeats) and configs[3] (inverse BWT of the 2^30-2 Markov text) on the same N GPUs."""
     import torch
     import torch.distributed as dist
     from msufsort_b200.api import Engine, torch_stream_handle
@@ -383,63 +542,186 @@ def run_sharded(args, wl):
     if args.n:
         n = args.n
     world = int(os.environ["WORLD_SIZE"]); rank = int(os.environ["RANK"]); local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — this framework has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     eng = Engine(local_rank)
-    text = gen_text(kind, n)                      # the same text on every rank
-    d_text = torch.from_numpy(text).cuda()
     sorter = ShardedSorter(eng, isa=args.isa)
-    for _ in range(args.warmup):
-        res = sorter.suffix_array_bwt(d_text)
-    dist.barrier(); torch.cuda.synchronize()
-    eng.profile_reset(); eng.set_profiling(True)
-    launches0 = eng.launch_count()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    sampler = ClockSampler(local_rank)
+    stream = torch_stream_handle()
+    peak, peak_src = load_peaks()
+
+    def barrier():
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        tt = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item())
+
+    def sum_over_ranks(x: int) -> int:
+        tt = torch.tensor([x], dtype=torch.int64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.SUM)
+        return int(tt.item())
+
+    def time_sharded(d_text, nn, steps, warmup, sample_clocks):
+        """K sharded SA + BWT steps of d_text: (ms per step, last result, rank-0 profile, launches per step summed over ranks, clocks)"""
+        for _ in range(warmup):
+            res = sorter.suffix_array_bwt(d_text)
+        barrier()
+        eng.profile_reset(); eng.set_profiling(True)
+        l0 = eng.launch_count()
+        sampler = ClockSampler(local_rank)
+        if sample_clocks and rank == 0:
+            sampler.start()
+            time.sleep(0.15)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        ev0.record()
+        for _ in range(steps):
+            res = sorter.suffix_array_bwt(d_text)
+        ev1.record()
+        barrier()
+        ms = max_over_ranks(ev0.elapsed_time(ev1)) / steps
+        clocks = sampler.stop() if sample_clocks and rank == 0 else None
+        prof = eng.profile(); eng.set_profiling(False)
+        launches = sum_over_ranks(eng.launch_count() - l0) // steps
+        # correctness outside the timed region: assemble the SA and let the GPU validator judge it
+        full_sa = sorter.gather_sa(res)
+        bad = eng.check_suffix_array_dev(d_text, nn, full_sa, stream)
+        if bad != 0:
+            raise SystemExit(f"bench.py: sharded SA has {bad} bad rows")
+        del full_sa
+        return ms, res, prof, launches, clocks
+
+    # ---- headline: the BASELINE.json configs[1] text, sharded
+    host_text = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+    np.copyto(host_text.numpy(), gen_text(kind, n))            # the same text on every rank
+    d_text = host_text.cuda()
+    ms_per_step, res, prof, launches, clocks = time_sharded(d_text, n, args.steps, args.warmup, True)
+    counts = sorter.owned_counts(res)
+    nvlink_bytes = res.exchanged_bytes
+    # end to end with host buffers: every rank uploads the text over its own PCIe link, the results leave as disjoint slices
+    h_sa = torch.empty(n + 1, dtype=torch.int32, pin_memory=True)
+    h_bwt = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+    e2e_times = []
+    for it in range(1 + args.steps):
+        barrier()
+        t0 = time.perf_counter()
+        r2 = sorter.suffix_array_bwt_host(host_text, h_sa, h_bwt)
+        dt = time.perf_counter() - t0
+        if it >= 1:
+            e2e_times.append(dt)
+    e2e_s = max_over_ranks(sum(e2e_times) / len(e2e_times))
+    slice_rows, slice_bytes = r2.row_end - r2.row_begin, r2.out_end - r2.out_begin
+    assert bool(torch.equal(h_sa[r2.row_begin:r2.row_end].cuda(), res.sa[res.row_begin:res.row_end]))
+    d2h_total = sum_over_ranks(4 * slice_rows + slice_bytes)
+    del h_sa, h_bwt, d_text, host_text, res, r2
+    eng.release_workspace()
+    torch.cuda.empty_cache()
+
+    # ---- configs[2]: 2^30-2 ACGT bases with repeats on the same GPUs
+    big = None
+    if not args.no_big:
+        try:
+            k2, n2, d2 = WORKLOADS["acgt_1GiB"]
+            if args.big_n:
+                n2 = args.big_n
+            d_big = torch.from_numpy(gen_text(k2, n2)).cuda()
+            ms2, res2, prof2, launches2, _ = time_sharded(d_big, n2, max(1, min(args.steps, 3)), 1, False)
+            big = {"workload": "acgt_1GiB", "description": d2, "n_bytes": n2, "value": n2 / (ms2 * 1e-3) / 1e6, "unit": "MB/s", "ms_per_step": ms2,
+                   "rounds": res2.rounds, "owned_suffixes_per_rank": sorter.owned_counts(res2), "gpu_launches": int(launches2),
+                   "nvlink_bytes_stored_by_rank0_per_step": res2.exchanged_bytes,
+                   "single_gpu_ms_round1": 141.0,
+                   "phases_rank0_ms": {k: v["ms"] / max(1, min(args.steps, 3)) for k, v in prof2["phases"].items() if v["launches"]}}
+            del d_big, res2
+            eng.release_workspace()
+            torch.cuda.empty_cache()
+        except Exception as exc:
+            # a rank that fails in the middle of a collective sequence cannot rejoin its peers: the whole job stops (torchrun
+            # then ends the other ranks) instead of hanging at the next barrier
+            sys.stderr.write(f"bench.py: rank {rank}: sharded configs[2] run failed: {exc}\n")
+            sys.stderr.flush()
+            os._exit(1)
+
+    # ---- configs[3]: inverse BWT of the 2^30-2 byte Markov text, walkers split over the ranks
+    unbwt = None
+    if not args.no_unbwt:
+        k3, n3, d3 = WORKLOADS[UNBWT_WORKLOAD]
+        if args.unbwt_n:
+            n3 = args.unbwt_n
+        d_t3 = torch.from_numpy(gen_text(k3, n3)).cuda()
+        r3 = sorter.suffix_array_bwt(d_t3)                       # the verified forward path produces the input
+        d_b3 = sorter.gather_bwt(r3)
+        s3 = r3.sentinel
+        del r3
+        eng.release_workspace()
+        torch.cuda.empty_cache()
+        back = sorter.inverse_bwt(d_b3, s3)
+        barrier()
+        usteps = max(1, min(args.steps, 5))
+        eng.profile_reset(); eng.set_profiling(True)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        ev0.record()
+        for _ in range(usteps):
+            back = sorter.inverse_bwt(d_b3, s3)
+        ev1.record()
+        barrier()
+        ms3 = max_over_ranks(ev0.elapsed_time(ev1)) / usteps
+        prof3 = eng.profile(); eng.set_profiling(False)
+        if not bool(torch.equal(back, d_t3)):
+            raise SystemExit("bench.py: the sharded inverse BWT did not restore the text")
+        unbwt = {"metric": "unbwt_input_throughput", "value": n3 / (ms3 * 1e-3) / 1e6, "unit": "MB/s", "ms_per_step": ms3, "n_bytes": n3,
+                 "config": {"workload": UNBWT_WORKLOAD + "_unbwt", "parallelism": f"psi table on every GPU, walkers split over {world} GPUs, bytes stored into the "
+                            "owner of their text position over NVLink, slices pulled from the peers (every rank ends with the whole text)"},
+                 "phases_rank0_ms": {"build": prof3["phases"]["unbwt_build"]["ms"] / usteps, "walk": prof3["phases"]["unbwt_walk"]["ms"] / usteps}}
+        del back, d_b3, d_t3
+
     if rank == 0:
-        sampler.start()
-    dist.barrier(); torch.cuda.synchronize()
-    ev0.record()
-    for _ in range(args.steps):
-        res = sorter.suffix_array_bwt(d_text)
-    ev1.record()
-    dist.barrier(); torch.cuda.synchronize()
-    ms = ev0.elapsed_time(ev1)
-    tt = torch.tensor([ms], dtype=torch.float64, device="cuda")
-    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    ms = float(tt.item())
-    clocks = sampler.stop() if rank == 0 else None
-    prof = eng.profile(); eng.set_profiling(False)
-    launches = eng.launch_count() - launches0
-    # correctness outside the timed region: assemble the SA and let the GPU validator judge it
-    full_sa = sorter.gather_sa(res)
-    bad = eng.check_suffix_array_dev(d_text, n, full_sa, torch_stream_handle())
-    if bad != 0:
-        raise SystemExit(f"bench.py: sharded SA has {bad} bad rows")
-    if rank == 0:
-        peak, peak_src = load_peaks()
         sp = prof["phases"]["sort_pass"]
         achieved = sp["alg_bytes"] / (sp["ms"] * 1e-3) / 1e9 if sp["ms"] > 0 else 0.0
-        ms_per_step = ms / args.steps
+        kernel_ms = sum(v["ms"] for v in prof["phases"].values()) / args.steps
         line = {
             "metric": "sa_bwt_input_throughput", "value": n / (ms_per_step * 1e-3) / 1e6, "unit": "MB/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "u8/int32 (u64 sort keys)", "data": "synthetic",
-            "config": {"workload": wl, "description": desc, "n_bytes": n, "parallelism": f"one text sharded by key range over {world} GPUs, ISA {args.isa}",
-                       "owned_suffixes_per_rank": res.counts, "rounds": res.rounds,
-                       "nccl_bytes_received_per_rank_per_step": res.exchanged_bytes},
-            "e2e": None, "gpu_launches": int(launches),
+            "config": {"workload": wl, "description": desc, "n_bytes": n,
+                       "parallelism": f"one text sharded by key range over {world} GPUs, ISA {args.isa}"
+                                      + (" (NVLink peer memory; round loop in C++, control plane = shared-memory barriers)" if args.isa == "peer" else " (NCCL)"),
+                       "l2": "working set per GPU (>= 44 n / N bytes + the n-byte text) far larger than the 126 MB L2; no flush needed",
+                       "owned_suffixes_per_rank": counts, "rounds": rounds_of(prof, args.steps)},
+            "e2e": {"value": n / e2e_s / 1e6, "unit": "MB/s", "ms_per_step": e2e_s * 1e3, "h2d_bytes_per_step": world * n, "d2h_bytes_per_step": d2h_total,
+                    "path": "ShardedSorter.suffix_array_bwt_host: pinned host text uploaded by every rank, b200sa_shard_sort, every rank downloads its rows of the "
+                            "suffix array and its bytes of the BWT"},
+            "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "k_onesweep_pass<u64> (rank 0)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak if peak else None, "traffic": None, "peak_source": peak_src},
+                         "frac": achieved / peak if peak else None, "traffic": None, "peak_source": peak_src,
+                         "launches": int(sp["launches"]), "avg_launch_ms": sp["ms"] / sp["launches"] if sp["launches"] else None},
+            "nvlink": {"bytes_stored_by_rank0_per_step": nvlink_bytes,
+                       "GBps_rank0_over_isa_phase": nvlink_bytes / (prof["phases"]["isa"]["ms"] / args.steps * 1e-3) / 1e9 if prof["phases"]["isa"]["ms"] else None,
+                       "peak_GBps_per_direction": 900.0,
+                       "note": "new (suffix, rank) pairs stored in bulk into the owners' inboxes; rank[suffix + h] is loaded from the owners' HBM by the "
+                               "group-sort / key-build kernels (4-byte remote loads, not counted here)"},
+            "limiter": {"kernel_ms_rank0": kernel_ms, "step_ms": ms_per_step, "kernel_share": kernel_ms / ms_per_step if ms_per_step else None,
+                        "note": "step - kernels = host round trips per doubling round (counter read-backs, 2 barriers) + waiting for the slowest rank"},
             "cpu_baseline": None, "clocks": clocks,
             "phases_rank0": {k: {"ms_per_step": v["ms"] / args.steps, "launches_per_step": v["launches"] / args.steps}
                              for k, v in prof["phases"].items() if v["launches"]},
+            "sharded_1GiB": big,
+            "unbwt": unbwt,
         }
         print(json.dumps(line))
     dist.barrier()
+    sorter.close()
     eng.close()
     dist.destroy_process_group()
     return 0
+
+
+def rounds_of(prof, steps):
+    return prof["rounds"] / steps
 
 
 def main():
@@ -450,18 +732,31 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="markov3_256MiB", choices=sorted(WORKLOADS))
     ap.add_argument("--n", type=int, default=0, help="override the text size (debugging)")
+    ap.add_argument("--big-n", type=int, default=0, help="override the size of the sharded configs[2] text (debugging)")
+    ap.add_argument("--unbwt-n", type=int, default=0, help="override the size of the inverse-BWT text (debugging)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the LCP / batched-blocks timings appended as 'extras'")
-    ap.add_argument("--isa", default="owner", choices=["owner", "replicated", "peer"], help="sharded mode: how the ISA travels (see msufsort_b200/sharded.py)")
-    ap.add_argument("--mode", default="independent", choices=["independent", "sharded"],
-                    help="N>1 only. independent (default): one text per GPU, no data-path collective, weak scaling. "
-                         "sharded: ONE text partitioned by key range over the N GPUs, ISA updates all-gathered over NCCL "
-                         "after every doubling round, strong scaling (north_star item 4)")
+    ap.add_argument("--no-facade", action="store_true", help="skip the C++ facade end-to-end run ('e2e_facade')")
+    ap.add_argument("--no-unbwt", action="store_true", help="skip the inverse-BWT record ('unbwt')")
+    ap.add_argument("--no-big", action="store_true", help="N>1: skip the 2^30-2 ACGT record ('sharded_1GiB')")
+    ap.add_argument("--isa", default="peer", choices=["owner", "replicated", "peer"], help="sharded mode: how the ISA travels (see msufsort_b200/sharded.py)")
+    ap.add_argument("--mode", default="sharded", choices=["independent", "sharded"],
+                    help="N>1 only. sharded (default): ONE text partitioned by key range over the N GPUs, the inverse suffix array in "
+                         "NVLink peer memory, strong scaling (north_star item 4). independent: one text per GPU, no data-path exchange, "
+                         "weak scaling (batches of independent blocks)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args, args.workload)
     if args.mode == "sharded" and int(os.environ.get("WORLD_SIZE", "1")) > 1:
-        return run_sharded(args, args.workload)
+        try:
+            return run_sharded(args, args.workload)
+        except BaseException as exc:  # see run_sharded: never leave the peers waiting at a barrier
+            if isinstance(exc, SystemExit) and exc.code in (0, None):
+                raise
+            import traceback
+            traceback.print_exc()
+            sys.stderr.flush()
+            os._exit(1)
     return run_ours(args, args.workload)
 
 

@@ -299,6 +299,51 @@ B200SA_API int b200sa_unbwt_shard_segments(b200sa_ctx* ctx, int direction, int64
                                            uint32_t* d_len, uint32_t* d_next, void* stream);
 B200SA_API int b200sa_unbwt_shard_finish(b200sa_ctx* ctx, int64_t w_begin, int64_t w_end, uint8_t* d_text_out, void* stream);
 
+/* ---- one text over the GPUs of one box, driven from C++ (replaces the reference's static split of the
+ * text over its worker threads, msufsort.cpp:1576-1586, 1635-1643, and is what its numThreads knob, msufsort.h:50-53,
+ * 432-445, maps to here) ------------------------------------------------------------------------------------------
+ * Every GPU holds the text and sorts one key range of the suffixes (whole groups, so all later sorts are local); the
+ * inverse suffix array is sharded by text position and read / written through NVLink peer memory (CUDA IPC between
+ * processes, plain peer pointers inside one process).  The control plane — two barriers and one sum per doubling round
+ * — is a b200sa_comm: words in memory all ranks map, no collective library.
+ *
+ * b200sa_group_*: the whole thing behind one call with host buffers, one host thread + one context per listed device
+ * (a device may be listed several times: that is how the single-GPU test tier drives the sharded path).  The results
+ * leave the GPUs as disjoint slices over all PCIe links.  Texts shorter than 4096 bytes per GPU take one GPU. */
+typedef struct b200sa_group b200sa_group;
+B200SA_API int b200sa_group_create(b200sa_group** out, const int* devices, int count);
+B200SA_API void b200sa_group_destroy(b200sa_group* g);
+B200SA_API int b200sa_group_size(b200sa_group* g);
+B200SA_API b200sa_ctx* b200sa_group_context(b200sa_group* g, int rank);
+/* Replace make_suffix_array / forward_ / reverse_burrows_wheeler_transform exactly like the single-context calls above. */
+B200SA_API int b200sa_group_suffix_array(b200sa_group* g, const uint8_t* text, int64_t n, int32_t* sa_out);
+B200SA_API int b200sa_group_bwt(b200sa_group* g, uint8_t* text_inout, int64_t n, int32_t* sentinel_index_out);
+B200SA_API int b200sa_group_suffix_array_bwt(b200sa_group* g, const uint8_t* text, int64_t n, int32_t* sa_out, uint8_t* bwt_out,
+                                             int32_t* sentinel_index_out);
+B200SA_API int b200sa_group_unbwt(b200sa_group* g, uint8_t* bwt_inout, int64_t n, int32_t sentinel_index);
+
+/* The same with the caller owning the ranks (one process per GPU under torchrun: msufsort_b200/sharded.py, bench.py).
+ * b200sa_comm_create_local: nranks handles for the threads of one process.  b200sa_comm_create_shm: rank 0 creates the
+ * POSIX shared-memory segment `name` ("/..."; pick a fresh name per job), the other processes of the node attach to it.
+ * Collectives have a deadline (B200SA_COMM_TIMEOUT_MS, default 120 s) and fail with B200SA_ECOMM once any rank failed. */
+typedef struct b200sa_comm b200sa_comm;
+B200SA_API int b200sa_comm_create_local(b200sa_comm** out /* [nranks] */, int nranks);
+B200SA_API int b200sa_comm_create_shm(b200sa_comm** out, const char* name, int rank, int nranks);
+B200SA_API void b200sa_comm_destroy(b200sa_comm* comm);
+B200SA_API int b200sa_comm_barrier(b200sa_comm* comm);
+B200SA_API int b200sa_comm_allreduce_sum(b200sa_comm* comm, int64_t value, int64_t* sum_out);
+/* Collective over the ranks of `comm` (each with its own context and the same text in its HBM).  d_sa: n+1 int32, d_bwt
+ * (may be NULL): n bytes — both full-size on every rank; on return this rank holds rows [info[0], info[1]) of the suffix
+ * array and bytes [info[2], info[3]) of the BWT.  info_out: 8 words = row_begin, row_end, out_begin, out_end, sentinel
+ * index, doubling rounds, bytes this rank stored into peer memory, suffixes owned. */
+B200SA_API int b200sa_shard_sort(b200sa_ctx* ctx, b200sa_comm* comm, const uint8_t* d_text, int64_t n, int32_t* d_sa, uint8_t* d_bwt,
+                                 int64_t* info_out, void* stream);
+/* Collective inverse BWT: walkers split over the ranks, bytes stored into the owner of their text position over NVLink.
+ * This rank owns text bytes [*slice_begin_out, *slice_end_out); they are copied to d_text_out (may be NULL) at their text
+ * offsets.  gather_all != 0: the other slices are pulled from the peers as well, d_text_out holds the whole text. */
+B200SA_API int b200sa_shard_unbwt(b200sa_ctx* ctx, b200sa_comm* comm, const uint8_t* d_bwt, int64_t n, int32_t sentinel_index,
+                                  uint8_t* d_text_out, int gather_all, int64_t* slice_begin_out, int64_t* slice_end_out, void* stream);
+
 /* ---- instrumentation --------------------------------------------------------------------- */
 
 enum {

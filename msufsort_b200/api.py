@@ -106,6 +106,21 @@ ABI = [
     ("b200sa_unbwt_shard_measure", C.c_int, [_P, C.c_int64, C.c_int64, _P]),
     ("b200sa_unbwt_shard_segments", C.c_int, [_P, C.c_int, C.c_int64, C.c_int64, _P, _P, _P]),
     ("b200sa_unbwt_shard_finish", C.c_int, [_P, C.c_int64, C.c_int64, _P, _P]),
+    ("b200sa_group_create", C.c_int, [C.POINTER(_P), C.POINTER(C.c_int), C.c_int]),
+    ("b200sa_group_destroy", None, [_P]),
+    ("b200sa_group_size", C.c_int, [_P]),
+    ("b200sa_group_context", _P, [_P, C.c_int]),
+    ("b200sa_group_suffix_array", C.c_int, [_P, _P, C.c_int64, _P]),
+    ("b200sa_group_bwt", C.c_int, [_P, _P, C.c_int64, C.POINTER(C.c_int32)]),
+    ("b200sa_group_suffix_array_bwt", C.c_int, [_P, _P, C.c_int64, _P, _P, C.POINTER(C.c_int32)]),
+    ("b200sa_group_unbwt", C.c_int, [_P, _P, C.c_int64, C.c_int32]),
+    ("b200sa_comm_create_local", C.c_int, [C.POINTER(_P), C.c_int]),
+    ("b200sa_comm_create_shm", C.c_int, [C.POINTER(_P), C.c_char_p, C.c_int, C.c_int]),
+    ("b200sa_comm_destroy", None, [_P]),
+    ("b200sa_comm_barrier", C.c_int, [_P]),
+    ("b200sa_comm_allreduce_sum", C.c_int, [_P, C.c_int64, C.POINTER(C.c_int64)]),
+    ("b200sa_shard_sort", C.c_int, [_P, _P, _P, C.c_int64, _P, _P, C.POINTER(C.c_int64), _P]),
+    ("b200sa_shard_unbwt", C.c_int, [_P, _P, _P, C.c_int64, C.c_int32, _P, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64), _P]),
     ("b200sa_set_profiling", C.c_int, [_P, C.c_int]),
     ("b200sa_profile_reset", C.c_int, [_P]),
     ("b200sa_profile_get", C.c_int, [_P, C.POINTER(_Profile)]),
@@ -418,6 +433,21 @@ class Engine:
                                                                  m, begin_bit, end_bit, C.byref(side), self._st(stream)))
         return int(side.value)
 
+    # ---- one text over several GPUs, round loop in C++ (include/b200sa.h "driven from C++") -------------------
+    def shard_sort(self, comm: "Comm", d_text, n: int, d_sa, d_bwt=None, stream: Optional[int] = None) -> dict:
+        """collective over the ranks of ``comm``; returns this rank's row / byte ranges and counters"""
+        info = (C.c_int64 * 8)()
+        self.lib.check(self.lib.cdll.b200sa_shard_sort(self._ctx, comm._c, _ptr(d_text), n, _ptr(d_sa), _ptr(d_bwt), info, self._st(stream)))
+        keys = ("row_begin", "row_end", "out_begin", "out_end", "sentinel", "rounds", "sent_bytes", "n_local")
+        return dict(zip(keys, (int(v) for v in info)))
+
+    def shard_unbwt(self, comm: "Comm", d_bwt, n: int, sentinel_index: int, d_out, gather_all: bool = True, stream: Optional[int] = None):
+        """collective inverse BWT; returns the text range [begin, end) this rank owns"""
+        b, e = C.c_int64(0), C.c_int64(0)
+        self.lib.check(self.lib.cdll.b200sa_shard_unbwt(self._ctx, comm._c, _ptr(d_bwt), n, int(sentinel_index), _ptr(d_out), 1 if gather_all else 0,
+                                                        C.byref(b), C.byref(e), self._st(stream)))
+        return int(b.value), int(e.value)
+
     # ---- sharded building blocks (see msufsort_b200/sharded.py) ----------------------------------
     def shard_begin(self, d_text, n: int, d_sa, part: int, nparts: int, stream: Optional[int] = None) -> int:
         out = C.c_int64(0)
@@ -523,6 +553,92 @@ class Engine:
 
     def release_workspace(self) -> None:
         self.lib.check(self.lib.cdll.b200sa_release_workspace(self._ctx))
+
+
+class Comm:
+    """Control plane of a sharded run (include/b200sa.h b200sa_comm_*): barriers and sums through memory all ranks map."""
+
+    def __init__(self, handle, library: Library):
+        self._c = handle
+        self.lib = library
+
+    @classmethod
+    def local(cls, nranks: int, library: Optional[Library] = None) -> list:
+        """``nranks`` handles for the threads of this process"""
+        lib = library if library is not None else load_library()
+        arr = (_P * nranks)()
+        lib.check(lib.cdll.b200sa_comm_create_local(arr, nranks))
+        return [cls(_P(arr[r]), lib) for r in range(nranks)]
+
+    @classmethod
+    def shared_memory(cls, name: str, rank: int, nranks: int, library: Optional[Library] = None) -> "Comm":
+        """the processes of one node; ``name`` = a fresh POSIX shared-memory name starting with '/'"""
+        lib = library if library is not None else load_library()
+        h = _P()
+        lib.check(lib.cdll.b200sa_comm_create_shm(C.byref(h), name.encode(), rank, nranks))
+        return cls(h, lib)
+
+    def barrier(self) -> None:
+        self.lib.check(self.lib.cdll.b200sa_comm_barrier(self._c))
+
+    def allreduce_sum(self, value: int) -> int:
+        out = C.c_int64(0)
+        self.lib.check(self.lib.cdll.b200sa_comm_allreduce_sum(self._c, int(value), C.byref(out)))
+        return int(out.value)
+
+    def close(self) -> None:
+        if getattr(self, "_c", None):
+            self.lib.cdll.b200sa_comm_destroy(self._c)
+            self._c = None
+
+
+class Group:
+    """Several GPUs behind the reference's three calls (include/b200sa.h b200sa_group_*): one host thread and one context
+    per listed device, one text sharded over them.  ``devices`` may list a device more than once."""
+
+    def __init__(self, devices, library: Optional[Library] = None):
+        self.lib = library if library is not None else load_library()
+        devs = (C.c_int * len(devices))(*devices)
+        self._g = _P()
+        self.lib.check(self.lib.cdll.b200sa_group_create(C.byref(self._g), devs, len(devices)))
+        self.size = len(devices)
+
+    def make_suffix_array(self, data) -> np.ndarray:
+        buf = np.ascontiguousarray(np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else data)
+        sa = np.empty(buf.size + 1, dtype=np.int32)
+        self.lib.check(self.lib.cdll.b200sa_group_suffix_array(self._g, _ptr(buf) if buf.size else None, buf.size, _ptr(sa)))
+        return sa
+
+    def forward_burrows_wheeler_transform(self, buf: np.ndarray) -> int:
+        s = C.c_int32(0)
+        self.lib.check(self.lib.cdll.b200sa_group_bwt(self._g, _ptr(buf) if buf.size else None, buf.size, C.byref(s)))
+        return int(s.value)
+
+    def suffix_array_and_bwt(self, data):
+        buf = np.ascontiguousarray(np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else data)
+        sa = np.empty(buf.size + 1, dtype=np.int32)
+        bwt = np.empty(buf.size, dtype=np.uint8)
+        s = C.c_int32(0)
+        self.lib.check(self.lib.cdll.b200sa_group_suffix_array_bwt(self._g, _ptr(buf) if buf.size else None, buf.size, _ptr(sa),
+                                                                   _ptr(bwt) if buf.size else None, C.byref(s)))
+        return sa, bwt, int(s.value)
+
+    def reverse_burrows_wheeler_transform(self, buf: np.ndarray, sentinel_index: int) -> None:
+        self.lib.check(self.lib.cdll.b200sa_group_unbwt(self._g, _ptr(buf) if buf.size else None, buf.size, int(sentinel_index)))
+
+    def launch_count(self) -> int:
+        return sum(int(self.lib.cdll.b200sa_launch_count(self.lib.cdll.b200sa_group_context(self._g, r))) for r in range(self.size))
+
+    def close(self) -> None:
+        if getattr(self, "_g", None):
+            self.lib.cdll.b200sa_group_destroy(self._g)
+            self._g = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class Pipeline:

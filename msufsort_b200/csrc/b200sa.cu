@@ -132,6 +132,7 @@ int Engine::init(int dev)
     if (const char* e12 = getenv("B200SA_LCP_DIRECT")) lcp_direct = atoi(e12) != 0;
     if (const char* e11 = getenv("B200SA_NUM_SMS")) { const int v = atoi(e11); if (v >= 1 && v <= 1024) num_sms = v; }  // tests: small persistent grids
     if (const char* e13 = getenv("B200SA_COPY_THREADS")) copy_threads = atoi(e13);
+    if (const char* e14 = getenv("B200SA_BWT_SCATTER_MIN")) bwt_scatter_min = (size_t)strtoull(e14, nullptr, 10);
     if (const char* e6 = getenv("B200SA_UNBWT_CAP_MULT")) unbwt_cap_mult = (u32)strtoul(e6, nullptr, 10);
     if (unbwt_cap_mult < 1) unbwt_cap_mult = 1;
     if (groupsort_tiny > (u32)GS_TINY) groupsort_tiny = GS_TINY;
@@ -140,6 +141,8 @@ int Engine::init(int dev)
     {
         auto k64 = k_onesweep_pass<u64, true>;
         auto k8 = k_onesweep_pass<u8, false>;
+        auto k32b = k_onesweep_pass<u32, true, u8>;
+        B200SA_CU(cudaFuncSetAttribute(k32b, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_pass_smem_bytes<u32>()));
         auto k32 = k_onesweep_pass<u32, true>;
         B200SA_CU(cudaFuncSetAttribute(k32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_pass_smem_bytes<u32>()));
         B200SA_CU(cudaFuncSetAttribute(k64, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_pass_smem_bytes<u64>()));
@@ -156,6 +159,7 @@ int Engine::release_workspace()
     misc.release(); text_ws.release(); bwt_ws.release(); walk.release();
     batch_text.release(); batch_meta.release(); batch_out.release();
     peer_inbox.release();
+    peer_out.release();
     return 0;
 }
 
@@ -538,71 +542,64 @@ int Engine::sort_begin(const u8* d_text, u32 n, i32* d_sa, int part, int nparts,
     B200SA_TRY(phase_begin(B200SA_PH_ALPHABET, st));
     B200SA_CU(cudaMemsetAsync(d_hist, 0, 256 * sizeof(u32), st));
     prof.memsets++;
+    // a rank of a sharded sort driven by sharded_sort() counts only its slice of the text; the counts are summed over the ranks
+    const bool split_hist = shard_comm != nullptr && nparts > 1;
+    const u64 h_lo = split_hist ? (u64)n * (u64)part / (u64)nparts : 0ull;
+    const u64 h_hi = split_hist ? (u64)n * (u64)(part + 1) / (u64)nparts : (u64)n;
     {
-        const u64 nvec = (u64)n / 16 + 1;
+        const u64 nvec = (h_hi - h_lo) / 16 + 1;
         const u32 grid = (u32)(div_up_u64(nvec, BH_THREADS) < (u64)(num_sms * 8) ? div_up_u64(nvec, BH_THREADS) : (u64)(num_sms * 8));
-        B200SA_LAUNCH(k_byte_hist, grid, BH_THREADS, 0, st, d_text, (u64)n, d_hist);
+        B200SA_LAUNCH(k_byte_hist, grid, BH_THREADS, 0, st, d_text + h_lo, h_hi - h_lo, d_hist);
         count_launch(B200SA_PH_ALPHABET);
     }
     B200SA_TRY(phase_end(st));
-    prof.alg_bytes[B200SA_PH_ALPHABET] += n;
+    prof.alg_bytes[B200SA_PH_ALPHABET] += h_hi - h_lo;
     u32 h_hist[256];
     B200SA_CU(cudaMemcpyAsync(h_hist, d_hist, sizeof(h_hist), cudaMemcpyDeviceToHost, st));
     B200SA_CU(cudaStreamSynchronize(st));
+    if (split_hist) {
+        static_assert(sizeof(h_hist) <= (size_t)kCommSlotBytes, "histogram fits a comm slot");
+        std::vector<u32> all((size_t)256 * nparts);
+        B200SA_TRY(shard_comm->allgather(h_hist, sizeof(h_hist), all.data()));
+        for (int c = 0; c < 256; ++c) {
+            u32 t = 0;
+            for (int g = 0; g < nparts; ++g) t += all[(size_t)g * 256 + c];
+            h_hist[c] = t;
+        }
+    }
     if (ss.batch_count) h_hist[0] -= ss.batch_count;  // the separator slots of a batch are not symbols
     ss.plan = plan_alphabet(h_hist, ss.batch_bits, max_key_bits, pack_radix);
     const AlphabetPlan& plan = ss.plan;
     B200SA_CU(cudaMemcpyAsync(d_code, plan.code, 256, cudaMemcpyHostToDevice, st));
 
-    // ---- initial keys for every suffix
+    // ---- initial keys
     B200SA_LAUNCH(k_sa_init, 1, 32, 0, st, rank.as<u32>(), d_sa, n);
     count_launch(B200SA_PH_PACK);
-    B200SA_TRY(phase_begin(B200SA_PH_PACK, st));
-    {
-        const u32 tiles = (u32)div_up_u64(n, PK_TILE);
-        const u32 grid = tiles < (u32)(num_sms * 4) ? tiles : (u32)(num_sms * 4);
-        if (plan.radix) {
-            u64* d_pow = (u64*)(misc.as<u32>() + 320);  // 66 words of u64 behind the symbol codes
-            B200SA_CU(cudaMemcpyAsync(d_pow, plan.pow, sizeof(plan.pow), cudaMemcpyHostToDevice, st));
-            if (ss.batch_count) {
-                auto kp = k_pack_keys_batch<true>;
-                B200SA_LAUNCH(kp, grid, PK_THREADS, 0, st, d_text, n, (const u8*)d_code, plan.key_bits, plan.k, 0, plan.radix, (const u64*)d_pow,
-                              ss.batch_ends, ss.batch_count, keys[0].as<u64>());
-            } else {
-                auto kp = k_pack_keys<true>;
-                B200SA_LAUNCH(kp, grid, PK_THREADS, 0, st, d_text, n, (const u8*)d_code, 0, plan.k, 0, plan.radix, plan.pow[plan.k - 1], keys[0].as<u64>());
-            }
-        } else if (ss.batch_count) {
-            auto kp = k_pack_keys_batch<false>;
-            B200SA_LAUNCH(kp, grid, PK_THREADS, 0, st, d_text, n, (const u8*)d_code, plan.bits, plan.k, plan.len_bits, (u64)0, (const u64*)nullptr,
-                          ss.batch_ends, ss.batch_count, keys[0].as<u64>());
-        } else {
-            auto kp = k_pack_keys<false>;
-            B200SA_LAUNCH(kp, grid, PK_THREADS, 0, st, d_text, n, (const u8*)d_code, plan.bits, plan.k, plan.len_bits, (u64)0, (u64)0, keys[0].as<u64>());
-        }
-        count_launch(B200SA_PH_PACK);
-    }
-    B200SA_TRY(phase_end(st));
-    prof.alg_bytes[B200SA_PH_PACK] += (u64)n * 9;
-    B200SA_CU(cudaGetLastError());
-
     u64* k2[2] = {keys[0].as<u64>(), keys[1].as<u64>()};
     u32* v2[2] = {idx[0].as<u32>(), idx[1].as<u32>()};
     const int key_bits = plan.key_bits + ss.batch_bits;
+    const u32 pk_tiles = (u32)div_up_u64(n, PK_TILE);
+    const u32 pk_grid = pk_tiles < (u32)(num_sms * 4) ? pk_tiles : (u32)(num_sms * 4);
+    u64* d_pow = (u64*)(misc.as<u32>() + 320);  // 66 words of u64 behind the symbol codes (mixed-radix keys)
+    if (plan.radix) B200SA_CU(cudaMemcpyAsync(d_pow, plan.pow, sizeof(plan.pow), cudaMemcpyHostToDevice, st));
     int side = 0;
     u32 count = n;
     if (nparts > 1) {
-        // ---- splitters from a sorted sample of the keys (same text + same kernels on every GPU =>
-        // identical splitters everywhere, no communication), then keep only this part's key range
+        // ---- splitters from a sorted regular sample of the keys, then pack only this part's key range
         u32 nsample = n < (1u << 18) ? n : (1u << 18);
         const u32 stride = n / nsample;
-        u64* smp[2] = {(u64*)slot[0].p, (u64*)slot[1].p};  // the slot maps are not in use yet (8 * 2^18 bytes each fits: n >= nsample)
-        B200SA_TRY(slot[0].ensure((size_t)nsample * 8 + 64));
+        B200SA_TRY(slot[0].ensure((size_t)nsample * 8 + 64));  // the slot maps are not in use yet
         B200SA_TRY(slot[1].ensure((size_t)nsample * 8 + 64));
-        smp[0] = (u64*)slot[0].p; smp[1] = (u64*)slot[1].p;
+        u64* smp[2] = {(u64*)slot[0].p, (u64*)slot[1].p};
         B200SA_TRY(agg_max.ensure((size_t)nsample * 8 + 64));
         u32* sv[2] = {agg_max.as<u32>(), agg_max.as<u32>() + nsample};
-        B200SA_LAUNCH(k_sample_keys, (u32)div_up_u64(nsample, 256), 256, 0, st, (const u64*)k2[0], nsample, stride, smp[0]);
+        if (plan.radix) {
+            auto ks = k_sample_keys_text<true>;
+            B200SA_LAUNCH(ks, (u32)div_up_u64(nsample, 256), 256, 0, st, d_text, n, (const u8*)d_code, 0, plan.k, 0, plan.radix, nsample, stride, smp[0]);
+        } else {
+            auto ks = k_sample_keys_text<false>;
+            B200SA_LAUNCH(ks, (u32)div_up_u64(nsample, 256), 256, 0, st, d_text, n, (const u8*)d_code, plan.bits, plan.k, plan.len_bits, (u64)0, nsample, stride, smp[0]);
+        }
         count_launch(B200SA_PH_PACK);
         int sside = 0;
         B200SA_TRY(radix_sort_pairs(smp, sv, true, nsample, 0, key_bits, &sside, st));
@@ -611,19 +608,27 @@ int Engine::sort_begin(const u8* d_text, u32 n, i32* d_sa, int part, int nparts,
         B200SA_CU(cudaStreamSynchronize(st));
         const u64 lo = part == 0 ? 0ull : h_sample[(size_t)((u64)part * nsample / nparts)];
         const u64 hi = part == nparts - 1 ? ~0ull : h_sample[(size_t)((u64)(part + 1) * nsample / nparts)];
-        const bool hi_inclusive = part == nparts - 1;
+        const int hi_inclusive = part == nparts - 1 ? 1 : 0;
         u32* d_count = misc.as<u32>() + 536;
         B200SA_CU(cudaMemsetAsync(d_count, 0, 4, st));
         prof.memsets++;
         B200SA_TRY(phase_begin(B200SA_PH_PACK, st));
-        B200SA_LAUNCH(k_filter_range, (u32)div_up_u64(n, FR_THREADS * FR_IPT), FR_THREADS, 0, st, (const u64*)k2[0], n, lo, hi,
-                      hi_inclusive ? 1 : 0, k2[1], v2[1], d_count);
+        if (plan.radix) {
+            auto kp = k_pack_keys<true, true>;
+            B200SA_LAUNCH(kp, pk_grid, PK_THREADS, 0, st, d_text, n, (const u8*)d_code, 0, plan.k, 0, plan.radix, plan.pow[plan.k - 1], k2[1],
+                          lo, hi, hi_inclusive, v2[1], d_count);
+        } else {
+            auto kp = k_pack_keys<false, true>;
+            B200SA_LAUNCH(kp, pk_grid, PK_THREADS, 0, st, d_text, n, (const u8*)d_code, plan.bits, plan.k, plan.len_bits, (u64)0, (u64)0, k2[1],
+                          lo, hi, hi_inclusive, v2[1], d_count);
+        }
         count_launch(B200SA_PH_PACK);
         B200SA_TRY(phase_end(st));
+        B200SA_CU(cudaGetLastError());
         B200SA_CU(cudaMemcpyAsync(h_pinned + 16, d_count, 4, cudaMemcpyDeviceToHost, st));
         B200SA_CU(cudaStreamSynchronize(st));
         count = h_pinned[16];
-        prof.alg_bytes[B200SA_PH_PACK] += (u64)n * 8 + (u64)count * 12;
+        prof.alg_bytes[B200SA_PH_PACK] += (u64)n + (u64)count * 12;
         // sort this part: input on side 1
         u64* kk[2] = {k2[1], k2[0]};
         u32* vv[2] = {v2[1], v2[0]};
@@ -631,6 +636,30 @@ int Engine::sort_begin(const u8* d_text, u32 n, i32* d_sa, int part, int nparts,
         B200SA_TRY(radix_sort_pairs(kk, vv, false, count, 0, key_bits, &rs, st));
         side = 1 ^ rs;
     } else {
+        B200SA_TRY(phase_begin(B200SA_PH_PACK, st));
+        if (plan.radix) {
+            if (ss.batch_count) {
+                auto kp = k_pack_keys_batch<true>;
+                B200SA_LAUNCH(kp, pk_grid, PK_THREADS, 0, st, d_text, n, (const u8*)d_code, plan.key_bits, plan.k, 0, plan.radix, (const u64*)d_pow,
+                              ss.batch_ends, ss.batch_count, k2[0]);
+            } else {
+                auto kp = k_pack_keys<true, false>;
+                B200SA_LAUNCH(kp, pk_grid, PK_THREADS, 0, st, d_text, n, (const u8*)d_code, 0, plan.k, 0, plan.radix, plan.pow[plan.k - 1], k2[0],
+                              (u64)0, (u64)0, 0, (u32*)nullptr, (u32*)nullptr);
+            }
+        } else if (ss.batch_count) {
+            auto kp = k_pack_keys_batch<false>;
+            B200SA_LAUNCH(kp, pk_grid, PK_THREADS, 0, st, d_text, n, (const u8*)d_code, plan.bits, plan.k, plan.len_bits, (u64)0, (const u64*)nullptr,
+                          ss.batch_ends, ss.batch_count, k2[0]);
+        } else {
+            auto kp = k_pack_keys<false, false>;
+            B200SA_LAUNCH(kp, pk_grid, PK_THREADS, 0, st, d_text, n, (const u8*)d_code, plan.bits, plan.k, plan.len_bits, (u64)0, (u64)0, k2[0],
+                          (u64)0, (u64)0, 0, (u32*)nullptr, (u32*)nullptr);
+        }
+        count_launch(B200SA_PH_PACK);
+        B200SA_TRY(phase_end(st));
+        prof.alg_bytes[B200SA_PH_PACK] += (u64)n * 9;
+        B200SA_CU(cudaGetLastError());
         B200SA_TRY(radix_sort_pairs(k2, v2, true, n, 0, key_bits, &side, st));
     }
     prof.rounds++;
@@ -678,7 +707,7 @@ int Engine::sort_round(u32* m_local, cudaStream_t st)
     const int gid_bits = ss.groups <= 1 ? 0 : bit_length_u64((u64)ss.groups - 1);
     int sorted_side = -1;
     // where rank[suffix + h] is read from: this GPU's array, or the shards of all GPUs through peer memory
-    const bool use_peer = peer.active && ss.nparts > 1;
+    const bool use_peer = peer.active && peer.has_isa && ss.nparts > 1;
     if (use_peer && (peer.view.n != n || peer.nparts != ss.nparts)) return set_error(B200SA_EINVAL, "peer ISA attached for another text size / GPU count");
     LocalRank local_rank{rank.as<u32>(), n};
     PeerRank peer_rank{peer.view};
@@ -835,13 +864,51 @@ int Engine::suffix_array_dev(const u8* d_text, i64 n64, i32* d_sa, cudaStream_t 
 int Engine::bwt_rows(const u8* d_text, u32 n, const i32* d_sa, u32 o_begin, u32 o_end, u8* d_bwt, cudaStream_t st, bool defer_sync)
 {
     i32* d_sent = (i32*)(misc.as<u32>() + 528);
+    const bool whole = o_begin == 0 && o_end == n && !(peer.active && peer.has_isa && ss.nparts > 1);
+    if (whole && (size_t)n >= bwt_scatter_min) {
+        // ---- text-order route (bwt_kernels.cuh): one sweep of (rank[i], T[i-1]) by row window, then an L2-resident scatter.
+        // The sort buffers are free by now: bucketed rows -> keys[0], bucketed bytes -> idx[0].
+        B200SA_TRY(keys[0].ensure((size_t)n * 4 + 64));
+        B200SA_TRY(idx[0].ensure((size_t)n + 64));
+        const int nbits = bit_length_u64((u64)n);
+        const int shift = nbits > RS_RADIX_BITS ? nbits - RS_RADIX_BITS : 0;
+        const u32 tiles = (u32)div_up_u64(n, RS_TILE);
+        const size_t status_bytes = (size_t)tiles * RS_RADIX * sizeof(u64);
+        B200SA_TRY(sortmeta.ensure(kSortMetaHeader + status_bytes));
+        u32* ghist = sortmeta.as<u32>();
+        u32* counters = ghist + RS_MAX_PASSES * RS_RADIX;
+        u64* status = (u64*)((u8*)sortmeta.p + kSortMetaHeader);
+        B200SA_CU(cudaMemsetAsync(sortmeta.p, 0, kSortMetaHeader + status_bytes, st));
+        prof.memsets++;
+        B200SA_TRY(phase_begin(B200SA_PH_BWT, st));
+        B200SA_LAUNCH(k_bwt_bins, 1, 256, 0, st, (const u32*)rank.as<u32>(), n, shift, ghist, d_sent);
+        count_launch(B200SA_PH_BWT);
+        auto kp = k_onesweep_pass<u32, true, u8>;
+        B200SA_LAUNCH(kp, tiles, RS_THREADS, rs_pass_smem_bytes<u32>(), st, (const u32*)(rank.as<u32>() + 1), keys[0].as<u32>(), d_text, idx[0].as<u8>(),
+                      n, shift, 0xffffffffu, (const u32*)ghist, status, counters);
+        count_launch(B200SA_PH_BWT);
+        {
+            const u32 want = (u32)div_up_u64(n, BS_THREADS * BS_IPT);
+            const u32 grid = want < (u32)(num_sms * 16) ? want : (u32)(num_sms * 16);
+            B200SA_LAUNCH(k_bwt_scatter, grid, BS_THREADS, 0, st, (const u32*)keys[0].as<u32>(), (const u8*)idx[0].as<u8>(), n,
+                          (const u32*)rank.as<u32>(), d_bwt);
+            count_launch(B200SA_PH_BWT);
+        }
+        B200SA_TRY(phase_end(st));
+        prof.alg_bytes[B200SA_PH_BWT] += (u64)n * (5 + 5 + 5 + 1);
+        B200SA_CU(cudaGetLastError());
+        if (defer_sync) return 0;
+        B200SA_CU(cudaMemcpyAsync(h_pinned + 8, d_sent, sizeof(i32), cudaMemcpyDeviceToHost, st));
+        B200SA_CU(cudaStreamSynchronize(st));
+        return 0;
+    }
     B200SA_TRY(phase_begin(B200SA_PH_BWT, st));
     {
         const u32 groups = (u32)div_up_u64(o_end - o_begin, 4);
         const u32 want = (u32)div_up_u64(groups, BW_THREADS * BW_STEPS);
         const u32 grid = want < (u32)(num_sms * 16) ? (want ? want : 1u) : (u32)(num_sms * 16);
         // rank[0] (the sentinel row) lives on GPU 0 when the ISA is sharded in peer memory
-        const u32* rank0 = (peer.active && ss.nparts > 1) ? (const u32*)peer.view.base[0] : (const u32*)rank.as<u32>();
+        const u32* rank0 = (peer.active && peer.has_isa && ss.nparts > 1) ? (const u32*)peer.view.base[0] : (const u32*)rank.as<u32>();
         B200SA_LAUNCH(k_bwt_gather, grid, BW_THREADS, 0, st, d_text, d_sa, rank0, o_begin, o_end, d_bwt, d_sent);
         count_launch(B200SA_PH_BWT);
     }
@@ -958,7 +1025,7 @@ int Engine::unbwt_measure(u32 w_begin, u32 w_end, cudaStream_t st)
     return 0;
 }
 
-int Engine::unbwt_finish(u32 w_begin, u32 w_end, u8* d_out, cudaStream_t st)
+int Engine::unbwt_finish(u32 w_begin, u32 w_end, u8* d_out, cudaStream_t st, const ShardedOut* so)
 {
     if (us.stage < 1 || w_begin > w_end || w_end > us.nwalkers) return set_error(B200SA_EINVAL, "unbwt_finish: bad state or range");
     const size_t W = us.nwalkers;
@@ -977,9 +1044,18 @@ int Engine::unbwt_finish(u32 w_begin, u32 w_end, u8* d_out, cudaStream_t st)
     }
     if (w_end > w_begin) {
         const u32 start_walker = (us.s & (us.D - 1u)) ? us.nreg : (us.s >> us.dshift);
-        B200SA_LAUNCH(k_unbwt_place, (u32)div_up_u64(w_end - w_begin, UP_THREADS / 32), UP_THREADS, 0, st, (const u32*)keys[0].as<u32>(),
-                      (const u32*)(misc.as<u32>() + 600), (const u32*)ds[cur], (const u32*)nx[cur], (const u32*)idx[0].as<u32>(), (const u32*)ovf,
-                      (const u8*)keys[1].as<u8>(), us.cap, w_begin, w_end, us.n, start_walker, d_out, d_bad);
+        const u32 grid = (u32)div_up_u64(w_end - w_begin, UP_THREADS / 32);
+        if (so) {
+            auto kp = k_unbwt_place<ShardedOut>;
+            B200SA_LAUNCH(kp, grid, UP_THREADS, 0, st, (const u32*)keys[0].as<u32>(),
+                          (const u32*)(misc.as<u32>() + 600), (const u32*)ds[cur], (const u32*)nx[cur], (const u32*)idx[0].as<u32>(), (const u32*)ovf,
+                          (const u8*)keys[1].as<u8>(), us.cap, w_begin, w_end, us.n, start_walker, *so, d_bad);
+        } else {
+            auto kp = k_unbwt_place<LocalOut>;
+            B200SA_LAUNCH(kp, grid, UP_THREADS, 0, st, (const u32*)keys[0].as<u32>(),
+                          (const u32*)(misc.as<u32>() + 600), (const u32*)ds[cur], (const u32*)nx[cur], (const u32*)idx[0].as<u32>(), (const u32*)ovf,
+                          (const u8*)keys[1].as<u8>(), us.cap, w_begin, w_end, us.n, start_walker, LocalOut{d_out}, d_bad);
+        }
         count_launch(B200SA_PH_UNBWT_WALK);
     }
     B200SA_TRY(phase_end(st));
@@ -1045,6 +1121,7 @@ int Engine::check_sa_dev(const u8* d_text, i64 n64, const i32* d_sa, i64* bad_ro
 
 #include "engine_lcp.inl"
 #include "engine_batch.inl"
+#include "engine_shard.inl"
 
 }  // namespace b200sa
 

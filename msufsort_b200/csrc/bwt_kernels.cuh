@@ -59,6 +59,52 @@ k_bwt_gather(const u8* __restrict__ text, const i32* __restrict__ sa, const u32*
 }
 
 // ---------------------------------------------------------------------------------------------
+// Forward BWT of a text that does not fit the L2 cache, in TEXT order instead of row order: the finished ISA says where
+// every byte goes — T[i-1] belongs to row rank[i] (i = 1..n, rank[n] = 0), i.e. to out[row - (row > s)].  The gather
+// above pays one random 32-byte DRAM sector per output byte once the text is larger than L2 (256 MiB: 4.3 ms = 6 x the
+// algorithmic bytes); here ONE radix sweep on the top 8 bits of the row (keys = rank[1..n] read in place, values = the
+// text bytes read in place, radix_sort.cuh with ValT = u8) brings the pairs into 256 row windows, and the scatter of a
+// window then stays inside n/256 output bytes that live in L2.  The keys are a permutation of {0..n} \ {s}, so the digit
+// offsets need no histogram pass.
+__global__ void __launch_bounds__(256)
+k_bwt_bins(const u32* __restrict__ rank, u32 n, int shift, u32* __restrict__ bins /*256 exclusive offsets*/, i32* __restrict__ sentinel_out)
+{
+    const u32 s = rank[0];
+    const u32 t = threadIdx.x;
+    const u64 lo = (u64)t << shift;
+    u64 below = lo < (u64)n + 1 ? lo : (u64)n + 1;  // rows 0..n smaller than lo
+    if ((u64)s < lo) below -= 1;                      // row s (suffix 0) has no preceding byte
+    bins[t] = (u32)below;
+    if (t == 0 && sentinel_out) *sentinel_out = (i32)s;
+}
+
+static const int BS_THREADS = 256;
+static const int BS_IPT = 8;
+
+__global__ void __launch_bounds__(BS_THREADS)
+k_bwt_scatter(const u32* __restrict__ rows, const u8* __restrict__ bytes, u32 n, const u32* __restrict__ rank, u8* __restrict__ out)
+{
+    const u32 s = rank[0];
+    const u32 tile = BS_THREADS * BS_IPT;
+    const u32 ntiles = (u32)div_up_u64(n, tile);
+    for (u32 t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const u32 base = t * tile + threadIdx.x;
+        u32 r[BS_IPT];
+        u8 b[BS_IPT];
+#pragma unroll
+        for (int q = 0; q < BS_IPT; ++q) {
+            const u32 j = base + (u32)q * BS_THREADS;
+            if (j < n) { r[q] = ld_stream(rows + j); b[q] = ld_stream(bytes + j); }
+        }
+#pragma unroll
+        for (int q = 0; q < BS_IPT; ++q) {
+            const u32 j = base + (u32)q * BS_THREADS;
+            if (j < n) out[r[q] - (r[q] > s ? 1u : 0u)] = b[q];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // *differ |= (a[0..n) != b[0..n)).  Both buffers are workspace allocations (16-byte aligned).  Used by the host entry points
 // to recognise that the text they are handed is byte for byte the one whose suffix array is still resident (the
 // reference's users call make_suffix_array and forward_burrows_wheeler_transform on the same bytes: one sort serves both).
@@ -190,15 +236,46 @@ k_unbwt_jump(const u32* __restrict__ next_in, const u32* __restrict__ dist_in,
     next_out[w] = next_in[nx];
 }
 
+// Where pass B stores text byte p.  LocalOut: this GPU's buffer.  ShardedOut: the text is sharded by position over the GPUs
+// of the box (byte p lives on GPU p >> shift, at offset p of that GPU's peer-mapped buffer) and a walker's bytes are
+// stored over NVLink in runs of a whole segment.
+struct LocalOut {
+    u8* out;
+    __device__ __forceinline__ u8& operator()(u32 p) const { return out[p]; }
+};
+struct ShardedOut {
+    u8* base[kMaxPeers];
+    int shift;
+    __device__ __forceinline__ u8& operator()(u32 p) const { return base[p >> shift][p]; }
+};
+
+// Sharded inverse BWT: the (length, successor) entries of walkers [w_begin, w_end) go to word w (lengths) and word W + w
+// (successors) of every peer's inbox payload.
+struct PeerBcast {
+    u32* dst[kMaxPeers];  // null for this GPU itself
+    int nparts;
+};
+__global__ void __launch_bounds__(256)
+k_peer_bcast_segments(const u32* __restrict__ seg_len, const u32* __restrict__ seg_next, u32 w_begin, u32 w_end, u32 W, PeerBcast pb)
+{
+    for (u32 w = w_begin + blockIdx.x * blockDim.x + threadIdx.x; w < w_end; w += gridDim.x * blockDim.x) {
+        const u32 l = seg_len[w], x = seg_next[w];
+        for (int g = 0; g < pb.nparts; ++g) {
+            if (pb.dst[g]) { pb.dst[g][w] = l; pb.dst[g][W + w] = x; }
+        }
+    }
+}
+
 // Pass B: one warp per walker copies the decoded window to its final place (text offset n - dist[w]);
 // the few walkers that outgrew their window continue decoding from ovf_row straight into the text.
 // start_walker = the walker seeded at row s (text offset 0): it must be exactly n bytes from the end.
 static const int UP_THREADS = 256;
 
+template <typename OutT>
 __global__ void __launch_bounds__(UP_THREADS)
 k_unbwt_place(const u32* __restrict__ psi, const u32* __restrict__ fstart, const u32* __restrict__ dist, const u32* __restrict__ final_next,
               const u32* __restrict__ seg_len, const u32* __restrict__ ovf_row, const u8* __restrict__ scratch, u32 cap,
-              u32 w_begin, u32 w_end, u32 n, u32 start_walker, u8* __restrict__ out, u32* __restrict__ bad)
+              u32 w_begin, u32 w_end, u32 n, u32 start_walker, OutT out, u32* __restrict__ bad)
 {
     __shared__ u32 s_f[257];
     for (u32 i = threadIdx.x; i < 257; i += UP_THREADS) s_f[i] = fstart[i];
@@ -215,14 +292,14 @@ k_unbwt_place(const u32* __restrict__ psi, const u32* __restrict__ fstart, const
     const u32 pos = n - d;
     const u32 stored = len < cap ? len : cap;
     const u8* src = scratch + (u64)w * cap;
-    for (u32 i = lane; i < stored; i += 32u) out[pos + i] = src[i];
+    for (u32 i = lane; i < stored; i += 32u) out(pos + i) = src[i];
     if (len > cap && lane == 0) {
         u32 cur = ovf_row[w];
         u32 nxt = psi[cur];
         u32 o = pos + cap;
         for (u32 k = cap; k < len; ++k) {
             const u32 nxt2 = psi[nxt];
-            out[o++] = (u8)ub_row_symbol(s_f, cur);
+            out(o++) = (u8)ub_row_symbol(s_f, cur);
             cur = nxt;
             nxt = nxt2;
         }

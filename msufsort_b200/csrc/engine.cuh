@@ -10,6 +10,7 @@
 #include "lcp_kernels.cuh"
 #include "batch_kernels.cuh"
 #include "../../include/b200sa.h"
+#include "comm.cuh"
 
 #include <string>
 #include <vector>
@@ -81,6 +82,10 @@ struct Engine {
     u32 groupsort_max_avg = 16;
     u32 groupsort_tiny = GS_TINY;
     u32 groupsort_medium = GS_MEDIUM;
+
+    // forward BWT: texts of at least this many bytes (they do not fit L2 next to the suffix array stream) take the text-order
+    // bucketed scatter instead of the row-order gather (B200SA_BWT_SCATTER_MIN; tests set 0 to drive it at small n)
+    size_t bwt_scatter_min = (size_t)96 << 20;
 
     // inverse BWT: bytes of decode window per walker = unbwt_cap_mult * D (D = mean segment length)
     u32 unbwt_cap_mult = 4;
@@ -175,13 +180,29 @@ struct Engine {
         bool active = false;
         int part = 0, nparts = 1;
         RankView view{};
+        bool has_isa = false;               // view.base[] is mapped (suffix sort); otherwise out[] is (inverse BWT)
         u8* inbox[kMaxPeers] = {};          // every GPU's inbox (own one included)
+        u8* out[kMaxPeers] = {};            // every GPU's inverse-BWT output buffer
         u64 region_off[kMaxPeers] = {};     // region of source s inside any inbox
         u32 region_cap[kMaxPeers] = {};
         bool laid_out = false;
         std::vector<std::pair<std::string, void*>> opened;  // IPC handle bytes -> mapped pointer
     } peer;
-    DevBuf peer_inbox;
+    DevBuf peer_inbox, peer_out;
+    // how one peer's ISA array and inbox are reached: a CUDA IPC handle pair (another process) or plain pointers (a context
+    // of this process, possibly on another device: peer access is enabled on attach)
+    struct PeerDesc {
+        u64 pid;
+        int device;
+        int pad;
+        void* rank_ptr;
+        void* inbox_ptr;
+        void* out_ptr;
+        unsigned char ipc[192];  // handles of: ISA array, inbox, inverse-BWT output buffer
+    };
+    // isa = true: the ISA array and the inbox are shared (suffix sort); false: the inbox and the output buffer (inverse BWT)
+    int peer_describe(u64 n, bool with_ipc, bool isa, PeerDesc* out);
+    int peer_attach_desc(int part, int nparts, int shift, u64 n, bool isa, const PeerDesc* descs);
     int peer_export(u64 n, unsigned char* handles_out /*128*/);
     int peer_layout(const i64* counts, int nparts);
     int peer_apply(cudaStream_t st);
@@ -190,6 +211,15 @@ struct Engine {
     int peer_detach();
     struct BatchDesc { const u32* d_ends = nullptr; u32 count = 0; } next_batch;  // consumed by the next sort_begin
     int sort_begin(const u8* d_text, u32 n, i32* d_sa, int part, int nparts, u32* n_local, cudaStream_t st);
+    // the whole sharded sort of one rank, control plane through `cm` (comm.cuh): attach the peers' memory, begin, round 0,
+    // doubling rounds with their two barriers each, this rank's rows of the BWT (d_bwt may be null)
+    struct ShardInfo { i64 row_begin, row_end, out_begin, out_end, sentinel, rounds, sent_bytes, n_local; };
+    Comm* shard_comm = nullptr;  // set while sharded_sort runs: sort_begin then histograms only this rank's slice of the text
+    int sharded_sort(Comm& cm, const u8* d_text, i64 n, i32* d_sa, u8* d_bwt, ShardInfo* info, cudaStream_t st);
+    // inverse BWT with the walkers split over the ranks; every rank leaves its slice of the text in d_out and, with
+    // gather_all, copies the other slices from the peers' buffers (peer memory) so that d_out holds the whole text
+    int sharded_unbwt(Comm& cm, const u8* d_bwt, i64 n, i64 sentinel, u8* d_out, bool gather_all, i64* slice_begin, i64* slice_end,
+                      cudaStream_t st);
     int sort_round0(u32 slot_base, u32* m_local, cudaStream_t st);
     int sort_round(u32* m_local, cudaStream_t st);
 
@@ -203,7 +233,8 @@ struct Engine {
     struct UnbwtState { int stage = 0, dshift = 6; u32 n = 0, s = 0, D = 0, nreg = 0, nwalkers = 0, cap = 0; } us;
     int unbwt_build(const u8* d_bwt, u32 n, u32 s, u32* nwalkers_out, cudaStream_t st);
     int unbwt_measure(u32 w_begin, u32 w_end, cudaStream_t st);
-    int unbwt_finish(u32 w_begin, u32 w_end, u8* d_out, cudaStream_t st);
+    // so != nullptr: the bytes go to the owners of their text positions through peer memory instead of d_out
+    int unbwt_finish(u32 w_begin, u32 w_end, u8* d_out, cudaStream_t st, const ShardedOut* so = nullptr);
     int unbwt_dev(const u8* d_bwt, i64 n, i64 sentinel, u8* d_out, cudaStream_t st, i64 max_n = B200SA_MAX_N_INT32);
     int check_sa_dev(const u8* d_text, i64 n, const i32* d_sa, i64* bad_rows, cudaStream_t st, i64 max_n = B200SA_MAX_N_INT32);
     int lcp_dev(const u8* d_text, i64 n, const i32* d_sa, i32* d_lcp, cudaStream_t st, i64 max_n = B200SA_MAX_N_INT32);

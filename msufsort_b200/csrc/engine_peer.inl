@@ -8,17 +8,41 @@
 
 static const size_t kInboxHeader = 256;  // u32 count[kMaxPeers] written by the sources, padded
 
+int Engine::peer_describe(u64 n, bool with_ipc, bool isa, PeerDesc* out)
+{
+    if (n == 0 || n > (u64)B200SA_MAX_N_INT32 || !out) return set_error(B200SA_EINVAL, "bad argument");
+    B200SA_CU(cudaSetDevice(device));
+    if (isa) {
+        B200SA_TRY(ensure_sa_workspace(n));  // the ISA array keeps its address as long as n does not grow
+        B200SA_TRY(peer_inbox.ensure(kInboxHeader + (size_t)n * 8 + 64));
+    } else {
+        B200SA_TRY(peer_inbox.ensure(kInboxHeader + (size_t)8 * (((size_t)1 << 21) + 64)));  // (length, successor) of <= 2^21 + 2 walkers
+        B200SA_TRY(peer_out.ensure((size_t)n + 64));
+    }
+    memset(out, 0, sizeof(*out));
+    out->pid = (u64)getpid();
+    out->device = device;
+    out->rank_ptr = isa ? rank.p : nullptr;
+    out->inbox_ptr = peer_inbox.p;
+    out->out_ptr = isa ? nullptr : peer_out.p;
+    if (with_ipc) {
+        cudaIpcMemHandle_t h[3];
+        static_assert(sizeof(h[0]) == 64, "IPC handle size");
+        memset(h, 0, sizeof(h));
+        if (isa) B200SA_CU(cudaIpcGetMemHandle(&h[0], rank.p));
+        B200SA_CU(cudaIpcGetMemHandle(&h[1], peer_inbox.p));
+        if (!isa) B200SA_CU(cudaIpcGetMemHandle(&h[2], peer_out.p));
+        memcpy(out->ipc, h, 192);
+    }
+    return 0;
+}
+
 int Engine::peer_export(u64 n, unsigned char* handles_out)
 {
-    if (n == 0 || n > (u64)B200SA_MAX_N_INT32 || !handles_out) return set_error(B200SA_EINVAL, "bad argument");
-    B200SA_CU(cudaSetDevice(device));
-    B200SA_TRY(ensure_sa_workspace(n));  // the ISA array keeps its address as long as n does not grow
-    B200SA_TRY(peer_inbox.ensure(kInboxHeader + (size_t)n * 8 + 64));
-    cudaIpcMemHandle_t h[2];
-    static_assert(sizeof(h[0]) == 64, "IPC handle size");
-    B200SA_CU(cudaIpcGetMemHandle(&h[0], rank.p));
-    B200SA_CU(cudaIpcGetMemHandle(&h[1], peer_inbox.p));
-    memcpy(handles_out, h, 128);
+    if (!handles_out) return set_error(B200SA_EINVAL, "bad argument");
+    PeerDesc d;
+    B200SA_TRY(peer_describe(n, true, true, &d));
+    memcpy(handles_out, d.ipc, 128);
     return 0;
 }
 
@@ -32,13 +56,28 @@ int Engine::peer_detach()
 
 int Engine::peer_attach(int part, int nparts, int shift, u64 n, const unsigned char* handles)
 {
-    if (nparts < 2 || nparts > kMaxPeers || part < 0 || part >= nparts || shift < 0 || shift > 31 || !handles || n == 0 ||
+    if (nparts < 2 || nparts > kMaxPeers || !handles) return set_error(B200SA_EINVAL, "bad argument (at most %d GPUs)", kMaxPeers);
+    PeerDesc descs[kMaxPeers];
+    memset(descs, 0, sizeof(descs));
+    for (int g = 0; g < nparts; ++g) {
+        descs[g].pid = ~(u64)0;  // handles only: every peer is treated as another process
+        memcpy(descs[g].ipc, handles + (size_t)g * 128, 128);
+    }
+    return peer_attach_desc(part, nparts, shift, n, true, descs);
+}
+
+int Engine::peer_attach_desc(int part, int nparts, int shift, u64 n, bool isa, const PeerDesc* descs)
+{
+    if (nparts < 2 || nparts > kMaxPeers || part < 0 || part >= nparts || shift < 0 || shift > 31 || !descs || n == 0 ||
         n > (u64)B200SA_MAX_N_INT32)
         return set_error(B200SA_EINVAL, "bad argument (at most %d GPUs)", kMaxPeers);
     if (((n - 1) >> shift) >= (u64)nparts) return set_error(B200SA_EINVAL, "shift %d does not spread %llu positions over %d GPUs", shift, (unsigned long long)n, nparts);
     B200SA_CU(cudaSetDevice(device));
-    B200SA_TRY(ensure_sa_workspace(n));
-    B200SA_TRY(peer_inbox.ensure(kInboxHeader + (size_t)n * 8 + 64));
+    {
+        PeerDesc self;  // sizes the shared buffers exactly as peer_describe did on the peers
+        B200SA_TRY(peer_describe(n, false, isa, &self));
+    }
+    const u64 mypid = (u64)getpid();
     // mappings of an earlier attach are reused when the peer still exports the same allocation
     std::vector<std::pair<std::string, void*>> keep;
     PeerState next;
@@ -62,12 +101,34 @@ int Engine::peer_attach(int part, int nparts, int shift, u64 n, const unsigned c
     };
     int rc = 0;
     for (int g = 0; g < nparts && rc == 0; ++g) {
-        if (g == part) { next.view.base[g] = rank.as<u32>(); next.inbox[g] = peer_inbox.as<u8>(); continue; }
-        void *pr = nullptr, *pi = nullptr;
-        rc = open_one(handles + (size_t)g * 128, &pr);
-        if (rc == 0) rc = open_one(handles + (size_t)g * 128 + 64, &pi);
+        if (g == part) { next.view.base[g] = rank.as<u32>(); next.inbox[g] = peer_inbox.as<u8>(); next.out[g] = peer_out.as<u8>(); continue; }
+        void *pr = nullptr, *pi = nullptr, *po = nullptr;
+        if (descs[g].pid == mypid) {
+            // a context of this process: its pointers are valid here; across devices the hardware path is the same NVLink
+            // peer mapping, enabled once per device pair
+            pr = descs[g].rank_ptr;
+            pi = descs[g].inbox_ptr;
+            po = descs[g].out_ptr;
+#ifndef B200SA_EMU
+            if (descs[g].device != device) {
+                int can = 0;
+                cudaDeviceCanAccessPeer(&can, device, descs[g].device);
+                if (!can) rc = set_error(B200SA_ECOMM, "GPU %d cannot access the memory of GPU %d", device, descs[g].device);
+                else {
+                    cudaError_t e = cudaDeviceEnablePeerAccess(descs[g].device, 0);
+                    if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) rc = set_error(B200SA_ECOMM, "cudaDeviceEnablePeerAccess failed: %s", cudaGetErrorString(e));
+                    cudaGetLastError();
+                }
+            }
+#endif
+        } else {
+            if (isa) rc = open_one(descs[g].ipc, &pr);
+            if (rc == 0) rc = open_one(descs[g].ipc + 64, &pi);
+            if (rc == 0 && !isa) rc = open_one(descs[g].ipc + 128, &po);
+        }
         next.view.base[g] = (u32*)pr;
         next.inbox[g] = (u8*)pi;
+        next.out[g] = (u8*)po;
     }
     for (auto& o : peer.opened)
         if (o.second) cudaIpcCloseMemHandle(o.second);
@@ -79,6 +140,7 @@ int Engine::peer_attach(int part, int nparts, int shift, u64 n, const unsigned c
     }
     next.opened = keep;
     next.active = true;
+    next.has_isa = isa;
     next.part = part;
     next.nparts = nparts;
     next.view.shift = shift;

@@ -82,14 +82,22 @@ static const int PK_HALO = 64;                   // k <= 58
 
 // RADIX = true (experimental): key = sum_{j<k} digit_j * B^(k-1-j) with digit = code + 1 inside the text and 0 past its end
 // (B = sigma + 1, top_pow = B^(k-1)) — the same order, no length field, no bits wasted on odd alphabet sizes.
-template <bool RADIX>
+//
+// RANGE = true (sharded runs): only the keys inside [lo, hi) (hi inclusive for the last part) are kept, as (key, suffix) pairs
+// compacted through an atomic cursor.  Every GPU of a sharded sort holds the whole text and runs this over all n positions:
+// it reads n bytes and writes n/G pairs, instead of packing all n keys and filtering them in a second pass (round 1: 1.35 of
+// 8 kernel-ms per step on eight GPUs).  The order of the kept pairs is irrelevant (equal keys form one group whatever
+// their order).
+template <bool RADIX, bool RANGE>
 __global__ void __launch_bounds__(PK_THREADS)
 k_pack_keys(const u8* __restrict__ text, u32 n, const u8* __restrict__ code, int bits, int k, int len_bits, u64 B, u64 top_pow,
-            u64* __restrict__ keys)
+            u64* __restrict__ keys, u64 lo, u64 hi, int hi_inclusive, u32* __restrict__ out_idx, u32* __restrict__ cursor)
 {
     __shared__ u8 s_code[256];
     __shared__ __align__(16) u8 s_sym[PK_TILE + PK_HALO];
-    __shared__ u64 s_out[PK_THREADS / 32][PK_IPT * 33];
+    __shared__ u64 s_out[RANGE ? 1 : PK_THREADS / 32][RANGE ? 1 : PK_IPT * 33];
+    __shared__ u32 s_wsum[PK_THREADS / 32];
+    __shared__ u32 s_base;
     const u32 tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     s_code[tid] = RADIX ? (u8)(code[tid] + 1u) : code[tid];  // sigma <= 255 in the mixed-radix layout: digits fit a byte
     __syncthreads();
@@ -117,42 +125,96 @@ k_pack_keys(const u8* __restrict__ text, u32 n, const u8* __restrict__ code, int
         const u32 p0 = tid * PK_IPT;
         u64 win = 0;
         for (int j = 0; j < k; ++j) win = RADIX ? win * B + (u64)s_sym[p0 + j] : ((win << bits) | (u64)s_sym[p0 + j]);
+        if (RANGE) {
+            u64 kreg[PK_IPT];
+            u32 keep = 0;
 #pragma unroll
-        for (int i = 0; i < PK_IPT; ++i) {
-            const u32 gp = base + p0 + i;
-            if (RADIX) {
-                s_out[warp][i * 33 + lane] = win;
-                win = (win - (u64)s_sym[p0 + i] * top_pow) * B + (u64)s_sym[p0 + i + k];
-            } else {
-                const u32 rem = gp < n ? n - gp : 0u;
-                const u64 key = (win << len_bits) | (u64)(rem < (u32)k ? rem : (u32)k);
-                s_out[warp][i * 33 + lane] = key;
-                win = ((win << bits) | (u64)s_sym[p0 + i + k]) & sym_mask;
+            for (int i = 0; i < PK_IPT; ++i) {
+                const u32 gp = base + p0 + i;
+                u64 key;
+                if (RADIX) {
+                    key = win;
+                    win = (win - (u64)s_sym[p0 + i] * top_pow) * B + (u64)s_sym[p0 + i + k];
+                } else {
+                    const u32 rem = gp < n ? n - gp : 0u;
+                    key = (win << len_bits) | (u64)(rem < (u32)k ? rem : (u32)k);
+                    win = ((win << bits) | (u64)s_sym[p0 + i + k]) & sym_mask;
+                }
+                kreg[i] = key;
+                if (gp < n && key >= lo && (hi_inclusive ? key <= hi : key < hi)) keep |= 1u << i;
             }
-        }
-        __syncwarp();
-        // the warp's 512 keys are positions base + warp*512 + lane*16 + i; write them coalesced
-        const u32 wb = base + warp * (32u * PK_IPT);
+            const u32 cnt = (u32)__popc(keep);
+            const u32 incl = warp_incl_scan_u32(cnt);
+            if (lane == 31) s_wsum[warp] = incl;
+            __syncthreads();
+            if (tid == 0) {
+                u32 tot = 0;
+                for (int w = 0; w < PK_THREADS / 32; ++w) { const u32 c = s_wsum[w]; s_wsum[w] = tot; tot += c; }
+                s_base = tot ? atomicAdd(cursor, tot) : 0u;  // one cursor bump per tile
+            }
+            __syncthreads();
+            u32 d = s_base + s_wsum[warp] + incl - cnt;
 #pragma unroll
-        for (int r = 0; r < PK_IPT; ++r) {
-            const u32 q = (u32)r * 32u + lane;  // 0..511 within the warp's chunk
-            const u32 src_lane = q / PK_IPT, src_i = q % PK_IPT;
-            const u32 gp = wb + q;
-            if (gp < n) st_stream(keys + gp, s_out[warp][src_i * 33 + src_lane]);
+            for (int i = 0; i < PK_IPT; ++i) {
+                if ((keep >> i) & 1u) {
+                    keys[d] = kreg[i];
+                    out_idx[d] = base + p0 + (u32)i;
+                    ++d;
+                }
+            }
+            __syncthreads();
+        } else {
+#pragma unroll
+            for (int i = 0; i < PK_IPT; ++i) {
+                const u32 gp = base + p0 + i;
+                if (RADIX) {
+                    s_out[warp][i * 33 + lane] = win;
+                    win = (win - (u64)s_sym[p0 + i] * top_pow) * B + (u64)s_sym[p0 + i + k];
+                } else {
+                    const u32 rem = gp < n ? n - gp : 0u;
+                    const u64 key = (win << len_bits) | (u64)(rem < (u32)k ? rem : (u32)k);
+                    s_out[warp][i * 33 + lane] = key;
+                    win = ((win << bits) | (u64)s_sym[p0 + i + k]) & sym_mask;
+                }
+            }
+            __syncwarp();
+            // the warp's 512 keys are positions base + warp*512 + lane*16 + i; write them coalesced
+            const u32 wb = base + warp * (32u * PK_IPT);
+#pragma unroll
+            for (int r = 0; r < PK_IPT; ++r) {
+                const u32 q = (u32)r * 32u + lane;  // 0..511 within the warp's chunk
+                const u32 src_lane = q / PK_IPT, src_i = q % PK_IPT;
+                const u32 gp = wb + q;
+                if (gp < n) st_stream(keys + gp, s_out[warp][src_i * 33 + src_lane]);
+            }
+            __syncthreads();
         }
-        __syncthreads();
     }
 }
 
 // ---------------------------------------------------------------------------------------------
-// Sharded runs: every GPU packs all n keys, sorts a regular sample of them to pick splitters, and
-// keeps the (key, suffix) pairs of its own key range.  Output order is irrelevant (equal keys form
-// one group whatever their order), so the compaction uses a warp-aggregated atomic cursor.
+// Sharded runs: the splitters come from a sorted regular sample of the initial keys.  The sample keys are computed straight
+// from the text (the same key as k_pack_keys: same text + same kernels on every GPU => identical splitters everywhere, no
+// communication); k_pack_keys<.., RANGE> then keeps this GPU's key range.
+template <bool RADIX>
 __global__ void __launch_bounds__(256)
-k_sample_keys(const u64* __restrict__ keys, u32 nsample, u32 stride, u64* __restrict__ out)
+k_sample_keys_text(const u8* __restrict__ text, u32 n, const u8* __restrict__ code, int bits, int k, int len_bits, u64 B,
+                   u32 nsample, u32 stride, u64* __restrict__ out)
 {
+    __shared__ u8 s_code[256];
+    s_code[threadIdx.x] = RADIX ? (u8)(code[threadIdx.x] + 1u) : code[threadIdx.x];
+    __syncthreads();
     const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < nsample) out[i] = keys[(u64)i * stride];
+    if (i >= nsample) return;
+    const u64 p = (u64)i * stride;
+    u64 win = 0;
+    for (int j = 0; j < k; ++j) {
+        const u64 q = p + (u64)j;
+        const u64 sym = q < (u64)n ? (u64)s_code[text[q]] : 0ull;
+        win = RADIX ? win * B + sym : ((win << bits) | sym);
+    }
+    const u64 rem = (u64)n - p;
+    out[i] = RADIX ? win : ((win << len_bits) | (rem < (u64)k ? rem : (u64)k));
 }
 
 // owner-sharded ISA (multi-GPU): positions whose ranks the next round will read, and the serving gather
@@ -172,54 +234,6 @@ __global__ void __launch_bounds__(256)
 k_gather_u32(const u32* __restrict__ pos, u32 count, const u32* __restrict__ table, u32* __restrict__ out)
 {
     for (u32 j = blockIdx.x * blockDim.x + threadIdx.x; j < count; j += gridDim.x * blockDim.x) out[j] = table[pos[j]];
-}
-
-static const int FR_THREADS = 256;
-static const int FR_IPT = 8;
-
-__global__ void __launch_bounds__(FR_THREADS)
-k_filter_range(const u64* __restrict__ keys, u32 n, u64 lo, u64 hi, int hi_inclusive,
-               u64* __restrict__ out_keys, u32* __restrict__ out_idx, u32* __restrict__ cursor)
-{
-    __shared__ u32 s_wcnt[FR_THREADS / 32];
-    __shared__ u32 s_base;
-    const u32 lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-    const u32 base = blockIdx.x * (u32)(FR_THREADS * FR_IPT) + threadIdx.x;
-    u64 k[FR_IPT];
-    u32 bal[FR_IPT];
-    u32 wtotal = 0;
-#pragma unroll
-    for (int q = 0; q < FR_IPT; ++q) {
-        const u32 i = base + (u32)q * FR_THREADS;
-        bool keep = false;
-        k[q] = 0;
-        if (i < n) {
-            k[q] = ld_stream(keys + i);
-            keep = k[q] >= lo && (hi_inclusive ? k[q] <= hi : k[q] < hi);
-        }
-        bal[q] = __ballot_sync(B200SA_FULL_MASK, keep);
-        wtotal += (u32)__popc(bal[q]);
-    }
-    // one cursor bump per block (a bump per warp made 8.4 M same-address atomics: 6 ms for 2^28 keys)
-    if (lane == 0) s_wcnt[warp] = wtotal;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        u32 tot = 0;
-        for (int w = 0; w < FR_THREADS / 32; ++w) { const u32 c = s_wcnt[w]; s_wcnt[w] = tot; tot += c; }
-        s_base = tot ? atomicAdd(cursor, tot) : 0u;
-    }
-    __syncthreads();
-    u32 pos = s_base + s_wcnt[warp];
-    const u32 lt = lanemask_lt();
-#pragma unroll
-    for (int q = 0; q < FR_IPT; ++q) {
-        if ((bal[q] >> lane) & 1u) {
-            const u32 d = pos + (u32)__popc(bal[q] & lt);
-            out_keys[d] = k[q];
-            out_idx[d] = base + (u32)q * FR_THREADS;
-        }
-        pos += (u32)__popc(bal[q]);
-    }
 }
 
 // ---------------------------------------------------------------------------------------------

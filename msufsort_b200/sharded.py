@@ -14,10 +14,12 @@ Scheme (north_star item 4; include/b200sa.h "sharded building blocks"):
     ranks it is about to read (all-to-all of positions, all-to-all of values) and caches the replies in its
     own array — all three exchanges and all ISA work scale with 1/G.  ``isa="replicated"``: the pairs are
     all-gathered and every rank applies all of them (simpler, but the ISA update is replicated work);
-    ``isa="peer"`` (the NVLink-native variant): the ISA is sharded the same way, but every rank maps the arrays
-    of all peers (CUDA IPC) and the kernels load rank[suffix + h] from, and store new ranks into, the owner's HBM
-    directly in bulk (an inbox per GPU, applied locally); the only collectives left are three tiny all-reduces
-    per round that separate its phases (and carry the termination test);
+    ``isa="peer"`` (the NVLink-native variant, what bench.py runs): the ISA is sharded the same way, but every rank
+    maps the arrays of all peers (CUDA IPC) and the kernels load rank[suffix + h] from, and store new ranks into, the
+    owner's HBM directly in bulk (an inbox per GPU, applied locally).  The round loop of this variant lives in C++
+    (b200sa_shard_sort, csrc/engine_shard.inl); its control plane — two barriers and a sum per round — is a
+    shared-memory segment the ranks of the node map (csrc/comm.cuh), so no collective library call is left on the
+    path; torch.distributed only hands out the segment's name once;
   * a rank ends up owning a contiguous slice of the suffix array and of the BWT.
 The exchanges are the only collectives on the data path; counts and the termination test are tiny.
 """
@@ -28,7 +30,9 @@ from typing import Optional
 import torch
 import torch.distributed as dist
 
-from .api import torch_stream_handle
+import os
+
+from .api import Comm, torch_stream_handle
 
 
 class ShardedResult:
@@ -42,23 +46,37 @@ class ShardedResult:
         self.sentinel = 0
         self.rounds = 0
         self.exchanged_bytes = 0  # bytes this rank received in update all-gathers
-        self.counts = []          # suffixes owned by every rank
+        self.counts = None        # suffixes owned by every rank (ShardedSorter.owned_counts)
+        self.n_local = 0          # suffixes owned by this rank
 
 
 class ShardedSorter:
-    def __init__(self, engine, group: Optional[dist.ProcessGroup] = None, isa: str = "owner", merged_barrier: bool = False):
+    def __init__(self, engine, group: Optional[dist.ProcessGroup] = None, isa: str = "peer"):
         assert isa in ("owner", "replicated", "peer")
         self.eng = engine
         self.group = group
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
         self.isa = isa
-        # isa="peer": fold the "everybody has finished reading" all-reduce into the "all sends have landed" one (sends go to
-        # the inboxes, which no reader touches; a rank reaches the second barrier only after its own round).  Two instead of
-        # three collectives per round; not yet measured on hardware, hence off by default.
-        self.merged_barrier = merged_barrier
+        self.comm: Optional[Comm] = None
         assert self.world <= 256, "the owner routing sweep has 256 buckets"
         assert isa != "peer" or self.world <= 16, "the peer table holds 16 GPUs (one NVSwitch domain)"
+
+    def _get_comm(self) -> Comm:
+        """the shared-memory control plane of the C++ round loop; rank 0 picks a fresh segment name"""
+        if self.comm is None:
+            name = [None]
+            if self.rank == 0:
+                name[0] = "/b200sa_%d_%s" % (os.getpid(), os.urandom(6).hex())
+            src = dist.get_global_rank(self.group, 0) if self.group is not None else 0
+            dist.broadcast_object_list(name, src=src, group=self.group)
+            self.comm = Comm.shared_memory(name[0], self.rank, self.world, library=self.eng.lib)
+        return self.comm
+
+    def close(self) -> None:
+        if self.comm is not None:
+            self.comm.close()
+            self.comm = None
 
     # -- owner-sharded ISA ---------------------------------------------------------------------------
     def _owner_shift(self, n: int) -> int:
@@ -112,18 +130,6 @@ class ShardedSorter:
         if cnt:
             self.eng.shard_apply_updates(kout[:cnt], replies, cnt, stream)
 
-    # -- ISA in peer memory ----------------------------------------------------------------------------
-    def _attach_peers(self, n: int, shift: int, device) -> None:
-        mine = torch.frombuffer(bytearray(self.eng.shard_peer_export(n)), dtype=torch.uint8).to(device)
-        allh = torch.empty(128 * self.world, dtype=torch.uint8, device=device)
-        dist.all_gather_into_tensor(allh, mine, group=self.group)
-        self.eng.shard_peer_attach(self.rank, self.world, shift, n, bytes(allh.cpu().numpy().tobytes()))
-
-    def _sum_int(self, value: int, device) -> int:
-        t = torch.tensor([value], dtype=torch.int64, device=device)
-        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
-        return int(t.item())
-
     # -- tiny collectives ------------------------------------------------------------------------
     def _gather_int(self, value: int, device) -> list:
         t = torch.tensor([value], dtype=torch.int64, device=device)
@@ -162,31 +168,22 @@ class ShardedSorter:
         res.sa = torch.empty(n + 1, dtype=torch.int32, device=device)
         shift = self._owner_shift(n)
         if self.isa == "peer" and self.world > 1:
-            self._attach_peers(n, shift, device)
+            if want_bwt:
+                res.bwt = torch.empty(n, dtype=torch.uint8, device=device)
+            info = self.eng.shard_sort(self._get_comm(), d_text, n, res.sa, res.bwt, stream)
+            res.row_begin, res.row_end = info["row_begin"], info["row_end"]
+            res.out_begin, res.out_end = info["out_begin"], info["out_end"]
+            res.sentinel, res.rounds, res.exchanged_bytes = info["sentinel"], info["rounds"], info["sent_bytes"]
+            res.n_local = info["n_local"]   # owned_counts() gathers these outside the hot path
+            return res
         n_local = self.eng.shard_begin(d_text, n, res.sa, self.rank, self.world, stream)
+        res.n_local = n_local
         res.counts = self._gather_int(n_local, device)
         assert sum(res.counts) == n, "key-range parts do not cover the text"
         slot_base = sum(res.counts[: self.rank])
-        if self.isa == "peer" and self.world > 1:
-            self.eng.shard_peer_layout(res.counts)
         m_local = self.eng.shard_round0(slot_base, stream)
         res.rounds = 1
-        while self.isa == "peer" and self.world > 1:
-            # every rank has finished READING ranks (its round is complete) ...
-            total = None if self.merged_barrier else self._sum_int(m_local, device)
-            _, _, cnt = self.eng.shard_updates()
-            self.eng.shard_peer_scatter(stream)          # ... new ranks are stored into the owners' inboxes ...
-            res.exchanged_bytes += 8 * cnt * (self.world - 1) // self.world
-            t2 = self._sum_int(m_local if self.merged_barrier else 0, device)   # ... all of them have landed ...
-            if self.merged_barrier:
-                total = t2
-            self.eng.shard_peer_apply(stream)            # ... every owner updates its ISA shard ...
-            self._sum_int(0, device)                     # ... and all shards are current before anyone reads again
-            if total == 0:
-                break
-            m_local = self.eng.shard_round(stream)
-            res.rounds += 1
-        while self.isa != "peer" or self.world == 1:
+        while True:
             if self.isa == "owner":
                 self._route_updates(device, stream, res, shift)
             else:
@@ -224,6 +221,11 @@ class ShardedSorter:
         n = d_bwt.numel()
         device = d_bwt.device
         stream = torch_stream_handle() if device.type == "cuda" else 0
+        if self.isa == "peer" and self.world > 1:
+            # C++ path: bytes stored into the owner of their text position over NVLink, slices pulled from the peers
+            out = torch.empty(n, dtype=torch.uint8, device=device)
+            self.eng.shard_unbwt(self._get_comm(), d_bwt, n, sentinel_index, out, True, stream)
+            return out
         W = self.eng.unbwt_shard_build(d_bwt, n, sentinel_index, stream)
         per = (W + self.world - 1) // self.world
         spans = [(min(W, p * per), min(W, (p + 1) * per)) for p in range(self.world)]
@@ -243,6 +245,23 @@ class ShardedSorter:
         self.eng.unbwt_shard_finish(wb, we, out, stream)
         dist.all_reduce(out, op=dist.ReduceOp.SUM, group=self.group)
         return out
+
+    def suffix_array_bwt_host(self, h_text: torch.Tensor, h_sa: torch.Tensor, h_bwt: Optional[torch.Tensor]) -> ShardedResult:
+        """Host buffers in, host buffers out (pinned tensors; every rank passes the same text): the text is uploaded on
+        every rank over its own PCIe link, the suffix array and the BWT leave as this rank's rows / bytes only — the
+        caller's host arrays are filled by the ranks together (shared pinned memory) or gathered by the caller."""
+        d_text = h_text.to("cuda", non_blocking=True)
+        res = self.suffix_array_bwt(d_text, want_bwt=h_bwt is not None)
+        h_sa[res.row_begin:res.row_end].copy_(res.sa[res.row_begin:res.row_end], non_blocking=True)
+        if h_bwt is not None and res.out_end > res.out_begin:
+            h_bwt[res.out_begin:res.out_end].copy_(res.bwt[res.out_begin:res.out_end], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return res
+
+    def owned_counts(self, res: ShardedResult) -> list:
+        if res.counts is None:
+            res.counts = self._gather_int(res.n_local, res.sa.device)
+        return res.counts
 
     # -- helpers for callers that want the whole result on every rank -------------------------------
     def gather_sa(self, res: ShardedResult) -> torch.Tensor:

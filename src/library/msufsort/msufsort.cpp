@@ -5,16 +5,71 @@
 #include <b200sa.h>
 
 #include <cstdlib>
+#include <cstring>
 #include <mutex>
 #include <stdexcept>
 #include <string>
+#include <vector>
 
 namespace
 {
+    // What one msufsort object computes with: one GPU context, or a group of contexts that shards every text over several
+    // GPUs (MSUFSORT_NUM_GPUS).  The reference's free templates build a short-lived msufsort object per call
+    // (msufsort.h:432-476: a fresh worker pool every time); here such objects borrow a backend from a process-wide pool, so
+    // the device workspace — and the suffix array kept resident for a following forward_burrows_wheeler_transform of the
+    // same bytes — outlive them.  The pool is emptied at process exit.
+    struct backend
+    {
+        b200sa_ctx * context = nullptr;
+        b200sa_group * group = nullptr;
+        std::vector<int> devices;
+    };
+
     int selected_device()
     {
         char const * env = std::getenv("MSUFSORT_DEVICE");
         return env ? std::atoi(env) : 0;
+    }
+
+    // Which GPUs an msufsort(numThreads) object uses:
+    //   MSUFSORT_DEVICES=a,b,c   exactly these (a device may be listed more than once: several shards on one GPU)
+    //   MSUFSORT_NUM_GPUS=N      GPUs 0..N-1; "auto": as many as the caller asked threads for (the reference's one
+    //                            parallelism knob, msufsort.h:50-53), at most all of them
+    //   neither                  one GPU, MSUFSORT_DEVICE (default 0)
+    std::vector<int> selected_devices(std::int32_t numThreads)
+    {
+        std::vector<int> devices;
+        if (char const * list = std::getenv("MSUFSORT_DEVICES"))
+        {
+            for (char const * p = list; *p;)
+            {
+                char * end = nullptr;
+                long v = std::strtol(p, &end, 10);
+                if (end == p)
+                    break;
+                devices.push_back(static_cast<int>(v));
+                p = (*end == ',') ? end + 1 : end;
+            }
+            if (devices.size() > 16)
+                devices.resize(16);
+            if (!devices.empty())
+                return devices;
+        }
+        char const * env = std::getenv("MSUFSORT_NUM_GPUS");
+        if (env && *env)
+        {
+            int available = b200sa_device_count();
+            int wanted = (std::strcmp(env, "auto") == 0) ? numThreads : std::atoi(env);
+            if (wanted > available)
+                wanted = available;
+            if (wanted > 16)
+                wanted = 16;
+            for (int g = 0; g < wanted; ++g)
+                devices.push_back(g);
+        }
+        if (devices.empty())
+            devices.push_back(selected_device());
+        return devices;
     }
 
     [[noreturn]] void fail(char const * what, int code)
@@ -22,29 +77,82 @@ namespace
         throw std::runtime_error(std::string("msufsort (b200): ") + what + " failed with status " + std::to_string(code) + ": " + b200sa_last_error());
     }
 
-    b200sa_ctx * create_context()
+    class backend_pool
     {
-        b200sa_ctx * context = nullptr;
-        int status = b200sa_create(&context, selected_device());
-        if (status != B200SA_OK)
-            fail("b200sa_create", status);
-        return context;
-    }
+    public:
+        ~backend_pool()
+        {
+            for (auto * b : idle_)
+                destroy(b);
+        }
 
-    // the static reverse transform has no object to hang a context on: one lazily created,
-    // mutex-guarded context per process serves it (the reference spawns fresh std::threads per
-    // call there, msufsort.cpp:1858-1879).
-    std::mutex sharedContextMutex;
-    b200sa_ctx * sharedContext = nullptr;
+        backend * acquire(std::vector<int> const & devices)
+        {
+            {
+                std::lock_guard<std::mutex> guard(mutex_);
+                for (std::size_t i = 0; i < idle_.size(); ++i)
+                    if (idle_[i]->devices == devices)
+                    {
+                        backend * b = idle_[i];
+                        idle_.erase(idle_.begin() + static_cast<std::ptrdiff_t>(i));
+                        return b;
+                    }
+            }
+            backend * b = new backend;
+            b->devices = devices;
+            bool const sharded = devices.size() > 1;
+            int status = sharded ? b200sa_group_create(&b->group, devices.data(), static_cast<int>(devices.size()))
+                                 : b200sa_create(&b->context, devices[0]);
+            if (status != B200SA_OK)
+            {
+                delete b;
+                fail(sharded ? "b200sa_group_create" : "b200sa_create", status);
+            }
+            return b;
+        }
+
+        void release(backend * b)
+        {
+            {
+                std::lock_guard<std::mutex> guard(mutex_);
+                if (idle_.size() < max_idle)
+                {
+                    idle_.push_back(b);
+                    return;
+                }
+            }
+            destroy(b);
+        }
+
+    private:
+        static void destroy(backend * b)
+        {
+            if (b->group)
+                b200sa_group_destroy(b->group);
+            if (b->context)
+                b200sa_destroy(b->context);
+            delete b;
+        }
+
+        static constexpr std::size_t max_idle = 2;
+        std::mutex mutex_;
+        std::vector<backend *> idle_;
+    };
+
+    backend_pool & pool()
+    {
+        static backend_pool instance;
+        return instance;
+    }
 }
 
 
 //==============================================================================
 maniscalco::msufsort::msufsort
 (
-    std::int32_t /* numThreads: host threads are not used; kept for source compatibility */
+    std::int32_t numThreads // host threads are not used; see selected_devices for what the knob can select
 ):
-    context_(create_context())
+    backend_(pool().acquire(selected_devices(numThreads)))
 {
 }
 
@@ -52,7 +160,7 @@ maniscalco::msufsort::msufsort
 //==============================================================================
 maniscalco::msufsort::~msufsort()
 {
-    b200sa_destroy(context_);
+    pool().release(static_cast<backend *>(backend_));
 }
 
 
@@ -63,9 +171,11 @@ auto maniscalco::msufsort::make_suffix_array
     std::uint8_t const * inputEnd
 ) -> suffix_array
 {
+    backend * b = static_cast<backend *>(backend_);
     std::int64_t inputSize = inputEnd - inputBegin;
     suffix_array suffixArray(static_cast<std::size_t>(inputSize) + 1);
-    int status = b200sa_suffix_array(context_, inputBegin, inputSize, suffixArray.data());
+    int status = b->group ? b200sa_group_suffix_array(b->group, inputBegin, inputSize, suffixArray.data())
+                          : b200sa_suffix_array(b->context, inputBegin, inputSize, suffixArray.data());
     if (status != B200SA_OK)
         fail("make_suffix_array", status);
     return suffixArray;
@@ -79,8 +189,10 @@ int32_t maniscalco::msufsort::forward_burrows_wheeler_transform
     std::uint8_t * inputEnd
 )
 {
+    backend * b = static_cast<backend *>(backend_);
     std::int32_t sentinelIndex = 0;
-    int status = b200sa_bwt(context_, inputBegin, inputEnd - inputBegin, &sentinelIndex);
+    int status = b->group ? b200sa_group_bwt(b->group, inputBegin, inputEnd - inputBegin, &sentinelIndex)
+                          : b200sa_bwt(b->context, inputBegin, inputEnd - inputBegin, &sentinelIndex);
     if (status != B200SA_OK)
         fail("forward_burrows_wheeler_transform", status);
     return sentinelIndex;
@@ -93,13 +205,16 @@ void maniscalco::msufsort::reverse_burrows_wheeler_transform
     std::uint8_t * inputBegin,
     std::uint8_t * inputEnd,
     std::int32_t sentinelIndex,
-    std::int32_t /* numThreads */
+    std::int32_t numThreads
 )
 {
-    std::lock_guard<std::mutex> guard(sharedContextMutex);
-    if (sharedContext == nullptr)
-        sharedContext = create_context();
-    int status = b200sa_unbwt(sharedContext, inputBegin, inputEnd - inputBegin, sentinelIndex);
+    // static in the reference too (it spawns fresh std::threads per call, msufsort.cpp:1858-1879): a backend is borrowed
+    // for the call, so concurrent callers do not serialise on one context
+    backend * b = pool().acquire(selected_devices(numThreads));
+    int status = b->group ? b200sa_group_unbwt(b->group, inputBegin, inputEnd - inputBegin, sentinelIndex)
+                          : b200sa_unbwt(b->context, inputBegin, inputEnd - inputBegin, sentinelIndex);
+    std::string message = status != B200SA_OK ? b200sa_last_error() : "";
+    pool().release(b);
     if (status != B200SA_OK)
-        fail("reverse_burrows_wheeler_transform", status);
+        throw std::runtime_error("msufsort (b200): reverse_burrows_wheeler_transform failed with status " + std::to_string(status) + ": " + message);
 }

@@ -10,18 +10,25 @@
 // context and every method is one call into the C ABI of include/b200sa.h.
 //
 // Differences a caller can observe:
-//   * numThreads is accepted and ignored (results never depended on it).
+//   * numThreads never changes a result (it did not in the reference either).  No host threads are spawned
+//     for it.  What the reference's one parallelism knob can select here is the number of GPUs: with the environment
+//     variable MSUFSORT_NUM_GPUS=auto a msufsort(numThreads) object shards every text over min(numThreads, GPUs
+//     present) GPUs; MSUFSORT_NUM_GPUS=N fixes the count; MSUFSORT_DEVICES=a,b,c names them; unset = one GPU.
+//   * make_suffix_array followed by forward_burrows_wheeler_transform of the same bytes (what the reference's demo and
+//     its users do) costs ONE suffix sort: the suffix array stays resident on the GPU and the second call recognises the
+//     text after uploading it.  This also holds for the free templates below (their short-lived objects borrow their GPU
+//     context from a process-wide pool).
+//   * a buffer that is not the Burrows-Wheeler transform of any text (corrupted data) makes
+//     reverse_burrows_wheeler_transform throw and leaves the buffer unchanged; the reference returns garbage.
 //   * failures (no CUDA device, out of device memory, bad sentinel index) throw
 //     std::runtime_error with the b200sa_last_error() text; the reference had no error path.
 //   * n == 0 is defined (SA = {0}, BWT returns 0); inputs up to 2^31-2 bytes are handled, the
 //     reference silently corrupts above 2^30-2 (its int32 flag bits, msufsort.h:84-93).
-//   * the GPU is chosen with the MSUFSORT_DEVICE environment variable (default 0).
+//   * the GPU of the single-GPU mode is chosen with the MSUFSORT_DEVICE environment variable (default 0).
 
 #include <cstdint>
 #include <stdint.h>
 #include <vector>
-
-struct b200sa_ctx;
 
 namespace maniscalco
 {
@@ -65,7 +72,7 @@ namespace maniscalco
 
     private:
 
-        b200sa_ctx * context_;
+        void * backend_;   // one GPU context or a group of them, borrowed from the process-wide pool (msufsort.cpp)
 
     }; // class msufsort
 

@@ -28,6 +28,7 @@
 #include <cstring>
 #include <chrono>
 #include <functional>
+#include <mutex>
 #include <vector>
 
 /* ---- qualifiers ------------------------------------------------------------------------- */
@@ -173,6 +174,9 @@ inline void run_block(unsigned nthreads)
 
 inline void launch(dim3 grid, dim3 block, size_t smem, const std::function<void()>& body)
 {
+    /* one kernel at a time, whatever host thread launches it (b200sa_group_* runs one host thread per context) */
+    static std::mutex launch_mu;
+    std::lock_guard<std::mutex> launch_lock(launch_mu);
     State& s = S();
     if (s.cur && s.cur->state != ST_DONE && s.live) { fprintf(stderr, "cuda_emu: nested launch\n"); abort(); }
     s.body = &body;

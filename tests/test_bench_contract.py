@@ -28,6 +28,18 @@ def test_reference_arm_line(ref):
     e = d["e2e"]
     assert e["value"] == d["value"] and e["unit"] == d["unit"] and e["h2d_bytes_per_step"] == 0 and e["d2h_bytes_per_step"] == 0
     assert d["config"]["workload"] == "rand_16MiB"
+    # the reference arm runs on the WHOLE text of the configuration (same config as our arm) and also reports its inverse BWT
+    assert d["config"]["sample_bytes"] == d["config"]["n_bytes"] == 1 << 24
+    assert d["unbwt"]["value"] > 0 and d["unbwt"]["unit"] == "MB/s"
+
+
+def test_default_mode_for_several_gpus_is_the_sharded_text():
+    """`bench.py --gpus N` under torchrun must measure ONE text sharded over the ranks (strong scaling), not N replicas"""
+    import re
+    src = open(os.path.join(ROOT, "bench.py")).read()
+    assert re.search(r'add_argument\("--mode", default="sharded"', src)
+    assert re.search(r'add_argument\("--isa", default="peer"', src)
+    assert '"scaling": "strong"' in src
 
 
 @pytest.mark.skipif(has_gpu(), reason="no-GPU behaviour")

@@ -1,0 +1,90 @@
+"""One text sharded over several contexts through the C++ round loop (b200sa_group_*, b200sa_shard_sort): the ranks are
+host threads of this process, the control plane is comm.cuh, the ISA lives in (peer) memory of the contexts.
+
+CPU tier: the emulator build, 2..5 contexts.  GPU tier: several contexts on ONE device (what a single-GPU box can run:
+the same kernels, the same peer-pointer loads and stores, the same barriers as on eight GPUs) and, when the box has them,
+one context per GPU."""
+import os
+
+import numpy as np
+import pytest
+
+from cases import gen
+from conftest import ROOT
+from msufsort_b200.api import B200SAError, Group, Library
+
+CASES = [("markov3", 40000), ("acgt_rep", 30011), ("abcabca", 9000), ("zeros", 5000), ("fib", 10000), ("periodic7", 8191), ("rand", 20000)]
+
+
+def _check(group, oracle, x):
+    sa, bwt, s = group.suffix_array_and_bwt(x)
+    want = oracle.sa(x)
+    assert np.array_equal(sa, want)
+    wb, ws = oracle.bwt_from_sa(x, want)
+    assert s == ws and np.array_equal(bwt, wb)
+    assert np.array_equal(group.make_suffix_array(x), want)
+    b = x.copy()
+    assert group.forward_burrows_wheeler_transform(b) == ws and np.array_equal(b, wb)
+    group.reverse_burrows_wheeler_transform(b, ws)
+    assert np.array_equal(b, x)
+
+
+@pytest.mark.parametrize("world", [2, 3, 5])
+def test_emu_group(oracle, world, monkeypatch):
+    monkeypatch.setenv("B200SA_GROUPSORT_TINY", "4")      # reach the CTA and the radix paths at these sizes too
+    monkeypatch.setenv("B200SA_GROUPSORT_MEDIUM", "64")
+    if world != 3:
+        monkeypatch.setenv("B200SA_ISA_DIRECT_BYTES", "0")
+        monkeypatch.setenv("B200SA_ISA_MIN_UPDATES", "1")
+    g = Group([0] * world, library=Library(os.path.join(ROOT, "tests", "emu", "libb200sa_emu.so")))
+    try:
+        for family, n in CASES:
+            _check(g, oracle, gen(family, n))
+        _check(g, oracle, gen("rand", 100))      # fewer than 4096 bytes per GPU: one context does it
+    finally:
+        g.close()
+
+
+def test_emu_group_untrusted_bwt_and_recovery(oracle):
+    g = Group([0, 0, 0], library=Library(os.path.join(ROOT, "tests", "emu", "libb200sa_emu.so")))
+    try:
+        x = gen("markov3", 30000)
+        bwt, s = oracle.bwt(x)
+        bad = bwt.copy()
+        bad[1234] ^= np.uint8(4)
+        keep = bad.copy()
+        with pytest.raises(B200SAError) as ei:
+            g.reverse_burrows_wheeler_transform(bad, s)
+        assert ei.value.code == 1 and np.array_equal(bad, keep)
+        _check(g, oracle, x)                      # the group (its comm included) stays usable after a failed call
+    finally:
+        g.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_gpu_group_contexts_on_one_device(oracle, world):
+    """the sharded path on a single-GPU box: `world` contexts on cuda:0"""
+    g = Group([0] * world)
+    try:
+        for family, n in [("markov3", (1 << 22) + 5), ("acgt_rep", 1 << 22), ("rand", 1 << 20), ("abcabca", 1 << 20), ("fib", 1 << 19),
+                          ("zeros", 1 << 18), ("periodic7", 300007)]:
+            before = g.launch_count()
+            _check(g, oracle, gen(family, n))
+            assert g.launch_count() > before
+    finally:
+        g.close()
+
+
+@pytest.mark.gpu
+def test_gpu_group_one_context_per_gpu(oracle):
+    import torch
+    ng = torch.cuda.device_count()
+    if ng < 2:
+        pytest.skip("one context per GPU needs at least 2 GPUs (the sharded path itself is covered by test_gpu_group_contexts_on_one_device)")
+    g = Group(list(range(min(ng, 8))))
+    try:
+        for family, n in [("markov3", (1 << 24) + 5), ("acgt_rep", 1 << 23), ("fib", 1 << 20)]:
+            _check(g, oracle, gen(family, n))
+    finally:
+        g.close()

@@ -40,7 +40,7 @@ def _worker(rank, world, port, family, n, q, isa="owner"):
         back = sorter.inverse_bwt(sorter.gather_bwt(res), res.sentinel)
         assert bool((back.cpu() == d_text.cpu()).all()), "sharded inverse BWT did not restore the text"
         if rank == 0:
-            q.put((sa, bwt, res.sentinel, res.counts, res.rounds))
+            q.put((sa, bwt, res.sentinel, sorter.owned_counts(res), res.rounds))
         dist.barrier()
         eng.close()
     finally:
@@ -170,3 +170,58 @@ def test_peer_isa_lockstep_fuzz(oracle):
             e.close()
 
     run()
+
+
+# ---- the control plane of the C++ round loop between PROCESSES: a POSIX shared-memory segment (csrc/comm.cuh) ----------
+def _comm_worker(rank, world, name, q, fail):
+    from msufsort_b200.api import B200SAError, Comm, Library
+    if fail:
+        os.environ["B200SA_COMM_TIMEOUT_MS"] = "300"
+    lib = Library(os.path.join(ROOT, "tests", "emu", "libb200sa_emu.so"))
+    c = Comm.shared_memory(name, rank, world, library=lib)
+    try:
+        if fail:
+            if rank == 1:
+                q.put((rank, "left"))        # never shows up at the barrier
+                return
+            try:
+                c.barrier()
+                q.put((rank, "no error"))
+            except B200SAError as e:
+                q.put((rank, "code %d" % e.code))
+            return
+        for i in range(3000):
+            assert c.allreduce_sum(rank * 1000 + i) == sum(r * 1000 + i for r in range(world))
+            if i % 7 == 0:
+                c.barrier()
+        q.put((rank, "ok"))
+    finally:
+        c.close()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_shm_comm_between_processes(world):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    name = "/b200sa_test_%d_%s" % (os.getpid(), os.urandom(4).hex())
+    procs = [ctx.Process(target=_comm_worker, args=(r, world, name, q, False)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = sorted(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert got == [(r, "ok") for r in range(world)]
+
+
+def test_shm_comm_times_out_instead_of_hanging():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    name = "/b200sa_test_%d_%s" % (os.getpid(), os.urandom(4).hex())
+    procs = [ctx.Process(target=_comm_worker, args=(r, 2, name, q, True)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+    assert got[1] == "left" and got[0] == "code 6"   # B200SA_ECOMM

@@ -40,9 +40,11 @@ def _worker(rank, world, port, family, n, q, isa="owner"):
         bwt = sorter.gather_bwt(res).cpu().numpy()
         back = sorter.inverse_bwt(sorter.gather_bwt(res), res.sentinel)
         assert bool((back.cpu() == d_text.cpu()).all()), "sharded inverse BWT did not restore the text"
+        counts = sorter.owned_counts(res)
         if rank == 0:
-            q.put((sa, bwt, res.sentinel, res.counts, res.rounds))
+            q.put((sa, bwt, res.sentinel, counts, res.rounds))
         dist.barrier()
+        sorter.close()
         eng.close()
     finally:
         dist.destroy_process_group()

@@ -9,6 +9,21 @@ import pytest
 from cases import EDGE_SIZES, gen
 
 
+def _lcp_u32(eng, x, sa):
+    """b200sa_lcp_u32_dev on host arrays (emulator) or device tensors (GPU)"""
+    n = x.size
+    if eng.lib.path.endswith("libb200sa_emu.so"):
+        out = np.empty(n + 1, dtype=np.uint32)
+        eng.lcp_u32_dev(x, n, sa, out)
+        return out
+    import torch
+    d_x = torch.from_numpy(x).cuda()
+    d_sa = torch.from_numpy(sa.view(np.int32)).cuda()
+    d_out = torch.empty(n + 1, dtype=torch.int32, device="cuda")
+    eng.lcp_u32_dev(d_x, n, d_sa, d_out)
+    return d_out.cpu().numpy().view(np.uint32)
+
+
 def _check_small(eng, oracle):
     for family in ["markov3", "zeros", "fib", "rand", "abcabca"]:
         for n in EDGE_SIZES[:12] + [4097, 30011]:
@@ -18,6 +33,12 @@ def _check_small(eng, oracle):
             assert sa.dtype == np.uint32 and np.array_equal(sa.astype(np.int64), want.astype(np.int64)), (family, n)
             wb, ws = oracle.bwt_from_sa(x, want)
             assert s == ws and np.array_equal(bwt, wb), (family, n)
+            # wide inverse transform (int64 sentinel index) and wide LCP array (uint32 entries)
+            back = bwt.copy()
+            eng.reverse_burrows_wheeler_transform_u32(back, s)
+            assert np.array_equal(back, x), (family, n)
+            lcp = _lcp_u32(eng, x, sa)
+            assert np.array_equal(lcp.astype(np.int64), oracle.lcp(x, want, kasai=True).astype(np.int64)), (family, n)
     sa, bwt, s = eng.suffix_array_and_bwt_u32(np.empty(0, np.uint8))
     assert sa.tolist() == [0] and s == 0
 

@@ -132,7 +132,6 @@ int Engine::init(int dev)
     if (const char* e12 = getenv("B200SA_LCP_DIRECT")) lcp_direct = atoi(e12) != 0;
     if (const char* e11 = getenv("B200SA_NUM_SMS")) { const int v = atoi(e11); if (v >= 1 && v <= 1024) num_sms = v; }  // tests: small persistent grids
     if (const char* e13 = getenv("B200SA_COPY_THREADS")) copy_threads = atoi(e13);
-    if (const char* e14 = getenv("B200SA_BWT_SCATTER_MIN")) bwt_scatter_min = (size_t)strtoull(e14, nullptr, 10);
     if (const char* e6 = getenv("B200SA_UNBWT_CAP_MULT")) unbwt_cap_mult = (u32)strtoul(e6, nullptr, 10);
     if (unbwt_cap_mult < 1) unbwt_cap_mult = 1;
     if (groupsort_tiny > (u32)GS_TINY) groupsort_tiny = GS_TINY;
@@ -141,8 +140,6 @@ int Engine::init(int dev)
     {
         auto k64 = k_onesweep_pass<u64, true>;
         auto k8 = k_onesweep_pass<u8, false>;
-        auto k32b = k_onesweep_pass<u32, true, u8>;
-        B200SA_CU(cudaFuncSetAttribute(k32b, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_pass_smem_bytes<u32>()));
         auto k32 = k_onesweep_pass<u32, true>;
         B200SA_CU(cudaFuncSetAttribute(k32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_pass_smem_bytes<u32>()));
         B200SA_CU(cudaFuncSetAttribute(k64, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_pass_smem_bytes<u64>()));
@@ -864,44 +861,6 @@ int Engine::suffix_array_dev(const u8* d_text, i64 n64, i32* d_sa, cudaStream_t 
 int Engine::bwt_rows(const u8* d_text, u32 n, const i32* d_sa, u32 o_begin, u32 o_end, u8* d_bwt, cudaStream_t st, bool defer_sync)
 {
     i32* d_sent = (i32*)(misc.as<u32>() + 528);
-    const bool whole = o_begin == 0 && o_end == n && !(peer.active && peer.has_isa && ss.nparts > 1);
-    if (whole && (size_t)n >= bwt_scatter_min) {
-        // ---- text-order route (bwt_kernels.cuh): one sweep of (rank[i], T[i-1]) by row window, then an L2-resident scatter.
-        // The sort buffers are free by now: bucketed rows -> keys[0], bucketed bytes -> idx[0].
-        B200SA_TRY(keys[0].ensure((size_t)n * 4 + 64));
-        B200SA_TRY(idx[0].ensure((size_t)n + 64));
-        const int nbits = bit_length_u64((u64)n);
-        const int shift = nbits > RS_RADIX_BITS ? nbits - RS_RADIX_BITS : 0;
-        const u32 tiles = (u32)div_up_u64(n, RS_TILE);
-        const size_t status_bytes = (size_t)tiles * RS_RADIX * sizeof(u64);
-        B200SA_TRY(sortmeta.ensure(kSortMetaHeader + status_bytes));
-        u32* ghist = sortmeta.as<u32>();
-        u32* counters = ghist + RS_MAX_PASSES * RS_RADIX;
-        u64* status = (u64*)((u8*)sortmeta.p + kSortMetaHeader);
-        B200SA_CU(cudaMemsetAsync(sortmeta.p, 0, kSortMetaHeader + status_bytes, st));
-        prof.memsets++;
-        B200SA_TRY(phase_begin(B200SA_PH_BWT, st));
-        B200SA_LAUNCH(k_bwt_bins, 1, 256, 0, st, (const u32*)rank.as<u32>(), n, shift, ghist, d_sent);
-        count_launch(B200SA_PH_BWT);
-        auto kp = k_onesweep_pass<u32, true, u8>;
-        B200SA_LAUNCH(kp, tiles, RS_THREADS, rs_pass_smem_bytes<u32>(), st, (const u32*)(rank.as<u32>() + 1), keys[0].as<u32>(), d_text, idx[0].as<u8>(),
-                      n, shift, 0xffffffffu, (const u32*)ghist, status, counters);
-        count_launch(B200SA_PH_BWT);
-        {
-            const u32 want = (u32)div_up_u64(n, BS_THREADS * BS_IPT);
-            const u32 grid = want < (u32)(num_sms * 16) ? want : (u32)(num_sms * 16);
-            B200SA_LAUNCH(k_bwt_scatter, grid, BS_THREADS, 0, st, (const u32*)keys[0].as<u32>(), (const u8*)idx[0].as<u8>(), n,
-                          (const u32*)rank.as<u32>(), d_bwt);
-            count_launch(B200SA_PH_BWT);
-        }
-        B200SA_TRY(phase_end(st));
-        prof.alg_bytes[B200SA_PH_BWT] += (u64)n * (5 + 5 + 5 + 1);
-        B200SA_CU(cudaGetLastError());
-        if (defer_sync) return 0;
-        B200SA_CU(cudaMemcpyAsync(h_pinned + 8, d_sent, sizeof(i32), cudaMemcpyDeviceToHost, st));
-        B200SA_CU(cudaStreamSynchronize(st));
-        return 0;
-    }
     B200SA_TRY(phase_begin(B200SA_PH_BWT, st));
     {
         const u32 groups = (u32)div_up_u64(o_end - o_begin, 4);

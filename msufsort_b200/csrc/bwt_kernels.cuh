@@ -10,6 +10,12 @@ namespace b200sa {
 // copy-out loop (:1811-1815).  Row 0 holds SA = n, so it emits T[n-1] without a special case.
 // Each thread produces 4 consecutive output bytes per step (one 32-bit store); SA is read with
 // consecutive lanes on consecutive 16-byte chunks, the text bytes are gathered.
+// Once the text is larger than L2 every gathered byte costs one random 32-byte DRAM sector (256 MiB: 4.2 ms, ~64 G
+// gathers/s — the random-access rate of HBM, the same rate the LCP probes and the inverse BWT see).  The alternative
+// measured in round 2 — text order: one radix sweep of (rank[i], T[i-1]) pairs by row window, then a scatter inside
+// L2-resident windows — LOST on B200: the sweep takes 1.46 ms, but 2^28 one-byte stores take 3.3 ms (sub-word stores are
+// read-modify-write operations for the ECC-protected L2: ncu shows 6.9 GB of DRAM traffic for 1.6 GB of algorithmic
+// bytes), 4.3 ms with 32-bit OR reductions; 4.9 / 5.8 ms against 4.2 ms for this gather (profiles/r02_negative_results.md).
 static const int BW_THREADS = 256;
 static const int BW_STEPS = 4;  // independent 4-byte groups in flight per thread
 
@@ -54,52 +60,6 @@ k_bwt_gather(const u8* __restrict__ text, const i32* __restrict__ sa, const u32*
                     for (u32 b = 0; b < 4u && o + b < o_end; ++b) out[o + b] = (u8)(packed[st] >> (8 * b));
                 }
             }
-        }
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
-// Forward BWT of a text that does not fit the L2 cache, in TEXT order instead of row order: the finished ISA says where
-// every byte goes — T[i-1] belongs to row rank[i] (i = 1..n, rank[n] = 0), i.e. to out[row - (row > s)].  The gather
-// above pays one random 32-byte DRAM sector per output byte once the text is larger than L2 (256 MiB: 4.3 ms = 6 x the
-// algorithmic bytes); here ONE radix sweep on the top 8 bits of the row (keys = rank[1..n] read in place, values = the
-// text bytes read in place, radix_sort.cuh with ValT = u8) brings the pairs into 256 row windows, and the scatter of a
-// window then stays inside n/256 output bytes that live in L2.  The keys are a permutation of {0..n} \ {s}, so the digit
-// offsets need no histogram pass.
-__global__ void __launch_bounds__(256)
-k_bwt_bins(const u32* __restrict__ rank, u32 n, int shift, u32* __restrict__ bins /*256 exclusive offsets*/, i32* __restrict__ sentinel_out)
-{
-    const u32 s = rank[0];
-    const u32 t = threadIdx.x;
-    const u64 lo = (u64)t << shift;
-    u64 below = lo < (u64)n + 1 ? lo : (u64)n + 1;  // rows 0..n smaller than lo
-    if ((u64)s < lo) below -= 1;                      // row s (suffix 0) has no preceding byte
-    bins[t] = (u32)below;
-    if (t == 0 && sentinel_out) *sentinel_out = (i32)s;
-}
-
-static const int BS_THREADS = 256;
-static const int BS_IPT = 8;
-
-__global__ void __launch_bounds__(BS_THREADS)
-k_bwt_scatter(const u32* __restrict__ rows, const u8* __restrict__ bytes, u32 n, const u32* __restrict__ rank, u8* __restrict__ out)
-{
-    const u32 s = rank[0];
-    const u32 tile = BS_THREADS * BS_IPT;
-    const u32 ntiles = (u32)div_up_u64(n, tile);
-    for (u32 t = blockIdx.x; t < ntiles; t += gridDim.x) {
-        const u32 base = t * tile + threadIdx.x;
-        u32 r[BS_IPT];
-        u8 b[BS_IPT];
-#pragma unroll
-        for (int q = 0; q < BS_IPT; ++q) {
-            const u32 j = base + (u32)q * BS_THREADS;
-            if (j < n) { r[q] = ld_stream(rows + j); b[q] = ld_stream(bytes + j); }
-        }
-#pragma unroll
-        for (int q = 0; q < BS_IPT; ++q) {
-            const u32 j = base + (u32)q * BS_THREADS;
-            if (j < n) out[r[q] - (r[q] > s ? 1u : 0u)] = b[q];
         }
     }
 }

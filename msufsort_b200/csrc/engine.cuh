@@ -83,10 +83,6 @@ struct Engine {
     u32 groupsort_tiny = GS_TINY;
     u32 groupsort_medium = GS_MEDIUM;
 
-    // forward BWT: texts of at least this many bytes (they do not fit L2 next to the suffix array stream) take the text-order
-    // bucketed scatter instead of the row-order gather (B200SA_BWT_SCATTER_MIN; tests set 0 to drive it at small n)
-    size_t bwt_scatter_min = (size_t)96 << 20;
-
     // inverse BWT: bytes of decode window per walker = unbwt_cap_mult * D (D = mean segment length)
     u32 unbwt_cap_mult = 4;
 

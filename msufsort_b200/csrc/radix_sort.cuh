@@ -164,11 +164,10 @@ __device__ unsigned long long g_phase_cycles[8];
 #define PT_MARK(i) do { } while (0)
 #endif
 
-//   ValT            -> u32 everywhere except the forward BWT, which carries the byte T[i-1] next to rank[i] (bwt_kernels.cuh)
-template <typename KeyT, bool WRITE_KEYS, typename ValT = u32>
+template <typename KeyT, bool WRITE_KEYS>
 __global__ void __launch_bounds__(RS_THREADS, RS_MIN_BLOCKS)
 k_onesweep_pass(const KeyT* __restrict__ kin, KeyT* __restrict__ kout,
-                const ValT* __restrict__ vin, ValT* __restrict__ vout,
+                const u32* __restrict__ vin, u32* __restrict__ vout,
                 u32 m, int shift, u32 gen_skip,
                 const u32* __restrict__ bins, u64* __restrict__ status, u32* __restrict__ tile_counter)
 {
@@ -185,7 +184,7 @@ k_onesweep_pass(const KeyT* __restrict__ kin, KeyT* __restrict__ kout,
 #else
     KeyT* skeys = (KeyT*)(s_wtot + 16);  // [TILE]
 #endif
-    ValT* svals = (ValT*)(skeys + TILE);   // [TILE]
+    u32* svals = (u32*)(skeys + TILE);   // [TILE]
     __shared__ u32 s_tile;
 
     const u32 tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
@@ -208,7 +207,7 @@ k_onesweep_pass(const KeyT* __restrict__ kin, KeyT* __restrict__ kout,
 
     // ---- load (warp-striped): element order inside the tile is (warp, item, lane)
     KeyT key[IPT];
-    ValT val[IPT];
+    u32 val[IPT];
     RS_POS_DECL(IPT);
     const u32 wbase = warp * (32u * IPT) + lane;
     const bool full = valid == (u32)TILE;  // block-uniform: no bounds checks on the common path
@@ -269,21 +268,21 @@ k_onesweep_pass(const KeyT* __restrict__ kin, KeyT* __restrict__ kout,
     // the 80-register budget of 3 CTAs/SM); their latency overlaps the tile-level scan below
     if (vin) {
         if (full) {
-            const ValT* vp = vin + base + wbase;
+            const u32* vp = vin + base + wbase;
 #pragma unroll
             for (int k = 0; k < IPT; ++k) val[k] = ld_stream(vp + k * 32);
         } else {
 #pragma unroll
             for (int k = 0; k < IPT; ++k) {
                 const u32 li = wbase + (u32)k * 32u;
-                val[k] = li < valid ? ld_stream(vin + base + li) : (ValT)0;
+                val[k] = li < valid ? ld_stream(vin + base + li) : 0u;
             }
         }
     } else {
 #pragma unroll
         for (int k = 0; k < IPT; ++k) {
             const u32 gi = base + wbase + (u32)k * 32u;
-            val[k] = (ValT)(gi + (gi >= gen_skip ? 1u : 0u));
+            val[k] = gi + (gi >= gen_skip ? 1u : 0u);
         }
     }
     __syncthreads();

@@ -97,7 +97,9 @@ k_pack_keys(const u8* __restrict__ text, u32 n, const u8* __restrict__ code, int
     __shared__ __align__(16) u8 s_sym[PK_TILE + PK_HALO];
     __shared__ u64 s_out[RANGE ? 1 : PK_THREADS / 32][RANGE ? 1 : PK_IPT * 33];
     __shared__ u32 s_wsum[PK_THREADS / 32];
-    __shared__ u32 s_base;
+    __shared__ u32 s_base, s_total;
+    __shared__ u64 s_ck[RANGE ? PK_TILE : 1];  // kept keys of the tile, compacted, so that the global stores are coalesced
+    __shared__ u16 s_cp[RANGE ? PK_TILE : 1];  // their positions inside the tile
     const u32 tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     s_code[tid] = RADIX ? (u8)(code[tid] + 1u) : code[tid];  // sigma <= 255 in the mixed-radix layout: digits fit a byte
     __syncthreads();
@@ -150,17 +152,24 @@ k_pack_keys(const u8* __restrict__ text, u32 n, const u8* __restrict__ code, int
             if (tid == 0) {
                 u32 tot = 0;
                 for (int w = 0; w < PK_THREADS / 32; ++w) { const u32 c = s_wsum[w]; s_wsum[w] = tot; tot += c; }
+                s_total = tot;
                 s_base = tot ? atomicAdd(cursor, tot) : 0u;  // one cursor bump per tile
             }
             __syncthreads();
-            u32 d = s_base + s_wsum[warp] + incl - cnt;
+            u32 d = s_wsum[warp] + incl - cnt;
 #pragma unroll
             for (int i = 0; i < PK_IPT; ++i) {
                 if ((keep >> i) & 1u) {
-                    keys[d] = kreg[i];
-                    out_idx[d] = base + p0 + (u32)i;
+                    s_ck[d] = kreg[i];
+                    s_cp[d] = (u16)(p0 + (u32)i);
                     ++d;
                 }
+            }
+            __syncthreads();
+            const u32 tot = s_total, gb = s_base;
+            for (u32 j = tid; j < tot; j += PK_THREADS) {
+                keys[gb + j] = s_ck[j];
+                out_idx[gb + j] = base + (u32)s_cp[j];
             }
             __syncthreads();
         } else {

@@ -140,27 +140,6 @@ def test_emu_inverse_bwt_window_overflow(oracle, cap_mult, monkeypatch):
         eng.close()
 
 
-def test_emu_bwt_text_order_scatter(oracle, monkeypatch):
-    """forward BWT through the text-order bucketed scatter (taken for texts larger than L2 on the GPU; forced here)"""
-    import os
-    from conftest import ROOT
-    from msufsort_b200.api import Engine, Library
-    monkeypatch.setenv("B200SA_BWT_SCATTER_MIN", "0")
-    eng = Engine(0, library=Library(os.path.join(ROOT, "tests", "emu", "libb200sa_emu.so")))
-    try:
-        for family in FAMILIES:
-            for n in (1, 2, 3, 255, 256, 257, 4095, 4097, 30011):
-                x = gen(family, n)
-                want = oracle.sa(x)
-                wb, ws = oracle.bwt_from_sa(x, want)
-                sa, bwt, s = eng.suffix_array_and_bwt(x)
-                assert np.array_equal(sa, want) and s == ws and np.array_equal(bwt, wb), (family, n)
-                b = x.copy()
-                assert eng.forward_burrows_wheeler_transform(b) == ws and np.array_equal(b, wb), (family, n)
-    finally:
-        eng.close()
-
-
 def test_emu_resident_suffix_array_is_reused(emu_engine, oracle):
     """make_suffix_array then forward_burrows_wheeler_transform of the same bytes: one sort; of other bytes: two"""
     x = gen("markov3", 20011)

@@ -692,8 +692,8 @@ def run_sharded(args, wl):
                                       + (" (NVLink peer memory; round loop in C++, control plane = shared-memory barriers)" if args.isa == "peer" else " (NCCL)"),
                        "l2": "working set per GPU (>= 44 n / N bytes + the n-byte text) far larger than the 126 MB L2; no flush needed",
                        "owned_suffixes_per_rank": counts, "rounds": rounds_of(prof, args.steps)},
-            "e2e": {"value": n / e2e_s / 1e6, "unit": "MB/s", "ms_per_step": e2e_s * 1e3, "h2d_bytes_per_step": world * n, "d2h_bytes_per_step": d2h_total,
-                    "path": "ShardedSorter.suffix_array_bwt_host: pinned host text uploaded by every rank, b200sa_shard_sort, every rank downloads its rows of the "
+            "e2e": {"value": n / e2e_s / 1e6, "unit": "MB/s", "ms_per_step": e2e_s * 1e3, "h2d_bytes_per_step": n, "d2h_bytes_per_step": d2h_total,
+                    "path": "ShardedSorter.suffix_array_bwt_host: every rank uploads 1/N of the pinned host text and the slices are all-gathered over NVLink, b200sa_shard_sort, every rank downloads its rows of the "
                             "suffix array and its bytes of the BWT"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "k_onesweep_pass<u64> (rank 0)", "achieved": achieved, "peak": peak, "unit": "GB/s",

@@ -256,7 +256,7 @@ B200SA_API int b200sa_shard_apply_updates(b200sa_ctx* ctx, const uint32_t* d_idx
  * [g*B, (g+1)*B), B a power of two.  After a round the producer of a new rank sends it to the owner of
  * that suffix (all-to-all), and before the next round every GPU asks the owners for the ranks it is
  * about to read (all-to-all of positions, all-to-all of values) and drops the replies into its own
- * rank[] as a cache.  shard_partition routes pairs by owner (bucket = (key >> shift) & 255, stable),
+ * rank[] as a cache.  shard_partition routes pairs by owner (bucket = (key >> shift) & 255; a multi-split, not stable),
  * shard_requests lists the positions the next round reads, shard_gather_ranks serves a request list. */
 B200SA_API int b200sa_shard_partition(b200sa_ctx* ctx, const uint32_t* d_keys, const uint32_t* d_vals, int64_t count,
                                       int shift, uint32_t* d_keys_out, uint32_t* d_vals_out, uint32_t* counts_out /*256, host*/,

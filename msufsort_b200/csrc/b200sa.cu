@@ -141,7 +141,9 @@ int Engine::init(int dev)
         auto k64 = k_onesweep_pass<u64, true>;
         auto k8 = k_onesweep_pass<u8, false>;
         auto k32 = k_onesweep_pass<u32, true>;
+        auto k32u = k_onesweep_pass<u32, true, false>;
         B200SA_CU(cudaFuncSetAttribute(k32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_pass_smem_bytes<u32>()));
+        B200SA_CU(cudaFuncSetAttribute(k32u, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_pass_smem_bytes<u32>()));
         B200SA_CU(cudaFuncSetAttribute(k64, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_pass_smem_bytes<u64>()));
         B200SA_CU(cudaFuncSetAttribute(k8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_pass_smem_bytes<u8>()));
     }
@@ -440,7 +442,7 @@ int Engine::isa_update(const u32* d_idx, const u32* d_val, u32 count, u32 n, u32
             B200SA_LAUNCH(k_radix_scan_bins, 1, RS_RADIX, 0, st, ghist);
             count_launch(B200SA_PH_ISA);
         }
-        auto kp = k_onesweep_pass<u32, true>;
+        auto kp = k_onesweep_pass<u32, true, false>;  // a multi-split suffices: the pairs are only bucketed for the scatter
         B200SA_LAUNCH(kp, tiles, RS_THREADS, rs_pass_smem_bytes<u32>(), st, d_idx, bk_key, d_val, bk_val,
                       count, shift, 0xffffffffu, (const u32*)ghist, status, counters);
         count_launch(B200SA_PH_ISA);
@@ -600,11 +602,15 @@ int Engine::sort_begin(const u8* d_text, u32 n, i32* d_sa, int part, int nparts,
         count_launch(B200SA_PH_PACK);
         int sside = 0;
         B200SA_TRY(radix_sort_pairs(smp, sv, true, nsample, 0, key_bits, &sside, st));
-        std::vector<u64> h_sample(nsample);
-        B200SA_CU(cudaMemcpyAsync(h_sample.data(), smp[sside], (size_t)nsample * 8, cudaMemcpyDeviceToHost, st));
+        // only this part's two splitters travel to the host (pinned words 450..453)
+        u64* h_split = (u64*)(h_pinned + 450);
+        h_split[0] = 0ull;
+        h_split[1] = ~0ull;
+        if (part > 0) B200SA_CU(cudaMemcpyAsync(&h_split[0], smp[sside] + (size_t)((u64)part * nsample / nparts), 8, cudaMemcpyDeviceToHost, st));
+        if (part < nparts - 1)
+            B200SA_CU(cudaMemcpyAsync(&h_split[1], smp[sside] + (size_t)((u64)(part + 1) * nsample / nparts), 8, cudaMemcpyDeviceToHost, st));
         B200SA_CU(cudaStreamSynchronize(st));
-        const u64 lo = part == 0 ? 0ull : h_sample[(size_t)((u64)part * nsample / nparts)];
-        const u64 hi = part == nparts - 1 ? ~0ull : h_sample[(size_t)((u64)(part + 1) * nsample / nparts)];
+        const u64 lo = h_split[0], hi = h_split[1];
         const int hi_inclusive = part == nparts - 1 ? 1 : 0;
         u32* d_count = misc.as<u32>() + 536;
         B200SA_CU(cudaMemsetAsync(d_count, 0, 4, st));

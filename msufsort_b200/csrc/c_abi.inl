@@ -693,7 +693,7 @@ int b200sa_shard_bwt(b200sa_ctx* ctx, int64_t row_begin, int64_t row_end, uint8_
     return 0;
 }
 
-// Stable partition of (key, value) pairs by (key >> shift) & 255 — the routing step of every all-to-all of the
+// Partition (multi-split, not stable) of (key, value) pairs by (key >> shift) & 255 — the routing step of every all-to-all of the
 // owner-sharded ISA (bucket = owning GPU).  counts_out: 256 host words.  d_vals may be NULL.
 int b200sa_shard_partition(b200sa_ctx* ctx, const uint32_t* d_keys, const uint32_t* d_vals, int64_t count, int shift,
                            uint32_t* d_keys_out, uint32_t* d_vals_out, uint32_t* counts_out, void* stream)
@@ -725,7 +725,7 @@ int b200sa_shard_partition(b200sa_ctx* ctx, const uint32_t* d_keys, const uint32
     B200SA_CU(cudaStreamSynchronize(st));
     B200SA_LAUNCH(b200sa::k_radix_scan_bins, 1, b200sa::RS_RADIX, 0, st, ghist);
     e.count_launch(B200SA_PH_ISA);
-    auto kp = b200sa::k_onesweep_pass<u32, true>;
+    auto kp = b200sa::k_onesweep_pass<u32, true, false>;  // multi-split: order inside a bucket is irrelevant
     B200SA_LAUNCH(kp, tiles, b200sa::RS_THREADS, b200sa::rs_pass_smem_bytes<u32>(), st, d_keys, d_keys_out, d_vals, d_vals_out,
                   m, shift, 0xffffffffu, (const u32*)ghist, status, counters);
     e.count_launch(B200SA_PH_ISA);
@@ -907,6 +907,29 @@ struct b200sa_group {
     std::vector<b200sa_comm*> comms;
     std::mutex mu;  // one job at a time, like one msufsort object
 
+    // Upload of a host buffer every rank needs in full: rank r moves only its 1/G slice over its own PCIe link, then pulls the
+    // other slices from its peers' HBM over NVLink (G x less host-memory and PCIe traffic than G full uploads).  `which`
+    // selects the per-context destination buffer (it has been sized by the caller).
+    int upload_shared(int r, const uint8_t* host, int64_t n, b200sa::DevBuf Engine::*which)
+    {
+        const int G = (int)ctxs.size();
+        Engine& e = ctxs[(size_t)r]->eng;
+        cudaStream_t st = e.own_stream;
+        auto lo = [&](int g) { return (size_t)((unsigned __int128)n * (unsigned)g / (unsigned)G) & ~(size_t)15; };
+        auto hi = [&](int g) { return g == G - 1 ? (size_t)n : lo(g + 1); };
+        u8* mine = (e.*which).as<u8>();
+        if (hi(r) > lo(r)) B200SA_TRY(e.copy_in(mine + lo(r), host + lo(r), hi(r) - lo(r), st));
+        B200SA_CU(cudaStreamSynchronize(st));
+        B200SA_TRY(comms[(size_t)r]->c->barrier());  // every slice is in its owner's HBM
+        for (int k = 1; k < G; ++k) {
+            const int g = (r + k) % G;               // start with the right-hand neighbour: G readers on G different sources
+            if (hi(g) > lo(g))
+                B200SA_CU(cudaMemcpyAsync(mine + lo(g), (ctxs[(size_t)g]->eng.*which).as<u8>() + lo(g), hi(g) - lo(g), cudaMemcpyDefault, st));
+        }
+        B200SA_CU(cudaStreamSynchronize(st));
+        return comms[(size_t)r]->c->barrier();       // nobody's buffer is overwritten (next call) while a peer still reads it
+    }
+
     template <typename F> int run(F&& per_rank)
     {
         const int G = (int)ctxs.size();
@@ -951,6 +974,17 @@ int b200sa_group_create(b200sa_group** out, const int* devices, int count)
         if (rc != 0) { for (auto* q : g->ctxs) b200sa_destroy(q); delete g; return rc; }
         g->ctxs.push_back(c);
     }
+#ifndef B200SA_EMU
+    // the contexts read each other's HBM (shared uploads, the sharded ISA): enable the NVLink peer mappings once
+    for (int i = 0; i < count; ++i)
+        for (int j = 0; j < count; ++j)
+            if (devices[i] != devices[j]) {
+                int can = 0;
+                cudaDeviceCanAccessPeer(&can, devices[i], devices[j]);
+                if (can && cudaSetDevice(devices[i]) == cudaSuccess) cudaDeviceEnablePeerAccess(devices[j], 0);
+                cudaGetLastError();  // already enabled is fine
+            }
+#endif
     g->comms.resize((size_t)count);
     const int rc = b200sa_comm_create_local(g->comms.data(), count);
     if (rc != 0) { for (auto* q : g->ctxs) b200sa_destroy(q); delete g; return rc; }
@@ -992,8 +1026,8 @@ int b200sa_group_suffix_array_bwt(b200sa_group* g, const uint8_t* text, int64_t 
         B200SA_TRY(e.text_ws.ensure((size_t)n + 64));
         B200SA_TRY(e.sa_ws.ensure(((size_t)n + 1) * 4));
         if (want_bwt) B200SA_TRY(e.bwt_ws.ensure((size_t)n + 64));
-        // every GPU pulls the whole text over its own PCIe link; the results leave as disjoint slices over all links
-        B200SA_TRY(e.copy_in(e.text_ws.p, text, (size_t)n, st));
+        // every GPU uploads one slice of the text and pulls the rest from its peers; the results leave as disjoint slices
+        B200SA_TRY(g->upload_shared(r, text, n, &Engine::text_ws));
         Engine::ShardInfo& info = infos[(size_t)r];
         B200SA_TRY(e.sharded_sort(*g->comms[(size_t)r]->c, e.text_ws.as<u8>(), n, e.sa_ws.as<i32>(), want_bwt ? e.bwt_ws.as<u8>() : nullptr, &info, st));
         if (sa_out && info.row_end > info.row_begin)
@@ -1039,7 +1073,7 @@ int b200sa_group_unbwt(b200sa_group* g, uint8_t* bwt_inout, int64_t n, int32_t s
         B200SA_CU(cudaSetDevice(e.device));
         cudaStream_t st = e.own_stream;
         B200SA_TRY(e.bwt_ws.ensure((size_t)n + 64));
-        B200SA_TRY(e.copy_in(e.bwt_ws.p, bwt_inout, (size_t)n, st));
+        B200SA_TRY(g->upload_shared(r, bwt_inout, n, &Engine::bwt_ws));
         return e.sharded_unbwt(*g->comms[(size_t)r]->c, e.bwt_ws.as<u8>(), n, sentinel_index, nullptr, false, &lo[(size_t)r], &hi[(size_t)r], st);
     });
     if (rc) return rc;

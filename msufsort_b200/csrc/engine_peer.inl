@@ -209,7 +209,7 @@ int Engine::peer_scatter(cudaStream_t st)
         count_launch(B200SA_PH_ISA);
         B200SA_LAUNCH(k_radix_scan_bins, 1, RS_RADIX, 0, st, ghist);
         count_launch(B200SA_PH_ISA);
-        auto kp = k_onesweep_pass<u32, true>;
+        auto kp = k_onesweep_pass<u32, true, false>;  // multi-split: order inside a bucket is irrelevant
         B200SA_LAUNCH(kp, tiles, RS_THREADS, rs_pass_smem_bytes<u32>(), st, ss.upd_idx, bk_key, ss.upd_rank, bk_val, count, bshift,
                       0xffffffffu, (const u32*)ghist, status, counters);
         count_launch(B200SA_PH_ISA);
@@ -236,18 +236,29 @@ int Engine::peer_apply(cudaStream_t st)
     const int G = peer.nparts;
     B200SA_CU(cudaMemcpyAsync(h_pinned + 400, peer_inbox.p, kMaxPeers * 4, cudaMemcpyDeviceToHost, st));
     B200SA_CU(cudaStreamSynchronize(st));
+    InboxRegions ir;
+    memset(&ir, 0, sizeof(ir));
+    u32 tiles = 0;
+    u64 pairs = 0;
     for (int s = 0; s < G; ++s) {
         const u32 cnt = h_pinned[400 + s];
         if (cnt == 0) continue;
         if (cnt > peer.region_cap[s]) return set_error(B200SA_EINTERNAL, "GPU %d announced %u pairs for a region of %u", s, cnt, peer.region_cap[s]);
-        const u32* keys_s = (const u32*)(peer_inbox.as<u8>() + peer.region_off[s]);
-        const u32* vals_s = keys_s + peer.region_cap[s];
-        // the run arrives bucketed by the top bits of the suffix index: the stores walk through L2-sized windows
+        // a run arrives bucketed by the top bits of the suffix index: the stores walk through L2-sized windows
+        const int r = ir.nregions++;
+        ir.keys[r] = (const u32*)(peer_inbox.as<u8>() + peer.region_off[s]);
+        ir.vals[r] = ir.keys[r] + peer.region_cap[s];
+        ir.count[r] = cnt;
+        tiles += (u32)div_up_u64(cnt, SP_THREADS * SP_IPT);
+        ir.tile_end[r] = tiles;
+        pairs += cnt;
+    }
+    if (ir.nregions) {
         B200SA_TRY(phase_begin(B200SA_PH_ISA, st));
-        B200SA_LAUNCH(k_scatter_pairs, (u32)div_up_u64(cnt, SP_THREADS * SP_IPT), SP_THREADS, 0, st, keys_s, vals_s, cnt, rank.as<u32>());
+        B200SA_LAUNCH(k_scatter_regions, tiles, SP_THREADS, 0, st, ir, rank.as<u32>());
         count_launch(B200SA_PH_ISA);
         B200SA_TRY(phase_end(st));
-        prof.alg_bytes[B200SA_PH_ISA] += (u64)cnt * 12;
+        prof.alg_bytes[B200SA_PH_ISA] += pairs * 12;
     }
     B200SA_CU(cudaGetLastError());
     B200SA_CU(cudaStreamSynchronize(st));

@@ -164,7 +164,11 @@ __device__ unsigned long long g_phase_cycles[8];
 #define PT_MARK(i) do { } while (0)
 #endif
 
-template <typename KeyT, bool WRITE_KEYS>
+//   STABLE=false    -> a multi-split: pairs with equal digits may change their relative order.  That is all the ISA update and
+//                      the routing of pairs to their owner GPU need (they only bucket pairs for a scatter), and it replaces
+//                      the within-warp ranking — eight ballots, per-warp counters and their reduction over the warps, 40 % of
+//                      the sweep's instructions — by ONE shared-memory atomicAdd per pair on the tile's digit counters.
+template <typename KeyT, bool WRITE_KEYS, bool STABLE = true>
 __global__ void __launch_bounds__(RS_THREADS, RS_MIN_BLOCKS)
 k_onesweep_pass(const KeyT* __restrict__ kin, KeyT* __restrict__ kout,
                 const u32* __restrict__ vin, u32* __restrict__ vout,
@@ -189,11 +193,15 @@ k_onesweep_pass(const KeyT* __restrict__ kin, KeyT* __restrict__ kout,
 
     const u32 tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     if (tid == 0) s_tile = atomicAdd(tile_counter, 1u);
-    for (u32 i = tid; i < (u32)(WARPS * RS_RADIX); i += THREADS) {
-        whist[i] = 0;
+    if (STABLE) {
+        for (u32 i = tid; i < (u32)(WARPS * RS_RADIX); i += THREADS) {
+            whist[i] = 0;
 #if B200SA_RS_PEERS_ATOMIC_OR
-        wmask[i] = 0;
+            wmask[i] = 0;
 #endif
+        }
+    } else {
+        if (tid < (u32)RS_RADIX) s_cnt[tid] = 0;
     }
     __syncthreads();
     const u32 tile = s_tile;
@@ -239,29 +247,39 @@ k_onesweep_pass(const KeyT* __restrict__ kin, KeyT* __restrict__ kout,
     u32* mymask = wmask + warp * RS_RADIX;
     const u32 mybit = 1u << lane;
 #endif
+    if (STABLE) {
 #pragma unroll
-    for (int k = 0; k < IPT; ++k) {
-        const u32 d = rs_digit<KeyT>(key[k], shift);
+        for (int k = 0; k < IPT; ++k) {
+            const u32 d = rs_digit<KeyT>(key[k], shift);
 #if B200SA_RS_PEERS_ATOMIC_OR
-        atomicOr(&mymask[d], mybit);
-        __syncwarp();
-        const u32 peers = mymask[d];
+            atomicOr(&mymask[d], mybit);
+            __syncwarp();
+            const u32 peers = mymask[d];
 #elif defined(B200SA_ABLATE_BALLOTS)
-        const u32 peers = 1u << lane;  // timing experiment only: wrong ranks
+            const u32 peers = 1u << lane;  // timing experiment only: wrong ranks
 #else
-        const u32 peers = warp_peers_digit8(d);
+            const u32 peers = warp_peers_digit8(d);
 #endif
-        const u32 prev = mywh[d];
-        __syncwarp();
-        const u32 below = (u32)__popc(peers & lt);
-        if (below == 0) {
+            const u32 prev = mywh[d];
+            __syncwarp();
+            const u32 below = (u32)__popc(peers & lt);
+            if (below == 0) {
 #if B200SA_RS_PEERS_ATOMIC_OR
-            mymask[d] = 0;
+                mymask[d] = 0;
 #endif
-            mywh[d] = prev + (u32)__popc(peers);
+                mywh[d] = prev + (u32)__popc(peers);
+            }
+            __syncwarp();
+            RS_POS_SET(k, prev + below);
         }
-        __syncwarp();
-        RS_POS_SET(k, prev + below);
+    } else {
+        // rank inside the tile = the old value of the tile's digit counter; pads of the last tile are not counted
+#pragma unroll
+        for (int k = 0; k < IPT; ++k) {
+            const bool real = full || (wbase + (u32)k * 32u < valid);
+            const u32 p = real ? atomicAdd(&s_cnt[rs_digit<KeyT>(key[k], shift)], 1u) : 0u;
+            RS_POS_SET(k, p);
+        }
     }
     PT_MARK(1);  // ranking
     // values are fetched only now: during ranking they would cost 16 more live registers (spills at
@@ -291,11 +309,15 @@ k_onesweep_pass(const KeyT* __restrict__ kin, KeyT* __restrict__ kout,
     u32 my_cnt = 0;
     if (tid < (u32)RS_RADIX) {
         u32 acc = 0;
+        if (STABLE) {
 #pragma unroll
-        for (int w = 0; w < WARPS; ++w) {
-            const u32 c = whist[w * RS_RADIX + tid];
-            whist[w * RS_RADIX + tid] = acc;
-            acc += c;
+            for (int w = 0; w < WARPS; ++w) {
+                const u32 c = whist[w * RS_RADIX + tid];
+                whist[w * RS_RADIX + tid] = acc;
+                acc += c;
+            }
+        } else {
+            acc = s_cnt[tid];
         }
         my_cnt = acc;
         st_relaxed_u64(status + (u64)tile * RS_RADIX + tid, (tile == 0 ? RS_FLAG_INCLUSIVE : RS_FLAG_PARTIAL) | (u64)acc);
@@ -310,9 +332,11 @@ k_onesweep_pass(const KeyT* __restrict__ kin, KeyT* __restrict__ kout,
         for (u32 w = 0; w < warp; ++w) prefix += s_wtot[w];
         const u32 off = s_cnt[tid] + prefix;
         s_coff[tid] = off;
-        // fold the digit's slot into every warp's exclusive prefix: staging then needs one lookup per key
+        if (STABLE) {
+            // fold the digit's slot into every warp's exclusive prefix: staging then needs one lookup per key
 #pragma unroll
-        for (int w = 0; w < WARPS; ++w) whist[w * RS_RADIX + tid] += off;
+            for (int w = 0; w < WARPS; ++w) whist[w * RS_RADIX + tid] += off;
+        }
     }
     __syncthreads();
 
@@ -322,9 +346,15 @@ k_onesweep_pass(const KeyT* __restrict__ kin, KeyT* __restrict__ kout,
 #pragma unroll
     for (int k = 0; k < IPT; ++k) {
         const u32 d = rs_digit<KeyT>(key[k], shift);
-        const u32 p = RS_POS_GET(k) + mywh[d];
-        skeys[p] = key[k];
-        svals[p] = val[k];
+        if (STABLE) {
+            const u32 p = RS_POS_GET(k) + mywh[d];
+            skeys[p] = key[k];
+            svals[p] = val[k];
+        } else if (full || (wbase + (u32)k * 32u < valid)) {
+            const u32 p = RS_POS_GET(k) + s_coff[d];
+            skeys[p] = key[k];
+            svals[p] = val[k];
+        }
     }
 
     PT_MARK(3);  // staging

@@ -615,6 +615,40 @@ k_scatter_pairs(const u32* __restrict__ key, const u32* __restrict__ val, u32 m,
     }
 }
 
+// The owner's side of the sharded ISA: apply what the G sources left in this GPU's inbox — one launch for all regions (one
+// launch per region cost 8 x 3 rounds of launch latency per step on eight GPUs).  A block finds its region by prefix search.
+struct InboxRegions {
+    const u32* keys[kMaxPeers];
+    const u32* vals[kMaxPeers];
+    u32 tile_end[kMaxPeers];  // inclusive prefix of the regions' tile counts
+    u32 count[kMaxPeers];
+    int nregions;
+};
+
+__global__ void __launch_bounds__(SP_THREADS)
+k_scatter_regions(InboxRegions ir, u32* __restrict__ rank)
+{
+    int g = 0;
+    while (g < ir.nregions - 1 && blockIdx.x >= ir.tile_end[g]) ++g;
+    const u32 first_tile = g ? ir.tile_end[g - 1] : 0u;
+    const u32* __restrict__ key = ir.keys[g];
+    const u32* __restrict__ val = ir.vals[g];
+    const u32 m = ir.count[g];
+    const u32 tile = SP_THREADS * SP_IPT;
+    const u32 base = (blockIdx.x - first_tile) * tile + threadIdx.x;
+    u32 k[SP_IPT], v[SP_IPT];
+#pragma unroll
+    for (int q = 0; q < SP_IPT; ++q) {
+        const u32 j = base + (u32)q * SP_THREADS;
+        if (j < m) { k[q] = ld_stream(key + j); v[q] = ld_stream(val + j); }
+    }
+#pragma unroll
+    for (int q = 0; q < SP_IPT; ++q) {
+        const u32 j = base + (u32)q * SP_THREADS;
+        if (j < m) rank[k[q]] = v[q];
+    }
+}
+
 // Sharded ISA in peer memory, write phase: the pairs arrive here sorted by the top 8 bits of the suffix index, hence
 // routed by owner (a run of consecutive digits per owner); run d is copied into this GPU's region of owner d's inbox with consecutive threads on consecutive
 // addresses, i.e. full 128-byte stores over NVLink (direct 4-byte stores of the ranks into the owners' ISA arrays

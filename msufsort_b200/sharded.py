@@ -247,10 +247,22 @@ class ShardedSorter:
         return out
 
     def suffix_array_bwt_host(self, h_text: torch.Tensor, h_sa: torch.Tensor, h_bwt: Optional[torch.Tensor]) -> ShardedResult:
-        """Host buffers in, host buffers out (pinned tensors; every rank passes the same text): the text is uploaded on
-        every rank over its own PCIe link, the suffix array and the BWT leave as this rank's rows / bytes only — the
-        caller's host arrays are filled by the ranks together (shared pinned memory) or gathered by the caller."""
-        d_text = h_text.to("cuda", non_blocking=True)
+        """Host buffers in, host buffers out (pinned tensors; every rank passes the same text): every rank uploads 1/G of
+        the text over its own PCIe link and the slices are all-gathered over NVLink; the suffix array and the BWT leave
+        as this rank's rows / bytes only — the caller's host arrays are filled by the ranks together (shared pinned
+        memory) or gathered by the caller."""
+        n = h_text.numel()
+        if self.world > 1 and n >= 16 * self.world:
+            # every rank uploads one slice over its own PCIe link; the slices are all-gathered over NVLink
+            per = -(-n // self.world)
+            d_all = torch.empty(per * self.world, dtype=torch.uint8, device="cuda")
+            lo, hi = min(n, self.rank * per), min(n, (self.rank + 1) * per)
+            mine = d_all[self.rank * per: self.rank * per + (hi - lo)]
+            mine.copy_(h_text[lo:hi], non_blocking=True)
+            dist.all_gather_into_tensor(d_all, d_all[self.rank * per:(self.rank + 1) * per], group=self.group)
+            d_text = d_all[:n]
+        else:
+            d_text = h_text.to("cuda", non_blocking=True)
         res = self.suffix_array_bwt(d_text, want_bwt=h_bwt is not None)
         h_sa[res.row_begin:res.row_end].copy_(res.sa[res.row_begin:res.row_end], non_blocking=True)
         if h_bwt is not None and res.out_end > res.out_begin:

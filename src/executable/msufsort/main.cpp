@@ -17,6 +17,7 @@
 #include <b200sa.h>
 
 #include <algorithm>
+#include <cctype>
 #include <chrono>
 #include <cstdint>
 #include <cstdio>
@@ -64,9 +65,10 @@ namespace
         }
     };
 
-    // suffix a sorts before suffix b: first differing byte decides, a proper prefix is smaller
+    // suffix a sorts strictly before suffix b: first differing byte decides, a proper prefix is smaller
     bool suffix_less(bytes const & t, std::size_t base, std::size_t n, std::int32_t a, std::int32_t b)
     {
+        if (a == b) return false;
         while (a < (std::int32_t)n && b < (std::int32_t)n && t[base + a] == t[base + b]) { ++a; ++b; }
         if (a == (std::int32_t)n) return true;
         if (b == (std::int32_t)n) return false;
@@ -144,7 +146,10 @@ namespace
         return bad ? 1 : 0;
     }
 
-    int run_self_test(int max_symbols, int max_size)
+    // The reference's hidden self test (main.cpp:389-435) over its own inputs (main.cpp:274-286): for every alphabet size,
+    // length and thread count, srand(symbols * length * threads) and bytes rand() % symbols.  There the thread count selects
+    // the worker pool; here it only selects the input, and all inputs of one alphabet size are transformed as ONE batch.
+    int run_self_test(int max_symbols, int max_size, int max_threads)
     {
         gpu_context gpu;
         std::size_t errors = 0, inputs = 0;
@@ -152,20 +157,28 @@ namespace
         {
             bytes blocks;
             std::vector<std::int64_t> offsets{0};
-            std::mt19937 rng((unsigned)sigma);
             for (int size = 1; size <= max_size; ++size)
-            {
-                for (int i = 0; i < size; ++i) blocks.push_back((std::uint8_t)(rng() % (unsigned)sigma));
-                offsets.push_back((std::int64_t)blocks.size());
-            }
+                for (int threads = 1; threads <= max_threads; ++threads)
+                {
+                    std::srand((unsigned)(sigma * size * threads));
+                    for (int i = 0; i < size; ++i) blocks.push_back((std::uint8_t)(std::rand() % sigma));
+                    offsets.push_back((std::int64_t)blocks.size());
+                }
             std::int64_t const count = (std::int64_t)offsets.size() - 1;
             std::vector<std::int32_t> sa(blocks.size() + (std::size_t)count), sentinels((std::size_t)count);
             gpu.check(b200sa_suffix_array_batch(gpu.ctx, blocks.data(), offsets.data(), count, sa.data()), "b200sa_suffix_array_batch");
+            std::vector<char> seen;
             for (std::int64_t b = 0; b < count; ++b)
             {
                 std::size_t const base = (std::size_t)offsets[b], n = (std::size_t)(offsets[b + 1] - offsets[b]);
                 std::int32_t const * s = sa.data() + base + b;
                 bool ok = s[0] == (std::int32_t)n;
+                seen.assign(n + 1, 0);
+                for (std::size_t r = 0; r <= n && ok; ++r)   // a permutation of 0..n
+                {
+                    ok = s[r] >= 0 && (std::size_t)s[r] <= n && !seen[(std::size_t)s[r]];
+                    if (ok) seen[(std::size_t)s[r]] = 1;
+                }
                 for (std::size_t r = 1; r < n && ok; ++r) ok = suffix_less(blocks, base, n, s[r], s[r + 1]);
                 if (!ok) { ++errors; std::printf("**** suffix array error: %d symbols, length %zu\n", sigma, n); }
             }
@@ -185,7 +198,7 @@ namespace
     {
         std::puts("msufsort (B200 engine)\n"
                   "usage: msufsort b|s|l <input file> [num threads]\n"
-                  "       msufsort t [max symbols = 255] [max length = 1023]\n"
+                  "       msufsort t [max symbols = 255] [max length = 1023] [thread counts = 2]\n"
                   "  b = burrows wheeler transform + inverse, s = suffix array, l = suffix array + lcp array, t = self test");
     }
 }
@@ -197,7 +210,7 @@ int main(int argc, char ** argv)
     try
     {
         if (mode == 't')
-            return run_self_test(argc > 2 ? std::atoi(argv[2]) : 255, argc > 3 ? std::atoi(argv[3]) : 1023);
+            return run_self_test(argc > 2 ? std::atoi(argv[2]) : 255, argc > 3 ? std::atoi(argv[3]) : 1023, argc > 4 ? std::atoi(argv[4]) : 2);
         if (argc < 3 || std::strchr("bsl", mode) == nullptr || argv[1][1] != 0) { usage(); return 0; }
         bytes data = read_file(argv[2]);
         std::printf("loaded %zu bytes from %s\n", data.size(), argv[2]);

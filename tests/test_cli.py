@@ -56,7 +56,7 @@ def test_cli_emu_modes(tmp_path):
 
 def test_cli_emu_self_test_grid():
     out = run(build_emu_cli(), "t", "5", "60")
-    assert out.returncode == 0 and "300 inputs, 0 errors" in out.stdout, out.stdout + out.stderr
+    assert out.returncode == 0 and "600 inputs, 0 errors" in out.stdout, out.stdout + out.stderr
 
 
 @pytest.mark.gpu
@@ -65,4 +65,4 @@ def test_cli_gpu(tmp_path):
     assert os.path.exists(exe), "run `make cli`"
     _modes(exe, tmp_path, 1 << 20)
     out = run(exe, "t", "12", "300")
-    assert out.returncode == 0 and "3600 inputs, 0 errors" in out.stdout, out.stdout + out.stderr
+    assert out.returncode == 0 and "7200 inputs, 0 errors" in out.stdout, out.stdout + out.stderr

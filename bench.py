@@ -700,9 +700,11 @@ def run_sharded(args, wl):
                          "frac": achieved / peak if peak else None, "traffic": None, "peak_source": peak_src,
                          "launches": int(sp["launches"]), "avg_launch_ms": sp["ms"] / sp["launches"] if sp["launches"] else None},
             "nvlink": {"bytes_stored_by_rank0_per_step": nvlink_bytes,
-                       "GBps_rank0_over_isa_phase": nvlink_bytes / (prof["phases"]["isa"]["ms"] / args.steps * 1e-3) / 1e9 if prof["phases"]["isa"]["ms"] else None,
+                       "send_ms_rank0_per_step": prof["phases"]["peer_send"]["ms"] / args.steps,
+                       "GBps_rank0_during_sends": nvlink_bytes / (prof["phases"]["peer_send"]["ms"] / args.steps * 1e-3) / 1e9 if prof["phases"]["peer_send"]["ms"] else None,
+                       "bytes_per_round_rank0": nvlink_bytes / max(1.0, rounds_of(prof, args.steps)),
                        "peak_GBps_per_direction": 900.0,
-                       "note": "new (suffix, rank) pairs stored in bulk into the owners' inboxes; rank[suffix + h] is loaded from the owners' HBM by the "
+                       "note": "new (suffix, rank) pairs stored in bulk into the owners' inboxes (k_peer_send); rank[suffix + h] is loaded from the owners' HBM by the "
                                "group-sort / key-build kernels (4-byte remote loads, not counted here)"},
             "limiter": {"kernel_ms_rank0": kernel_ms, "step_ms": ms_per_step, "kernel_share": kernel_ms / ms_per_step if ms_per_step else None,
                         "note": "step - kernels = host round trips per doubling round (counter read-backs, 2 barriers) + waiting for the slowest rank"},

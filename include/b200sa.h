@@ -360,6 +360,8 @@ enum {
     B200SA_PH_SEGSORT = 10,   /* in-shared-memory sort of small groups (doubling rounds)      */
     B200SA_PH_ISA = 11,       /* bucketed ISA update: one radix sweep by suffix index + scatter */
     B200SA_PH_LCP = 12,       /* LCP array: PLCP levels + gather (the phi scatter is counted under ISA) */
+    B200SA_PH_PEER_SEND = 13, /* sharded ISA: bulk stores of routed (suffix, rank) pairs into the owners' inboxes over NVLink */
+    B200SA_PH_PEER_APPLY = 14,/* sharded ISA: the owner scatters its inbox into its ISA shard           */
     B200SA_PH_COUNT = 16
 };
 

@@ -21,7 +21,7 @@ PRODUCT_LIB = os.path.join(_HERE, "lib", "libb200sa.so")
 
 PHASES = {
     "alphabet": 0, "pack": 1, "sort_hist": 2, "sort_pass": 3, "build": 4, "rerank": 5,
-    "bwt": 6, "unbwt_build": 7, "unbwt_walk": 8, "check": 9, "segsort": 10, "isa": 11, "lcp": 12,
+    "bwt": 6, "unbwt_build": 7, "unbwt_walk": 8, "check": 9, "segsort": 10, "isa": 11, "lcp": 12, "peer_send": 13, "peer_apply": 14,
 }
 _PH_COUNT = 16
 

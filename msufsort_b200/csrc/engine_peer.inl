@@ -213,15 +213,18 @@ int Engine::peer_scatter(cudaStream_t st)
         B200SA_LAUNCH(kp, tiles, RS_THREADS, rs_pass_smem_bytes<u32>(), st, ss.upd_idx, bk_key, ss.upd_rank, bk_val, count, bshift,
                       0xffffffffu, (const u32*)ghist, status, counters);
         count_launch(B200SA_PH_ISA);
+        B200SA_TRY(phase_end(st));
+        prof.alg_bytes[B200SA_PH_ISA] += (u64)count * (4 + 16);
+        B200SA_TRY(phase_begin(B200SA_PH_PEER_SEND, st));
         const u32 want = (u32)div_up_u64(count, 256 * 4);
         const u32 grid = want < (u32)(num_sms * 16) ? want : (u32)(num_sms * 16);
         B200SA_LAUNCH(k_peer_send, grid, 256, 0, st, (const u32*)bk_key, (const u32*)bk_val, count, (const u32*)ghist, ps);
-        count_launch(B200SA_PH_ISA);
-        prof.alg_bytes[B200SA_PH_ISA] += (u64)count * (4 + 16 + 16);
+        count_launch(B200SA_PH_PEER_SEND);
+        prof.alg_bytes[B200SA_PH_PEER_SEND] += (u64)count * 16;
     } else {
         // nothing to send this round: the counts the owners read must still be reset (ghist is all zero)
         B200SA_LAUNCH(k_peer_send, 1, 256, 0, st, (const u32*)nullptr, (const u32*)nullptr, 0u, (const u32*)ghist, ps);
-        count_launch(B200SA_PH_ISA);
+        count_launch(B200SA_PH_PEER_SEND);
     }
     B200SA_TRY(phase_end(st));
     B200SA_CU(cudaGetLastError());
@@ -254,11 +257,11 @@ int Engine::peer_apply(cudaStream_t st)
         pairs += cnt;
     }
     if (ir.nregions) {
-        B200SA_TRY(phase_begin(B200SA_PH_ISA, st));
+        B200SA_TRY(phase_begin(B200SA_PH_PEER_APPLY, st));
         B200SA_LAUNCH(k_scatter_regions, tiles, SP_THREADS, 0, st, ir, rank.as<u32>());
-        count_launch(B200SA_PH_ISA);
+        count_launch(B200SA_PH_PEER_APPLY);
         B200SA_TRY(phase_end(st));
-        prof.alg_bytes[B200SA_PH_ISA] += pairs * 12;
+        prof.alg_bytes[B200SA_PH_PEER_APPLY] += pairs * 12;
     }
     B200SA_CU(cudaGetLastError());
     B200SA_CU(cudaStreamSynchronize(st));

@@ -32,6 +32,18 @@ int main(int argc, char ** argv)
     in.read(reinterpret_cast<char *>(text.data()), static_cast<std::streamsize>(n));
     try
     {
+        // what the return type alone costs: a value-initialised std::vector<int32_t>(n + 1) is allocated, zero-filled (first touch
+        // of every page) and freed in every make_suffix_array call — in the reference as well (msufsort.cpp:1754-1758)
+        double vector_alloc = 0;
+        for (int it = 0; it < 2; ++it)
+        {
+            double const t0 = now_s();
+            {
+                std::vector<std::int32_t> v(n + 1);
+                asm volatile("" : : "r"(v.data()) : "memory");
+            }
+            vector_alloc = now_s() - t0;
+        }
         double forward = 0, inverse = 0, sa_only = 0;
         std::int32_t sentinel = 0;
         bool ok = true;
@@ -49,10 +61,10 @@ int main(int argc, char ** argv)
             if (it >= warmup) { forward += t2 - t0; sa_only += t1 - t0; inverse += t3 - t2; }
         }
         std::printf("{\"n_bytes\": %zu, \"steps\": %d, \"warmup\": %d, \"sa_bwt_ms_per_step\": %.3f, \"sa_ms\": %.3f, \"bwt_ms\": %.3f, "
-                    "\"unbwt_ms_per_step\": %.3f, \"sa_bwt_MBps\": %.1f, \"unbwt_MBps\": %.1f, \"roundtrip_ok\": %s, "
+                    "\"unbwt_ms_per_step\": %.3f, \"sa_bwt_MBps\": %.1f, \"unbwt_MBps\": %.1f, \"roundtrip_ok\": %s, \"vector_alloc_zero_free_ms\": %.3f, "
                     "\"path\": \"maniscalco::make_suffix_array + forward_burrows_wheeler_transform (free templates, pageable std::vector), then reverse_burrows_wheeler_transform\"}\n",
                     n, steps, warmup, 1e3 * forward / steps, 1e3 * sa_only / steps, 1e3 * (forward - sa_only) / steps, 1e3 * inverse / steps,
-                    n * steps / forward / 1e6, n * steps / inverse / 1e6, ok ? "true" : "false");
+                    n * steps / forward / 1e6, n * steps / inverse / 1e6, ok ? "true" : "false", 1e3 * vector_alloc);
         return ok ? 0 : 1;
     }
     catch (std::exception const & e)

@@ -6,7 +6,7 @@
 // Two allocations per GPU are mapped by all peers: the ISA array (peers LOAD rank[suffix + h] from it) and an inbox
 // (peers STORE the new ranks of the suffixes this GPU owns into it, in bulk; the owner then applies them locally).
 
-static const size_t kInboxHeader = 256;  // u32 count[kMaxPeers] written by the sources, padded
+static const size_t kInboxHeader = 32768;  // pair counts and bucket offsets written by the sources (sa_kernels.cuh: kInboxCountWords, kInboxOffsStride), padded
 
 int Engine::peer_describe(u64 n, bool with_ipc, bool isa, PeerDesc* out)
 {
@@ -185,6 +185,7 @@ int Engine::peer_scatter(cudaStream_t st)
         ps.keys[g] = g < G ? (u32*)(peer.inbox[g] + peer.region_off[me]) : nullptr;
         ps.vals[g] = g < G ? ps.keys[g] + peer.region_cap[me] : nullptr;
         ps.count_slot[g] = g < G ? (u32*)peer.inbox[g] + me : nullptr;
+        ps.offs_slot[g] = g < G ? (u32*)peer.inbox[g] + kInboxCountWords + me * kInboxOffsStride : nullptr;
     }
     ps.nparts = G;
     ps.me = me;
@@ -239,26 +240,32 @@ int Engine::peer_apply(cudaStream_t st)
     const int G = peer.nparts;
     B200SA_CU(cudaMemcpyAsync(h_pinned + 400, peer_inbox.p, kMaxPeers * 4, cudaMemcpyDeviceToHost, st));
     B200SA_CU(cudaStreamSynchronize(st));
-    InboxRegions ir;
-    memset(&ir, 0, sizeof(ir));
-    u32 tiles = 0;
+    InboxArgs ia;
+    memset(&ia, 0, sizeof(ia));
     u64 pairs = 0;
     for (int s = 0; s < G; ++s) {
         const u32 cnt = h_pinned[400 + s];
-        if (cnt == 0) continue;
         if (cnt > peer.region_cap[s]) return set_error(B200SA_EINTERNAL, "GPU %d announced %u pairs for a region of %u", s, cnt, peer.region_cap[s]);
-        // a run arrives bucketed by the top bits of the suffix index: the stores walk through L2-sized windows
-        const int r = ir.nregions++;
-        ir.keys[r] = (const u32*)(peer_inbox.as<u8>() + peer.region_off[s]);
-        ir.vals[r] = ir.keys[r] + peer.region_cap[s];
-        ir.count[r] = cnt;
-        tiles += (u32)div_up_u64(cnt, SP_THREADS * SP_IPT);
-        ir.tile_end[r] = tiles;
+        ia.keys[s] = (const u32*)(peer_inbox.as<u8>() + peer.region_off[s]);
+        ia.vals[s] = ia.keys[s] + peer.region_cap[s];
         pairs += cnt;
     }
-    if (ir.nregions) {
+    if (pairs) {
+        // the same bucket geometry the senders used (peer_scatter)
+        const int nbits = bit_length_u64((u64)ss.n - 1);
+        int bshift = nbits > RS_RADIX_BITS ? nbits - RS_RADIX_BITS : 0;
+        if (bshift > peer.view.shift) bshift = peer.view.shift;
+        ia.header = (const u32*)peer_inbox.p;
+        ia.nparts = G;
+        ia.buckets = 1 << (peer.view.shift - bshift);
+        if (ia.buckets * G > kInboxMaxEntries) return set_error(B200SA_EINTERNAL, "%d buckets x %d GPUs exceed the inbox plan", ia.buckets, G);
+        B200SA_TRY(misc.ensure(16384));
+        u32* plan = misc.as<u32>() + 1100;  // 3 * kInboxMaxEntries + 2 words
+        const u32 tiles_bound = (u32)div_up_u64(pairs, SP_THREADS * SP_IPT) + (u32)(ia.buckets * G);
         B200SA_TRY(phase_begin(B200SA_PH_PEER_APPLY, st));
-        B200SA_LAUNCH(k_scatter_regions, tiles, SP_THREADS, 0, st, ir, rank.as<u32>());
+        B200SA_LAUNCH(k_inbox_plan, 1, kInboxMaxEntries, 0, st, ia, plan);
+        count_launch(B200SA_PH_PEER_APPLY);
+        B200SA_LAUNCH(k_scatter_plan, tiles_bound, SP_THREADS, 0, st, ia, (const u32*)plan, rank.as<u32>());
         count_launch(B200SA_PH_PEER_APPLY);
         B200SA_TRY(phase_end(st));
         prof.alg_bytes[B200SA_PH_PEER_APPLY] += pairs * 12;

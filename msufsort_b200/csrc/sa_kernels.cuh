@@ -88,13 +88,18 @@ static const int PK_HALO = 64;                   // k <= 58
 // it reads n bytes and writes n/G pairs, instead of packing all n keys and filtering them in a second pass (round 1: 1.35 of
 // 8 kernel-ms per step on eight GPUs).  The order of the kept pairs is irrelevant (equal keys form one group whatever
 // their order).
+// symbol at tile position p in the padded shared-memory layout of k_pack_keys
+#define PK_SYM(p) ((u64)s_sym[(p) + (((p) >> 4) << 2)])
 template <bool RADIX, bool RANGE>
 __global__ void __launch_bounds__(PK_THREADS)
 k_pack_keys(const u8* __restrict__ text, u32 n, const u8* __restrict__ code, int bits, int k, int len_bits, u64 B, u64 top_pow,
             u64* __restrict__ keys, u64 lo, u64 hi, int hi_inclusive, u32* __restrict__ out_idx, u32* __restrict__ cursor)
 {
     __shared__ u8 s_code[256];
-    __shared__ __align__(16) u8 s_sym[PK_TILE + PK_HALO];
+    // symbols of the tile (+ halo) as dense codes.  Thread t works on positions 16 t .. 16 t + 15 (+ k of halo), so a plain
+    // layout puts the 32 lanes of a warp on 8 banks (4-way conflicts on every byte access: ncu had this kernel bound by
+    // shared-memory wavefronts).  Four pad bytes after every 16 symbols make the lanes' word indices 5 t + c: conflict-free.
+    __shared__ __align__(16) u8 s_sym[(PK_TILE + PK_HALO) / 16 * 20];
     __shared__ u64 s_out[RANGE ? 1 : PK_THREADS / 32][RANGE ? 1 : PK_IPT * 33];
     __shared__ u32 s_wsum[PK_THREADS / 32];
     __shared__ u32 s_base, s_total;
@@ -112,21 +117,24 @@ k_pack_keys(const u8* __restrict__ text, u32 n, const u8* __restrict__ code, int
         for (u32 v = tid; v < (u32)(PK_TILE + PK_HALO) / 16; v += PK_THREADS) {
             const u32 g = base + v * 16;
             u32 w[4] = {0, 0, 0, 0};
+            u32 c[4] = {0, 0, 0, 0};
             if (aligned && g + 16 <= n) {
                 const uint4 q = *(const uint4*)(text + g);
                 w[0] = q.x; w[1] = q.y; w[2] = q.z; w[3] = q.w;
 #pragma unroll
-                for (int i = 0; i < 16; ++i) s_sym[v * 16 + i] = s_code[(w[i >> 2] >> (8 * (i & 3))) & 255u];
+                for (int i = 0; i < 16; ++i) c[i >> 2] |= (u32)s_code[(w[i >> 2] >> (8 * (i & 3))) & 255u] << (8 * (i & 3));
             } else {
 #pragma unroll
-                for (int i = 0; i < 16; ++i) s_sym[v * 16 + i] = (g + i < n) ? s_code[text[g + i]] : (u8)0;
+                for (int i = 0; i < 16; ++i) c[i >> 2] |= (u32)((g + i < n) ? s_code[text[g + i]] : (u8)0) << (8 * (i & 3));
             }
+            u32* dst = (u32*)(s_sym + v * 20u);  // 20 v is a multiple of 4
+            dst[0] = c[0]; dst[1] = c[1]; dst[2] = c[2]; dst[3] = c[3];
         }
         __syncthreads();
         // thread handles 16 consecutive positions with a sliding window
         const u32 p0 = tid * PK_IPT;
         u64 win = 0;
-        for (int j = 0; j < k; ++j) win = RADIX ? win * B + (u64)s_sym[p0 + j] : ((win << bits) | (u64)s_sym[p0 + j]);
+        for (int j = 0; j < k; ++j) win = RADIX ? win * B + (u64)PK_SYM(p0 + (u32)j) : ((win << bits) | (u64)PK_SYM(p0 + (u32)j));
         if (RANGE) {
             u64 kreg[PK_IPT];
             u32 keep = 0;
@@ -136,11 +144,11 @@ k_pack_keys(const u8* __restrict__ text, u32 n, const u8* __restrict__ code, int
                 u64 key;
                 if (RADIX) {
                     key = win;
-                    win = (win - (u64)s_sym[p0 + i] * top_pow) * B + (u64)s_sym[p0 + i + k];
+                    win = (win - (u64)PK_SYM(p0 + (u32)i) * top_pow) * B + (u64)PK_SYM(p0 + (u32)i + (u32)k);
                 } else {
                     const u32 rem = gp < n ? n - gp : 0u;
                     key = (win << len_bits) | (u64)(rem < (u32)k ? rem : (u32)k);
-                    win = ((win << bits) | (u64)s_sym[p0 + i + k]) & sym_mask;
+                    win = ((win << bits) | (u64)PK_SYM(p0 + (u32)i + (u32)k)) & sym_mask;
                 }
                 kreg[i] = key;
                 if (gp < n && key >= lo && (hi_inclusive ? key <= hi : key < hi)) keep |= 1u << i;
@@ -178,12 +186,12 @@ k_pack_keys(const u8* __restrict__ text, u32 n, const u8* __restrict__ code, int
                 const u32 gp = base + p0 + i;
                 if (RADIX) {
                     s_out[warp][i * 33 + lane] = win;
-                    win = (win - (u64)s_sym[p0 + i] * top_pow) * B + (u64)s_sym[p0 + i + k];
+                    win = (win - (u64)PK_SYM(p0 + (u32)i) * top_pow) * B + (u64)PK_SYM(p0 + (u32)i + (u32)k);
                 } else {
                     const u32 rem = gp < n ? n - gp : 0u;
                     const u64 key = (win << len_bits) | (u64)(rem < (u32)k ? rem : (u32)k);
                     s_out[warp][i * 33 + lane] = key;
-                    win = ((win << bits) | (u64)s_sym[p0 + i + k]) & sym_mask;
+                    win = ((win << bits) | (u64)PK_SYM(p0 + (u32)i + (u32)k)) & sym_mask;
                 }
             }
             __syncwarp();
@@ -200,6 +208,8 @@ k_pack_keys(const u8* __restrict__ text, u32 n, const u8* __restrict__ code, int
         }
     }
 }
+
+#undef PK_SYM
 
 // ---------------------------------------------------------------------------------------------
 // Sharded runs: the splitters come from a sorted regular sample of the initial keys.  The sample keys are computed straight
@@ -615,27 +625,64 @@ k_scatter_pairs(const u32* __restrict__ key, const u32* __restrict__ val, u32 m,
     }
 }
 
-// The owner's side of the sharded ISA: apply what the G sources left in this GPU's inbox — one launch for all regions (one
-// launch per region cost 8 x 3 rounds of launch latency per step on eight GPUs).  A block finds its region by prefix search.
-struct InboxRegions {
-    const u32* keys[kMaxPeers];
+// The owner's side of the sharded ISA: apply what the G sources left in this GPU's inbox.  Every source's run arrives
+// bucketed by the top bits of the suffix index (B buckets per owner) together with its B + 1 bucket offsets (inbox header).
+// The runs are applied in BUCKET-major order — bucket 0 of all sources, bucket 1 of all sources, ... — by one launch, so
+// that at any moment all CTAs store into the same L2-sized window of the ISA shard.  (Source-major order, one pass over the
+// whole shard per source, measured 56 G pairs/s on eight GPUs against 184 G/s for the single-GPU bucketed scatter.)
+static const int kInboxCountWords = 64;     // header: pair count per source ...
+static const int kInboxOffsStride = 260;    // ... then per source up to 257 bucket offsets (relative to the source's run)
+static const int kInboxMaxEntries = 512;    // (bucket, source) pairs of one owner
+
+struct InboxArgs {
+    const u32* keys[kMaxPeers];   // region of source s in this GPU's inbox
     const u32* vals[kMaxPeers];
-    u32 tile_end[kMaxPeers];  // inclusive prefix of the regions' tile counts
-    u32 count[kMaxPeers];
-    int nregions;
+    const u32* header;            // this GPU's inbox header
+    int nparts;
+    int buckets;                  // B
 };
 
-__global__ void __launch_bounds__(SP_THREADS)
-k_scatter_regions(InboxRegions ir, u32* __restrict__ rank)
+// plan layout (u32 words): [0 .. E] tile prefix, [kInboxMaxEntries + 1 + e] start of entry e inside its region, [2 * kInboxMaxEntries + 1 + e] count
+__global__ void __launch_bounds__(kInboxMaxEntries)
+k_inbox_plan(InboxArgs a, u32* __restrict__ plan)
 {
-    int g = 0;
-    while (g < ir.nregions - 1 && blockIdx.x >= ir.tile_end[g]) ++g;
-    const u32 first_tile = g ? ir.tile_end[g - 1] : 0u;
-    const u32* __restrict__ key = ir.keys[g];
-    const u32* __restrict__ val = ir.vals[g];
-    const u32 m = ir.count[g];
+    __shared__ u32 s_w[kInboxMaxEntries / 32];
+    const u32 e = threadIdx.x, lane = e & 31u, warp = e >> 5;
+    const u32 E = (u32)(a.buckets * a.nparts);
+    u32 tiles = 0;
+    if (e < E) {
+        const u32 j = e / (u32)a.nparts, src = e % (u32)a.nparts;
+        const u32* offs = a.header + kInboxCountWords + src * kInboxOffsStride;
+        const u32 lo = offs[j], hi = offs[j + 1u];
+        plan[kInboxMaxEntries + 1 + e] = lo;
+        plan[2 * kInboxMaxEntries + 1 + e] = hi - lo;
+        tiles = (u32)div_up_u64(hi - lo, SP_THREADS * SP_IPT);
+    }
+    const u32 incl = warp_incl_scan_u32(tiles);
+    if (lane == 31) s_w[warp] = incl;
+    __syncthreads();
+    u32 prefix = 0;
+    for (u32 w = 0; w < warp; ++w) prefix += s_w[w];
+    if (e < E) plan[e] = prefix + incl - tiles;
+    if (e == E - 1u) plan[E] = prefix + incl;
+}
+
+__global__ void __launch_bounds__(SP_THREADS)
+k_scatter_plan(InboxArgs a, const u32* __restrict__ plan, u32* __restrict__ rank)
+{
+    const u32 E = (u32)(a.buckets * a.nparts);
+    if (blockIdx.x >= plan[E]) return;  // the grid is an upper bound of the tile count
+    u32 lo = 0, hi = E;                 // the entry e with plan[e] <= blockIdx.x < plan[e + 1]
+    while (hi - lo > 1u) {
+        const u32 mid = (lo + hi) >> 1;
+        if (plan[mid] <= blockIdx.x) lo = mid; else hi = mid;
+    }
+    const u32 e = lo, src = e % (u32)a.nparts;
+    const u32 start = plan[kInboxMaxEntries + 1 + e], m = plan[2 * kInboxMaxEntries + 1 + e];
+    const u32* __restrict__ key = a.keys[src] + start;
+    const u32* __restrict__ val = a.vals[src] + start;
     const u32 tile = SP_THREADS * SP_IPT;
-    const u32 base = (blockIdx.x - first_tile) * tile + threadIdx.x;
+    const u32 base = (blockIdx.x - plan[e]) * tile + threadIdx.x;
     u32 k[SP_IPT], v[SP_IPT];
 #pragma unroll
     for (int q = 0; q < SP_IPT; ++q) {
@@ -657,6 +704,7 @@ struct PeerSend {
     u32* keys[kMaxPeers];        // destination of run d: keys, values
     u32* vals[kMaxPeers];
     u32* count_slot[kMaxPeers];  // where owner d reads how many pairs this GPU sent
+    u32* offs_slot[kMaxPeers];   // ... and the B + 1 bucket offsets of the run (relative to its start)
     int nparts;
     int me;                      // sending GPU: its copy loop starts with the run of owner me + 1 (see k_peer_send)
     int per_owner_log;           // the input is sorted by a 256-way digit; owner d holds digits [d << per_owner_log, (d+1) << per_owner_log)
@@ -672,7 +720,17 @@ k_peer_send(const u32* __restrict__ key, const u32* __restrict__ val, u32 m, con
         s_off[threadIdx.x] = (threadIdx.x < (u32)ps.nparts && first_digit < 256u) ? bins[first_digit] : m;
     }
     __syncthreads();
-    if (blockIdx.x == 0 && threadIdx.x < (u32)ps.nparts) *ps.count_slot[threadIdx.x] = s_off[threadIdx.x + 1] - s_off[threadIdx.x];
+    if (blockIdx.x == 0) {
+        if (threadIdx.x < (u32)ps.nparts) *ps.count_slot[threadIdx.x] = s_off[threadIdx.x + 1] - s_off[threadIdx.x];
+        const u32 B = 1u << ps.per_owner_log;
+        for (u32 t = threadIdx.x; t < (u32)ps.nparts * (B + 1u); t += blockDim.x) {
+            const u32 d = t / (B + 1u), j = t % (B + 1u);
+            const u32 digit = (d << ps.per_owner_log) + j;
+            u32 off = digit < 256u ? bins[digit] : m;
+            off = off < s_off[d + 1] ? off : s_off[d + 1];  // the last owner's run ends at m
+            ps.offs_slot[d][j] = off - s_off[d];
+        }
+    }
     // every GPU walks its runs starting with its right-hand neighbour's, so at any moment the G senders store into
     // G different inboxes (all starting with owner 0 measured G-fold ingress contention on that GPU's links)
     const u32 rot = s_off[(ps.me + 1) % ps.nparts];

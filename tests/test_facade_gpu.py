@@ -36,13 +36,18 @@ def test_facade_throws_without_gpu(tmp_path):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("devices", [None, "0,0,0"], ids=["one-gpu", "sharded-3-contexts"])
 @pytest.mark.parametrize("family,n", [("markov3", 300001), ("zeros", 5000), ("rand", 1), ("acgt_rep", 1 << 20)])
-def test_facade_matches_oracle(oracle, tmp_path, family, n):
+def test_facade_matches_oracle(oracle, tmp_path, family, n, devices):
+    """the reference-shaped C++ caller; with MSUFSORT_DEVICES the facade shards every text over a group of contexts"""
     build_exe()
     x = gen(family, n)
     f = tmp_path / "in.bin"
     f.write_bytes(x.tobytes())
-    out = subprocess.run([EXE, str(f)], capture_output=True, text=True, timeout=300)
+    env = dict(os.environ)
+    if devices:
+        env["MSUFSORT_DEVICES"] = devices
+    out = subprocess.run([EXE, str(f)], capture_output=True, text=True, timeout=300, env=env)
     assert out.returncode == 0, out.stdout + out.stderr
     lines = dict(l.split(" ", 1) for l in out.stdout.strip().splitlines())
     sa = oracle.sa(x)

@@ -57,6 +57,15 @@ static const int RS_RADIX = 256;
 #define RS_POS_SET(k, v) pos[k] = (v)
 #define RS_POS_GET(k) pos[k]
 #endif
+// 1: a full tile's keys (and values) are fetched by ONE bulk asynchronous copy each (cp.async.bulk, completion on an mbarrier)
+// into the staging buffers in shared memory and read from there, instead of sixteen 8-byte + sixteen 4-byte global loads per
+// thread (SASS: UBLKCP.S.G, SYNCS.ARRIVE.TRANS64, SYNCS.PHASECHK.TRANS64.TRYWAIT).  The copies are issued by the thread that
+// takes the tile ticket, before the counters are cleared, and the raw tile is consumed into registers before the same
+// buffers receive the digit-ordered tile.  Measured on B200 (profiles/r02_sweep_bulk.txt): 1.794 ms against 1.819 ms per
+// 2^28-pair sweep, 30.26 against 30.47 ms per SA + BWT step.  -DB200SA_RS_BULK_LOAD=0 restores the per-thread loads.
+#ifndef B200SA_RS_BULK_LOAD
+#define B200SA_RS_BULK_LOAD 1
+#endif
 static const int RS_THREADS = B200SA_RS_THREADS;
 static const int RS_IPT = B200SA_RS_IPT;
 static const int RS_TILE = RS_THREADS * RS_IPT;  // 4096 pairs per tile
@@ -73,6 +82,29 @@ __host__ __device__ constexpr size_t rs_pass_smem_bytes()
     return (size_t)(RS_THREADS / 32) * RS_RADIX * 4 * (B200SA_RS_PEERS_ATOMIC_OR ? 2 : 1) + 3 * RS_RADIX * 4 + 16 * 4 +
            (size_t)RS_TILE * sizeof(KeyT) + (size_t)RS_TILE * 4;
 }
+
+#if B200SA_RS_BULK_LOAD && !defined(B200SA_EMU)
+__device__ __forceinline__ u32 rs_smem_addr(const void* p) { return (u32)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void rs_mbar_init(u64* bar, u32 count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%1], %0;" ::"r"(count), "r"(rs_smem_addr(bar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void rs_mbar_expect_tx(u64* bar, u32 bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%1], %0;" ::"r"(bytes), "r"(rs_smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void rs_bulk_g2s(void* dst, const void* src, u32 bytes, u64* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(rs_smem_addr(dst)), "l"(src), "r"(bytes), "r"(rs_smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void rs_mbar_wait(u64* bar, u32 parity)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}"
+                 ::"r"(rs_smem_addr(bar)), "r"(parity) : "memory");
+}
+#endif
 
 template <typename KeyT>
 __device__ __forceinline__ u32 rs_digit(KeyT key, int shift)
@@ -190,9 +222,28 @@ k_onesweep_pass(const KeyT* __restrict__ kin, KeyT* __restrict__ kout,
 #endif
     u32* svals = (u32*)(skeys + TILE);   // [TILE]
     __shared__ u32 s_tile;
+#if B200SA_RS_BULK_LOAD && !defined(B200SA_EMU)
+    __shared__ __align__(8) u64 s_bar;
+#endif
 
     const u32 tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+#if B200SA_RS_BULK_LOAD && !defined(B200SA_EMU)
+    constexpr bool BULK = sizeof(KeyT) >= 4;  // bulk copies move multiples of 16 bytes from 16-byte aligned addresses
+    if (BULK && tid == 0) {
+        s_tile = atomicAdd(tile_counter, 1u);
+        rs_mbar_init(&s_bar, 1u);
+        const u32 tile0 = s_tile, base0 = tile0 * (u32)TILE;
+        // a full tile whose sources are 16-byte aligned: one copy for the keys, one for the values, both signalling s_bar
+        if (m - base0 >= (u32)TILE && ((((uintptr_t)kin) | ((uintptr_t)vin)) & 15u) == 0) {
+            rs_mbar_expect_tx(&s_bar, (u32)(TILE * sizeof(KeyT)) + (vin ? (u32)(TILE * 4) : 0u));
+            rs_bulk_g2s(skeys, kin + base0, (u32)(TILE * sizeof(KeyT)), &s_bar);
+            if (vin) rs_bulk_g2s(svals, vin + base0, (u32)(TILE * 4), &s_bar);
+        }
+    }
+    if (!BULK && tid == 0) s_tile = atomicAdd(tile_counter, 1u);
+#else
     if (tid == 0) s_tile = atomicAdd(tile_counter, 1u);
+#endif
     if (STABLE) {
         for (u32 i = tid; i < (u32)(WARPS * RS_RADIX); i += THREADS) {
             whist[i] = 0;
@@ -219,6 +270,14 @@ k_onesweep_pass(const KeyT* __restrict__ kin, KeyT* __restrict__ kout,
     RS_POS_DECL(IPT);
     const u32 wbase = warp * (32u * IPT) + lane;
     const bool full = valid == (u32)TILE;  // block-uniform: no bounds checks on the common path
+#if B200SA_RS_BULK_LOAD && !defined(B200SA_EMU)
+    const bool bulk = BULK && full && ((((uintptr_t)kin) | ((uintptr_t)vin)) & 15u) == 0;  // block-uniform, same test as the issuing thread
+    if (bulk) {
+        rs_mbar_wait(&s_bar, 0u);
+#pragma unroll
+        for (int k = 0; k < IPT; ++k) key[k] = skeys[wbase + (u32)k * 32u];
+    } else
+#endif
     if (full) {
         const KeyT* kp = kin + base + wbase;
 #pragma unroll
@@ -284,6 +343,12 @@ k_onesweep_pass(const KeyT* __restrict__ kin, KeyT* __restrict__ kout,
     PT_MARK(1);  // ranking
     // values are fetched only now: during ranking they would cost 16 more live registers (spills at
     // the 80-register budget of 3 CTAs/SM); their latency overlaps the tile-level scan below
+#if B200SA_RS_BULK_LOAD && !defined(B200SA_EMU)
+    if (bulk && vin) {
+#pragma unroll
+        for (int k = 0; k < IPT; ++k) val[k] = svals[wbase + (u32)k * 32u];
+    } else
+#endif
     if (vin) {
         if (full) {
             const u32* vp = vin + base + wbase;

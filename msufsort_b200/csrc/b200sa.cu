@@ -725,14 +725,13 @@ int Engine::sort_round(u32* m_local, cudaStream_t st)
         B200SA_CU(cudaMemsetAsync(d_cnt, 0, 16, st));
         prof.memsets++;
         B200SA_TRY(phase_begin(B200SA_PH_SEGSORT, st));
-        const u32 gt_grid = (u32)div_up_u64(m, GT_TILE);
         if (use_peer) {
-            auto kt = k_group_sort_tiles<PeerRank>;
-            B200SA_LAUNCH(kt, gt_grid, GT_THREADS, 0, st, (const u32*)gstart.as<u32>(), (const u32*)gid.as<u32>(), m, v2[act],
+            auto kt = k_group_sort_tiny<PeerRank>;
+            B200SA_LAUNCH(kt, (u32)div_up_u64(G, GS_THREADS), GS_THREADS, 0, st, (const u32*)gstart.as<u32>(), G, v2[act],
                           peer_rank, n, (u32)ss.h, ss.rank_bits, k2[act], groupsort_tiny, groupsort_medium, medium_list, huge_list, d_cnt);
         } else {
-            auto kt = k_group_sort_tiles<LocalRank>;
-            B200SA_LAUNCH(kt, gt_grid, GT_THREADS, 0, st, (const u32*)gstart.as<u32>(), (const u32*)gid.as<u32>(), m, v2[act],
+            auto kt = k_group_sort_tiny<LocalRank>;
+            B200SA_LAUNCH(kt, (u32)div_up_u64(G, GS_THREADS), GS_THREADS, 0, st, (const u32*)gstart.as<u32>(), G, v2[act],
                           local_rank, n, (u32)ss.h, ss.rank_bits, k2[act], groupsort_tiny, groupsort_medium, medium_list, huge_list, d_cnt);
         }
         count_launch(B200SA_PH_SEGSORT);

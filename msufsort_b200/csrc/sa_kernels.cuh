@@ -518,92 +518,42 @@ k_rerank(const u64* __restrict__ keys, const u32* __restrict__ idx_in, const u32
 // of one per compared byte.
 static const int GS_TINY = 32;
 static const int GS_MEDIUM = 4096;
+static const int GS_THREADS = 128;
 
-// Tiny groups (<= tiny_max <= GS_TINY members), tile-cooperative.  A CTA owns the groups that START inside its tile of
-// GT_TILE active slots (a group may reach up to GS_TINY - 1 slots into the next tile: loaded as halo).  One thread per slot:
-// suffix and group come in with coalesced loads, rank[suffix + h] is ONE gather per thread with all gathers of the tile in
-// flight together (they are loads from a peer GPU's HBM in sharded runs), then every slot counts the members of its group
-// that sort before it (shared memory, <= 32 steps) and the sorted tile goes back with coalesced stores — the array then
-// looks exactly as the radix sort would have left it.  Round 1 gave each group to one thread (serial loads into local
-// arrays: 1.8 ms for 5.3e7 slots on one GPU, 0.68 ms per step on eight GPUs where the loads are remote).
-// Larger groups are listed: counters [0] #medium groups, [1] #huge groups, [2] tuples in medium groups, [3] tuples in huge groups.
-static const int GT_THREADS = 256;
-static const int GT_IPT = 4;
-static const int GT_TILE = GT_THREADS * GT_IPT;   // slots owned per CTA
-static const int GT_SPAN = GT_TILE + GS_TINY;     // + halo
-
+// counters: [0] #medium groups, [1] #huge groups, [2] tuples in medium groups, [3] tuples in huge groups
 template <typename RankT>
-__global__ void __launch_bounds__(GT_THREADS)
-k_group_sort_tiles(const u32* __restrict__ gstart, const u32* __restrict__ gid, u32 m, u32* __restrict__ idx, RankT rank,
-                   u32 n, u32 h, int rank_bits, u64* __restrict__ keys, u32 tiny_max, u32 medium_max,
-                   u32* __restrict__ medium_list, u32* __restrict__ huge_list, u32* __restrict__ counters)
+__global__ void __launch_bounds__(GS_THREADS)
+k_group_sort_tiny(const u32* __restrict__ gstart, u32 groups, u32* __restrict__ idx, RankT rank,
+                  u32 n, u32 h, int rank_bits, u64* __restrict__ keys, u32 tiny_max, u32 medium_max,
+                  u32* __restrict__ medium_list, u32* __restrict__ huge_list, u32* __restrict__ counters)
 {
-    __shared__ u32 s_key[GT_SPAN], s_idx[GT_SPAN], s_okey[GT_SPAN], s_oidx[GT_SPAN];
-    __shared__ u32 s_g[GT_SPAN];    // group of the slot
-    __shared__ u16 s_l0[GT_SPAN];   // tile-local first slot of that group
-    __shared__ u16 s_sz[GT_SPAN];   // its size; 0 = not sorted here (starts before the tile, or larger than tiny_max)
-    const u32 tid = threadIdx.x;
-    const u32 base = blockIdx.x * (u32)GT_TILE;
-    u32 sfx[(GT_SPAN + GT_THREADS - 1) / GT_THREADS];
-#pragma unroll
-    for (int q = 0; q < (GT_SPAN + GT_THREADS - 1) / GT_THREADS; ++q) {
-        const u32 t = tid + (u32)q * GT_THREADS, j = base + t;
-        u32 sz = 0, l0 = 0, g = 0;
-        sfx[q] = 0;
-        if (t < (u32)GT_SPAN && j < m) {
-            g = gid[j];
-            const u32 gs = gstart[g], size = gstart[g + 1] - gs;
-            if (gs >= base && gs < base + (u32)GT_TILE) {  // the group starts in this tile
-                if (size <= tiny_max) {
-                    sz = size;
-                    l0 = gs - base;
-                    sfx[q] = ld_stream(idx + j);
-                } else if (j == gs) {
-                    if (size <= medium_max) {
-                        medium_list[atomicAdd(&counters[0], 1u)] = g;
-                        atomicAdd(&counters[2], size);
-                    } else {
-                        huge_list[atomicAdd(&counters[1], 1u)] = g;
-                        atomicAdd(&counters[3], size);
-                    }
-                }
-            }
+    const u32 g = blockIdx.x * GS_THREADS + threadIdx.x;
+    if (g >= groups) return;
+    const u32 s = gstart[g], sz = gstart[g + 1] - s;
+    if (sz > tiny_max) {
+        if (sz <= medium_max) {
+            medium_list[atomicAdd(&counters[0], 1u)] = g;
+            atomicAdd(&counters[2], sz);
+        } else {
+            huge_list[atomicAdd(&counters[1], 1u)] = g;
+            atomicAdd(&counters[3], sz);
         }
-        if (t < (u32)GT_SPAN) { s_sz[t] = (u16)sz; s_l0[t] = (u16)l0; s_g[t] = g; s_idx[t] = sfx[q]; }
+        return;
     }
-    // the gathers of the whole tile are issued back to back
-#pragma unroll
-    for (int q = 0; q < (GT_SPAN + GT_THREADS - 1) / GT_THREADS; ++q) {
-        const u32 t = tid + (u32)q * GT_THREADS;
-        if (t < (u32)GT_SPAN && s_sz[t]) s_key[t] = rank((u64)sfx[q] + h);
+    u32 a[GS_TINY], k2[GS_TINY];
+    for (u32 i = 0; i < sz; ++i) a[i] = idx[s + i];
+    for (u32 i = 0; i < sz; ++i) k2[i] = rank((u64)a[i] + h);
+    for (u32 i = 1; i < sz; ++i) {
+        const u32 x = k2[i], y = a[i];
+        u32 j = i;
+        while (j > 0 && k2[j - 1] > x) { k2[j] = k2[j - 1]; a[j] = a[j - 1]; --j; }
+        k2[j] = x;
+        a[j] = y;
     }
-    __syncthreads();
-#pragma unroll
-    for (int q = 0; q < (GT_SPAN + GT_THREADS - 1) / GT_THREADS; ++q) {
-        const u32 t = tid + (u32)q * GT_THREADS;
-        if (t < (u32)GT_SPAN) {
-            const u32 sz = s_sz[t];
-            if (sz) {
-                const u32 l0 = s_l0[t], mine = s_key[t];
-                u32 r = 0;
-                for (u32 u = l0; u < l0 + sz; ++u) {
-                    const u32 k = s_key[u];
-                    r += (k < mine || (k == mine && u < t)) ? 1u : 0u;
-                }
-                s_okey[l0 + r] = mine;
-                s_oidx[l0 + r] = s_idx[t];
-            }
-        }
-    }
-    __syncthreads();
-#pragma unroll
-    for (int q = 0; q < (GT_SPAN + GT_THREADS - 1) / GT_THREADS; ++q) {
-        const u32 t = tid + (u32)q * GT_THREADS;
-        if (t < (u32)GT_SPAN && s_sz[t]) {
-            const u32 j = base + t;
-            idx[j] = s_oidx[t];
-            keys[j] = ((u64)s_g[t] << rank_bits) | (u64)s_okey[t];
-        }
+    const u64 hi = (u64)g << rank_bits;
+    for (u32 i = 0; i < sz; ++i) {
+        idx[s + i] = a[i];
+        keys[s + i] = hi | (u64)k2[i];
     }
 }
 

@@ -633,7 +633,7 @@ def run_sharded(args, wl):
             big = {"workload": "acgt_1GiB", "description": d2, "n_bytes": n2, "value": n2 / (ms2 * 1e-3) / 1e6, "unit": "MB/s", "ms_per_step": ms2,
                    "rounds": res2.rounds, "owned_suffixes_per_rank": sorter.owned_counts(res2), "gpu_launches": int(launches2),
                    "nvlink_bytes_stored_by_rank0_per_step": res2.exchanged_bytes,
-                   "single_gpu_ms_round1": 141.0,
+                   "single_gpu_ms": 120.4, "single_gpu_source": "profiles/r02_bench_acgt_1GiB_n1.json (bench.py --workload acgt_1GiB on one B200, round 2)",
                    "phases_rank0_ms": {k: v["ms"] / max(1, min(args.steps, 3)) for k, v in prof2["phases"].items() if v["launches"]}}
             del d_big, res2
             eng.release_workspace()

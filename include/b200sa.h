@@ -104,7 +104,7 @@ B200SA_API int b200sa_unbwt(b200sa_ctx* ctx, uint8_t* bwt_inout, int64_t n, int3
  * The host-buffer calls keep the last text and its suffix array resident in the context: when b200sa_bwt (or this
  * call) is handed, right after b200sa_suffix_array, the same bytes — compared on the device after the upload — it
  * reuses that sort.  Pageable host buffers are moved by several threads through pinned staging buffers
- * (B200SA_COPY_THREADS, default 4); pinned / registered buffers are copied directly. */
+ * (B200SA_COPY_THREADS, default: half the host cores, 2..8); pinned / registered buffers are copied directly. */
 B200SA_API int b200sa_suffix_array_bwt(b200sa_ctx* ctx, const uint8_t* text, int64_t n,
                                        int32_t* sa_out, uint8_t* bwt_out, int32_t* sentinel_index_out);
 

@@ -317,6 +317,9 @@ static const int RR_CHUNKS = RR_IPT * RR_WARPS;  // 128 warp-rows of 32 items pe
 #ifndef B200SA_RR_MIN_BLOCKS
 #define B200SA_RR_MIN_BLOCKS 6
 #endif
+#ifndef B200SA_RR_PREFETCH
+#define B200SA_RR_PREFETCH 1
+#endif
 static const int RR_MIN_BLOCKS = B200SA_RR_MIN_BLOCKS;
 
 // descriptor A: flag(2) | kept heads (31) | kept, low 31 bits;  descriptor B: flag(2) | kept, bit 31 | 1 + last head slot (32).
@@ -390,6 +393,15 @@ k_rerank(const u64* __restrict__ keys, const u32* __restrict__ idx_in, const u32
         }
     }
     __syncthreads();
+#if B200SA_RR_PREFETCH
+    // the suffixes of the tile are fetched now (the key registers are dead): their latency hides behind the look-back below
+    u32 sfxr[RR_IPT];
+#pragma unroll
+    for (int q = 0; q < RR_IPT; ++q) {
+        const u32 j = base + (u32)q * RR_THREADS + tid;
+        sfxr[q] = j < m ? ld_stream(idx_in + j) : 0u;
+    }
+#endif
     // ---- warp 0: exclusive scan of the 128 chunk aggregates, then look-back for the tile prefix
     if (warp == 0) {
         u32 k4[4], h4[4], l4[4];
@@ -487,7 +499,11 @@ k_rerank(const u64* __restrict__ keys, const u32* __restrict__ idx_in, const u32
             else hs1 = pre_lh;
             const u32 hs = hs1 - 1u;
             const u32 gpos = slot_in ? slot_in[hs] : slot_base + hs;
+#if B200SA_RR_PREFETCH
+            const u32 sfx = sfxr[q];
+#else
             const u32 sfx = ld_stream(idx_in + j);
+#endif
             if (newrank_out) st_stream(newrank_out + j, gpos + 1u);  // ISA update deferred: bucketed scatter
             else rank[sfx] = gpos + 1u;
             const bool single = (bal_single[q] >> lane) & 1u;

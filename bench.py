@@ -658,7 +658,9 @@ def run_sharded(args, wl):
         del r3
         eng.release_workspace()
         torch.cuda.empty_cache()
-        back = sorter.inverse_bwt(d_b3, s3)
+        peer = args.isa == "peer"
+        inv = (lambda: sorter.inverse_bwt(d_b3, s3, gather_all=False)) if peer else (lambda: sorter.inverse_bwt(d_b3, s3))
+        back = inv()
         barrier()
         usteps = max(1, min(args.steps, 5))
         eng.profile_reset(); eng.set_profiling(True)
@@ -666,16 +668,22 @@ def run_sharded(args, wl):
         barrier()
         ev0.record()
         for _ in range(usteps):
-            back = sorter.inverse_bwt(d_b3, s3)
+            back = inv()
         ev1.record()
         barrier()
         ms3 = max_over_ranks(ev0.elapsed_time(ev1)) / usteps
         prof3 = eng.profile(); eng.set_profiling(False)
-        if not bool(torch.equal(back, d_t3)):
+        # correctness outside the timed region: this rank's slice of the text, and the slices together cover the text
+        if peer:
+            out3, b3, e3 = back
+            if not bool(torch.equal(out3[b3:e3], d_t3[b3:e3])) or sum_over_ranks(e3 - b3) != n3:
+                raise SystemExit("bench.py: the sharded inverse BWT did not restore the text")
+            del out3
+        elif not bool(torch.equal(back, d_t3)):
             raise SystemExit("bench.py: the sharded inverse BWT did not restore the text")
         unbwt = {"metric": "unbwt_input_throughput", "value": n3 / (ms3 * 1e-3) / 1e6, "unit": "MB/s", "ms_per_step": ms3, "n_bytes": n3,
                  "config": {"workload": UNBWT_WORKLOAD + "_unbwt", "parallelism": f"psi table on every GPU, walkers split over {world} GPUs, bytes stored into the "
-                            "owner of their text position over NVLink, slices pulled from the peers (every rank ends with the whole text)"},
+                            "owner of their text position over NVLink; every rank ends with its slice of the text (as it ends with its rows of the suffix array)"},
                  "phases_rank0_ms": {"build": prof3["phases"]["unbwt_build"]["ms"] / usteps, "walk": prof3["phases"]["unbwt_walk"]["ms"] / usteps}}
         del back, d_b3, d_t3
 

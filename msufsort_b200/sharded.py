@@ -214,18 +214,21 @@ class ShardedSorter:
         return res
 
     # -- the sharded inverse BWT ------------------------------------------------------------------------
-    def inverse_bwt(self, d_bwt: torch.Tensor, sentinel_index: int) -> torch.Tensor:
-        """psi table replicated, walkers partitioned: every rank measures and emits the segments of its slice
-        of the walkers; the (length, successor) entries are all-gathered for the list ranking and the disjoint
-        output slices are combined with a sum all-reduce.  Returns the whole text on every rank."""
+    def inverse_bwt(self, d_bwt: torch.Tensor, sentinel_index: int, gather_all: bool = True):
+        """Every rank passes the same BWT.  C++ path (isa="peer"): the psi table is built on every GPU, the walkers are split
+        over the ranks and the bytes are stored into the owner of their text position over NVLink.  gather_all=True: the
+        other slices are pulled from the peers as well and the whole text is returned on every rank.  gather_all=False:
+        returns (text tensor, begin, end) — only bytes [begin, end), the slice this rank owns, are valid (the analogue of
+        owning a slice of the suffix array after suffix_array_bwt).
+        NCCL path (other ISA modes): psi replicated, walkers partitioned, (length, successor) entries all-gathered, disjoint
+        output slices combined with a sum all-reduce; always returns the whole text."""
         n = d_bwt.numel()
         device = d_bwt.device
         stream = torch_stream_handle() if device.type == "cuda" else 0
         if self.isa == "peer" and self.world > 1:
-            # C++ path: bytes stored into the owner of their text position over NVLink, slices pulled from the peers
             out = torch.empty(n, dtype=torch.uint8, device=device)
-            self.eng.shard_unbwt(self._get_comm(), d_bwt, n, sentinel_index, out, True, stream)
-            return out
+            b, e = self.eng.shard_unbwt(self._get_comm(), d_bwt, n, sentinel_index, out, gather_all, stream)
+            return out if gather_all else (out, b, e)
         W = self.eng.unbwt_shard_build(d_bwt, n, sentinel_index, stream)
         per = (W + self.world - 1) // self.world
         spans = [(min(W, p * per), min(W, (p + 1) * per)) for p in range(self.world)]

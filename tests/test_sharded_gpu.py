@@ -40,6 +40,13 @@ def _worker(rank, world, port, family, n, q, isa="owner"):
         bwt = sorter.gather_bwt(res).cpu().numpy()
         back = sorter.inverse_bwt(sorter.gather_bwt(res), res.sentinel)
         assert bool((back.cpu() == d_text.cpu()).all()), "sharded inverse BWT did not restore the text"
+        if isa == "peer":
+            # without the final all-gather every rank holds its slice of the text; the slices tile [0, n)
+            out, b, e = sorter.inverse_bwt(sorter.gather_bwt(res), res.sentinel, gather_all=False)
+            assert bool(torch.equal(out[b:e], d_text[b:e]))
+            tot = torch.tensor([e - b], dtype=torch.int64, device="cuda")
+            dist.all_reduce(tot)
+            assert int(tot.item()) == n
         counts = sorter.owned_counts(res)
         if rank == 0:
             q.put((sa, bwt, res.sentinel, counts, res.rounds))

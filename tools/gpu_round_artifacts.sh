@@ -16,3 +16,5 @@ echo "launch list rc=$?"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_onesweep_pass -s 10 -c 2 -o gpurun_out/${TAG}_k_onesweep_pass -f \
     $BENCH --steps 1 --warmup 0 > gpurun_out/${TAG}_k_onesweep_pass.out 2>&1
 echo "full rc=$?"; ls -la gpurun_out/${TAG}_k_onesweep_pass.ncu-rep
+echo "== smoke"
+timeout 600 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2

@@ -138,6 +138,7 @@ int Engine::init(int dev)
         copy_threads = hw >= 16 ? 8 : (hw >= 4 ? (int)(hw / 2) : 2);
     }
     if (const char* e13 = getenv("B200SA_COPY_THREADS")) copy_threads = atoi(e13);
+    if (const char* e16 = getenv("B200SA_ISA_PULL_FRACTION")) isa_pull_fraction = (u32)strtoul(e16, nullptr, 10);
     if (const char* e6 = getenv("B200SA_UNBWT_CAP_MULT")) unbwt_cap_mult = (u32)strtoul(e6, nullptr, 10);
     if (unbwt_cap_mult < 1) unbwt_cap_mult = 1;
     if (groupsort_tiny > (u32)GS_TINY) groupsort_tiny = GS_TINY;
@@ -720,6 +721,26 @@ int Engine::sort_round(u32* m_local, cudaStream_t st)
     if (use_peer && (peer.view.n != n || peer.nparts != ss.nparts)) return set_error(B200SA_EINVAL, "peer ISA attached for another text size / GPU count");
     LocalRank local_rank{rank.as<u32>(), n};
     PeerRank peer_rank{peer.view};
+    // Sharded runs read rank[suffix + h] from the owners' HBM with 4-byte remote loads — fine while few suffixes are active,
+    // but a round over huge groups (periodic / Fibonacci texts: every suffix active for ~log n rounds) measured 10 G loads/s
+    // per GPU, half of the 2 GiB Fibonacci run on eight GPUs.  When this GPU is about to read more than n/12 ranks, pulling
+    // the peers' shards in bulk (4 n bytes over NVLink at several hundred GB/s) and gathering locally is cheaper.  The copies
+    // land in the unused part of this GPU's own full-size rank array; shards only change between rounds, behind barriers.
+    bool pulled = false;
+    auto pull_peer_shards = [&]() -> int {
+        if (pulled) return 0;
+        B200SA_TRY(phase_begin(B200SA_PH_PEER_SEND, st));
+        for (int k = 1; k < peer.nparts; ++k) {
+            const int g = (peer.part + k) % peer.nparts;
+            const u64 lo = (u64)g << peer.view.shift, hi = ((u64)(g + 1) << peer.view.shift) < (u64)n ? ((u64)(g + 1) << peer.view.shift) : (u64)n;
+            if (lo < hi) B200SA_CU(cudaMemcpyAsync(rank.as<u32>() + lo, peer.view.base[g] + lo, (size_t)(hi - lo) * 4, cudaMemcpyDefault, st));
+        }
+        B200SA_TRY(phase_end(st));
+        prof.alg_bytes[B200SA_PH_PEER_SEND] += (u64)n * 4;
+        pulled = true;
+        return 0;
+    };
+    const bool bulk_isa = use_peer && isa_pull_fraction > 0 && (u64)m * isa_pull_fraction > (u64)n;
 
     // ---- small groups: sort every group where it lies (no radix sweeps)
     if (groupsort_max_avg > 0 && (u64)m <= (u64)ss.groups * groupsort_max_avg) {
@@ -768,12 +789,13 @@ int Engine::sort_round(u32* m_local, cudaStream_t st)
                 for (u32 q = 0; q < nhuge; ++q)
                     B200SA_CU(cudaMemcpyAsync(&gs[2 * q], gstart.as<u32>() + hl[q], 8, cudaMemcpyDeviceToHost, st));
                 B200SA_CU(cudaStreamSynchronize(st));
+                if (bulk_isa) B200SA_TRY(pull_peer_shards());
                 for (u32 q = 0; q < nhuge; ++q) {
                     const u32 s0 = gs[2 * q], sz = gs[2 * q + 1] - s0;
                     B200SA_TRY(phase_begin(B200SA_PH_BUILD, st));
                     const u32 tiles = (u32)div_up_u64(sz, BK_THREADS * BK_IPT);
                     const u32 grid = tiles < (u32)(num_sms * 8) ? tiles : (u32)(num_sms * 8);
-                    if (use_peer) {
+                    if (use_peer && !bulk_isa) {
                         auto kb = k_build_keys<PeerRank>;
                         B200SA_LAUNCH(kb, grid, BK_THREADS, 0, st, (const u32*)(v2[act] + s0), (const u32*)(gid.as<u32>() + s0), peer_rank, sz, n,
                                       (u32)ss.h, ss.rank_bits, k2[act] + s0);
@@ -803,11 +825,12 @@ int Engine::sort_round(u32* m_local, cudaStream_t st)
     }
 
     if (sorted_side < 0) {
+        if (bulk_isa) B200SA_TRY(pull_peer_shards());
         B200SA_TRY(phase_begin(B200SA_PH_BUILD, st));
         {
             const u32 tiles = (u32)div_up_u64(m, BK_THREADS * BK_IPT);
             const u32 grid = tiles < (u32)(num_sms * 8) ? tiles : (u32)(num_sms * 8);
-            if (use_peer) {
+            if (use_peer && !bulk_isa) {
                 auto kb = k_build_keys<PeerRank>;
                 B200SA_LAUNCH(kb, grid, BK_THREADS, 0, st, (const u32*)v2[act], (const u32*)gid.as<u32>(), peer_rank, m, n, (u32)ss.h,
                               ss.rank_bits, k2[act]);

@@ -83,6 +83,10 @@ struct Engine {
     u32 groupsort_tiny = GS_TINY;
     u32 groupsort_medium = GS_MEDIUM;
 
+    // sharded radix rounds pull the peers' ISA shards in bulk when this GPU reads more than n / isa_pull_fraction ranks
+    // (B200SA_ISA_PULL_FRACTION; 0 = always load remotely, 1000000000 = always pull: tests)
+    u32 isa_pull_fraction = 12;
+
     // inverse BWT: bytes of decode window per walker = unbwt_cap_mult * D (D = mean segment length)
     u32 unbwt_cap_mult = 4;
 

@@ -152,19 +152,31 @@ static int sa_bwt_host(b200sa_ctx* ctx, const uint8_t* text, int64_t n, void* sa
     B200SA_TRY(e.sa_ws.ensure(((size_t)n + 1) * 4));
     const bool want_bwt = bwt_out != nullptr || sentinel_out != nullptr;
     if (want_bwt) B200SA_TRY(e.bwt_ws.ensure((size_t)n + 64));
-    bool reuse = false;
+    bool reuse = false, bwt_done = false;
     if (had_cache && want_bwt) {
-        // upload next to the resident text and compare on the device
+        // The text is uploaded next to the resident one and compared on the device (copy stream).  Meanwhile the BWT pass
+        // already runs from the resident text and suffix array (compute stream): if the bytes turn out to be the same — the
+        // drop-in sequence make_suffix_array, forward_burrows_wheeler_transform — its result is the answer; if not it is
+        // simply discarded.
         B200SA_TRY(e.misc.ensure(8192));
+        B200SA_TRY(e.keys[1].ensure((size_t)n + 64));
+        u8* d_new = e.keys[1].as<u8>();
         u32* d_diff = e.misc.as<u32>() + 548;
-        B200SA_CU(cudaMemsetAsync(d_diff, 0, 4, st));
-        B200SA_TRY(e.copy_in(e.bwt_ws.p, text, (size_t)n, st));
-        B200SA_LAUNCH(b200sa::k_bytes_differ, (u32)(e.num_sms * 8), 256, 0, st, (const u8*)e.text_ws.as<u8>(), (const u8*)e.bwt_ws.as<u8>(), (u64)n, d_diff);
-        e.count_launch(B200SA_PH_ALPHABET);
-        B200SA_CU(cudaMemcpyAsync(e.h_pinned + 25, d_diff, 4, cudaMemcpyDeviceToHost, st));
         B200SA_CU(cudaStreamSynchronize(st));
+        B200SA_TRY(e.bwt_rows(e.text_ws.as<u8>(), (u32)n, e.sa_ws.as<i32>(), 0, (u32)n, e.bwt_ws.as<u8>(), st, /*defer_sync=*/true));
+        cudaStream_t cs = e.copy_stream;
+        B200SA_CU(cudaMemsetAsync(d_diff, 0, 4, cs));
+        B200SA_TRY(e.copy_in(d_new, text, (size_t)n, cs));
+        B200SA_LAUNCH(b200sa::k_bytes_differ, (u32)(e.num_sms * 8), 256, 0, cs, (const u8*)e.text_ws.as<u8>(), (const u8*)d_new, (u64)n, d_diff);
+        e.count_launch(B200SA_PH_ALPHABET);
+        B200SA_CU(cudaMemcpyAsync(e.h_pinned + 25, d_diff, 4, cudaMemcpyDeviceToHost, cs));
+        B200SA_CU(cudaStreamSynchronize(cs));
         reuse = e.h_pinned[25] == 0;
-        if (!reuse) B200SA_CU(cudaMemcpyAsync(e.text_ws.p, e.bwt_ws.p, (size_t)n, cudaMemcpyDeviceToDevice, st));
+        bwt_done = reuse;
+        if (!reuse) {
+            B200SA_CU(cudaStreamSynchronize(st));  // the speculative pass still reads text_ws
+            B200SA_CU(cudaMemcpyAsync(e.text_ws.p, d_new, (size_t)n, cudaMemcpyDeviceToDevice, st));
+        }
     } else {
         B200SA_TRY(e.copy_in(e.text_ws.p, text, (size_t)n, st));
     }
@@ -175,9 +187,9 @@ static int sa_bwt_host(b200sa_ctx* ctx, const uint8_t* text, int64_t n, void* sa
         B200SA_CU(cudaStreamSynchronize(st));
         sentinel = (i64)e.h_pinned[26];
     }
-    if (want_bwt) {
+    if (want_bwt && !bwt_done) {
         // the gather runs while the suffix array travels to the host (pageable destination: the staging threads' streams;
-        // pinned: enqueued behind it on the same stream)
+        // pinned: the copy stream)
         B200SA_TRY(e.bwt_rows(e.text_ws.as<u8>(), (u32)n, e.sa_ws.as<i32>(), 0, (u32)n, e.bwt_ws.as<u8>(), st, /*defer_sync=*/true));
     }
     if (sa_out) B200SA_TRY(e.copy_out(sa_out, e.sa_ws.p, ((size_t)n + 1) * 4, st, /*independent=*/true));

@@ -183,6 +183,48 @@ def test_emu_pipeline(oracle):
         Pipeline(0, 0, library=lib)
 
 
+def test_emu_pipeline_waiters_never_hang(oracle):
+    """two threads waiting for one ticket, or a drain while a thread waits, must not leave a waiter blocked:
+    exactly one waiter collects the result, the others return EINVAL"""
+    import os
+    import threading
+    from conftest import ROOT
+    from msufsort_b200.api import B200SAError, Library, Pipeline
+    lib = Library(os.path.join(ROOT, "tests", "emu", "libb200sa_emu.so"))
+    with Pipeline(0, 1, library=lib) as pipe:
+        for round_ in range(3):
+            blocks = [gen("markov3", 20000 + 17 * round_) for _ in range(4)]
+            packed = np.concatenate(blocks)
+            offsets = np.concatenate([[0], np.cumsum([b.size for b in blocks])]).astype(np.int64)
+            sent = np.zeros(len(blocks), dtype=np.int32)
+            t = pipe.submit_bwt(packed, offsets, sent)
+            outcomes = []
+
+            def waiter():
+                try:
+                    pipe.wait(t)
+                    outcomes.append("ok")
+                except B200SAError as e:
+                    outcomes.append("err%d" % e.code)
+
+            threads = [threading.Thread(target=waiter) for _ in range(3)]
+            for th in threads:
+                th.start()
+            if round_ == 2:
+                try:
+                    pipe.drain()             # may collect the ticket before any waiter does
+                except B200SAError:
+                    pass
+            for th in threads:
+                th.join(timeout=120)
+                assert not th.is_alive(), "a waiter is blocked forever"
+            assert outcomes.count("ok") <= 1 and all(o in ("ok", "err1") for o in outcomes), outcomes
+            if round_ < 2:
+                assert outcomes.count("ok") == 1
+                want = [oracle.bwt(b) for b in blocks]
+                assert [w[1] for w in want] == sent.tolist()
+
+
 @pytest.mark.gpu
 def test_gpu_pipeline(gpu_engine, oracle):
     _pipeline_roundtrip(gpu_engine.lib, oracle, nbatches=8, blocks_per_batch=24, block_len=200000, depth=3)

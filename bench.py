@@ -592,7 +592,17 @@ def run_sharded(args, wl):
         bad = eng.check_suffix_array_dev(d_text, nn, full_sa, stream)
         if bad != 0:
             raise SystemExit(f"bench.py: sharded SA has {bad} bad rows")
-        del full_sa
+        # ... and the assembled BWT must be the gather of that suffix array (sentinel row = the row of suffix 0)
+        full_bwt = sorter.gather_bwt(res)
+        s = res.sentinel
+        if int(full_sa[s]) != 0:
+            raise SystemExit("bench.py: sharded sentinel index is not the row of suffix 0")
+        rows = torch.arange(0, nn + 1, device="cuda")
+        rows = rows[rows != s]
+        want = d_text[(full_sa[rows].long() - 1)]
+        if not bool(torch.equal(full_bwt, want)):
+            raise SystemExit("bench.py: sharded BWT differs from the gather of the validated suffix array")
+        del full_sa, full_bwt, rows, want
         return ms, res, prof, launches, clocks
 
     # ---- headline: the BASELINE.json configs[1] text, sharded

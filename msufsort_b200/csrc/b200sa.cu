@@ -138,6 +138,8 @@ int Engine::init(int dev)
         copy_threads = hw >= 16 ? 8 : (hw >= 4 ? (int)(hw / 2) : 2);
     }
     if (const char* e13 = getenv("B200SA_COPY_THREADS")) copy_threads = atoi(e13);
+    if (const char* e17 = getenv("B200SA_BWT_WINDOW_BYTES")) bwt_window_bytes = (size_t)strtoull(e17, nullptr, 10);
+    if (const char* e18 = getenv("B200SA_BWT_MAX_PASSES")) bwt_max_passes = (u32)strtoul(e18, nullptr, 10);
     if (const char* e16 = getenv("B200SA_ISA_PULL_FRACTION")) isa_pull_fraction = (u32)strtoul(e16, nullptr, 10);
     if (const char* e6 = getenv("B200SA_UNBWT_CAP_MULT")) unbwt_cap_mult = (u32)strtoul(e6, nullptr, 10);
     if (unbwt_cap_mult < 1) unbwt_cap_mult = 1;
@@ -903,8 +905,31 @@ int Engine::bwt_rows(const u8* d_text, u32 n, const i32* d_sa, u32 o_begin, u32 
         const u32 grid = want < (u32)(num_sms * 16) ? (want ? want : 1u) : (u32)(num_sms * 16);
         // rank[0] (the sentinel row) lives on GPU 0 when the ISA is sharded in peer memory
         const u32* rank0 = (peer.active && peer.has_isa && ss.nparts > 1) ? (const u32*)peer.view.base[0] : (const u32*)rank.as<u32>();
-        B200SA_LAUNCH(k_bwt_gather, grid, BW_THREADS, 0, st, d_text, d_sa, rank0, o_begin, o_end, d_bwt, d_sent);
-        count_launch(B200SA_PH_BWT);
+        // texts that do not fit L2: one pass per text window (bwt_kernels.cuh); otherwise, and for unaligned outputs, one pass
+        // (a pass costs about 1 ms per 2^28 rows whatever it hits, so more than bwt_max_passes windows lose against the one
+        // pass of random DRAM sectors: 2^30 bytes in 8 windows 31.6 ms, in one pass 25.5 ms)
+        u32 passes = bwt_window_bytes ? (u32)div_up_u64(n, bwt_window_bytes) : 1u;
+        if (passes > bwt_max_passes || o_end - o_begin < 64u) passes = 1u;
+        if (passes <= 1u) {
+            B200SA_LAUNCH(k_bwt_gather, grid, BW_THREADS, 0, st, d_text, d_sa, rank0, o_begin, o_end, d_bwt, d_sent);
+            count_launch(B200SA_PH_BWT);
+        } else {
+            // the windowed passes combine 32-bit words: the (up to three) bytes before the first aligned output word go through
+            // the single-pass kernel
+            const u32 head = (u32)((4u - (u32)(((uintptr_t)(d_bwt + o_begin)) & 3u)) & 3u);
+            if (head) {
+                B200SA_LAUNCH(k_bwt_gather, 1, BW_THREADS, 0, st, d_text, d_sa, rank0, o_begin, o_begin + head, d_bwt, d_sent);
+                count_launch(B200SA_PH_BWT);
+            }
+            const u32 win = (u32)div_up_u64(n, passes);
+            for (u32 p = 0; p < passes; ++p) {
+                const u64 lo = (u64)p * win, hi = lo + win < (u64)n ? lo + win : (u64)n;
+                B200SA_LAUNCH(k_bwt_gather_window, grid, BW_THREADS, 0, st, d_text, d_sa, rank0, o_begin + head, o_end, d_bwt, d_sent, (u32)lo, (u32)hi,
+                              p == 0 ? 1 : 0);
+                count_launch(B200SA_PH_BWT);
+            }
+            prof.alg_bytes[B200SA_PH_BWT] += (u64)(o_end - o_begin) * (4 + 2) * (passes - 1);  // suffix array re-read, output read-modify-write
+        }
     }
     B200SA_TRY(phase_end(st));
     prof.alg_bytes[B200SA_PH_BWT] += (u64)(o_end - o_begin) * 6;

@@ -83,6 +83,13 @@ struct Engine {
     u32 groupsort_tiny = GS_TINY;
     u32 groupsort_medium = GS_MEDIUM;
 
+    // forward BWT: the gather runs in passes over text windows of at most this many bytes, so that the gathered window stays in
+    // L2 (B200SA_BWT_WINDOW_BYTES; 0 = always one pass; tests set a few KB to drive the windowed kernel at small n).  Measured
+    // on B200 at 256 MiB (profiles/r02_bwt_window.txt): one pass 4.35 ms; windows of 96 / 64 / 48 / 32 MiB 3.22 / 3.23 / 3.75 /
+    // 4.84 ms.  Texts that would need more than bwt_max_passes windows take the single pass.
+    size_t bwt_window_bytes = (size_t)96 << 20;
+    u32 bwt_max_passes = 4;
+
     // sharded radix rounds pull the peers' ISA shards in bulk when this GPU reads more than n / isa_pull_fraction ranks
     // (B200SA_ISA_PULL_FRACTION; 0 = always load remotely, 1000000000 = always pull: tests)
     u32 isa_pull_fraction = 12;

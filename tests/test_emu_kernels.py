@@ -166,3 +166,39 @@ def test_emu_resident_suffix_array_is_reused(emu_engine, oracle):
     b = x.copy()
     emu_engine.forward_burrows_wheeler_transform(b)
     assert emu_engine.profile()["rounds"] > p2
+
+
+def test_emu_bwt_windowed_gather(oracle, monkeypatch):
+    """forward BWT in passes over text windows (taken for texts larger than L2 on the GPU; forced here with tiny windows),
+    aligned and unaligned output buffers, whole transforms and the row ranges of a sharded run"""
+    import os
+    from conftest import ROOT
+    from msufsort_b200.api import Engine, Group, Library
+    monkeypatch.setenv("B200SA_BWT_WINDOW_BYTES", "1000")
+    monkeypatch.setenv("B200SA_BWT_MAX_PASSES", "64")
+    lib = Library(os.path.join(ROOT, "tests", "emu", "libb200sa_emu.so"))
+    eng = Engine(0, library=lib)
+    try:
+        for family in FAMILIES:
+            for n in (63, 64, 65, 255, 4097, 30011):
+                x = gen(family, n)
+                want = oracle.sa(x)
+                wb, ws = oracle.bwt_from_sa(x, want)
+                sa, bwt, s = eng.suffix_array_and_bwt(x)
+                assert np.array_equal(sa, want) and s == ws and np.array_equal(bwt, wb), (family, n)
+                for shift in (1, 2, 3):                     # output buffer at every alignment
+                    buf = np.zeros(n + 8, dtype=np.uint8)
+                    view = buf[shift:shift + n]
+                    view[:] = x
+                    assert eng.forward_burrows_wheeler_transform(view) == ws and np.array_equal(view, wb), (family, n, shift)
+    finally:
+        eng.close()
+    g = Group([0, 0, 0], library=lib)
+    try:
+        for family, n in (("markov3", 40003), ("fib", 20000), ("zeros", 9000)):
+            x = gen(family, n)
+            sa, bwt, s = g.suffix_array_and_bwt(x)
+            wb, ws = oracle.bwt(x)
+            assert s == ws and np.array_equal(bwt, wb), (family, n)
+    finally:
+        g.close()

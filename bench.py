@@ -639,12 +639,12 @@ def run_sharded(args, wl):
             if args.big_n:
                 n2 = args.big_n
             d_big = torch.from_numpy(gen_text(k2, n2)).cuda()
-            ms2, res2, prof2, launches2, _ = time_sharded(d_big, n2, max(1, min(args.steps, 3)), 1, False)
+            ms2, res2, prof2, launches2, _ = time_sharded(d_big, n2, args.steps, 2, False)
             big = {"workload": "acgt_1GiB", "description": d2, "n_bytes": n2, "value": n2 / (ms2 * 1e-3) / 1e6, "unit": "MB/s", "ms_per_step": ms2,
                    "rounds": res2.rounds, "owned_suffixes_per_rank": sorter.owned_counts(res2), "gpu_launches": int(launches2),
                    "nvlink_bytes_stored_by_rank0_per_step": res2.exchanged_bytes,
                    "single_gpu_ms": 120.4, "single_gpu_source": "profiles/r02_bench_acgt_1GiB_n1.json (bench.py --workload acgt_1GiB on one B200, round 2)",
-                   "phases_rank0_ms": {k: v["ms"] / max(1, min(args.steps, 3)) for k, v in prof2["phases"].items() if v["launches"]}}
+                   "phases_rank0_ms": {k: v["ms"] / args.steps for k, v in prof2["phases"].items() if v["launches"]}}
             del d_big, res2
             eng.release_workspace()
             torch.cuda.empty_cache()

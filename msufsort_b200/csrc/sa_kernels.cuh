@@ -92,7 +92,7 @@ static const int PK_HALO = 64;                   // k <= 58
 #define PK_SYM(p) ((u64)s_sym[(p) + (((p) >> 4) << 2)])
 template <bool RADIX, bool RANGE>
 __global__ void __launch_bounds__(PK_THREADS)
-k_pack_keys(const u8* __restrict__ text, u32 n, const u8* __restrict__ code, int bits, int k, int len_bits, u64 B_, u64 top_pow,
+k_pack_keys(const u8* __restrict__ text, u32 n, const u8* __restrict__ code, int bits, int k, int len_bits, u64 B, u64 top_pow,
             u64* __restrict__ keys, u64 lo, u64 hi, int hi_inclusive, u32* __restrict__ out_idx, u32* __restrict__ cursor)
 {
     __shared__ u8 s_code[256];
@@ -106,7 +106,6 @@ k_pack_keys(const u8* __restrict__ text, u32 n, const u8* __restrict__ code, int
     __shared__ u64 s_ck[RANGE ? PK_TILE : 1];  // kept keys of the tile, compacted, so that the global stores are coalesced
     __shared__ u16 s_cp[RANGE ? PK_TILE : 1];  // their positions inside the tile
     const u32 tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    const u64 B = (u64)(u32)B_;  // the radix is sigma + 1 <= 256: tell the compiler the upper half is zero (cheaper 64-bit multiplies)
     s_code[tid] = RADIX ? (u8)(code[tid] + 1u) : code[tid];  // sigma <= 255 in the mixed-radix layout: digits fit a byte
     __syncthreads();
     const u32 ntiles = (u32)div_up_u64(n, PK_TILE);

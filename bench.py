@@ -628,7 +628,7 @@ def run_sharded(args, wl):
     assert bool(torch.equal(h_sa[r2.row_begin:r2.row_end].cuda(), res.sa[res.row_begin:res.row_end]))
     d2h_total = sum_over_ranks(4 * slice_rows + slice_bytes)
     del h_sa, h_bwt, d_text, host_text, res, r2
-    eng.release_workspace()
+    sorter.release()
     torch.cuda.empty_cache()
 
     # ---- configs[2]: 2^30-2 ACGT bases with repeats on the same GPUs
@@ -646,7 +646,7 @@ def run_sharded(args, wl):
                    "single_gpu_ms": 120.4, "single_gpu_source": "profiles/r02_bench_acgt_1GiB_n1.json (bench.py --workload acgt_1GiB on one B200, round 2)",
                    "phases_rank0_ms": {k: v["ms"] / args.steps for k, v in prof2["phases"].items() if v["launches"]}}
             del d_big, res2
-            eng.release_workspace()
+            sorter.release()
             torch.cuda.empty_cache()
         except Exception as exc:
             # a rank that fails in the middle of a collective sequence cannot rejoin its peers: the whole job stops (torchrun
@@ -666,7 +666,7 @@ def run_sharded(args, wl):
         d_b3 = sorter.gather_bwt(r3)
         s3 = r3.sentinel
         del r3
-        eng.release_workspace()
+        sorter.release()
         torch.cuda.empty_cache()
         peer = args.isa == "peer"
         inv = (lambda: sorter.inverse_bwt(d_b3, s3, gather_all=False)) if peer else (lambda: sorter.inverse_bwt(d_b3, s3))

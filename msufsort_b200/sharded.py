@@ -73,7 +73,19 @@ class ShardedSorter:
             self.comm = Comm.shared_memory(name[0], self.rank, self.world, library=self.eng.lib)
         return self.comm
 
+    def release(self) -> None:
+        """Frees the engine's device workspace on every rank — collectively: buffers that peers have mapped through CUDA IPC
+        must not be freed before every importer has closed its mapping (all ranks detach, meet, and only then free)."""
+        self.eng.shard_peer_detach()
+        if self.world > 1:
+            dist.barrier(group=self.group)
+        self.eng.release_workspace()
+
     def close(self) -> None:
+        """Collective: closes the peer mappings on every rank before any rank goes on to destroy its engine."""
+        self.eng.shard_peer_detach()
+        if self.world > 1:
+            dist.barrier(group=self.group)
         if self.comm is not None:
             self.comm.close()
             self.comm = None

@@ -40,7 +40,7 @@ try:
     bwt_slice = res.bwt[res.out_begin:res.out_end].clone()
     rb, re, ob, oe, s = res.row_begin, res.row_end, res.out_begin, res.out_end, res.sentinel
     res.sa = None; res.bwt = None
-    eng.release_workspace(); torch.cuda.empty_cache()
+    sorter.release(); torch.cuda.empty_cache()
     full = torch.empty(n + 1, dtype=torch.int32, device="cuda") if rank == 0 else None
     # slices travel to rank 0 one after the other (point-to-point: no G-fold staging buffers)
     for src in range(world):

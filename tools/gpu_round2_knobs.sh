@@ -1,4 +1,5 @@
 #!/bin/bash
+# (historical: the first GPU call of round 2.  The persistent sweep it measures was removed afterwards; results: profiles/r02_knobs.txt)
 # First GPU call of the next round: the experiments that are correct under the emulator but still unmeasured.
 #   B200SA_PACK_RADIX=1     mixed-radix round-0 keys (more symbols per key)
 #   B200SA_RS_PERSISTENT=1  persistent sweep with next-tile key prefetch

@@ -19,6 +19,31 @@ namespace b200sa {
 static const int BW_THREADS = 256;
 static const int BW_STEPS = 4;  // independent 4-byte groups in flight per thread
 
+// Suffix array entries of the four rows behind output bytes o .. o+3 (row = o + (o >= s)).  One 4-byte load per row made
+// the gather passes L2-REQUEST bound (2^28 requests per pass: 1.07 ms per pass of the windowed kernel whatever it hit).  Where
+// the group is complete and sa + o is 16-byte aligned the four (or five) entries come with one 128-bit load plus at most
+// one more word: rows before the sentinel row are sa[o .. o+3], rows behind it sa[o+1 .. o+4].
+__device__ __forceinline__ void bw_load_rows(const i32* __restrict__ sa, u32 o, u32 o_end, u32 s, bool vec_ok, u32 v[4])
+{
+    if (vec_ok && o + 4u <= o_end) {
+        const int4 q = ld_stream((const int4*)(sa + o));
+        const u32 a[4] = {(u32)q.x, (u32)q.y, (u32)q.z, (u32)q.w};
+        if (o + 3u < s) {
+            v[0] = a[0]; v[1] = a[1]; v[2] = a[2]; v[3] = a[3];
+        } else {
+            const u32 e = (u32)ld_stream(sa + o + 4u);  // o + 4 <= o_end <= n: inside the n + 1 entries
+#pragma unroll
+            for (int b = 0; b < 4; ++b) v[b] = (o + (u32)b >= s) ? (b < 3 ? a[b + 1] : e) : a[b];
+        }
+    } else {
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const u32 ob = o + (u32)b;
+            v[b] = ob < o_end ? (u32)ld_stream(sa + ob + (ob >= s ? 1u : 0u)) : 1u;  // 1: a harmless text position for bytes that are not produced
+        }
+    }
+}
+
 // Produces output bytes [o_begin, o_end) (the whole transform: 0 and n; a sharded run: the bytes
 // of the rows this GPU owns).
 __global__ void __launch_bounds__(BW_THREADS)
@@ -30,8 +55,15 @@ k_bwt_gather(const u8* __restrict__ text, const i32* __restrict__ sa, const u32*
     const u32 span = o_end - o_begin;
     const u32 ngroups = (u32)div_up_u64(span, 4);
     const bool out_aligned = (((uintptr_t)(out + o_begin)) & 3u) == 0;
+    const bool vec_ok = (((uintptr_t)(sa + o_begin)) & 15u) == 0;
     for (u32 g0 = (blockIdx.x * BW_THREADS + threadIdx.x); g0 < ngroups; g0 += gridDim.x * BW_THREADS * BW_STEPS) {
         u32 packed[BW_STEPS];
+        u32 v[BW_STEPS][4];
+#pragma unroll
+        for (int st = 0; st < BW_STEPS; ++st) {
+            const u32 g = g0 + (u32)st * gridDim.x * BW_THREADS;
+            if (g < ngroups) bw_load_rows(sa, o_begin + g * 4u, o_end, s, vec_ok, v[st]);
+        }
 #pragma unroll
         for (int st = 0; st < BW_STEPS; ++st) {
             const u32 g = g0 + (u32)st * gridDim.x * BW_THREADS;
@@ -40,11 +72,7 @@ k_bwt_gather(const u8* __restrict__ text, const i32* __restrict__ sa, const u32*
 #pragma unroll
                 for (int b = 0; b < 4; ++b) {
                     const u32 o = o_begin + g * 4u + (u32)b;
-                    if (o < o_end) {
-                        const u32 row = o + (o >= s ? 1u : 0u);
-                        const u32 v = (u32)sa[row];
-                        w |= (u32)text[v - 1u] << (8 * b);
-                    }
+                    if (o < o_end) w |= (u32)text[v[st][b] - 1u] << (8 * b);
                 }
             }
             packed[st] = w;
@@ -79,8 +107,15 @@ k_bwt_gather_window(const u8* __restrict__ text, const i32* __restrict__ sa, con
     const u32 span = o_end - o_begin;
     const u32 ngroups = (u32)div_up_u64(span, 4);
     u32* out32 = (u32*)(out + o_begin);
+    const bool vec_ok = (((uintptr_t)(sa + o_begin)) & 15u) == 0;
     for (u32 g0 = (blockIdx.x * BW_THREADS + threadIdx.x); g0 < ngroups; g0 += gridDim.x * BW_THREADS * BW_STEPS) {
         u32 packed[BW_STEPS];
+        u32 v[BW_STEPS][4];
+#pragma unroll
+        for (int st = 0; st < BW_STEPS; ++st) {
+            const u32 g = g0 + (u32)st * gridDim.x * BW_THREADS;
+            if (g < ngroups) bw_load_rows(sa, o_begin + g * 4u, o_end, s, vec_ok, v[st]);
+        }
 #pragma unroll
         for (int st = 0; st < BW_STEPS; ++st) {
             const u32 g = g0 + (u32)st * gridDim.x * BW_THREADS;
@@ -89,11 +124,8 @@ k_bwt_gather_window(const u8* __restrict__ text, const i32* __restrict__ sa, con
 #pragma unroll
                 for (int b = 0; b < 4; ++b) {
                     const u32 o = o_begin + g * 4u + (u32)b;
-                    if (o < o_end) {
-                        const u32 row = o + (o >= s ? 1u : 0u);
-                        const u32 t = (u32)ld_stream(sa + row) - 1u;
-                        if (t >= win_lo && t < win_hi) w |= (u32)text[t] << (8 * b);
-                    }
+                    const u32 t = v[st][b] - 1u;
+                    if (o < o_end && t >= win_lo && t < win_hi) w |= (u32)text[t] << (8 * b);
                 }
             }
             packed[st] = w;

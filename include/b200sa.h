@@ -322,6 +322,12 @@ B200SA_API int b200sa_group_suffix_array_bwt(b200sa_group* g, const uint8_t* tex
                                              int32_t* sentinel_index_out);
 B200SA_API int b200sa_group_unbwt(b200sa_group* g, uint8_t* bwt_inout, int64_t n, int32_t sentinel_index);
 
+/* The three reference calls without a context and with a GPU count — the C ABI SURVEY.md §8(b) sketched: GPUs
+ * 0 .. num_gpus-1 (num_gpus <= 0: every GPU present); the group behind a count is created on first use and kept. */
+B200SA_API int b200sa_suffix_array_gpus(const uint8_t* text, int64_t n, int32_t* sa_out, int num_gpus);
+B200SA_API int b200sa_bwt_gpus(uint8_t* text_inout, int64_t n, int32_t* sentinel_index_out, int num_gpus);
+B200SA_API int b200sa_unbwt_gpus(uint8_t* bwt_inout, int64_t n, int32_t sentinel_index, int num_gpus);
+
 /* The same with the caller owning the ranks (one process per GPU under torchrun: msufsort_b200/sharded.py, bench.py).
  * b200sa_comm_create_local: nranks handles for the threads of one process.  b200sa_comm_create_shm: rank 0 creates the
  * POSIX shared-memory segment `name` ("/..."; pick a fresh name per job), the other processes of the node attach to it.

@@ -114,6 +114,9 @@ ABI = [
     ("b200sa_group_bwt", C.c_int, [_P, _P, C.c_int64, C.POINTER(C.c_int32)]),
     ("b200sa_group_suffix_array_bwt", C.c_int, [_P, _P, C.c_int64, _P, _P, C.POINTER(C.c_int32)]),
     ("b200sa_group_unbwt", C.c_int, [_P, _P, C.c_int64, C.c_int32]),
+    ("b200sa_suffix_array_gpus", C.c_int, [_P, C.c_int64, _P, C.c_int]),
+    ("b200sa_bwt_gpus", C.c_int, [_P, C.c_int64, C.POINTER(C.c_int32), C.c_int]),
+    ("b200sa_unbwt_gpus", C.c_int, [_P, C.c_int64, C.c_int32, C.c_int]),
     ("b200sa_comm_create_local", C.c_int, [C.POINTER(_P), C.c_int]),
     ("b200sa_comm_create_shm", C.c_int, [C.POINTER(_P), C.c_char_p, C.c_int, C.c_int]),
     ("b200sa_comm_destroy", None, [_P]),

@@ -1101,6 +1101,54 @@ int b200sa_group_unbwt(b200sa_group* g, uint8_t* bwt_inout, int64_t n, int32_t s
     });
 }
 
+// ---- context-free calls with a GPU count (the shape SURVEY.md §8(b) proposed for the C ABI) --------------------
+// b200sa_*_gpus(..., num_gpus): GPUs 0 .. num_gpus-1 (num_gpus <= 0: all GPUs present); the group behind each count is
+// created on first use and kept for the life of the process.
+
+}  // extern "C"
+
+static b200sa_group* shared_group(int num_gpus)
+{
+    static std::mutex mu;
+    static std::map<int, b200sa_group*> groups;
+    const int present = b200sa_device_count();
+    if (present <= 0) {
+        b200sa::set_error(B200SA_ENODEVICE, "no CUDA device available; this library has no CPU fallback");
+        return nullptr;
+    }
+    if (num_gpus <= 0 || num_gpus > present) num_gpus = present;
+    if (num_gpus > b200sa::kMaxPeers) num_gpus = b200sa::kMaxPeers;
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = groups.find(num_gpus);
+    if (it != groups.end()) return it->second;
+    std::vector<int> devices;
+    for (int g = 0; g < num_gpus; ++g) devices.push_back(g);
+    b200sa_group* grp = nullptr;
+    if (b200sa_group_create(&grp, devices.data(), num_gpus) != 0) return nullptr;
+    groups[num_gpus] = grp;
+    return grp;
+}
+
+extern "C" {
+
+int b200sa_suffix_array_gpus(const uint8_t* text, int64_t n, int32_t* sa_out, int num_gpus)
+{
+    b200sa_group* g = shared_group(num_gpus);
+    return g ? b200sa_group_suffix_array(g, text, n, sa_out) : B200SA_ENODEVICE;
+}
+
+int b200sa_bwt_gpus(uint8_t* text_inout, int64_t n, int32_t* sentinel_index_out, int num_gpus)
+{
+    b200sa_group* g = shared_group(num_gpus);
+    return g ? b200sa_group_bwt(g, text_inout, n, sentinel_index_out) : B200SA_ENODEVICE;
+}
+
+int b200sa_unbwt_gpus(uint8_t* bwt_inout, int64_t n, int32_t sentinel_index, int num_gpus)
+{
+    b200sa_group* g = shared_group(num_gpus);
+    return g ? b200sa_group_unbwt(g, bwt_inout, n, sentinel_index) : B200SA_ENODEVICE;
+}
+
 // ---- instrumentation ---------------------------------------------------------------------------
 
 int b200sa_set_profiling(b200sa_ctx* ctx, int enabled)

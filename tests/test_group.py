@@ -90,3 +90,28 @@ def test_gpu_group_one_context_per_gpu(oracle):
             _check(g, oracle, gen(family, n))
     finally:
         g.close()
+
+
+def _gpus_calls(lib, oracle, n):
+    """the context-free calls with a GPU count (b200sa_*_gpus)"""
+    import ctypes as C
+    x = gen("markov3", n)
+    sa = np.empty(n + 1, dtype=np.int32)
+    lib.check(lib.cdll.b200sa_suffix_array_gpus(x.ctypes.data, n, sa.ctypes.data, 1))
+    assert np.array_equal(sa, oracle.sa(x))
+    b = x.copy()
+    s = C.c_int32(0)
+    lib.check(lib.cdll.b200sa_bwt_gpus(b.ctypes.data, n, C.byref(s), 0))      # 0 = every GPU present
+    wb, ws = oracle.bwt(x)
+    assert s.value == ws and np.array_equal(b, wb)
+    lib.check(lib.cdll.b200sa_unbwt_gpus(b.ctypes.data, n, s.value, 0))
+    assert np.array_equal(b, x)
+
+
+def test_emu_calls_with_gpu_count(oracle):
+    _gpus_calls(Library(os.path.join(ROOT, "tests", "emu", "libb200sa_emu.so")), oracle, 30011)
+
+
+@pytest.mark.gpu
+def test_gpu_calls_with_gpu_count(gpu_engine, oracle):
+    _gpus_calls(gpu_engine.lib, oracle, (1 << 20) + 7)

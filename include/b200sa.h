@@ -336,6 +336,7 @@ typedef struct b200sa_comm b200sa_comm;
 B200SA_API int b200sa_comm_create_local(b200sa_comm** out /* [nranks] */, int nranks);
 B200SA_API int b200sa_comm_create_shm(b200sa_comm** out, const char* name, int rank, int nranks);
 B200SA_API void b200sa_comm_destroy(b200sa_comm* comm);
+B200SA_API int b200sa_comm_set_timeout_ms(b200sa_comm* comm, int timeout_ms);   /* deadline of this rank's waits from now on */
 B200SA_API int b200sa_comm_barrier(b200sa_comm* comm);
 B200SA_API int b200sa_comm_allreduce_sum(b200sa_comm* comm, int64_t value, int64_t* sum_out);
 /* Collective over the ranks of `comm` (each with its own context and the same text in its HBM).  d_sa: n+1 int32, d_bwt

@@ -120,6 +120,7 @@ ABI = [
     ("b200sa_comm_create_local", C.c_int, [C.POINTER(_P), C.c_int]),
     ("b200sa_comm_create_shm", C.c_int, [C.POINTER(_P), C.c_char_p, C.c_int, C.c_int]),
     ("b200sa_comm_destroy", None, [_P]),
+    ("b200sa_comm_set_timeout_ms", C.c_int, [_P, C.c_int]),
     ("b200sa_comm_barrier", C.c_int, [_P]),
     ("b200sa_comm_allreduce_sum", C.c_int, [_P, C.c_int64, C.POINTER(C.c_int64)]),
     ("b200sa_shard_sort", C.c_int, [_P, _P, _P, C.c_int64, _P, _P, C.POINTER(C.c_int64), _P]),
@@ -580,6 +581,9 @@ class Comm:
         h = _P()
         lib.check(lib.cdll.b200sa_comm_create_shm(C.byref(h), name.encode(), rank, nranks))
         return cls(h, lib)
+
+    def set_timeout_ms(self, timeout_ms: int) -> None:
+        self.lib.check(self.lib.cdll.b200sa_comm_set_timeout_ms(self._c, int(timeout_ms)))
 
     def barrier(self) -> None:
         self.lib.check(self.lib.cdll.b200sa_comm_barrier(self._c))

@@ -873,6 +873,13 @@ void b200sa_comm_destroy(b200sa_comm* comm)
     delete comm;
 }
 
+int b200sa_comm_set_timeout_ms(b200sa_comm* comm, int timeout_ms)
+{
+    if (!comm || timeout_ms <= 0) return b200sa::set_error(B200SA_EINVAL, "bad argument");
+    comm->c->timeout_ms = timeout_ms;
+    return 0;
+}
+
 int b200sa_comm_barrier(b200sa_comm* comm)
 {
     if (!comm) return b200sa::set_error(B200SA_EINVAL, "null comm");

@@ -175,12 +175,11 @@ def test_peer_isa_lockstep_fuzz(oracle):
 # ---- the control plane of the C++ round loop between PROCESSES: a POSIX shared-memory segment (csrc/comm.cuh) ----------
 def _comm_worker(rank, world, name, q, fail):
     from msufsort_b200.api import B200SAError, Comm, Library
-    if fail:
-        os.environ["B200SA_COMM_TIMEOUT_MS"] = "300"
     lib = Library(os.path.join(ROOT, "tests", "emu", "libb200sa_emu.so"))
-    c = Comm.shared_memory(name, rank, world, library=lib)
+    c = Comm.shared_memory(name, rank, world, library=lib)   # the ranks meet here once (default deadline: slow process starts are fine)
     try:
         if fail:
+            c.set_timeout_ms(300)
             if rank == 1:
                 q.put((rank, "left"))        # never shows up at the barrier
                 return

@@ -115,3 +115,34 @@ def test_emu_calls_with_gpu_count(oracle):
 @pytest.mark.gpu
 def test_gpu_calls_with_gpu_count(gpu_engine, oracle):
     _gpus_calls(gpu_engine.lib, oracle, (1 << 20) + 7)
+
+
+def test_emu_group_fuzz(oracle):
+    """random small texts over tiny alphabets (deep rounds, huge groups, empty key ranges) sharded over 2..6 contexts:
+    suffix array, BWT and the sharded inverse against the oracle"""
+    from hypothesis import HealthCheck, given, settings, strategies as st
+    lib = Library(os.path.join(ROOT, "tests", "emu", "libb200sa_emu.so"))
+    groups = {}
+
+    @settings(max_examples=25, deadline=None, suppress_health_check=[HealthCheck.too_slow])
+    @given(seed=st.integers(0, 2**31), sigma=st.integers(1, 4), n=st.integers(4096 * 6, 4096 * 6 + 3000), world=st.integers(2, 6))
+    def run(seed, sigma, n, world):
+        rng = np.random.default_rng(seed)
+        x = rng.integers(0, sigma, size=n, dtype=np.uint8)
+        if seed % 3 == 0:
+            x[n // 2:] = x[: n - n // 2]                      # a long repeat: many rounds
+        g = groups.get(world) or groups.setdefault(world, Group([0] * world, library=lib))
+        sa, bwt, s = g.suffix_array_and_bwt(x)
+        want = oracle.sa(x)
+        assert np.array_equal(sa, want)
+        wb, ws = oracle.bwt_from_sa(x, want)
+        assert s == ws and np.array_equal(bwt, wb)
+        b = bwt.copy()
+        g.reverse_burrows_wheeler_transform(b, s)
+        assert np.array_equal(b, x)
+
+    try:
+        run()
+    finally:
+        for g in groups.values():
+            g.close()

@@ -42,7 +42,7 @@ static const int RS_RADIX = 256;
 #define B200SA_RS_THREADS 256
 #endif
 // 1: keep the sixteen within-warp ranks of a thread (each < 32 * IPT <= 65535) two to a register: the sweep then fits its
-// 80-register budget without spills (80 bytes of spills otherwise).  Measured on B200 (profiles/r02_knobs.txt, 2^28 pairs
+// 80-register budget with at most 4 bytes of spills (80 bytes otherwise).  Measured on B200 (profiles/r02_knobs.txt, 2^28 pairs
 // per sweep): 1.76 ms against 1.89 ms; the persistent variant with next-tile key prefetch measured 1.81 ms (1.82 ms with
 // packed ranks) and was removed.
 #ifndef B200SA_RS_PACK_POS

@@ -124,7 +124,7 @@ def test_emu_group_fuzz(oracle):
     lib = Library(os.path.join(ROOT, "tests", "emu", "libb200sa_emu.so"))
     groups = {}
 
-    @settings(max_examples=25, deadline=None, suppress_health_check=[HealthCheck.too_slow])
+    @settings(max_examples=12, deadline=None, suppress_health_check=[HealthCheck.too_slow])
     @given(seed=st.integers(0, 2**31), sigma=st.integers(1, 4), n=st.integers(4096 * 6, 4096 * 6 + 3000), world=st.integers(2, 6))
     def run(seed, sigma, n, world):
         rng = np.random.default_rng(seed)

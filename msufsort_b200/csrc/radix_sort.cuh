@@ -66,6 +66,17 @@ static const int RS_RADIX = 256;
 #ifndef B200SA_RS_BULK_LOAD
 #define B200SA_RS_BULK_LOAD 1
 #endif
+// 1: the per-warp digit counters are 16-bit (a warp sees at most 32 x IPT = 512 keys, a tile 4096): 4 KB instead of 8 KB of
+// shared memory per CTA, which is what a FOURTH resident CTA per SM needs next to the 48 KB of staging buffers (together with
+// -DB200SA_RS_MIN_BLOCKS=4, i.e. 64 registers per thread).
+#ifndef B200SA_RS_WHIST_U16
+#define B200SA_RS_WHIST_U16 0
+#endif
+#if B200SA_RS_WHIST_U16
+typedef u16 rs_whist_t;
+#else
+typedef u32 rs_whist_t;
+#endif
 static const int RS_THREADS = B200SA_RS_THREADS;
 static const int RS_IPT = B200SA_RS_IPT;
 static const int RS_TILE = RS_THREADS * RS_IPT;  // 4096 pairs per tile
@@ -79,7 +90,7 @@ static const u64 RS_VALUE_MASK = (1ull << 62) - 1;
 template <typename KeyT>
 __host__ __device__ constexpr size_t rs_pass_smem_bytes()
 {
-    return (size_t)(RS_THREADS / 32) * RS_RADIX * 4 * (B200SA_RS_PEERS_ATOMIC_OR ? 2 : 1) + 3 * RS_RADIX * 4 + 16 * 4 +
+    return (size_t)(RS_THREADS / 32) * RS_RADIX * (sizeof(rs_whist_t) + (B200SA_RS_PEERS_ATOMIC_OR ? 4 : 0)) + 3 * RS_RADIX * 4 + 16 * 4 +
            (size_t)RS_TILE * sizeof(KeyT) + (size_t)RS_TILE * 4;
 }
 
@@ -209,8 +220,8 @@ k_onesweep_pass(const KeyT* __restrict__ kin, KeyT* __restrict__ kout,
 {
     constexpr int THREADS = RS_THREADS, IPT = RS_IPT, WARPS = THREADS / 32, TILE = THREADS * IPT;
     B200SA_DYN_SMEM(smem);
-    u32* whist = (u32*)smem;             // [WARPS][256] per-warp digit counters, later warp-exclusive prefixes
-    u32* s_cnt = whist + WARPS * RS_RADIX;  // [256] tile digit counts
+    rs_whist_t* whist = (rs_whist_t*)smem;  // [WARPS][256] per-warp digit counters, later warp-exclusive prefixes
+    u32* s_cnt = (u32*)(whist + WARPS * RS_RADIX);  // [256] tile digit counts
     u32* s_coff = s_cnt + RS_RADIX;      // [256] exclusive scan of s_cnt (slot of the digit run in smem)
     u32* s_gdelta = s_coff + RS_RADIX;   // [256] global offset of the digit run minus s_coff
     u32* s_wtot = s_gdelta + RS_RADIX;   // [16]
@@ -300,7 +311,7 @@ k_onesweep_pass(const KeyT* __restrict__ kin, KeyT* __restrict__ kout,
     // keys), so the ballot form is faster in situ (R0 sweep 2.0 ms vs 2.4 ms) and is the default.
     // All peers then read the warp's running count for the digit (one broadcast word) and the lowest
     // peer bumps it by the group size.
-    u32* mywh = whist + warp * RS_RADIX;
+    rs_whist_t* mywh = whist + warp * RS_RADIX;
     const u32 lt = lanemask_lt();
 #if B200SA_RS_PEERS_ATOMIC_OR
     u32* mymask = wmask + warp * RS_RADIX;
@@ -326,7 +337,7 @@ k_onesweep_pass(const KeyT* __restrict__ kin, KeyT* __restrict__ kout,
 #if B200SA_RS_PEERS_ATOMIC_OR
                 mymask[d] = 0;
 #endif
-                mywh[d] = prev + (u32)__popc(peers);
+                mywh[d] = (rs_whist_t)(prev + (u32)__popc(peers));
             }
             __syncwarp();
             RS_POS_SET(k, prev + below);
@@ -378,7 +389,7 @@ k_onesweep_pass(const KeyT* __restrict__ kin, KeyT* __restrict__ kout,
 #pragma unroll
             for (int w = 0; w < WARPS; ++w) {
                 const u32 c = whist[w * RS_RADIX + tid];
-                whist[w * RS_RADIX + tid] = acc;
+                whist[w * RS_RADIX + tid] = (rs_whist_t)acc;
                 acc += c;
             }
         } else {
@@ -400,7 +411,7 @@ k_onesweep_pass(const KeyT* __restrict__ kin, KeyT* __restrict__ kout,
         if (STABLE) {
             // fold the digit's slot into every warp's exclusive prefix: staging then needs one lookup per key
 #pragma unroll
-            for (int w = 0; w < WARPS; ++w) whist[w * RS_RADIX + tid] += off;
+            for (int w = 0; w < WARPS; ++w) whist[w * RS_RADIX + tid] = (rs_whist_t)(whist[w * RS_RADIX + tid] + off);
         }
     }
     __syncthreads();

@@ -30,7 +30,7 @@ static const int RS_RADIX = 256;
 #define B200SA_RS_IPT 16
 #endif
 #ifndef B200SA_RS_MIN_BLOCKS
-#define B200SA_RS_MIN_BLOCKS 3
+#define B200SA_RS_MIN_BLOCKS 4
 #endif
 #ifndef B200SA_RS_LOOKBACK_DEPTH
 #define B200SA_RS_LOOKBACK_DEPTH 4
@@ -68,9 +68,11 @@ static const int RS_RADIX = 256;
 #endif
 // 1: the per-warp digit counters are 16-bit (a warp sees at most 32 x IPT = 512 keys, a tile 4096): 4 KB instead of 8 KB of
 // shared memory per CTA, which is what a FOURTH resident CTA per SM needs next to the 48 KB of staging buffers (together with
-// -DB200SA_RS_MIN_BLOCKS=4, i.e. 64 registers per thread).
+// B200SA_RS_MIN_BLOCKS = 4, i.e. 64 registers per thread: the u64 sweep then spills 72 bytes per thread, and still wins).
+// Measured on B200 (profiles/r02_sweep_4cta.txt): 1.708 ms against 1.796 ms per 2^28-pair sweep with three CTAs per SM,
+// 27.13 against 27.98 ms per SA + BWT step.  (-DB200SA_RS_WHIST_U16=0 -DB200SA_RS_MIN_BLOCKS=3 restores the old shape.)
 #ifndef B200SA_RS_WHIST_U16
-#define B200SA_RS_WHIST_U16 0
+#define B200SA_RS_WHIST_U16 1
 #endif
 #if B200SA_RS_WHIST_U16
 typedef u16 rs_whist_t;
@@ -80,7 +82,7 @@ typedef u32 rs_whist_t;
 static const int RS_THREADS = B200SA_RS_THREADS;
 static const int RS_IPT = B200SA_RS_IPT;
 static const int RS_TILE = RS_THREADS * RS_IPT;  // 4096 pairs per tile
-static const int RS_MIN_BLOCKS = B200SA_RS_MIN_BLOCKS;  // 3 CTAs/SM -> <= 85 registers per thread
+static const int RS_MIN_BLOCKS = B200SA_RS_MIN_BLOCKS;  // 4 CTAs/SM -> 64 registers per thread
 static const int RS_MAX_PASSES = 8;
 
 static const u64 RS_FLAG_PARTIAL = 1ull << 62;

@@ -15,7 +15,7 @@ NVCC_DEFS ?=
 NVCCFLAGS := $(ARCH) $(NVCC_DEFS) -lineinfo -O3 -std=c++17 -Xcompiler -fPIC,-fvisibility=hidden -Xptxas -v --expt-relaxed-constexpr
 CSRC      := msufsort_b200/csrc
 LIBDIR    := msufsort_b200/lib
-KSRC      := $(CSRC)/b200sa.cu $(CSRC)/comm.cuh $(CSRC)/engine_shard.inl $(CSRC)/engine_peer.inl $(CSRC)/engine_lcp.inl $(CSRC)/engine_batch.inl $(CSRC)/c_abi.inl $(CSRC)/engine.cuh $(CSRC)/common.cuh $(CSRC)/radix_sort.cuh $(CSRC)/sa_kernels.cuh $(CSRC)/bwt_kernels.cuh $(CSRC)/lcp_kernels.cuh $(CSRC)/batch_kernels.cuh include/b200sa.h
+KSRC      := $(CSRC)/b200sa.cu $(CSRC)/comm.cuh $(CSRC)/engine_shard.inl $(CSRC)/engine_peer.inl $(CSRC)/engine_lcp.inl $(CSRC)/engine_batch.inl $(CSRC)/c_abi.inl $(CSRC)/c_abi_group.inl $(CSRC)/engine.cuh $(CSRC)/common.cuh $(CSRC)/radix_sort.cuh $(CSRC)/sa_kernels.cuh $(CSRC)/bwt_kernels.cuh $(CSRC)/lcp_kernels.cuh $(CSRC)/batch_kernels.cuh include/b200sa.h
 
 all: lib textgen facade cli facade_bench oracle emu
 

@@ -1145,3 +1145,4 @@ int Engine::check_sa_dev(const u8* d_text, i64 n64, const i32* d_sa, i64* bad_ro
 }  // namespace b200sa
 
 #include "c_abi.inl"
+#include "c_abi_group.inl"

@@ -49,8 +49,16 @@ emu: tests/emu/libb200sa_emu.so
 tests/emu/libb200sa_emu.so: $(KSRC) tests/emu/cuda_emu.h
 	$(CXX) -O2 -g -std=c++17 -fPIC -shared -DB200SA_EMU -x c++ -Itests/emu -I$(CSRC) -Wno-unused-function -o $@ $(CSRC)/b200sa.cu
 
+# AddressSanitizer build of the emulator library (tools/emu_asan.sh runs the CPU tier's emulator tests over it): device
+# allocations have exact sizes and reused buffers poison the bytes past their current logical size
+emu-asan: tests/emu/asan/libb200sa_emu.so
+tests/emu/asan/libb200sa_emu.so: $(KSRC) tests/emu/cuda_emu.h
+	@mkdir -p tests/emu/asan
+	$(CXX) -O1 -g -fno-omit-frame-pointer -fsanitize=address -std=c++17 -fPIC -shared -DB200SA_EMU -DB200SA_EMU_ASAN -x c++ -Itests/emu -I$(CSRC) -Wno-unused-function -o $@ $(CSRC)/b200sa.cu
+
 clean:
+	rm -rf tests/emu/asan
 	rm -f $(LIBDIR)/*.so $(LIBDIR)/msufsort $(LIBDIR)/facade_bench $(LIBDIR)/ptxas.log tests/emu/*.so
 	$(MAKE) -C oracle clean
 
-.PHONY: all lib textgen facade cli facade_bench oracle emu clean
+.PHONY: all lib textgen facade cli facade_bench oracle emu emu-asan clean

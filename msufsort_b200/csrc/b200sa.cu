@@ -5,6 +5,9 @@
 // There is no CPU path in this file: every entry point needs a CUDA device.
 #include "engine.cuh"
 
+#ifdef B200SA_EMU_ASAN
+#include <sanitizer/asan_interface.h>
+#endif
 #include <mutex>
 #include <new>
 #include <thread>
@@ -31,10 +34,23 @@ int set_error(int code, const char* fmt, ...)
 
 int DevBuf::ensure(size_t bytes)
 {
+#ifdef B200SA_EMU_ASAN
+    bytes = (bytes + 3) & ~(size_t)3;  // whole words, as every real device allocation
+    // AddressSanitizer build of the emulator (tests only): the bytes past the size asked for LAST are poisoned, so a kernel that
+    // runs over the logical end of a reused buffer is reported although the allocation is larger
+    if (bytes <= cap) {
+        __asan_unpoison_memory_region(p, cap);
+        if (bytes < cap) __asan_poison_memory_region((char*)p + bytes, cap - bytes);
+        return 0;
+    }
+    if (p) { __asan_unpoison_memory_region(p, cap); cudaFree(p); p = nullptr; cap = 0; }
+    size_t want = bytes;
+#else
     if (bytes <= cap) return 0;
     if (p) { cudaFree(p); p = nullptr; cap = 0; }
     // round up so that slowly growing inputs do not reallocate every call
     size_t want = (bytes + ((size_t)1 << 20) - 1) & ~(((size_t)1 << 20) - 1);
+#endif
     cudaError_t e = cudaMalloc(&p, want);
     if (e != cudaSuccess) {
         p = nullptr;
@@ -47,6 +63,9 @@ int DevBuf::ensure(size_t bytes)
 
 void DevBuf::release()
 {
+#ifdef B200SA_EMU_ASAN
+    if (p) __asan_unpoison_memory_region(p, cap);
+#endif
     if (p) cudaFree(p);
     p = nullptr;
     cap = 0;

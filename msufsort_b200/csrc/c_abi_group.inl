@@ -279,46 +279,50 @@ int b200sa_group_unbwt(b200sa_group* g, uint8_t* bwt_inout, int64_t n, int32_t s
 
 }  // extern "C"
 
-static b200sa_group* shared_group(int num_gpus)
+// returns 0 and the group, or the status of what failed (the error text is already set)
+static int shared_group(int num_gpus, b200sa_group** out)
 {
     static std::mutex mu;
     static std::map<int, b200sa_group*> groups;
+    *out = nullptr;
     const int present = b200sa_device_count();
-    if (present <= 0) {
-        b200sa::set_error(B200SA_ENODEVICE, "no CUDA device available; this library has no CPU fallback");
-        return nullptr;
-    }
+    if (present <= 0) return b200sa::set_error(B200SA_ENODEVICE, "no CUDA device available; this library has no CPU fallback");
     if (num_gpus <= 0 || num_gpus > present) num_gpus = present;
     if (num_gpus > b200sa::kMaxPeers) num_gpus = b200sa::kMaxPeers;
     std::lock_guard<std::mutex> lk(mu);
     auto it = groups.find(num_gpus);
-    if (it != groups.end()) return it->second;
-    std::vector<int> devices;
-    for (int g = 0; g < num_gpus; ++g) devices.push_back(g);
-    b200sa_group* grp = nullptr;
-    if (b200sa_group_create(&grp, devices.data(), num_gpus) != 0) return nullptr;
-    groups[num_gpus] = grp;
-    return grp;
+    if (it == groups.end()) {
+        std::vector<int> devices;
+        for (int g = 0; g < num_gpus; ++g) devices.push_back(g);
+        b200sa_group* grp = nullptr;
+        B200SA_TRY(b200sa_group_create(&grp, devices.data(), num_gpus));
+        it = groups.emplace(num_gpus, grp).first;
+    }
+    *out = it->second;
+    return 0;
 }
 
 extern "C" {
 
 int b200sa_suffix_array_gpus(const uint8_t* text, int64_t n, int32_t* sa_out, int num_gpus)
 {
-    b200sa_group* g = shared_group(num_gpus);
-    return g ? b200sa_group_suffix_array(g, text, n, sa_out) : B200SA_ENODEVICE;
+    b200sa_group* g = nullptr;
+    B200SA_TRY(shared_group(num_gpus, &g));
+    return b200sa_group_suffix_array(g, text, n, sa_out);
 }
 
 int b200sa_bwt_gpus(uint8_t* text_inout, int64_t n, int32_t* sentinel_index_out, int num_gpus)
 {
-    b200sa_group* g = shared_group(num_gpus);
-    return g ? b200sa_group_bwt(g, text_inout, n, sentinel_index_out) : B200SA_ENODEVICE;
+    b200sa_group* g = nullptr;
+    B200SA_TRY(shared_group(num_gpus, &g));
+    return b200sa_group_bwt(g, text_inout, n, sentinel_index_out);
 }
 
 int b200sa_unbwt_gpus(uint8_t* bwt_inout, int64_t n, int32_t sentinel_index, int num_gpus)
 {
-    b200sa_group* g = shared_group(num_gpus);
-    return g ? b200sa_group_unbwt(g, bwt_inout, n, sentinel_index) : B200SA_ENODEVICE;
+    b200sa_group* g = nullptr;
+    B200SA_TRY(shared_group(num_gpus, &g));
+    return b200sa_group_unbwt(g, bwt_inout, n, sentinel_index);
 }
 
 }  // extern "C"

@@ -23,6 +23,26 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "slow: larger CPU-side cases")
 
 
+def _redirect_emu_library():
+    """B200SA_EMU_ASAN=1 (tools/emu_asan.sh): every test that loads tests/emu/libb200sa_emu.so gets the AddressSanitizer build of
+    the same sources (tests/emu/asan/, `make emu-asan`) instead.  Test infrastructure only."""
+    if os.environ.get("B200SA_EMU_ASAN") != "1":
+        return
+    from msufsort_b200 import api
+    plain = os.path.join(ROOT, "tests", "emu", "libb200sa_emu.so")
+    asan = os.path.join(ROOT, "tests", "emu", "asan", "libb200sa_emu.so")
+    init = api.Library.__init__
+
+    def patched(self, path_or_cdll):
+        if isinstance(path_or_cdll, str) and os.path.abspath(path_or_cdll) == plain:
+            path_or_cdll = asan
+        init(self, path_or_cdll)
+    api.Library.__init__ = patched
+
+
+_redirect_emu_library()
+
+
 def _make(target):
     subprocess.run(["make", "-s", target], cwd=ROOT, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE)
 

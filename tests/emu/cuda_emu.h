@@ -360,7 +360,13 @@ static inline cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return 0; }
 static inline cudaError_t cudaSetDevice(int) { return 0; }
 static inline cudaError_t cudaGetDevice(int* d) { *d = 0; return 0; }
 static inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp* p, int) { memset(p, 0, sizeof(*p)); p->multiProcessorCount = 148; p->major = 10; p->minor = 0; p->totalGlobalMem = (size_t)8 << 30; p->sharedMemPerBlockOptin = 227 * 1024; strcpy(p->name, "cuda_emu"); return 0; }
+#ifdef B200SA_EMU_ASAN
+// AddressSanitizer build (make emu-asan): exact sizes, so that a kernel reading or writing one element past a buffer is reported
+// (rounded up to whole 32-bit words: device allocations never end inside an aligned word, which the word-wise text loads rely on)
+static inline cudaError_t cudaMalloc(void** p, size_t n) { n = (n + 3) & ~(size_t)3; *p = nullptr; if (posix_memalign(p, 256, n ? n : 4) != 0) *p = nullptr; if (*p) memset(*p, 0xA5, n); return *p ? 0 : cudaErrorMemoryAllocation; }
+#else
 static inline cudaError_t cudaMalloc(void** p, size_t n) { size_t r = (n + 255) & ~(size_t)255; *p = aligned_alloc(256, r); if (*p) memset(*p, 0xA5, r); /* poison: device memory is never zero-initialised */ return *p ? 0 : cudaErrorMemoryAllocation; }
+#endif
 static inline cudaError_t cudaFree(void* p) { free(p); return 0; }
 // "IPC" inside one process: the handle carries the pointer (tests drive several contexts of one process in lock step)
 struct cudaIpcMemHandle_t { char reserved[64]; };

@@ -56,9 +56,16 @@ tests/emu/asan/libb200sa_emu.so: $(KSRC) tests/emu/cuda_emu.h
 	@mkdir -p tests/emu/asan
 	$(CXX) -O1 -g -fno-omit-frame-pointer -fsanitize=address -std=c++17 -fPIC -shared -DB200SA_EMU -DB200SA_EMU_ASAN -x c++ -Itests/emu -I$(CSRC) -Wno-unused-function -o $@ $(CSRC)/b200sa.cu
 
+# UndefinedBehaviorSanitizer build: shifts by the operand width or more (defined differently on the GPU), signed overflow,
+# misaligned vector accesses (a fault on the GPU)
+emu-ubsan: tests/emu/ubsan/libb200sa_emu.so
+tests/emu/ubsan/libb200sa_emu.so: $(KSRC) tests/emu/cuda_emu.h
+	@mkdir -p tests/emu/ubsan
+	$(CXX) -O1 -g -fno-omit-frame-pointer -fsanitize=undefined -fno-sanitize=vptr -fno-sanitize-recover=undefined -std=c++17 -fPIC -shared -DB200SA_EMU -x c++ -Itests/emu -I$(CSRC) -Wno-unused-function -o $@ $(CSRC)/b200sa.cu
+
 clean:
-	rm -rf tests/emu/asan
+	rm -rf tests/emu/asan tests/emu/ubsan
 	rm -f $(LIBDIR)/*.so $(LIBDIR)/msufsort $(LIBDIR)/facade_bench $(LIBDIR)/ptxas.log tests/emu/*.so
 	$(MAKE) -C oracle clean
 
-.PHONY: all lib textgen facade cli facade_bench oracle emu emu-asan clean
+.PHONY: all lib textgen facade cli facade_bench oracle emu emu-asan emu-ubsan clean

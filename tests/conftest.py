@@ -24,13 +24,14 @@ def pytest_configure(config):
 
 
 def _redirect_emu_library():
-    """B200SA_EMU_ASAN=1 (tools/emu_asan.sh): every test that loads tests/emu/libb200sa_emu.so gets the AddressSanitizer build of
-    the same sources (tests/emu/asan/, `make emu-asan`) instead.  Test infrastructure only."""
-    if os.environ.get("B200SA_EMU_ASAN") != "1":
+    """B200SA_EMU_SANITIZER=asan|ubsan (tools/emu_asan.sh): every test that loads tests/emu/libb200sa_emu.so gets the sanitizer
+    build of the same sources (tests/emu/asan/, tests/emu/ubsan/; `make emu-asan emu-ubsan`) instead.  Test infrastructure only."""
+    variant = os.environ.get("B200SA_EMU_SANITIZER", "")
+    if variant not in ("asan", "ubsan"):
         return
     from msufsort_b200 import api
     plain = os.path.join(ROOT, "tests", "emu", "libb200sa_emu.so")
-    asan = os.path.join(ROOT, "tests", "emu", "asan", "libb200sa_emu.so")
+    asan = os.path.join(ROOT, "tests", "emu", variant, "libb200sa_emu.so")
     init = api.Library.__init__
 
     def patched(self, path_or_cdll):

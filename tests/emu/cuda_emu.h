@@ -44,13 +44,14 @@
 #define __align__(x) __attribute__((aligned(x)))
 
 /* ---- vector types ----------------------------------------------------------------------- */
-struct uint2 { unsigned x, y; };
+// (alignments as in CUDA's vector_types.h: a misaligned 64- / 128-bit access faults on the GPU, and the UBSan build reports it)
+struct __attribute__((aligned(8))) uint2 { unsigned x, y; };
 struct uint3 { unsigned x, y, z; };
-struct uint4 { unsigned x, y, z, w; };
-struct int2 { int x, y; };
-struct int4 { int x, y, z, w; };
-struct ulonglong2 { unsigned long long x, y; };
-struct uchar4 { unsigned char x, y, z, w; };
+struct __attribute__((aligned(16))) uint4 { unsigned x, y, z, w; };
+struct __attribute__((aligned(8))) int2 { int x, y; };
+struct __attribute__((aligned(16))) int4 { int x, y, z, w; };
+struct __attribute__((aligned(16))) ulonglong2 { unsigned long long x, y; };
+struct __attribute__((aligned(4))) uchar4 { unsigned char x, y, z, w; };
 static inline uint2 make_uint2(unsigned x, unsigned y) { return uint2{x, y}; }
 static inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) { return uint4{x, y, z, w}; }
 static inline ulonglong2 make_ulonglong2(unsigned long long x, unsigned long long y) { return ulonglong2{x, y}; }

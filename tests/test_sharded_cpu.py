@@ -224,3 +224,28 @@ def test_shm_comm_times_out_instead_of_hanging():
     for p in procs:
         p.join(timeout=60)
     assert got[1] == "left" and got[0] == "code 6"   # B200SA_ECOMM
+
+
+# ---- the same control plane between THREADS (b200sa_group_*), under ThreadSanitizer ------------------------------------------
+@pytest.mark.parametrize("sanitize", [False, True])
+def test_comm_stress_between_threads(sanitize, tmp_path):
+    """tests/cpp/comm_stress.cpp: barriers, sums and all-gathers in a row on 2, 3 and 8 threads, plain stores that only the
+    barrier publishes, and a rank that fails while its peers wait (they leave with B200SA_ECOMM).  The sanitized build
+    reports a data race or a missing acquire / release pair in comm.cuh as a failure."""
+    import shutil
+    import subprocess
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else shutil.which("g++")
+    if cxx is None:
+        pytest.skip("no g++")
+    exe = str(tmp_path / "comm_stress")
+    cmd = [cxx, "-std=c++17", "-O1", "-g", "-DB200SA_EMU", "-I" + os.path.join(ROOT, "tests", "emu"),
+           "-I" + os.path.join(ROOT, "msufsort_b200", "csrc"), os.path.join(ROOT, "tests", "cpp", "comm_stress.cpp"), "-pthread", "-o", exe]
+    if sanitize:
+        cmd.insert(1, "-fsanitize=thread")
+    built = subprocess.run(cmd, capture_output=True, text=True)
+    if built.returncode != 0 and sanitize and "tsan" in built.stderr:
+        pytest.skip("ThreadSanitizer runtime not installed")
+    assert built.returncode == 0, built.stderr[-2000:]
+    env = dict(os.environ, TSAN_OPTIONS="halt_on_error=1")
+    out = subprocess.run([exe, "150" if sanitize else "2000"], capture_output=True, text=True, timeout=600, env=env)
+    assert out.returncode == 0 and "comm_stress: ok" in out.stdout, (out.stdout + out.stderr)[-3000:]

@@ -248,4 +248,6 @@ def test_comm_stress_between_threads(sanitize, tmp_path):
     assert built.returncode == 0, built.stderr[-2000:]
     env = dict(os.environ, TSAN_OPTIONS="halt_on_error=1")
     out = subprocess.run([exe, "150" if sanitize else "2000"], capture_output=True, text=True, timeout=600, env=env)
+    if sanitize and "unexpected memory mapping" in out.stderr:
+        pytest.skip("ThreadSanitizer cannot run under this kernel's address-space layout")
     assert out.returncode == 0 and "comm_stress: ok" in out.stdout, (out.stdout + out.stderr)[-3000:]

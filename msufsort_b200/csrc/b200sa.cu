@@ -180,6 +180,7 @@ int Engine::init(int dev)
 
 int Engine::release_workspace()
 {
+    sa_cache.valid = false;  // the resident text and suffix array go away
     if (peer.active) peer_detach();  // the ISA array and the inbox go away: peers must re-attach before the next sharded sort
     for (int i = 0; i < 2; ++i) { keys[i].release(); idx[i].release(); slot[i].release(); }
     gid.release(); gstart.release(); glist.release(); rank.release(); sa_ws.release(); sortmeta.release(); agg_cnt.release(); agg_max.release();

@@ -135,7 +135,7 @@ int b200sa_lcp_dev(b200sa_ctx* ctx, const uint8_t* d_text, int64_t n, const int3
 // (Engine::sa_cache); when the next call brings the same bytes only the missing result is computed.
 static int sa_bwt_host(b200sa_ctx* ctx, const uint8_t* text, int64_t n, void* sa_out, uint8_t* bwt_out, int64_t* sentinel_out, int64_t max_n)
 {
-    const bool had_cache = ctx && ctx->eng.sa_cache.valid && ctx->eng.sa_cache.n == (u64)n;
+    const bool had_cache = ctx && ctx->eng.sa_cache.valid && !ctx->eng.sa_cache.sharded && ctx->eng.sa_cache.n == (u64)n;
     B200SA_NEED_CTX(ctx);
     Engine& e = ctx->eng;
     if (n < 0 || n > max_n) return b200sa::set_error(B200SA_EINVAL, "n = %lld outside [0, %lld]", (long long)n, (long long)max_n);
@@ -199,6 +199,7 @@ static int sa_bwt_host(b200sa_ctx* ctx, const uint8_t* text, int64_t n, void* sa
     if (sentinel_out) *sentinel_out = sentinel;
     if (e.profiling) B200SA_TRY(e.collect_profile());
     e.sa_cache.valid = true;
+    e.sa_cache.sharded = false;
     e.sa_cache.n = (u64)n;
     e.sa_cache.sentinel = sentinel;
     return 0;

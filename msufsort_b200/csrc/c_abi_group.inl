@@ -90,25 +90,30 @@ struct b200sa_group {
     std::vector<b200sa_ctx*> ctxs;
     std::vector<b200sa_comm*> comms;
     std::mutex mu;  // one job at a time, like one msufsort object
+    // what the last sharded sort left resident on the contexts (Engine::sa_cache with sharded = true): every context holds the
+    // whole text and its rows of the suffix array.  A following call that brings the same bytes — the drop-in sequence
+    // make_suffix_array, forward_burrows_wheeler_transform — reuses that sort, as the single-GPU entry points do.
+    std::vector<Engine::ShardInfo> resident;
 
     // Upload of a host buffer every rank needs in full: rank r moves only its 1/G slice over its own PCIe link, then pulls the
     // other slices from its peers' HBM over NVLink (G x less host-memory and PCIe traffic than G full uploads).  `which`
     // selects the per-context destination buffer (it has been sized by the caller).
-    int upload_shared(int r, const uint8_t* host, int64_t n, b200sa::DevBuf Engine::*which)
+    typedef b200sa::DevBuf& (*BufOf)(Engine&);
+    int upload_shared(int r, const uint8_t* host, int64_t n, BufOf which)
     {
         const int G = (int)ctxs.size();
         Engine& e = ctxs[(size_t)r]->eng;
         cudaStream_t st = e.own_stream;
         auto lo = [&](int g) { return (size_t)((unsigned __int128)n * (unsigned)g / (unsigned)G) & ~(size_t)15; };
         auto hi = [&](int g) { return g == G - 1 ? (size_t)n : lo(g + 1); };
-        u8* mine = (e.*which).as<u8>();
+        u8* mine = which(e).as<u8>();
         if (hi(r) > lo(r)) B200SA_TRY(e.copy_in(mine + lo(r), host + lo(r), hi(r) - lo(r), st));
         B200SA_CU(cudaStreamSynchronize(st));
         B200SA_TRY(comms[(size_t)r]->c->barrier());  // every slice is in its owner's HBM
         for (int k = 1; k < G; ++k) {
             const int g = (r + k) % G;               // start with the right-hand neighbour: G readers on G different sources
             if (hi(g) > lo(g))
-                B200SA_CU(cudaMemcpyAsync(mine + lo(g), (ctxs[(size_t)g]->eng.*which).as<u8>() + lo(g), hi(g) - lo(g), cudaMemcpyDefault, st));
+                B200SA_CU(cudaMemcpyAsync(mine + lo(g), which(ctxs[(size_t)g]->eng).as<u8>() + lo(g), hi(g) - lo(g), cudaMemcpyDefault, st));
         }
         B200SA_CU(cudaStreamSynchronize(st));
         return comms[(size_t)r]->c->barrier();       // nobody's buffer is overwritten (next call) while a peer still reads it
@@ -201,6 +206,9 @@ int b200sa_group_suffix_array_bwt(b200sa_group* g, const uint8_t* text, int64_t 
     // texts too small to give every GPU work (or a single-GPU group) take the single-GPU path on the first context
     if (G == 1 || n < (int64_t)G * 4096) return b200sa_suffix_array_bwt(g->ctxs[0], text, n, sa_out, bwt_out, sentinel_index_out);
     const bool want_bwt = bwt_out != nullptr || sentinel_index_out != nullptr;
+    // is the result of the last sharded sort still resident on every context, for a text of this size?
+    bool had_resident = want_bwt && g->resident.size() == (size_t)G;
+    for (auto* c : g->ctxs) had_resident = had_resident && c->eng.sa_cache.valid && c->eng.sa_cache.sharded && c->eng.sa_cache.n == (u64)n;
     std::vector<Engine::ShardInfo> infos((size_t)G);
     const int rc = g->run([&](int r) -> int {
         Engine& e = g->ctxs[(size_t)r]->eng;
@@ -210,10 +218,38 @@ int b200sa_group_suffix_array_bwt(b200sa_group* g, const uint8_t* text, int64_t 
         B200SA_TRY(e.text_ws.ensure((size_t)n + 64));
         B200SA_TRY(e.sa_ws.ensure(((size_t)n + 1) * 4));
         if (want_bwt) B200SA_TRY(e.bwt_ws.ensure((size_t)n + 64));
-        // every GPU uploads one slice of the text and pulls the rest from its peers; the results leave as disjoint slices
-        B200SA_TRY(g->upload_shared(r, text, n, &Engine::text_ws));
         Engine::ShardInfo& info = infos[(size_t)r];
-        B200SA_TRY(e.sharded_sort(*g->comms[(size_t)r]->c, e.text_ws.as<u8>(), n, e.sa_ws.as<i32>(), want_bwt ? e.bwt_ws.as<u8>() : nullptr, &info, st));
+        bool reuse = false;
+        if (had_resident) {
+            // the text is uploaded next to the resident one (every GPU one slice, the rest from its peers) and compared on the
+            // device; all ranks must agree before any of them reuses its rows
+            B200SA_TRY(e.keys[1].ensure((size_t)n + 64));
+            B200SA_TRY(e.misc.ensure(8192));
+            B200SA_TRY(g->upload_shared(r, text, n, [](Engine& x) -> b200sa::DevBuf& { return x.keys[1]; }));
+            u32* d_diff = e.misc.as<u32>() + 548;
+            B200SA_CU(cudaMemsetAsync(d_diff, 0, 4, st));
+            B200SA_LAUNCH(b200sa::k_bytes_differ, (u32)(e.num_sms * 8), 256, 0, st, (const u8*)e.text_ws.as<u8>(), (const u8*)e.keys[1].as<u8>(), (u64)n, d_diff);
+            e.count_launch(B200SA_PH_ALPHABET);
+            B200SA_CU(cudaMemcpyAsync(e.h_pinned + 25, d_diff, 4, cudaMemcpyDeviceToHost, st));
+            B200SA_CU(cudaStreamSynchronize(st));
+            i64 differing = 0;
+            B200SA_TRY(g->comms[(size_t)r]->c->allreduce_sum((i64)(e.h_pinned[25] != 0), &differing));
+            reuse = differing == 0;
+            if (reuse) {
+                info = g->resident[(size_t)r];
+                if (info.out_end > info.out_begin)
+                    B200SA_TRY(e.bwt_rows(e.text_ws.as<u8>(), (u32)n, e.sa_ws.as<i32>(), (u32)info.out_begin, (u32)info.out_end, e.bwt_ws.as<u8>(), st));
+            } else {
+                // another text of the same size: it becomes the resident one (keys[1] is sort workspace; the peers' pulls from it
+                // ended inside upload_shared) and is sorted below
+                B200SA_CU(cudaMemcpyAsync(e.text_ws.p, e.keys[1].p, (size_t)n, cudaMemcpyDeviceToDevice, st));
+            }
+        } else {
+            // every GPU uploads one slice of the text and pulls the rest from its peers; the results leave as disjoint slices
+            B200SA_TRY(g->upload_shared(r, text, n, [](Engine& x) -> b200sa::DevBuf& { return x.text_ws; }));
+        }
+        if (!reuse)
+            B200SA_TRY(e.sharded_sort(*g->comms[(size_t)r]->c, e.text_ws.as<u8>(), n, e.sa_ws.as<i32>(), want_bwt ? e.bwt_ws.as<u8>() : nullptr, &info, st));
         if (sa_out && info.row_end > info.row_begin)
             B200SA_TRY(e.copy_out(sa_out + info.row_begin, e.sa_ws.as<i32>() + info.row_begin, (size_t)(info.row_end - info.row_begin) * 4, st));
         // in-place callers pass bwt_out == text: every rank has finished reading the text (the sort's barriers) before any
@@ -223,7 +259,14 @@ int b200sa_group_suffix_array_bwt(b200sa_group* g, const uint8_t* text, int64_t 
         B200SA_CU(cudaStreamSynchronize(st));
         return 0;
     });
-    if (rc == 0 && sentinel_index_out) *sentinel_index_out = (int32_t)infos[0].sentinel;
+    if (rc == 0) {
+        if (sentinel_index_out) *sentinel_index_out = (int32_t)infos[0].sentinel;
+        // the text and every rank's rows stay resident for a following call with the same bytes
+        g->resident = infos;
+        for (auto* c : g->ctxs) { c->eng.sa_cache.valid = true; c->eng.sa_cache.sharded = true; c->eng.sa_cache.n = (u64)n; c->eng.sa_cache.sentinel = infos[0].sentinel; }
+    } else {
+        g->resident.clear();
+    }
     return rc;
 }
 
@@ -257,7 +300,7 @@ int b200sa_group_unbwt(b200sa_group* g, uint8_t* bwt_inout, int64_t n, int32_t s
         B200SA_CU(cudaSetDevice(e.device));
         cudaStream_t st = e.own_stream;
         B200SA_TRY(e.bwt_ws.ensure((size_t)n + 64));
-        B200SA_TRY(g->upload_shared(r, bwt_inout, n, &Engine::bwt_ws));
+        B200SA_TRY(g->upload_shared(r, bwt_inout, n, [](Engine& x) -> b200sa::DevBuf& { return x.bwt_ws; }));
         return e.sharded_unbwt(*g->comms[(size_t)r]->c, e.bwt_ws.as<u8>(), n, sentinel_index, nullptr, false, &lo[(size_t)r], &hi[(size_t)r], st);
     });
     if (rc) return rc;

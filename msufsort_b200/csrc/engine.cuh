@@ -138,7 +138,9 @@ struct Engine {
     // The host entry points keep the last text and its suffix array resident (text_ws, sa_ws).  A following call that is
     // handed the same bytes (compared on the device after the upload) reuses the sort: make_suffix_array followed by
     // forward_burrows_wheeler_transform on one msufsort object costs one sort, not two.  Every other entry point drops it.
-    struct SaCache { bool valid = false; u64 n = 0; i64 sentinel = 0; } sa_cache;
+    // sharded: the resident result is this context's part of a group's sharded sort (b200sa_group_*): the whole text, but only
+    // this rank's rows of the suffix array — only the group may reuse it.
+    struct SaCache { bool valid = false; bool sharded = false; u64 n = 0; i64 sentinel = 0; } sa_cache;
     int stage_ensure();
     int copy_in(void* d_dst, const void* h_src, size_t bytes, cudaStream_t st);
     // independent: the source is complete already (the stream was synchronised after its producer) — the copy need not

@@ -146,3 +146,42 @@ def test_emu_group_fuzz(oracle):
     finally:
         for g in groups.values():
             g.close()
+
+
+def test_emu_group_reuses_the_resident_sort(oracle):
+    """make_suffix_array followed by forward_burrows_wheeler_transform of the same bytes on one group costs ONE sharded sort (as on
+    a single GPU); another text of the same size, or a call on one of the group's contexts in between, is sorted afresh"""
+    from msufsort_b200.api import Engine
+    lib = Library(os.path.join(ROOT, "tests", "emu", "libb200sa_emu.so"))
+    g = Group([0, 0, 0], library=lib)
+    try:
+        x = gen("markov3", 40000)
+        want = oracle.sa(x)
+        wb, ws = oracle.bwt_from_sa(x, want)
+        l0 = g.launch_count()
+        assert np.array_equal(g.make_suffix_array(x), want)
+        sort_launches = g.launch_count() - l0
+        b = x.copy()
+        l1 = g.launch_count()
+        assert g.forward_burrows_wheeler_transform(b) == ws and np.array_equal(b, wb)
+        reuse_launches = g.launch_count() - l1
+        assert reuse_launches <= 12 and reuse_launches * 4 < sort_launches       # compare + BWT rows per context, no sort
+        sa2, b2, s2 = g.suffix_array_and_bwt(x)                                  # both results from the resident sort
+        assert np.array_equal(sa2, want) and np.array_equal(b2, wb) and s2 == ws
+        # a different text of the same size must not be mistaken for the resident one
+        y = x.copy()
+        y[31337] ^= np.uint8(1)
+        wy = oracle.sa(y)
+        wyb, wys = oracle.bwt_from_sa(y, wy)
+        by = y.copy()
+        assert g.forward_burrows_wheeler_transform(by) == wys and np.array_equal(by, wyb)
+        assert np.array_equal(g.make_suffix_array(y), wy)
+        # a call on one of the group's contexts drops the resident result: the next group call sorts again
+        ctx = lib.cdll.b200sa_group_context(g._g, 1)
+        assert lib.cdll.b200sa_release_workspace(ctx) == 0
+        l2 = g.launch_count()
+        by = y.copy()
+        assert g.forward_burrows_wheeler_transform(by) == wys and np.array_equal(by, wyb)
+        assert g.launch_count() - l2 > reuse_launches * 2
+    finally:
+        g.close()

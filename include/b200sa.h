@@ -321,6 +321,19 @@ B200SA_API int b200sa_group_bwt(b200sa_group* g, uint8_t* text_inout, int64_t n,
 B200SA_API int b200sa_group_suffix_array_bwt(b200sa_group* g, const uint8_t* text, int64_t n, int32_t* sa_out, uint8_t* bwt_out,
                                              int32_t* sentinel_index_out);
 B200SA_API int b200sa_group_unbwt(b200sa_group* g, uint8_t* bwt_inout, int64_t n, int32_t sentinel_index);
+/* Batches of independent blocks over the GPUs of the group ("one group of blocks per GPU; no
+ * communication; results concatenated on host").  Arguments and results exactly as b200sa_*_batch above; the packed batch
+ * is cut into one contiguous run of blocks per GPU (about equal bytes), every GPU transforms its run by the single-GPU
+ * batch path and writes the results at the blocks' own places in the caller's buffers.  Each RUN must satisfy the 32-bit
+ * batch limit, so a group takes batches up to G times as large as one context.  The inverse writes nothing unless every
+ * GPU has accepted its blocks.  Replaces a caller's loop over forward_/reverse_burrows_wheeler_transform
+ * (msufsort.h:63-75, main.cpp:466-487) spread over the worker threads numThreads selects. */
+B200SA_API int b200sa_group_suffix_array_batch(b200sa_group* g, const uint8_t* blocks, const int64_t* offsets, int64_t count,
+                                               int32_t* sa_out);
+B200SA_API int b200sa_group_bwt_batch(b200sa_group* g, uint8_t* blocks_inout, const int64_t* offsets, int64_t count,
+                                      int32_t* sentinel_index_out);
+B200SA_API int b200sa_group_unbwt_batch(b200sa_group* g, uint8_t* blocks_inout, const int64_t* offsets, int64_t count,
+                                        const int32_t* sentinel_index);
 
 /* The three reference calls without a context and with a GPU count — the C ABI SURVEY.md §8(b) sketched: GPUs
  * 0 .. num_gpus-1 (num_gpus <= 0: every GPU present); the group behind a count is created on first use and kept. */

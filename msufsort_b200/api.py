@@ -114,6 +114,9 @@ ABI = [
     ("b200sa_group_bwt", C.c_int, [_P, _P, C.c_int64, C.POINTER(C.c_int32)]),
     ("b200sa_group_suffix_array_bwt", C.c_int, [_P, _P, C.c_int64, _P, _P, C.POINTER(C.c_int32)]),
     ("b200sa_group_unbwt", C.c_int, [_P, _P, C.c_int64, C.c_int32]),
+    ("b200sa_group_suffix_array_batch", C.c_int, [_P, _P, _P, C.c_int64, _P]),
+    ("b200sa_group_bwt_batch", C.c_int, [_P, _P, _P, C.c_int64, _P]),
+    ("b200sa_group_unbwt_batch", C.c_int, [_P, _P, _P, C.c_int64, _P]),
     ("b200sa_suffix_array_gpus", C.c_int, [_P, C.c_int64, _P, C.c_int]),
     ("b200sa_bwt_gpus", C.c_int, [_P, C.c_int64, C.POINTER(C.c_int32), C.c_int]),
     ("b200sa_unbwt_gpus", C.c_int, [_P, C.c_int64, C.c_int32, C.c_int]),
@@ -632,6 +635,32 @@ class Group:
 
     def reverse_burrows_wheeler_transform(self, buf: np.ndarray, sentinel_index: int) -> None:
         self.lib.check(self.lib.cdll.b200sa_group_unbwt(self._g, _ptr(buf) if buf.size else None, buf.size, int(sentinel_index)))
+
+    # ---- batches of independent blocks, one run of blocks per GPU (include/b200sa.h b200sa_group_*_batch) --------------------
+    def suffix_array_batch(self, blocks) -> list:
+        packed, offsets = Engine._pack_blocks(blocks)
+        count = len(offsets) - 1
+        sa = np.empty(int(offsets[-1]) + count, dtype=np.int32)
+        self.lib.check(self.lib.cdll.b200sa_group_suffix_array_batch(self._g, _ptr(packed) if packed.size else None, _ptr(offsets), count, _ptr(sa)))
+        return [sa[int(offsets[b]) + b: int(offsets[b + 1]) + b + 1] for b in range(count)]
+
+    def bwt_batch(self, blocks):
+        packed, offsets = Engine._pack_blocks(blocks)
+        count = len(offsets) - 1
+        sent = np.zeros(max(count, 1), dtype=np.int32)
+        packed = packed.copy()
+        self.lib.check(self.lib.cdll.b200sa_group_bwt_batch(self._g, _ptr(packed) if packed.size else None, _ptr(offsets), count, _ptr(sent)))
+        return [packed[int(offsets[b]): int(offsets[b + 1])] for b in range(count)], [int(v) for v in sent[:count]]
+
+    def unbwt_batch(self, blocks, sentinel_indices) -> list:
+        packed, offsets = Engine._pack_blocks(blocks)
+        count = len(offsets) - 1
+        sent = np.ascontiguousarray(np.asarray(list(sentinel_indices) + [0], dtype=np.int32))
+        if sent.size != count + 1:
+            raise ValueError("one sentinel index per block")
+        packed = packed.copy()
+        self.lib.check(self.lib.cdll.b200sa_group_unbwt_batch(self._g, _ptr(packed) if packed.size else None, _ptr(offsets), count, _ptr(sent)))
+        return [packed[int(offsets[b]): int(offsets[b + 1])] for b in range(count)]
 
     def launch_count(self) -> int:
         return sum(int(self.lib.cdll.b200sa_launch_count(self.lib.cdll.b200sa_group_context(self._g, r))) for r in range(self.size))

@@ -369,7 +369,10 @@ int b200sa_bwt_batch(b200sa_ctx* ctx, uint8_t* blocks_inout, const int64_t* offs
     return batch_host(ctx, blocks_inout, offsets, count, blocks_inout, nullptr, sentinel_index_out);
 }
 
-int b200sa_unbwt_batch(b200sa_ctx* ctx, uint8_t* blocks_inout, const int64_t* offsets, int64_t count, const int32_t* sentinel_index)
+// Inverse batch in two steps: decode into the context's text_ws (nothing of the caller's is written), then copy out.  The group
+// form (c_abi_group.inl) runs the first step on every GPU before any GPU starts the second.
+static int unbwt_batch_decode(b200sa_ctx* ctx, const uint8_t* blocks, const int64_t* offsets, int64_t count, const int32_t* sentinel_index,
+                              bool synchronise)
 {
     B200SA_NEED_CTX(ctx);
     Engine& e = ctx->eng;
@@ -383,16 +386,31 @@ int b200sa_unbwt_batch(b200sa_ctx* ctx, uint8_t* blocks_inout, const int64_t* of
         if (nb > 0 && (sentinel_index[b] < 1 || (int64_t)sentinel_index[b] > nb))
             return b200sa::set_error(B200SA_EINVAL, "sentinel index %d of block %lld outside [1, %lld]", sentinel_index[b], (long long)b, (long long)nb);
     }
-    if (total > 0 && !blocks_inout) return b200sa::set_error(B200SA_EINVAL, "null blocks");
+    if (total > 0 && !blocks) return b200sa::set_error(B200SA_EINVAL, "null blocks");
     B200SA_CU(cudaSetDevice(e.device));
     cudaStream_t st = e.own_stream;
     B200SA_TRY(e.bwt_ws.ensure((size_t)total + 64));
     B200SA_TRY(e.text_ws.ensure((size_t)total + 64));
-    int rc = total ? e.copy_in(e.bwt_ws.p, blocks_inout, (size_t)total, st) : 0;
+    int rc = total ? e.copy_in(e.bwt_ws.p, blocks, (size_t)total, st) : 0;
     if (rc == 0) rc = e.unbwt_batch_dev(e.bwt_ws.as<u8>(), offsets, count, sentinel_index, e.text_ws.as<u8>(), st);
-    if (rc == 0 && total) rc = e.copy_out(blocks_inout, e.text_ws.p, (size_t)total, st);
+    if ((rc != 0 || synchronise) && cudaStreamSynchronize(st) != cudaSuccess && rc == 0) rc = b200sa::set_error(B200SA_ECUDA, "stream synchronisation failed");
+    return rc;
+}
+
+static int unbwt_batch_copy_out(b200sa_ctx* ctx, uint8_t* blocks_out, int64_t total)
+{
+    Engine& e = ctx->eng;
+    B200SA_CU(cudaSetDevice(e.device));
+    cudaStream_t st = e.own_stream;
+    int rc = total > 0 ? e.copy_out(blocks_out, e.text_ws.p, (size_t)total, st) : 0;
     if (cudaStreamSynchronize(st) != cudaSuccess && rc == 0) rc = b200sa::set_error(B200SA_ECUDA, "stream synchronisation failed");
     return rc;
+}
+
+int b200sa_unbwt_batch(b200sa_ctx* ctx, uint8_t* blocks_inout, const int64_t* offsets, int64_t count, const int32_t* sentinel_index)
+{
+    B200SA_TRY(unbwt_batch_decode(ctx, blocks_inout, offsets, count, sentinel_index, /*synchronise=*/false));
+    return count > 0 ? unbwt_batch_copy_out(ctx, blocks_inout, offsets[count]) : 0;
 }
 
 // ---- streaming pipeline over batches --------------------------------------------------------------

@@ -316,11 +316,117 @@ int b200sa_group_unbwt(b200sa_group* g, uint8_t* bwt_inout, int64_t n, int32_t s
     });
 }
 
+}  // extern "C"
+
+// ---- batches of independent blocks over the GPUs of a group ----------------------------------------
+// Blocks are independent, so nothing is exchanged: the packed batch is cut into G contiguous runs of blocks of about equal
+// size, every GPU transforms its run with the single-GPU batch path (one launch sequence per GPU, engine_batch.inl) and the
+// results land at the blocks' own places in the caller's buffers.  Each run must fit the 32-bit batch limit, so a group takes
+// batches up to G times as large as one context.
+
+static void split_blocks(const int64_t* offsets, int64_t count, int G, std::vector<int64_t>& cut)
+{
+    cut.assign((size_t)G + 1, count);
+    cut[0] = 0;
+    const unsigned __int128 total = (unsigned __int128)(offsets[count] + count);  // one separator slot per block, as the sort sees it
+    int64_t b = 0;
+    for (int g = 1; g < G; ++g) {
+        const int64_t target = (int64_t)(total * (unsigned)g / (unsigned)G);
+        while (b < count && offsets[b] + b < target) ++b;
+        cut[(size_t)g] = b;
+    }
+}
+
+static int check_block_table(const int64_t* offsets, int64_t count)
+{
+    if (count < 0 || (count > 0 && !offsets)) return b200sa::set_error(B200SA_EINVAL, "bad block table");
+    if (count > 0 && offsets[0] != 0) return b200sa::set_error(B200SA_EINVAL, "offsets[0] must be 0");
+    for (int64_t b = 0; b < count; ++b)
+        if (offsets[b + 1] < offsets[b]) return b200sa::set_error(B200SA_EINVAL, "offsets must not decrease (block %lld)", (long long)b);
+    return 0;
+}
+
+// the block table of run [b0, b1) with offsets relative to the run's first byte
+static std::vector<int64_t> run_offsets(const int64_t* offsets, int64_t b0, int64_t b1)
+{
+    std::vector<int64_t> sub((size_t)(b1 - b0) + 1);
+    for (int64_t b = b0; b <= b1; ++b) sub[(size_t)(b - b0)] = offsets[b] - offsets[b0];
+    return sub;
+}
+
+static int group_batch(b200sa_group* g, const uint8_t* blocks, const int64_t* offsets, int64_t count, uint8_t* bwt_out, int32_t* sa_out,
+                       int32_t* sentinel_index_out)
+{
+    if (!g) return b200sa::set_error(B200SA_EINVAL, "null group");
+    B200SA_TRY(check_block_table(offsets, count));
+    if (count == 0) return 0;
+    if (offsets[count] > 0 && !blocks) return b200sa::set_error(B200SA_EINVAL, "null blocks");
+    std::lock_guard<std::mutex> lk(g->mu);
+    const int G = (int)g->ctxs.size();
+    if (G == 1 || count < (int64_t)G || offsets[count] < (int64_t)G * 4096)
+        return batch_host(g->ctxs[0], blocks, offsets, count, bwt_out, sa_out, sentinel_index_out);
+    std::vector<int64_t> cut;
+    split_blocks(offsets, count, G, cut);
+    return g->run([&](int r) -> int {
+        const int64_t b0 = cut[(size_t)r], b1 = cut[(size_t)r + 1];
+        g->ctxs[(size_t)r]->eng.sa_cache.valid = false;
+        if (b1 <= b0) return 0;
+        const std::vector<int64_t> sub = run_offsets(offsets, b0, b1);
+        const int64_t base = offsets[b0];
+        return batch_host(g->ctxs[(size_t)r], blocks ? blocks + base : nullptr, sub.data(), b1 - b0, bwt_out ? bwt_out + base : nullptr,
+                          sa_out ? sa_out + base + b0 : nullptr, sentinel_index_out ? sentinel_index_out + b0 : nullptr);
+    });
+}
+
+extern "C" {
+
+int b200sa_group_suffix_array_batch(b200sa_group* g, const uint8_t* blocks, const int64_t* offsets, int64_t count, int32_t* sa_out)
+{
+    if (count > 0 && !sa_out) return b200sa::set_error(B200SA_EINVAL, "null sa_out");
+    return group_batch(g, blocks, offsets, count, nullptr, sa_out, nullptr);
+}
+
+int b200sa_group_bwt_batch(b200sa_group* g, uint8_t* blocks_inout, const int64_t* offsets, int64_t count, int32_t* sentinel_index_out)
+{
+    if (count > 0 && !sentinel_index_out) return b200sa::set_error(B200SA_EINVAL, "null sentinel_index_out");
+    return group_batch(g, blocks_inout, offsets, count, blocks_inout, nullptr, sentinel_index_out);
+}
+
+int b200sa_group_unbwt_batch(b200sa_group* g, uint8_t* blocks_inout, const int64_t* offsets, int64_t count, const int32_t* sentinel_index)
+{
+    if (!g) return b200sa::set_error(B200SA_EINVAL, "null group");
+    B200SA_TRY(check_block_table(offsets, count));
+    if (count == 0) return 0;
+    if (!sentinel_index) return b200sa::set_error(B200SA_EINVAL, "null sentinel_index");
+    std::lock_guard<std::mutex> lk(g->mu);
+    const int G = (int)g->ctxs.size();
+    if (G == 1 || count < (int64_t)G || offsets[count] < (int64_t)G * 4096)
+        return b200sa_unbwt_batch(g->ctxs[0], blocks_inout, offsets, count, sentinel_index);
+    std::vector<int64_t> cut;
+    split_blocks(offsets, count, G, cut);
+    // step 1: every GPU decodes its run; nothing is written to the caller's buffer until all runs have been accepted
+    int rc = g->run([&](int r) -> int {
+        const int64_t b0 = cut[(size_t)r], b1 = cut[(size_t)r + 1];
+        g->ctxs[(size_t)r]->eng.sa_cache.valid = false;
+        if (b1 <= b0) return 0;
+        const std::vector<int64_t> sub = run_offsets(offsets, b0, b1);
+        return unbwt_batch_decode(g->ctxs[(size_t)r], blocks_inout ? blocks_inout + offsets[b0] : nullptr, sub.data(), b1 - b0, sentinel_index + b0,
+                                  /*synchronise=*/true);
+    });
+    if (rc) return rc;
+    // step 2: the decoded runs leave over all PCIe links
+    return g->run([&](int r) -> int {
+        const int64_t b0 = cut[(size_t)r], b1 = cut[(size_t)r + 1];
+        if (b1 <= b0) return 0;
+        return unbwt_batch_copy_out(g->ctxs[(size_t)r], blocks_inout + offsets[b0], offsets[b1] - offsets[b0]);
+    });
+}
+
+}  // extern "C"
+
 // ---- context-free calls with a GPU count (the shape SURVEY.md §8(b) proposed for the C ABI) --------------------
 // b200sa_*_gpus(..., num_gpus): GPUs 0 .. num_gpus-1 (num_gpus <= 0: all GPUs present); the group behind each count is
 // created on first use and kept for the life of the process.
-
-}  // extern "C"
 
 // returns 0 and the group, or the status of what failed (the error text is already set)
 static int shared_group(int num_gpus, b200sa_group** out)

@@ -1,0 +1,36 @@
+"""GPU tier, batches of independent blocks over the contexts of a group (b200sa_group_*_batch).
+These entry points were added after the round's last GPU run: the file sorts last so that the GPU tier reaches it after
+everything that had already been verified on a B200.  The emulator tier of the same code is tests/test_group.py."""
+import numpy as np
+import pytest
+
+from cases import gen
+from msufsort_b200.api import Group
+from test_group import _batch_blocks, _check_batch
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world", [2, 3])
+def test_gpu_group_batch_contexts_on_one_device(oracle, world):
+    rng = np.random.default_rng(100 + world)
+    g = Group([0] * world)
+    try:
+        before = g.launch_count()
+        _check_batch(g, oracle, _batch_blocks(rng, 6 << 20, 96))
+        _check_batch(g, oracle, [gen("markov3", 1 << 20)] + [gen("rand", 1000)] * 7)
+        assert g.launch_count() > before
+    finally:
+        g.close()
+
+
+@pytest.mark.gpu
+def test_gpu_group_batch_one_context_per_gpu(oracle):
+    import torch
+    ng = torch.cuda.device_count()
+    if ng < 2:
+        pytest.skip("one context per GPU needs at least 2 GPUs (test_gpu_group_batch_contexts_on_one_device covers the path)")
+    g = Group(list(range(min(ng, 8))))
+    try:
+        _check_batch(g, oracle, _batch_blocks(np.random.default_rng(7), 32 << 20, 512))
+    finally:
+        g.close()

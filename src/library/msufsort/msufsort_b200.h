@@ -6,6 +6,7 @@
 //   forward_burrows_wheeler_transform(blocks)        a whole batch of blocks in ONE launch sequence
 //   reverse_burrows_wheeler_transform(blocks, idx)   (what a block-sorting compressor loops over, main.cpp:466-487)
 //   make_suffix_arrays(blocks)
+//   the same three with a gpu_group instead of a context: the batch spread over several GPUs
 //
 // Header-only over the C ABI (include/b200sa.h); link libb200sa.  Failures throw std::runtime_error with the
 // b200sa_last_error() text.  The GPU is chosen with MSUFSORT_DEVICE (default 0), as in msufsort.cpp.
@@ -108,6 +109,57 @@ namespace maniscalco
             std::vector<std::int32_t> suffixArrays(blocks.bytes.size() + static_cast<std::size_t>(blocks.size()));
             context::check(b200sa_suffix_array_batch(gpu.get(), blocks.bytes.data(), blocks.offsets.data(), blocks.size(), suffixArrays.data()),
                            "make_suffix_arrays (batch)");
+            return suffixArrays;
+        }
+
+        // Several GPUs behind the same batch calls: the blocks are cut into one contiguous run per GPU (b200sa_group_*_batch).
+        // devices: CUDA device numbers, e.g. {0, 1, 2, 3}; default: MSUFSORT_NUM_GPUS (or every GPU present)
+        class gpu_group
+        {
+        public:
+            explicit gpu_group(std::vector<int> devices = {})
+            {
+                if (devices.empty())
+                {
+                    char const * env = std::getenv("MSUFSORT_NUM_GPUS");
+                    int count = env ? std::atoi(env) : b200sa_device_count();
+                    if (count < 1)
+                        count = 1;
+                    for (int d = 0; d < count; ++d)
+                        devices.push_back(d);
+                }
+                context::check(b200sa_group_create(&group_, devices.data(), static_cast<int>(devices.size())), "b200sa_group_create");
+            }
+            ~gpu_group() { b200sa_group_destroy(group_); }
+            gpu_group(gpu_group const &) = delete;
+            gpu_group & operator = (gpu_group const &) = delete;
+            b200sa_group * get() const { return group_; }
+
+        private:
+            b200sa_group * group_ = nullptr;
+        };
+
+        inline std::vector<std::int32_t> forward_burrows_wheeler_transform(gpu_group & gpus, packed_blocks & blocks)
+        {
+            std::vector<std::int32_t> sentinelIndices(static_cast<std::size_t>(blocks.size()));
+            context::check(b200sa_group_bwt_batch(gpus.get(), blocks.bytes.data(), blocks.offsets.data(), blocks.size(), sentinelIndices.data()),
+                           "forward_burrows_wheeler_transform (batch, several GPUs)");
+            return sentinelIndices;
+        }
+
+        inline void reverse_burrows_wheeler_transform(gpu_group & gpus, packed_blocks & blocks, std::vector<std::int32_t> const & sentinelIndices)
+        {
+            if (static_cast<std::int64_t>(sentinelIndices.size()) != blocks.size())
+                throw std::invalid_argument("one sentinel index per block");
+            context::check(b200sa_group_unbwt_batch(gpus.get(), blocks.bytes.data(), blocks.offsets.data(), blocks.size(), sentinelIndices.data()),
+                           "reverse_burrows_wheeler_transform (batch, several GPUs)");
+        }
+
+        inline std::vector<std::int32_t> make_suffix_arrays(gpu_group & gpus, packed_blocks const & blocks)
+        {
+            std::vector<std::int32_t> suffixArrays(blocks.bytes.size() + static_cast<std::size_t>(blocks.size()));
+            context::check(b200sa_group_suffix_array_batch(gpus.get(), blocks.bytes.data(), blocks.offsets.data(), blocks.size(), suffixArrays.data()),
+                           "make_suffix_arrays (batch, several GPUs)");
             return suffixArrays;
         }
     } // namespace b200

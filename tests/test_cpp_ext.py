@@ -12,11 +12,25 @@ from conftest import ROOT
 SRC = os.path.join(ROOT, "tests", "cpp", "ext_test.cpp")
 
 
-def _build(exe, libdir, lib):
-    if not os.path.exists(exe) or os.path.getmtime(exe) < max(os.path.getmtime(SRC), os.path.getmtime(os.path.join(ROOT, "src", "library", "msufsort", "msufsort_b200.h"))):
-        subprocess.run(["g++", "-std=c++17", "-O2", f"-I{ROOT}/src", f"-I{ROOT}/include", SRC, "-o", exe, f"-L{libdir}", f"-l{lib}",
+GROUP_SRC = os.path.join(ROOT, "tests", "cpp", "ext_group_test.cpp")
+
+
+def _build(exe, libdir, lib, src=SRC):
+    if not os.path.exists(exe) or os.path.getmtime(exe) < max(os.path.getmtime(src), os.path.getmtime(os.path.join(ROOT, "src", "library", "msufsort", "msufsort_b200.h"))):
+        subprocess.run(["g++", "-std=c++17", "-O2", f"-I{ROOT}/src", f"-I{ROOT}/include", src, "-o", exe, f"-L{libdir}", f"-l{lib}",
                         f"-Wl,-rpath,{libdir}"], check=True)
     return exe
+
+
+def check_group_caller(exe, tmp_path, n, block, devices):
+    """tests/cpp/ext_group_test.cpp: a batch spread over `devices` (maniscalco::b200::gpu_group) equals the one-context batch"""
+    f = tmp_path / "in.bin"
+    f.write_bytes(gen("markov3", n).tobytes())
+    out = subprocess.run([exe, str(f), str(block), devices], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout + out.stderr
+    lines = out.stdout.strip().splitlines()
+    assert lines[0] == f"GROUP {len(devices.split(','))} BLOCKS {(n + block - 1) // block + 1}"
+    assert lines[1:] == ["SA same", "BWT same", "ROUNDTRIP ok"], out.stdout
 
 
 def _check(exe, oracle, tmp_path, n, block):
@@ -46,6 +60,12 @@ def test_cpp_extension_header_emu(oracle, tmp_path):
         subprocess.run(["make", "-s", "emu"], cwd=ROOT, check=True)
     exe = _build(os.path.join(ROOT, "tests", "cpp", "ext_test_emu"), emudir, "b200sa_emu")
     _check(exe, oracle, tmp_path, 30011, 7000)
+
+
+def test_cpp_extension_header_group_emu(tmp_path):
+    emudir = os.path.join(ROOT, "tests", "emu")
+    exe = _build(os.path.join(ROOT, "tests", "cpp", "ext_group_test_emu"), emudir, "b200sa_emu", GROUP_SRC)
+    check_group_caller(exe, tmp_path, 60011, 3000, "0,0,0")
 
 
 @pytest.mark.gpu

@@ -1,11 +1,15 @@
 """GPU tier, batches of independent blocks over the contexts of a group (b200sa_group_*_batch).
 These entry points were added after the round's last GPU run: the file sorts last so that the GPU tier reaches it after
 everything that had already been verified on a B200.  The emulator tier of the same code is tests/test_group.py."""
+import os
+
 import numpy as np
 import pytest
 
 from cases import gen
 from msufsort_b200.api import Group
+from conftest import ROOT
+from test_cpp_ext import GROUP_SRC, _build, check_group_caller
 from test_group import _batch_blocks, _check_batch
 
 
@@ -34,3 +38,11 @@ def test_gpu_group_batch_one_context_per_gpu(oracle):
         _check_batch(g, oracle, _batch_blocks(np.random.default_rng(7), 32 << 20, 512))
     finally:
         g.close()
+
+
+@pytest.mark.gpu
+def test_gpu_cpp_group_caller(tmp_path):
+    """the C++ extension header's gpu_group (tests/cpp/ext_group_test.cpp) against the product library: three contexts on cuda:0"""
+    libdir = os.path.join(ROOT, "msufsort_b200", "lib")
+    exe = _build(os.path.join(ROOT, "tests", "cpp", "ext_group_test"), libdir, "b200sa", GROUP_SRC)
+    check_group_caller(exe, tmp_path, (4 << 20) + 13, 50000, "0,0,0")

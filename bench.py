@@ -53,6 +53,18 @@ CPU_MAX_BYTES = 1 << 28     # reference arm / cpu_baseline: the whole text up to
 REF_BUILD_NOTE = "oracle/_ref: unmodified reference, g++ -O3 -march=x86-64-v3 (portable across build and GPU box; the reference's own flags use -march=native)"
 
 
+def cpu_model() -> str:
+    """the host CPU the reference arm ran on (print the core count and CPU model beside the CPU baseline)"""
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.lower().startswith("model name"):
+                    return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
 def load_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -188,7 +200,7 @@ def run_reference(args, wl):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True,
         "scaling": "strong" if args.gpus > 1 and args.mode == "sharded" else "weak", "vs_baseline": None, "dtype": "u8/int32", "data": "synthetic",
         "config": {"workload": wl, "description": desc, "n_bytes": n, "sample_bytes": ns},
-        "cpu_baseline": {"value": value, "unit": "MB/s", "cores": threads, "kind": "reference", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "MB/s", "cores": threads, "cpu_model": cpu_model(), "kind": "reference", "sample": sample},
         "e2e": {"value": value, "unit": "MB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "unbwt": {"value": ns / un_s / 1e6, "unit": "MB/s", "ms": 1e3 * un_s, "cores": threads,
                   "sample": f"reverse_burrows_wheeler_transform of the BWT of {whole} ({ns} bytes), 1 repetition"},
@@ -339,7 +351,7 @@ def run_ours(args, wl):
             work = np.empty(ns, dtype=np.uint8)
             t, s_ref = reference_step(lib, text, sa, work, threads)
             whole = "the whole workload text" if ns == n else f"the first {ns} bytes of the workload text"
-            cpu = {"value": ns / t / 1e6, "unit": "MB/s", "cores": threads, "kind": "reference",
+            cpu = {"value": ns / t / 1e6, "unit": "MB/s", "cores": threads, "cpu_model": cpu_model(), "kind": "reference",
                    "sample": f"{whole}, SA + BWT via the reference's two public calls, 1 repetition, {threads} threads; {REF_BUILD_NOTE}"}
             if ns == n and (s_ref != sentinel or not np.array_equal(work, h_work.numpy())):
                 raise SystemExit("bench.py: the reference's BWT of the workload text differs from ours")

@@ -193,6 +193,12 @@ def run_reference(args, wl):
     value = ns * args.steps / total / 1e6
     # the inverse transform of the BWT the last step left in `work` (one repetition; the reference needs ~4 s at 256 MiB)
     un_s = reference_unbwt(lib, work, sentinel, threads, text)
+    # the same step with numThreads = 1 beside it (one repetition, ~16 s at 256 MiB; N = 1 runs only)
+    single = None
+    if args.gpus == 1 and not args.no_single_thread:
+        t1, s1 = reference_step(lib, text, sa, work, 1)
+        single = {"value": ns / t1 / 1e6, "unit": "MB/s", "ms_per_step": 1e3 * t1, "cores": 1, "sample": "one repetition of the same step, numThreads = 1"}
+        assert s1 == sentinel
     whole = "the whole workload text" if ns == n else f"the first {ns} bytes of the workload text"
     sample = f"{whole}, SA + BWT via the reference's two public calls, {threads} threads; {REF_BUILD_NOTE}"
     line = {
@@ -204,6 +210,7 @@ def run_reference(args, wl):
         "e2e": {"value": value, "unit": "MB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "unbwt": {"value": ns / un_s / 1e6, "unit": "MB/s", "ms": 1e3 * un_s, "cores": threads,
                   "sample": f"reverse_burrows_wheeler_transform of the BWT of {whole} ({ns} bytes), 1 repetition"},
+        "single_thread": single,
     }
     print(json.dumps(line))
     return 0
@@ -767,6 +774,7 @@ def main():
     ap.add_argument("--big-n", type=int, default=0, help="override the size of the sharded configs[2] text (debugging)")
     ap.add_argument("--unbwt-n", type=int, default=0, help="override the size of the inverse-BWT text (debugging)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-single-thread", action="store_true", help="reference arm: skip the numThreads = 1 repetition")
     ap.add_argument("--no-extras", action="store_true", help="skip the LCP / batched-blocks timings appended as 'extras'")
     ap.add_argument("--no-facade", action="store_true", help="skip the C++ facade end-to-end run ('e2e_facade')")
     ap.add_argument("--no-unbwt", action="store_true", help="skip the inverse-BWT record ('unbwt')")

@@ -208,6 +208,9 @@ B200SA_API int b200sa_unbwt_batch_dev(b200sa_ctx* ctx, const uint8_t* d_bwt, con
  * b200sa_*_batch calls.  The reference has no counterpart (its callers loop over blocks, main.cpp:466-487). */
 typedef struct b200sa_pipeline b200sa_pipeline;
 B200SA_API int b200sa_pipeline_create(b200sa_pipeline** out, int device, int depth);
+/* The same with `depth` contexts on EVERY listed device behind the one queue: the stream of batches spreads over all GPUs
+ * and their PCIe links (nothing is exchanged between GPUs). */
+B200SA_API int b200sa_pipeline_create_devices(b200sa_pipeline** out, const int* devices, int count, int depth);
 B200SA_API void b200sa_pipeline_destroy(b200sa_pipeline* p);
 B200SA_API int b200sa_pipeline_submit_bwt(b200sa_pipeline* p, uint8_t* blocks_inout, const int64_t* offsets, int64_t count,
                                           int32_t* sentinel_index_out, int64_t* ticket_out);

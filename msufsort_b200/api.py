@@ -79,6 +79,7 @@ ABI = [
     ("b200sa_batch_dev", C.c_int, [_P, _P, _P, C.c_int64, _P, _P, _P, _P]),
     ("b200sa_unbwt_batch_dev", C.c_int, [_P, _P, _P, C.c_int64, _P, _P, _P]),
     ("b200sa_pipeline_create", C.c_int, [C.POINTER(_P), C.c_int, C.c_int]),
+    ("b200sa_pipeline_create_devices", C.c_int, [C.POINTER(_P), C.POINTER(C.c_int), C.c_int, C.c_int]),
     ("b200sa_pipeline_destroy", None, [_P]),
     ("b200sa_pipeline_submit_bwt", C.c_int, [_P, _P, _P, C.c_int64, _P, C.POINTER(C.c_int64)]),
     ("b200sa_pipeline_submit_unbwt", C.c_int, [_P, _P, _P, C.c_int64, _P, C.POINTER(C.c_int64)]),
@@ -682,10 +683,15 @@ class Pipeline:
     overlap the sort of another (b200sa_pipeline_*).  Buffers passed to submit must stay alive and untouched
     until ``wait``; numpy arrays are kept referenced here until then."""
 
-    def __init__(self, device: int = 0, depth: int = 2, library: Optional[Library] = None):
+    def __init__(self, device: int = 0, depth: int = 2, library: Optional[Library] = None, devices=None):
+        """devices: a list of CUDA devices — ``depth`` contexts on EACH of them serve the one queue (b200sa_pipeline_create_devices)"""
         self.lib = library if library is not None else load_library()
         self._p = _P()
-        self.lib.check(self.lib.cdll.b200sa_pipeline_create(C.byref(self._p), device, depth))
+        if devices is not None:
+            devs = (C.c_int * len(devices))(*devices)
+            self.lib.check(self.lib.cdll.b200sa_pipeline_create_devices(C.byref(self._p), devs, len(devices), depth))
+        else:
+            self.lib.check(self.lib.cdll.b200sa_pipeline_create(C.byref(self._p), device, depth))
         self._keep = {}
 
     def submit_bwt(self, packed: np.ndarray, offsets: np.ndarray, sentinels_out: np.ndarray) -> int:

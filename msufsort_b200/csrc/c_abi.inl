@@ -483,26 +483,35 @@ struct b200sa_pipeline {
 
 extern "C" {
 
-int b200sa_pipeline_create(b200sa_pipeline** out, int device, int depth)
+// `depth` contexts on every listed device behind ONE queue: with several devices the stream of batches spreads over all
+// GPUs and all PCIe links (batches are independent: nothing is exchanged)
+int b200sa_pipeline_create_devices(b200sa_pipeline** out, const int* devices, int count, int depth)
 {
     if (!out) return b200sa::set_error(B200SA_EINVAL, "null out pointer");
     *out = nullptr;
+    if (!devices || count < 1 || count > b200sa::kMaxPeers) return b200sa::set_error(B200SA_EINVAL, "between 1 and %d devices", b200sa::kMaxPeers);
     if (depth < 1 || depth > 8) return b200sa::set_error(B200SA_EINVAL, "pipeline depth %d outside [1, 8]", depth);
     b200sa_pipeline* p = new (std::nothrow) b200sa_pipeline();
     if (!p) return b200sa::set_error(B200SA_ENOMEM, "out of host memory");
-    for (int i = 0; i < depth; ++i) {
-        b200sa_ctx* c = nullptr;
-        const int rc = b200sa_create(&c, device);
-        if (rc != 0) {
-            for (auto* q : p->ctxs) b200sa_destroy(q);
-            delete p;
-            return rc;
+    for (int i = 0; i < depth; ++i)
+        for (int d = 0; d < count; ++d) {
+            b200sa_ctx* c = nullptr;
+            const int rc = b200sa_create(&c, devices[d]);
+            if (rc != 0) {
+                for (auto* q : p->ctxs) b200sa_destroy(q);
+                delete p;
+                return rc;
+            }
+            p->ctxs.push_back(c);
         }
-        p->ctxs.push_back(c);
-    }
-    for (int i = 0; i < depth; ++i) p->workers.emplace_back([p, i] { p->run((size_t)i); });
+    for (size_t i = 0; i < p->ctxs.size(); ++i) p->workers.emplace_back([p, i] { p->run(i); });
     *out = p;
     return 0;
+}
+
+int b200sa_pipeline_create(b200sa_pipeline** out, int device, int depth)
+{
+    return b200sa_pipeline_create_devices(out, &device, 1, depth);
 }
 
 void b200sa_pipeline_destroy(b200sa_pipeline* p)

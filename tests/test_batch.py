@@ -132,11 +132,11 @@ def test_gpu_batch_many_blocks_device_resident(gpu_engine, oracle):
 
 
 # ---- streaming pipeline ---------------------------------------------------------------------------
-def _pipeline_roundtrip(lib, oracle, nbatches, blocks_per_batch, block_len, depth):
+def _pipeline_roundtrip(lib, oracle, nbatches, blocks_per_batch, block_len, depth, devices=None):
     from msufsort_b200.api import Pipeline
     rng = np.random.default_rng(depth)
     jobs = []
-    with Pipeline(0, depth, library=lib) as pipe:
+    with Pipeline(0, depth, library=lib, devices=devices) as pipe:
         for j in range(nbatches):
             blocks = [gen(["markov3", "rand", "acgt_rep", "zeros"][(j + b) % 4], int(rng.integers(1, block_len))) for b in range(blocks_per_batch)]
             packed = np.concatenate(blocks)
@@ -181,6 +181,10 @@ def test_emu_pipeline(oracle):
             pipe.wait(t)                     # a ticket can be collected once
     with pytest.raises(B200SAError):
         Pipeline(0, 0, library=lib)
+    # two contexts on each of three listed devices behind the one queue (b200sa_pipeline_create_devices)
+    _pipeline_roundtrip(lib, oracle, nbatches=7, blocks_per_batch=4, block_len=2500, depth=2, devices=[0, 0, 0])
+    with pytest.raises(B200SAError):
+        Pipeline(library=lib, devices=[])
 
 
 def test_emu_pipeline_waiters_never_hang(oracle):

@@ -46,3 +46,17 @@ def test_gpu_cpp_group_caller(tmp_path):
     libdir = os.path.join(ROOT, "msufsort_b200", "lib")
     exe = _build(os.path.join(ROOT, "tests", "cpp", "ext_group_test"), libdir, "b200sa", GROUP_SRC)
     check_group_caller(exe, tmp_path, (4 << 20) + 13, 50000, "0,0,0")
+
+
+@pytest.mark.gpu
+def test_gpu_pipeline_over_listed_devices(oracle):
+    """b200sa_pipeline_create_devices: two contexts on every listed device behind one queue (here cuda:0 listed twice, and every
+    GPU of the box when there are several)"""
+    import torch
+    from msufsort_b200.api import load_library
+    from test_batch import _pipeline_roundtrip
+    lib = load_library()
+    _pipeline_roundtrip(lib, oracle, nbatches=6, blocks_per_batch=8, block_len=200000, depth=2, devices=[0, 0])
+    ng = torch.cuda.device_count()
+    if ng >= 2:
+        _pipeline_roundtrip(lib, oracle, nbatches=2 * ng, blocks_per_batch=8, block_len=200000, depth=2, devices=list(range(min(ng, 8))))
